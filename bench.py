@@ -1,0 +1,273 @@
+#!/usr/bin/env python
+"""bench.py — graph edges/sec (construct + transitive reduction), BASELINE.json's metric.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload c3]
+
+A step is one pass of the hot path (classify -> ordered containment -> re-trim -> final containment ->
+edge list + CSR -> transitive reduction) over one batch of synthetic overlaps:
+  N = 1 : BASELINE.json configs[2] — 100 Mbp genome, 40x, 10 kbp reads (~400k reads, ~14M overlap
+          records listed once per pair), read ids shuffled, flat pile table [15, len-15).
+  N > 1 : the same shape per GPU (weak scaling): genome = N x 100 Mbp, records sharded by contiguous
+          range, CSR replicated by all-gather, marks merged by all-reduce (rala_b200/multi.py).
+`value` = E / t with the inputs resident in HBM; `e2e` = the same through the C ABI with HOST (pinned)
+buffers: H2D of records + piles and D2H of edges + marks inside the timed region.
+`--impl reference` times the reference's own CPU implementation of the path (oracle/_ref/rala_ref
+hotpath: the unmodified reference's Overlap::trim/type, Graph::Node/Edge and
+remove_transitive_edges driven in memory) on this box's host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (genome bp per GPU, coverage, read length, description)
+    "c3": (100_000_000, 40, 10000, "configs[2]: synthetic 100 Mbp genome, 40x 10 kbp reads (~400k reads), shuffled read ids"),
+    "c1": (5_000_000, 30, 10000, "configs[0]: synthetic 5 Mbp genome, 30x 10 kbp reads (~15k reads)"),
+    "c4s": (387_500_000, 30, 10000, "configs[3] shard: 3.1 Gbp / 8 per GPU, 30x 10 kbp reads"),
+}
+K1_BYTES_PER_OVERLAP = 41      # 24 read + 16 trimmed coords + 1 type (+ pile table amortised)
+K3_BYTES_PER_VISIT = 8         # each two-hop visit streams one (dst, len)
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.samples, self.stop_flag, self.th = index, [], threading.Event(), None
+
+    def _run(self):
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self.stop_flag.wait(0.1)
+
+    def start(self):
+        self.th = threading.Thread(target=self._run, daemon=True)
+        self.th.start()
+
+    def stop(self) -> dict:
+        self.stop_flag.set()
+        if self.th:
+            self.th.join(timeout=6)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"], "samples": 0}
+        sm = sorted(float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(s[3 + i].lower().startswith("active") for s in self.samples)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(self.samples[0][1]),
+                "power_w_max": max(float(s[2]) for s in self.samples), "reasons": reasons, "samples": len(self.samples)}
+
+
+def make_dataset(workload: str, n_gpus: int, seed: int = 3):
+    from rala_b200 import synth
+    genome, cov, rl, _ = WORKLOADS[workload]
+    return synth.generate(genome * n_gpus, cov, rl, seed=seed)
+
+
+def cpu_reference_run(ds, piles, repeat: int = 1) -> dict:
+    """The reference's own CPU path on in-memory inputs (oracle/_ref), else the plain-C oracle port."""
+    from oracle import oracle as O
+    cores_used = 1   # the reference runs this path on its main thread whatever -t is (SURVEY.md finding 1)
+    if O.have_ref():
+        with tempfile.TemporaryDirectory() as tmp:
+            prefix = os.path.join(tmp, "w")
+            O.write_hotpath_inputs(prefix, ds.records, piles, None, None, ds.read_len)
+            r = json.loads(O.ref_run(["hotpath", prefix, "-", repeat]).strip().splitlines()[-1])
+        t = r["t_classify"] + r["t_preprocess"] + r["t_nodes"] + r["t_edges"] + r["t_transitive"]
+        return {"kind": "reference", "edges": r["edges"], "seconds": t, "cores": cores_used, "phases": r}
+    t0 = time.perf_counter()
+    P = O.Pipeline(ds.records, piles).run()
+    t = time.perf_counter() - t0
+    return {"kind": "port", "edges": int(P.edges.shape[0]), "seconds": t, "cores": cores_used, "phases": {}}
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    ds = make_dataset(args.workload, 1)
+    piles = ds.flat_piles()
+    times, edges, kind = [], 0, "port"
+    for i in range(args.warmup + args.steps):
+        r = cpu_reference_run(ds, piles)
+        edges, kind = r["edges"], r["kind"]
+        if i >= args.warmup:
+            times.append(r["seconds"])
+    t = sum(times) / len(times)
+    value = edges / t
+    sample = f"full {args.workload} batch: {ds.n_overlaps} overlap records, {ds.n_reads} reads, {edges} edges"
+    print(json.dumps({
+        "impl": "reference", "metric": "graph_edges_per_sec", "value": value, "unit": "edges/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u32+f64", "data": "synthetic",
+        "config": {"workload": WORKLOADS[args.workload][3], "n_overlaps": ds.n_overlaps, "n_reads": ds.n_reads, "edges": edges},
+        "cpu_baseline": {"value": value, "unit": "edges/s", "cores": 1, "kind": kind, "sample": sample,
+                         "host_cores_available": os.cpu_count(),
+                         "note": "the reference runs this path single-threaded regardless of -t (graph.cpp:443-518, 576-632, 1281-1335)"},
+        "e2e": {"value": value, "unit": "edges/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def run_single(args):
+    import torch
+    from rala_b200 import api
+
+    ds = make_dataset(args.workload, 1)
+    piles = ds.flat_piles()
+    n_ovl, n_reads = ds.n_overlaps, ds.n_reads
+    ctx = api.Context(0)
+    G = api.Graph(ctx)
+
+    # pinned host buffers for the end-to-end path
+    rec_pin = torch.from_numpy(ds.records).pin_memory()
+    piles_pin = torch.from_numpy(piles).pin_memory()
+
+    # ---- resident: inputs uploaded once, K steps of the whole device pipeline -------------------
+    G.set_piles(piles_pin).set_hills(None).set_overlaps(rec_pin)
+    for _ in range(args.warmup):
+        G.run()
+    ctx.synchronize()
+    counts = G.counts()
+    E = counts["n_edges"]
+    sampler = ClockSampler(0)
+    sampler.start()
+    launches0 = ctx.launch_count
+    stage_acc = {}
+    ctx.synchronize()
+    t0 = time.perf_counter()
+    ctx.event_record(0)
+    for _ in range(args.steps):
+        G.run()     # classify() restores the pile table it started from (device copy, inside the timed region)
+    ctx.event_record(1)
+    dev_ms = ctx.event_elapsed_ms()
+    ctx.synchronize()
+    wall_ms = 1e3 * (time.perf_counter() - t0)
+    launches = ctx.launch_count - launches0
+    stage_ms = G.stage_ms()            # last step's per-stage / per-kernel device times
+    ms_per_step = dev_ms / args.steps
+    value = E / (ms_per_step * 1e-3)
+
+    # per-kernel durations averaged over a few extra (untimed) steps for the roofline object
+    k1, k3 = [], []
+    for _ in range(max(3, min(args.steps, 10))):
+        G.run()
+        s = G.stage_ms()
+        k1.append(s["k1_classify_kernel"])
+        k3.append(s["k3_transitive_kernels"])
+        for k, v in s.items():
+            stage_acc.setdefault(k, []).append(v)
+    clocks = sampler.stop()
+    k1_ms, k3_ms = float(np.mean(k1)), float(np.mean(k3))
+    peak, peak_src = measured_peaks()
+    k1_bytes = K1_BYTES_PER_OVERLAP * n_ovl
+    k3_bytes = K3_BYTES_PER_VISIT * counts["n_two_hop"] + 9 * E + 8 * counts["n_nodes"]
+    k1_gbs = k1_bytes / (k1_ms * 1e-3) / 1e9
+    k3_gbs = k3_bytes / (k3_ms * 1e-3) / 1e9 if k3_ms > 0 else 0.0
+    dominant = "k_classify_first" if k1_ms >= k3_ms else "k_transitive_light+heavy"
+    roof = {"bound": "hbm", "kernel": dominant, "achieved": k1_gbs if k1_ms >= k3_ms else k3_gbs, "peak": peak,
+            "unit": "GB/s", "frac": (k1_gbs if k1_ms >= k3_ms else k3_gbs) / peak, "traffic": None, "peak_source": peak_src,
+            "kernels": {"k_classify_first": {"ms": k1_ms, "algorithmic_bytes": k1_bytes, "gbs": k1_gbs, "frac": k1_gbs / peak},
+                        "k_transitive": {"ms": k3_ms, "algorithmic_bytes": k3_bytes, "gbs": k3_gbs, "frac": k3_gbs / peak}},
+            "stage_ms": {k: float(np.mean(v)) for k, v in stage_acc.items()}}
+
+    # ---- end to end through the C ABI with host buffers ------------------------------------------
+    edges_pin = torch.empty((max(E, 1), 3), dtype=torch.int32).pin_memory()
+    marked_pin = torch.empty(max(E, 1), dtype=torch.uint8).pin_memory()
+    e2e_steps = max(3, min(args.steps, 10))
+
+    def e2e_step():
+        G.set_piles(piles_pin).set_overlaps(rec_pin)
+        G.run()
+        G.edges(out=edges_pin)
+        G.marked(out=marked_pin)
+
+    e2e_step()
+    ctx.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    ctx.synchronize()
+    e2e_s = (time.perf_counter() - t0) / e2e_steps
+    h2d = ds.records.nbytes + piles.nbytes
+    d2h = 12 * E + E + 4 * 30
+
+    # ---- CPU baseline on the same batch (rank 0, N = 1) -----------------------------------------
+    cpu = None
+    if not args.no_cpu_baseline:
+        r = cpu_reference_run(ds, piles)
+        cpu = {"value": r["edges"] / r["seconds"], "unit": "edges/s", "cores": r["cores"], "kind": r["kind"],
+               "sample": f"full batch ({n_ovl} overlap records, {r['edges']} edges) in {r['seconds']:.2f} s",
+               "host_cores_available": os.cpu_count(), "phases_s": {k: v for k, v in r["phases"].items() if k.startswith("t_")}}
+        assert r["edges"] == E, f"CPU baseline built {r['edges']} edges, GPU {E}"
+
+    line = {
+        "metric": "graph_edges_per_sec", "value": value, "unit": "edges/s", "n_gpus": 1, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u32+f64", "data": "synthetic",
+        "config": {"workload": WORKLOADS[args.workload][3], "n_overlaps": n_ovl, "n_reads": n_reads, "edges": E,
+                   "nodes": counts["n_nodes"], "two_hop_visits": counts["n_two_hop"], "transitive_pairs": counts["n_transitive_pairs"],
+                   "containment_events": counts["n_candidates"], "fixpoint_rounds": counts["n_rounds"],
+                   "heavy_items": counts["n_heavy_items"], "retrim_passes_executed": 0,
+                   "l2": f"inputs larger than L2 ({ds.records.nbytes / 1e6:.0f} MB of records streamed per step)",
+                   "parallelism": "1 GPU"},
+        "wall_ms_per_step": wall_ms / args.steps,
+        "e2e": {"value": E / e2e_s, "unit": "edges/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                "ms_per_step": 1e3 * e2e_s},
+        "gpu_launches": int(launches),
+        "roofline": roof, "cpu_baseline": cpu, "clocks": clocks,
+    }
+    print(json.dumps(line))
+    G.close()
+    ctx.close()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c3", choices=list(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.gpus > 1 or world > 1:
+        from rala_b200 import multi
+        multi.bench_main(args)
+        return
+    run_single(args)
+
+
+if __name__ == "__main__":
+    main()

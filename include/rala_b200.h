@@ -1,0 +1,172 @@
+/* rala_b200.h — C ABI of the B200-native assembly-graph hot path (librala_b200.so).
+ *
+ * The reference (rvaser/rala) has no plugin / FFI interface: `rala` is one executable and the state
+ * of rala::Graph is private.  The boundary is therefore cut at the two member functions its CLI
+ * already calls:
+ *     Graph::construct               /root/reference/src/graph.cpp:427-640   (main.cpp:74)
+ *     Graph::remove_transitive_edges /root/reference/src/graph.cpp:1281-1335 (via simplify, graph.cpp:646)
+ * Each entry point below names the reference lines it replaces.  INTEGRATION.md shows the
+ * reference-side patch (plain C++ calls; no binding layer is needed since the reference is C++).
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes; no CUDA, torch or C++ types in any signature.
+ *   - every function returns 0 on success or a negative rala_b200_status; the message is available
+ *     from rala_b200_last_error().  The host shim keeps the reference's own convention on top of
+ *     that: fprintf(stderr, "[rala::Graph::construct] error: %s!\n", ...); exit(1);  (cf. graph.cpp:418-421)
+ *   - called from one host thread at a time per context (the reference drives this path from its
+ *     main thread only, SURVEY.md finding 1).
+ *   - there is NO CPU fallback: without a CUDA device rala_b200_create() fails.
+ *
+ * Limits: ids, coordinates and counts are 32-bit; read lengths < 2^30;
+ * overlap records per context < 2^31.
+ */
+#ifndef RALA_B200_H
+#define RALA_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RALA_B200_ABI_VERSION 1
+
+/* One PAF/MHAP overlap after name->id translation; replaces the numeric members of rala::Overlap
+ * (overlap.hpp:104-116).  Records are passed in FILE ORDER: the position of a record is its
+ * processing time in the reference's order-dependent containment removal (graph.cpp:448-480). */
+typedef struct {
+    uint32_t a_id, b_id;       /* sequence ids (Overlap::a_id_/b_id_ after transmute, overlap.cpp:36-82) */
+    uint32_t a_begin, a_end;   /* on a's forward strand */
+    uint32_t b_begin, b_end;   /* on b's forward strand */
+    uint32_t flags;            /* bit0: orientation_ (overlap.cpp:18, 29); bit1: record is invalid —
+                                  is_valid_overlap_ false (graph.cpp:450) or a name that is not in name_to_id_ */
+} rala_ovl_t;
+#define RALA_OVL_RC       1u
+#define RALA_OVL_INVALID  2u
+
+/* Valid region [begin, end) of one read's pile (Pile::begin()/end(), pile.hpp:33-42).
+ * end == 0 means the pile is dead (piles_[i] == nullptr in the reference). */
+typedef struct { uint32_t begin, end; } rala_pile_t;
+
+/* per-pile flag byte */
+#define RALA_PILE_HAS_HILL    1u   /* Pile::has_chimeric_hill()   (pile.hpp:107) */
+#define RALA_PILE_HAS_REGION  2u   /* Pile::has_chimeric_region() (pile.hpp:121) */
+
+/* One chimeric hill (Pile::chimeric_hills_[k]); rows grouped by ascending pile id, in the pile's own order. */
+typedef struct { uint32_t pile, begin, end; } rala_hill_t;
+
+/* One directed edge; row index = edge id, pair(e) = e ^ 1, pair(node) = node ^ 1 (graph.cpp:553-632). */
+typedef struct { uint32_t src, dst, len; } rala_edge_t;
+
+/* Overlap::type() values (overlap.hpp:27-33) + 255 for "rejected by trim / dead pile / invalid". */
+enum { RALA_KX = 0, RALA_KA = 1, RALA_KB = 2, RALA_KAB = 3, RALA_KBA = 4, RALA_REJECTED = 255 };
+
+typedef enum {
+    RALA_B200_OK = 0,
+    RALA_B200_ERR_CUDA = -1,        /* a CUDA call failed (message has the CUDA error string) */
+    RALA_B200_ERR_ARG = -2,         /* bad argument */
+    RALA_B200_ERR_STATE = -3,       /* stage called out of order */
+    RALA_B200_ERR_NO_DEVICE = -4,   /* no sm_100 device: there is no CPU fallback */
+    RALA_B200_ERR_LIMIT = -5        /* a documented limit was exceeded */
+} rala_b200_status;
+
+typedef struct rala_b200_ctx rala_b200_ctx;      /* one CUDA device + stream + scratch arena */
+typedef struct rala_b200_graph rala_b200_graph;  /* device-resident state of one construct + reduce */
+
+int rala_b200_abi_version(void);
+int rala_b200_create(rala_b200_ctx** out, int device);
+void rala_b200_destroy(rala_b200_ctx* ctx);
+const char* rala_b200_last_error(const rala_b200_ctx* ctx);
+/* Number of kernels this context has launched so far (bench.py's gpu_launches). */
+uint64_t rala_b200_launch_count(const rala_b200_ctx* ctx);
+/* CUDA events on the context's stream: record(0) ... record(1), then elapsed_ms waits for event 1. */
+int rala_b200_event_record(rala_b200_ctx* ctx, int which);
+int rala_b200_event_elapsed_ms(rala_b200_ctx* ctx, float* ms);
+int rala_b200_synchronize(rala_b200_ctx* ctx);
+
+/* ------------------------------------------------------------------------------------------------
+ * Stateless stages on HOST buffers (copies inside): the unit-level boundary.
+ * ---------------------------------------------------------------------------------------------- */
+
+/* Overlap::trim + Overlap::type (overlap.cpp:117-259) for n independent records: coordinates are
+ * trimmed in place, type_out[i] is RALA_K* or RALA_REJECTED. */
+int rala_b200_trim_classify(rala_b200_ctx* ctx, rala_ovl_t* ovl, uint64_t n,
+                            const rala_pile_t* piles, uint32_t n_piles, uint8_t* type_out);
+
+/* Graph::remove_transitive_edges (graph.cpp:1281-1318) on an arbitrary edge list:
+ * marked_out[e] = 1 for every edge the reference removes; *n_pairs = its return value. */
+int rala_b200_transitive_reduce(rala_b200_ctx* ctx, uint32_t n_nodes, uint64_t n_edges,
+                                const rala_edge_t* edges, uint8_t* marked_out, uint64_t* n_pairs);
+
+/* ------------------------------------------------------------------------------------------------
+ * Graph session: the drop-in for Graph::construct's hot loops and Graph::remove_transitive_edges.
+ * Call order (what the patched Graph::construct does):
+ *   set_piles, set_hills, set_overlaps        inputs produced by the unchanged Graph::initialize
+ *   classify                                  graph.cpp:443-518
+ *   get_hill_coverage, [host: Pile::break_over_chimeric_hills], set_piles      :704-720
+ *   retrim                                    :722-736
+ *   loop { get_connections, [host: components, medians, Pile::break_over_chimeric_pits], set_piles,
+ *          retrim_promote(&changed) } until !changed                           :738-829
+ *   finalize                                  :831-877
+ *   get_piles                                 pile liveness for Sequence trimming / node creation (:527-574)
+ *   build                                     :552-632 (ids, edge list, adjacency)
+ *   get_edges, get_seq_to_node                re-materialise Node/Edge objects on the host
+ *   transitive                                :1281-1318
+ *   get_marked                                then the unchanged :1320-1334 on the host
+ * rala_b200_graph_run() chains classify..transitive with the pile table frozen and no host
+ * synchronisation in between (clean data: no hills, no pits).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+    uint64_t n_records;      /* as set */
+    uint64_t n_overlaps;     /* current `overlaps` list */
+    uint64_t n_internals;    /* current `internals` list */
+    uint64_t n_candidates;   /* containment events fed to the last ordered-containment resolution */
+    uint32_t n_rounds;       /* fixed-point rounds it took */
+    uint32_t n_piles, n_alive_piles;
+    uint32_t n_nodes;        /* nodes_.size() */
+    uint64_t n_edges;        /* edges_.size() */
+    uint64_t n_two_hop;      /* H = sum over edges (a->b) of outdegree(b): two-hop visits of the transitive pass */
+    uint64_t n_transitive_pairs; /* return value of remove_transitive_edges */
+    uint32_t n_heavy_items;  /* block-per-node work items of the last transitive pass */
+} rala_b200_counts_t;
+
+int rala_b200_graph_create(rala_b200_ctx* ctx, rala_b200_graph** out);
+void rala_b200_graph_destroy(rala_b200_graph* g);
+
+int rala_b200_graph_set_overlaps(rala_b200_graph* g, const rala_ovl_t* ovl, uint64_t n);
+int rala_b200_graph_set_piles(rala_b200_graph* g, const rala_pile_t* piles, const uint8_t* flags /* nullable */,
+                              uint32_t n_piles);
+int rala_b200_graph_set_hills(rala_b200_graph* g, const rala_hill_t* hills, uint32_t n_hills);
+
+int rala_b200_graph_classify(rala_b200_graph* g);
+int rala_b200_graph_retrim(rala_b200_graph* g);
+int rala_b200_graph_retrim_promote(rala_b200_graph* g, int* is_changed);
+int rala_b200_graph_finalize(rala_b200_graph* g);
+int rala_b200_graph_build(rala_b200_graph* g);
+int rala_b200_graph_transitive(rala_b200_graph* g);
+int rala_b200_graph_run(rala_b200_graph* g);
+
+/* synchronises the stream and reads the device-side counters */
+int rala_b200_graph_counts(rala_b200_graph* g, rala_b200_counts_t* out);
+
+int rala_b200_graph_get_hill_coverage(rala_b200_graph* g, uint32_t* cov_out /* n_hills */);
+int rala_b200_graph_get_piles(rala_b200_graph* g, rala_pile_t* piles_out /* n_piles */);
+/* (a_id, b_id) of every entry of `overlaps`, for the host's component search (graph.cpp:740-744) */
+int rala_b200_graph_get_connections(rala_b200_graph* g, uint32_t* ab_out /* 2 * n_overlaps */);
+int rala_b200_graph_get_lists(rala_b200_graph* g, rala_ovl_t* overlaps_out /* nullable */,
+                              rala_ovl_t* internals_out /* nullable */);
+int rala_b200_graph_get_seq_to_node(rala_b200_graph* g, uint32_t* out /* n_piles; 0xFFFFFFFF = dead */);
+int rala_b200_graph_get_edges(rala_b200_graph* g, rala_edge_t* out /* n_edges */);
+int rala_b200_graph_get_marked(rala_b200_graph* g, uint8_t* out /* n_edges */);
+
+/* Device time of the last run of each stage, CUDA events on the context's stream (ms).
+ * Order: classify, retrim, finalize, build, transitive (whole stages), then single kernels:
+ * K1 first-pass classify kernel, K1b containment fixed point, K3 transitive kernels (light + heavy).
+ * For bench.py's roofline object. */
+#define RALA_B200_N_STAGES 8
+int rala_b200_graph_stage_ms(rala_b200_graph* g, float* ms_out /* RALA_B200_N_STAGES */);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,331 @@
+"""ctypes binding of librala_b200.so (include/rala_b200.h) and the host-side mirror of the two
+reference entry points it replaces:
+
+    rala::Graph::construct               /root/reference/src/graph.cpp:427-640
+    rala::Graph::remove_transitive_edges /root/reference/src/graph.cpp:1281-1335
+
+There is no CPU fallback: if the shared library is missing, or there is no sm_100 device, every
+entry point raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "librala_b200.so")
+N_STAGES = 8
+STAGE_NAMES = ("classify", "retrim", "finalize", "build", "transitive", "k1_classify_kernel", "k1b_fixpoint_kernel",
+               "k3_transitive_kernels")
+
+KX, KA, KB, KAB, KBA, REJECTED = 0, 1, 2, 3, 4, 255
+
+
+class RalaB200Error(RuntimeError):
+    pass
+
+
+class Counts(C.Structure):
+    _fields_ = [("n_records", C.c_uint64), ("n_overlaps", C.c_uint64), ("n_internals", C.c_uint64),
+                ("n_candidates", C.c_uint64), ("n_rounds", C.c_uint32), ("n_piles", C.c_uint32),
+                ("n_alive_piles", C.c_uint32), ("n_nodes", C.c_uint32), ("n_edges", C.c_uint64),
+                ("n_two_hop", C.c_uint64), ("n_transitive_pairs", C.c_uint64), ("n_heavy_items", C.c_uint32)]
+
+    def as_dict(self):
+        return {k: int(getattr(self, k)) for k, _ in self._fields_}
+
+
+EXPORTS = [
+    "rala_b200_abi_version", "rala_b200_create", "rala_b200_destroy", "rala_b200_last_error",
+    "rala_b200_launch_count", "rala_b200_event_record", "rala_b200_event_elapsed_ms", "rala_b200_synchronize",
+    "rala_b200_trim_classify", "rala_b200_transitive_reduce",
+    "rala_b200_graph_create", "rala_b200_graph_destroy", "rala_b200_graph_set_overlaps",
+    "rala_b200_graph_set_piles", "rala_b200_graph_set_hills", "rala_b200_graph_classify",
+    "rala_b200_graph_retrim", "rala_b200_graph_retrim_promote", "rala_b200_graph_finalize",
+    "rala_b200_graph_build", "rala_b200_graph_transitive", "rala_b200_graph_run", "rala_b200_graph_counts",
+    "rala_b200_graph_get_hill_coverage", "rala_b200_graph_get_piles", "rala_b200_graph_get_connections",
+    "rala_b200_graph_get_lists", "rala_b200_graph_get_seq_to_node", "rala_b200_graph_get_edges",
+    "rala_b200_graph_get_marked", "rala_b200_graph_stage_ms",
+]
+
+_LIB = None
+
+
+def load():
+    """Load the CUDA extension; raises (never falls back) when it has not been built."""
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(LIB_PATH):
+            raise RalaB200Error(f"{LIB_PATH} is missing: run `python -m rala_b200.build` (there is no CPU fallback)")
+        lib = C.CDLL(LIB_PATH)
+        lib.rala_b200_last_error.restype = C.c_char_p
+        lib.rala_b200_launch_count.restype = C.c_uint64
+        lib.rala_b200_destroy.restype = None
+        lib.rala_b200_graph_destroy.restype = None
+        _LIB = lib
+    return _LIB
+
+
+def _ptr(a):
+    """Raw address of a numpy array or a (CPU, possibly pinned) torch tensor."""
+    if a is None:
+        return None
+    if hasattr(a, "data_ptr"):
+        return C.c_void_p(a.data_ptr())
+    return C.c_void_p(a.ctypes.data)
+
+
+def _np(a, dtype, cols=None):
+    if hasattr(a, "data_ptr"):   # torch tensor: must already be contiguous and of the right dtype
+        if not a.is_contiguous() or a.device.type != "cpu":
+            raise RalaB200Error("host buffers must be contiguous CPU tensors")
+        return a
+    a = np.ascontiguousarray(a, dtype=dtype)
+    if cols is not None:
+        a = a.reshape(-1, cols)
+    return a
+
+
+class Context:
+    """One CUDA device + stream (rala_b200_ctx)."""
+
+    def __init__(self, device: int = 0):
+        self.lib = load()
+        self.handle = C.c_void_p()
+        rc = self.lib.rala_b200_create(C.byref(self.handle), C.c_int(device))
+        if rc != 0:
+            raise RalaB200Error(f"rala_b200_create(device={device}) failed with status {rc}: "
+                                "an sm_100 (B200) device is required, there is no CPU fallback")
+        self.device = device
+
+    def check(self, rc: int, what: str):
+        if rc != 0:
+            msg = self.lib.rala_b200_last_error(self.handle)
+            raise RalaB200Error(f"{what}: status {rc}: {msg.decode() if msg else ''}")
+
+    @property
+    def launch_count(self) -> int:
+        return int(self.lib.rala_b200_launch_count(self.handle))
+
+    def event_record(self, which: int):
+        self.check(self.lib.rala_b200_event_record(self.handle, C.c_int(which)), "event_record")
+
+    def event_elapsed_ms(self) -> float:
+        ms = C.c_float(0)
+        self.check(self.lib.rala_b200_event_elapsed_ms(self.handle, C.byref(ms)), "event_elapsed_ms")
+        return float(ms.value)
+
+    def synchronize(self):
+        self.check(self.lib.rala_b200_synchronize(self.handle), "synchronize")
+
+    def close(self):
+        if self.handle:
+            self.lib.rala_b200_destroy(self.handle)
+            self.handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- stateless stages -------------------------------------------------------------------
+    def trim_classify(self, records, piles):
+        """Overlap::trim + Overlap::type (overlap.cpp:117-259) -> (trimmed records, types)."""
+        rec = np.array(records, dtype=np.uint32, copy=True).reshape(-1, 7)
+        piles = _np(piles, np.uint32, 2)
+        types = np.zeros(rec.shape[0], dtype=np.uint8)
+        self.check(self.lib.rala_b200_trim_classify(self.handle, _ptr(rec), C.c_uint64(rec.shape[0]), _ptr(piles),
+                                                    C.c_uint32(piles.shape[0]), _ptr(types)), "trim_classify")
+        return rec, types
+
+    def transitive_reduce(self, n_nodes: int, edges):
+        """Graph::remove_transitive_edges (graph.cpp:1281-1318) on an injected edge list -> (marked, n_pairs)."""
+        edges = _np(edges, np.uint32, 3)
+        marked = np.zeros(edges.shape[0], dtype=np.uint8)
+        n_pairs = C.c_uint64(0)
+        self.check(self.lib.rala_b200_transitive_reduce(self.handle, C.c_uint32(n_nodes), C.c_uint64(edges.shape[0]),
+                                                        _ptr(edges), _ptr(marked), C.byref(n_pairs)), "transitive_reduce")
+        return marked, int(n_pairs.value)
+
+
+class Graph:
+    """Host-side mirror of rala::Graph for the hot path (graph.hpp:37-60).
+
+    `construct()` is Graph::construct's hot half (graph.cpp:443-632) on numeric inputs — what the
+    unchanged Graph::initialize leaves behind: overlap records in file order with their validity
+    bit, the pile table with flags, the chimeric hills.  `remove_transitive_edges()` is
+    graph.cpp:1281-1335 including the host-side tail (transitive_edges_, stable adjacency compaction).
+    """
+
+    def __init__(self, ctx: Context | None = None, device: int = 0):
+        self.ctx = ctx or Context(device)
+        self.lib = self.ctx.lib
+        self.handle = C.c_void_p()
+        self.ctx.check(self.lib.rala_b200_graph_create(self.ctx.handle, C.byref(self.handle)), "graph_create")
+        self.n_piles = 0
+        self.n_hills = 0
+        self._keep = []   # host buffers referenced by in-flight async copies
+        self.transitive_edges = None
+
+    def close(self):
+        if self.handle:
+            self.lib.rala_b200_graph_destroy(self.handle)
+            self.handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _call(self, name, *args):
+        self.ctx.check(getattr(self.lib, name)(self.handle, *args), name)
+
+    # ---- inputs ------------------------------------------------------------------------------
+    def set_overlaps(self, records):
+        rec = _np(records, np.uint32, 7)
+        n = rec.shape[0]
+        self._keep = [rec]
+        self._call("rala_b200_graph_set_overlaps", _ptr(rec), C.c_uint64(n))
+        return self
+
+    def set_piles(self, piles, flags=None):
+        p = _np(piles, np.uint32, 2)
+        f = None if flags is None else _np(flags, np.uint8)
+        self.n_piles = p.shape[0]
+        self._keep += [p, f]
+        self._call("rala_b200_graph_set_piles", _ptr(p), _ptr(f), C.c_uint32(self.n_piles))
+        return self
+
+    def set_hills(self, hills):
+        h = _np(np.zeros((0, 3)) if hills is None else hills, np.uint32, 3)
+        self.n_hills = h.shape[0]
+        self._call("rala_b200_graph_set_hills", _ptr(h), C.c_uint32(self.n_hills))
+        return self
+
+    # ---- stages (same boundaries as the reference's construct) ---------------------------------
+    def classify(self):
+        self._call("rala_b200_graph_classify")
+        return self
+
+    def retrim(self):
+        self._call("rala_b200_graph_retrim")
+        return self
+
+    def retrim_promote(self) -> bool:
+        changed = C.c_int(0)
+        self._call("rala_b200_graph_retrim_promote", C.byref(changed))
+        return bool(changed.value)
+
+    def finalize(self):
+        self._call("rala_b200_graph_finalize")
+        return self
+
+    def build(self):
+        self._call("rala_b200_graph_build")
+        return self
+
+    def transitive(self):
+        self._call("rala_b200_graph_transitive")
+        return self
+
+    def run(self):
+        """classify .. transitive with the pile table frozen; no host synchronisation inside."""
+        self._call("rala_b200_graph_run")
+        return self
+
+    # ---- outputs -----------------------------------------------------------------------------
+    def counts(self) -> dict:
+        c = Counts()
+        self._call("rala_b200_graph_counts", C.byref(c))
+        return c.as_dict()
+
+    def hill_coverage(self):
+        out = np.zeros(self.n_hills, dtype=np.uint32)
+        self._call("rala_b200_graph_get_hill_coverage", _ptr(out))
+        return out
+
+    def piles(self):
+        out = np.zeros((self.n_piles, 2), dtype=np.uint32)
+        self._call("rala_b200_graph_get_piles", _ptr(out))
+        return out
+
+    def connections(self):
+        n = self.counts()["n_overlaps"]
+        out = np.zeros((n, 2), dtype=np.uint32)
+        self._call("rala_b200_graph_get_connections", _ptr(out))
+        return out
+
+    def lists(self):
+        c = self.counts()
+        ovl = np.zeros((c["n_overlaps"], 7), dtype=np.uint32)
+        inl = np.zeros((c["n_internals"], 7), dtype=np.uint32)
+        self._call("rala_b200_graph_get_lists", _ptr(ovl), _ptr(inl))
+        return ovl, inl
+
+    def seq_to_node(self):
+        out = np.zeros(self.n_piles, dtype=np.uint32)
+        self._call("rala_b200_graph_get_seq_to_node", _ptr(out))
+        return out
+
+    def edges(self, out=None):
+        n = self.counts()["n_edges"]
+        if out is None:
+            out = np.zeros((n, 3), dtype=np.uint32)
+        self._call("rala_b200_graph_get_edges", _ptr(out))
+        return out
+
+    def marked(self, out=None):
+        n = self.counts()["n_edges"]
+        if out is None:
+            out = np.zeros(n, dtype=np.uint8)
+        self._call("rala_b200_graph_get_marked", _ptr(out))
+        return out
+
+    def stage_ms(self) -> dict:
+        ms = (C.c_float * N_STAGES)()
+        self._call("rala_b200_graph_stage_ms", ms)
+        return dict(zip(STAGE_NAMES, [float(x) for x in ms]))
+
+    # ---- the reference's two entry points ------------------------------------------------------
+    def construct(self, records, piles, flags=None, hills=None, pile_ops=None):
+        """Graph::construct's hot half.  `pile_ops` stands for the host-side Pile calls the reference
+        makes between the passes (they stay on the host):
+            pile_ops.break_over_chimeric_hills(hill_coverage) -> (piles, flags) | None   graph.cpp:704-720
+            pile_ops.break_over_chimeric_pits(connections)    -> (piles, flags) | None   graph.cpp:740-797
+        With pile_ops=None the pile table is frozen (clean data)."""
+        self.set_piles(piles, flags).set_hills(hills).set_overlaps(records)
+        self.classify()
+        if pile_ops is not None:
+            upd = pile_ops.break_over_chimeric_hills(self.hill_coverage())
+            if upd is not None:
+                self.set_piles(*upd)
+        self.retrim()
+        while True:
+            if pile_ops is not None:
+                upd = pile_ops.break_over_chimeric_pits(self.connections())
+                if upd is not None:
+                    self.set_piles(*upd)
+            if not self.retrim_promote():
+                break
+        self.finalize().build()
+        c = self.counts()
+        self.n_nodes, self.n_edges = c["n_nodes"], c["n_edges"]
+        return self
+
+    def remove_transitive_edges(self) -> int:
+        """graph.cpp:1281-1335.  Device: marks.  Host tail: transitive_edges_ (:1320-1330)."""
+        self.transitive()
+        c = self.counts()
+        marked = self.marked()
+        e = self.edges()
+        odd = np.nonzero(marked[1::2])[0] * 2 + 1
+        s, d = e[odd, 0] & ~np.uint32(1), e[odd, 1] & ~np.uint32(1)
+        pairs = np.concatenate([np.stack([s, d], 1), np.stack([d, s], 1)])
+        order = np.lexsort((pairs[:, 1], pairs[:, 0]))
+        self.transitive_edges = pairs[order]
+        self.removed = marked
+        return c["n_transitive_pairs"]

@@ -1,0 +1,861 @@
+// api.cu — the C ABI (include/rala_b200.h): context, stateless stages, and the graph session that
+// chains the kernels of classify.cu / graph_build.cu / transitive.cu with no host synchronisation
+// between stages (every data-dependent size stays on the device).
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/rala_b200.h"
+#include "kernels.h"
+#include "lists.cuh"
+
+using namespace rb;
+
+struct rala_b200_ctx {
+    cudaEvent_t ev[2]{};
+    int device = 0;
+    Launch L{nullptr, 0};
+    std::string error;
+    int coop_blocks = 0;
+};
+
+static int fail(rala_b200_ctx* ctx, int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    if (ctx) ctx->error = buf;
+    return code;
+}
+
+#define CU(ctx, call)                                                                                   \
+    do {                                                                                                \
+        cudaError_t err__ = (call);                                                                     \
+        if (err__ != cudaSuccess)                                                                       \
+            return fail((ctx), RALA_B200_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(err__), \
+                        __FILE__, __LINE__);                                                            \
+    } while (0)
+
+extern "C" int rala_b200_abi_version(void) { return RALA_B200_ABI_VERSION; }
+
+extern "C" int rala_b200_create(rala_b200_ctx** out, int device) {
+    if (!out) return RALA_B200_ERR_ARG;
+    *out = nullptr;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0 || device < 0 || device >= n) return RALA_B200_ERR_NO_DEVICE;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return RALA_B200_ERR_NO_DEVICE;
+    if (prop.major != 10) return RALA_B200_ERR_NO_DEVICE;   // sm_100a SASS only: no other target, no fallback
+    rala_b200_ctx* ctx = new rala_b200_ctx();
+    ctx->device = device;
+    if (cudaSetDevice(device) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&ctx->L.stream, cudaStreamNonBlocking) != cudaSuccess) {
+        delete ctx;
+        return RALA_B200_ERR_CUDA;
+    }
+    ctx->coop_blocks = fixpoint_max_blocks();
+    cudaEventCreate(&ctx->ev[0]);
+    cudaEventCreate(&ctx->ev[1]);
+    *out = ctx;
+    return RALA_B200_OK;
+}
+
+extern "C" void rala_b200_destroy(rala_b200_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->L.stream) cudaStreamDestroy(ctx->L.stream);
+    delete ctx;
+}
+
+extern "C" int rala_b200_event_record(rala_b200_ctx* ctx, int which) {
+    if (!ctx || which < 0 || which > 1) return RALA_B200_ERR_ARG;
+    CU(ctx, cudaSetDevice(ctx->device));
+    CU(ctx, cudaEventRecord(ctx->ev[which], ctx->L.stream));
+    return RALA_B200_OK;
+}
+
+extern "C" int rala_b200_event_elapsed_ms(rala_b200_ctx* ctx, float* ms) {
+    if (!ctx || !ms) return RALA_B200_ERR_ARG;
+    CU(ctx, cudaSetDevice(ctx->device));
+    CU(ctx, cudaEventSynchronize(ctx->ev[1]));
+    CU(ctx, cudaEventElapsedTime(ms, ctx->ev[0], ctx->ev[1]));
+    return RALA_B200_OK;
+}
+
+extern "C" int rala_b200_synchronize(rala_b200_ctx* ctx) {
+    if (!ctx) return RALA_B200_ERR_ARG;
+    CU(ctx, cudaSetDevice(ctx->device));
+    CU(ctx, cudaStreamSynchronize(ctx->L.stream));
+    return RALA_B200_OK;
+}
+
+extern "C" const char* rala_b200_last_error(const rala_b200_ctx* ctx) { return ctx ? ctx->error.c_str() : "no context"; }
+extern "C" uint64_t rala_b200_launch_count(const rala_b200_ctx* ctx) { return ctx ? ctx->L.count : 0; }
+
+// ---------------------------------------------------------------------------------------------
+// device buffer helper
+// ---------------------------------------------------------------------------------------------
+struct DevBuf {
+    void* p = nullptr;
+    size_t bytes = 0;
+    cudaError_t reserve(size_t want) {
+        if (want <= bytes) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        bytes = 0;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) bytes = want;
+        return e;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        bytes = 0;
+    }
+    template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+struct ListBuf {
+    DevBuf buf;
+    List view{};
+    cudaError_t reserve(uint32_t cap) {
+        size_t col = align_up((size_t) cap * 4, 256);
+        cudaError_t e = buf.reserve(col * 6 + align_up(cap, 256));
+        if (e != cudaSuccess) return e;
+        char* b = buf.as<char>();
+        view.a = (uint32_t*) b;
+        view.b = (uint32_t*) (b + col);
+        view.ab = (uint32_t*) (b + 2 * col);
+        view.ae = (uint32_t*) (b + 3 * col);
+        view.bb = (uint32_t*) (b + 4 * col);
+        view.be = (uint32_t*) (b + 5 * col);
+        view.tag = (uint8_t*) (b + 6 * col);
+        return cudaSuccess;
+    }
+};
+
+enum Stage { ST_CLASSIFY = 0, ST_RETRIM, ST_FINALIZE, ST_BUILD, ST_TRANSITIVE, ST_K1_KERNEL, ST_K1B_KERNEL, ST_K3_KERNELS };
+
+struct rala_b200_graph {
+    rala_b200_ctx* ctx = nullptr;
+    // inputs
+    DevBuf rec;
+    uint32_t n_rec = 0;
+    DevBuf piles, piles_raw, pile_flags_raw, piles_initial;
+    bool piles_fresh = false;       // set_piles since the last classify
+    uint32_t n_piles = 0;
+    DevBuf hills;   // 4 columns of n_hills: pile begin end cov
+    uint32_t n_hills = 0;
+    // lists
+    uint32_t cap = 0;   // capacity of every list / event array
+    ListBuf P, ovl[2], inl[2];
+    int ovl_cur = 0, inl_cur = 0;
+    int slot_ovl = C_LIST0, slot_inl = C_LIST0 + 1, next_slot = C_LIST0 + 2;
+    DevBuf events, hill_rec;
+    DevBuf dbuf, flags;
+    DevBuf counters;
+    DevBuf scan_pool;
+    size_t scan_pool_words = 0, scan_used = 0;
+    // graph
+    DevBuf seq_to_node, edges, row_ptr, cursor, col, col_eid, T, marked, heavy, work_counter;
+    uint32_t edge_cap = 0, heavy_cap = 0, n_nodes_max = 0;
+    // bookkeeping
+    bool piles_dirty = true;        // pile table changed since the lists were last trimmed against it
+    bool skip_clean_retrim = true;  // re-trimming against an unchanged table is the identity: skip the pass
+    int state = 0;                  // 0 empty, 1 inputs set, 2 classified, 3 finalized, 4 built, 5 reduced
+    uint32_t retrim_passes = 0;
+    cudaEvent_t ev_start[RALA_B200_N_STAGES]{}, ev_stop[RALA_B200_N_STAGES]{};
+    bool ev_valid[RALA_B200_N_STAGES]{};
+
+    uint32_t* cnt() const { return counters.as<uint32_t>(); }
+    Events events_view() const {
+        Events e;
+        size_t col = align_up((size_t) cap * 4, 256);
+        char* b = events.as<char>();
+        e.v = (uint32_t*) b;
+        e.c = (uint32_t*) (b + col);
+        e.t = (uint32_t*) (b + 2 * col);
+        return e;
+    }
+    GraphArrays graph_view() const {
+        GraphArrays g;
+        size_t col_b = align_up((size_t) edge_cap * 4, 256);
+        g.seq_to_node = seq_to_node.as<uint32_t>();
+        g.src = (uint32_t*) edges.as<char>();
+        g.dst = (uint32_t*) (edges.as<char>() + col_b);
+        g.len = (uint32_t*) (edges.as<char>() + 2 * col_b);
+        g.row_ptr = row_ptr.as<uint32_t>();
+        g.cursor = cursor.as<uint32_t>();
+        g.col = col.as<uint2>();
+        g.col_eid = col_eid.as<uint32_t>();
+        g.T = T.as<uint8_t>();
+        g.marked = marked.as<uint8_t>();
+        return g;
+    }
+    HeavyItems heavy_view() const {
+        HeavyItems h;
+        size_t colb = align_up((size_t) heavy_cap * 4, 256);
+        h.node = (uint32_t*) heavy.as<char>();
+        h.hash_chunk = (uint32_t*) (heavy.as<char>() + colb);
+        h.nbr_chunk = (uint32_t*) (heavy.as<char>() + 2 * colb);
+        h.cap = heavy_cap;
+        return h;
+    }
+    int new_slot() {
+        int s = next_slot;
+        next_slot = next_slot + 1 >= C_COUNT ? C_LIST0 : next_slot + 1;
+        if (s == slot_ovl || s == slot_inl) return new_slot();
+        return s;
+    }
+};
+
+static size_t tiles_of(uint64_t n) { return (size_t) ((n + kTile - 1) / kTile) + 1; }
+
+// a fresh, zeroed (status words, ticket) pair from the pool for one look-back kernel
+static void scan_state(rala_b200_graph* g, uint64_t n_max, unsigned long long** status, uint32_t** ticket) {
+    size_t words = tiles_of(n_max) + 1;
+    if (g->scan_used + words > g->scan_pool_words) g->scan_used = 0;   // never happens within one stage (pool is sized for it)
+    unsigned long long* base = g->scan_pool.as<unsigned long long>() + g->scan_used;
+    *ticket = reinterpret_cast<uint32_t*>(base);
+    *status = base + 1;
+    g->scan_used += words;
+}
+
+static cudaError_t begin_stage(rala_b200_graph* g, int stage) {
+    g->scan_used = 0;
+    cudaError_t e = cudaMemsetAsync(g->scan_pool.p, 0, g->scan_pool_words * 8, g->ctx->L.stream);
+    if (e != cudaSuccess) return e;
+    return cudaEventRecord(g->ev_start[stage], g->ctx->L.stream);
+}
+
+static cudaError_t end_stage(rala_b200_graph* g, int stage) {
+    g->ev_valid[stage] = true;
+    return cudaEventRecord(g->ev_stop[stage], g->ctx->L.stream);
+}
+
+static cudaError_t zero_counter(rala_b200_graph* g, int slot, int n = 1) {
+    return cudaMemsetAsync(g->cnt() + slot, 0, 4 * (size_t) n, g->ctx->L.stream);
+}
+
+extern "C" int rala_b200_graph_create(rala_b200_ctx* ctx, rala_b200_graph** out) {
+    if (!ctx || !out) return RALA_B200_ERR_ARG;
+    CU(ctx, cudaSetDevice(ctx->device));
+    rala_b200_graph* g = new rala_b200_graph();
+    g->ctx = ctx;
+    for (int i = 0; i < RALA_B200_N_STAGES; ++i) {
+        cudaEventCreate(&g->ev_start[i]);
+        cudaEventCreate(&g->ev_stop[i]);
+    }
+    cudaError_t e = g->counters.reserve(C_COUNT * 4);
+    if (e == cudaSuccess) e = g->flags.reserve(64);
+    if (e == cudaSuccess) e = g->work_counter.reserve(64);
+    if (e == cudaSuccess) e = cudaMemset(g->counters.p, 0, C_COUNT * 4);
+    if (e != cudaSuccess) {
+        delete g;
+        return fail(ctx, RALA_B200_ERR_CUDA, "graph_create: %s", cudaGetErrorString(e));
+    }
+    *out = g;
+    return RALA_B200_OK;
+}
+
+extern "C" void rala_b200_graph_destroy(rala_b200_graph* g) {
+    if (!g) return;
+    cudaSetDevice(g->ctx->device);
+    cudaStreamSynchronize(g->ctx->L.stream);
+    DevBuf* bufs[] = {&g->rec, &g->piles, &g->piles_raw, &g->pile_flags_raw, &g->piles_initial, &g->hills, &g->P.buf, &g->ovl[0].buf,
+                      &g->ovl[1].buf, &g->inl[0].buf, &g->inl[1].buf, &g->events, &g->hill_rec, &g->dbuf, &g->flags,
+                      &g->counters, &g->scan_pool, &g->seq_to_node, &g->edges, &g->row_ptr, &g->cursor, &g->col,
+                      &g->col_eid, &g->T, &g->marked, &g->heavy, &g->work_counter};
+    for (DevBuf* b : bufs) b->release();
+    for (int i = 0; i < RALA_B200_N_STAGES; ++i) {
+        cudaEventDestroy(g->ev_start[i]);
+        cudaEventDestroy(g->ev_stop[i]);
+    }
+    delete g;
+}
+
+static int reserve_scan_pool(rala_b200_graph* g) {
+    size_t words = 8 * (tiles_of(g->n_rec) + tiles_of(2ull * g->n_piles + 8) + 8);
+    if (words > g->scan_pool_words) {
+        CU(g->ctx, g->scan_pool.reserve(words * 8));
+        g->scan_pool_words = words;
+    }
+    return RALA_B200_OK;
+}
+
+extern "C" int rala_b200_graph_set_overlaps(rala_b200_graph* g, const rala_ovl_t* ovl, uint64_t n) {
+    if (!g || (n && !ovl)) return RALA_B200_ERR_ARG;
+    rala_b200_ctx* ctx = g->ctx;
+    if (n >= (1ull << 31)) return fail(ctx, RALA_B200_ERR_LIMIT, "too many overlap records (%llu >= 2^31)", (unsigned long long) n);
+    CU(ctx, cudaSetDevice(ctx->device));
+    CU(ctx, g->rec.reserve(align_up((size_t) n * sizeof(rala_ovl_t) + 16, 256)));
+    if (n) CU(ctx, cudaMemcpyAsync(g->rec.p, ovl, (size_t) n * sizeof(rala_ovl_t), cudaMemcpyHostToDevice, ctx->L.stream));
+    g->n_rec = (uint32_t) n;
+    // worst case every record survives; very large inputs get half and rely on the overflow check
+    uint32_t cap = (uint32_t) (n <= (1ull << 27) ? n : n / 2);
+    if (cap < 1024) cap = 1024;
+    if (cap > g->cap) {
+        CU(ctx, g->P.reserve(cap));
+        for (int i = 0; i < 2; ++i) {
+            CU(ctx, g->ovl[i].reserve(cap));
+            CU(ctx, g->inl[i].reserve(cap));
+        }
+        CU(ctx, g->events.reserve(align_up((size_t) cap * 4, 256) * 3));
+        CU(ctx, g->hill_rec.reserve((size_t) cap * 4));
+        g->cap = cap;
+        g->edge_cap = 2 * cap;
+        CU(ctx, g->edges.reserve(align_up((size_t) g->edge_cap * 4, 256) * 3));
+        CU(ctx, g->col.reserve((size_t) g->edge_cap * 8));
+        CU(ctx, g->col_eid.reserve((size_t) g->edge_cap * 4));
+        CU(ctx, g->T.reserve(align_up(g->edge_cap, 256)));
+        CU(ctx, g->marked.reserve(align_up(g->edge_cap, 256)));
+        g->heavy_cap = g->edge_cap / 16 + 4096;
+        CU(ctx, g->heavy.reserve(align_up((size_t) g->heavy_cap * 4, 256) * 3));
+    } else {
+        // views depend on cap: re-derive them for the (unchanged) capacity
+    }
+    int rc = reserve_scan_pool(g);
+    if (rc) return rc;
+    if (g->state < 1 && g->n_piles) g->state = 1;
+    if (g->state > 1) g->state = 1;
+    return RALA_B200_OK;
+}
+
+extern "C" int rala_b200_graph_set_piles(rala_b200_graph* g, const rala_pile_t* piles, const uint8_t* flags,
+                                         uint32_t n_piles) {
+    if (!g || (n_piles && !piles)) return RALA_B200_ERR_ARG;
+    rala_b200_ctx* ctx = g->ctx;
+    CU(ctx, cudaSetDevice(ctx->device));
+    if (n_piles >= (1u << 31)) return fail(ctx, RALA_B200_ERR_LIMIT, "too many piles");
+    CU(ctx, g->piles.reserve((size_t) n_piles * 8 + 16));
+    CU(ctx, g->piles_raw.reserve((size_t) n_piles * 8 + 16));
+    CU(ctx, g->piles_initial.reserve((size_t) n_piles * 8 + 16));
+    CU(ctx, g->pile_flags_raw.reserve((size_t) n_piles + 16));
+    CU(ctx, cudaMemcpyAsync(g->piles_raw.p, piles, (size_t) n_piles * 8, cudaMemcpyHostToDevice, ctx->L.stream));
+    if (flags) CU(ctx, cudaMemcpyAsync(g->pile_flags_raw.p, flags, n_piles, cudaMemcpyHostToDevice, ctx->L.stream));
+    launch_pack_piles(ctx->L, g->piles_raw.as<uint2>(), flags ? g->pile_flags_raw.as<uint8_t>() : nullptr,
+                      g->piles.as<uint2>(), n_piles);
+    if (n_piles != g->n_piles) {
+        g->n_piles = n_piles;
+        g->n_nodes_max = 2 * n_piles;
+        CU(ctx, g->dbuf.reserve((size_t) n_piles * 16 + 16));
+        CU(ctx, g->seq_to_node.reserve((size_t) n_piles * 4 + 16));
+        CU(ctx, g->row_ptr.reserve(((size_t) g->n_nodes_max + 8) * 4));
+        CU(ctx, g->cursor.reserve(((size_t) g->n_nodes_max + 8) * 4));
+        int rc = reserve_scan_pool(g);
+        if (rc) return rc;
+    }
+    g->piles_dirty = true;
+    g->piles_fresh = true;
+    if (g->state < 1 && g->n_rec) g->state = 1;
+    return RALA_B200_OK;
+}
+
+extern "C" int rala_b200_graph_set_hills(rala_b200_graph* g, const rala_hill_t* hills, uint32_t n_hills) {
+    if (!g || (n_hills && !hills)) return RALA_B200_ERR_ARG;
+    rala_b200_ctx* ctx = g->ctx;
+    CU(ctx, cudaSetDevice(ctx->device));
+    g->n_hills = n_hills;
+    if (!n_hills) return RALA_B200_OK;
+    std::vector<uint32_t> cols((size_t) n_hills * 4, 0u);
+    for (uint32_t i = 0; i < n_hills; ++i) {
+        if (i && hills[i].pile < hills[i - 1].pile) return fail(ctx, RALA_B200_ERR_ARG, "hills must be grouped by ascending pile id");
+        cols[i] = hills[i].pile;
+        cols[n_hills + i] = hills[i].begin;
+        cols[2 * (size_t) n_hills + i] = hills[i].end;
+    }
+    CU(ctx, g->hills.reserve(cols.size() * 4));
+    CU(ctx, cudaMemcpyAsync(g->hills.p, cols.data(), cols.size() * 4, cudaMemcpyHostToDevice, ctx->L.stream));
+    CU(ctx, cudaStreamSynchronize(ctx->L.stream));   // cols is a stack-owned staging vector
+    return RALA_B200_OK;
+}
+
+static int resolve_containment(rala_b200_graph* g) {
+    rala_b200_ctx* ctx = g->ctx;
+    launch_fill_u32(ctx->L, g->dbuf.as<uint32_t>(), kInf, (size_t) g->n_piles * 4);
+    CU(ctx, cudaMemsetAsync(g->flags.p, 0, 64, ctx->L.stream));
+    int blocks = ctx->coop_blocks;
+    launch_fixpoint(ctx->L, g->events_view(), g->cnt() + C_EV, g->cap, g->dbuf.as<uint32_t>(), g->n_piles,
+                    g->flags.as<uint32_t>(), g->cnt(), blocks);
+    CU(ctx, cudaGetLastError());
+    return RALA_B200_OK;
+}
+
+// graph.cpp:443-518
+extern "C" int rala_b200_graph_classify(rala_b200_graph* g) {
+    if (!g) return RALA_B200_ERR_ARG;
+    rala_b200_ctx* ctx = g->ctx;
+    if (g->state < 1) return fail(ctx, RALA_B200_ERR_STATE, "classify: set_overlaps and set_piles first");
+    CU(ctx, cudaSetDevice(ctx->device));
+    // classify kills piles in the working table: keep the table it started from, so that calling classify
+    // again without a new set_piles re-runs on the same input (bench loops, retries)
+    if (g->piles_fresh)
+        CU(ctx, cudaMemcpyAsync(g->piles_initial.p, g->piles.p, (size_t) g->n_piles * 8, cudaMemcpyDeviceToDevice, ctx->L.stream));
+    else
+        CU(ctx, cudaMemcpyAsync(g->piles.p, g->piles_initial.p, (size_t) g->n_piles * 8, cudaMemcpyDeviceToDevice, ctx->L.stream));
+    g->piles_fresh = false;
+    CU(ctx, begin_stage(g, ST_CLASSIFY));
+    CU(ctx, cudaMemsetAsync(g->counters.p, 0, C_COUNT * 4, ctx->L.stream));
+    if (g->n_hills) CU(ctx, cudaMemsetAsync(g->hills.as<uint32_t>() + 3 * (size_t) g->n_hills, 0, (size_t) g->n_hills * 4, ctx->L.stream));
+    unsigned long long* status;
+    uint32_t* ticket;
+    scan_state(g, g->n_rec, &status, &ticket);
+    CU(ctx, cudaEventRecord(g->ev_start[ST_K1_KERNEL], ctx->L.stream));
+    launch_classify_first(ctx->L, g->rec.as<uint32_t>(), g->n_rec, 0u, g->piles.as<uint2>(), g->n_piles, g->P.view, g->cap,
+                          g->events_view(), g->cap, g->hill_rec.as<uint32_t>(), g->cap, g->cnt(), status, ticket);
+    CU(ctx, end_stage(g, ST_K1_KERNEL));
+    CU(ctx, cudaEventRecord(g->ev_start[ST_K1B_KERNEL], ctx->L.stream));
+    int rc = resolve_containment(g);
+    if (rc) return rc;
+    CU(ctx, end_stage(g, ST_K1B_KERNEL));
+    if (g->n_hills) {
+        const uint32_t* h = g->hills.as<uint32_t>();
+        launch_hill_coverage(ctx->L, g->rec.as<uint32_t>(), 0u, g->piles.as<uint2>(), g->hill_rec.as<uint32_t>(), g->cap, h,
+                             h + g->n_hills, h + 2 * (size_t) g->n_hills, g->n_hills,
+                             g->hills.as<uint32_t>() + 3 * (size_t) g->n_hills, g->dbuf.as<uint32_t>(), g->n_piles, g->cnt());
+    }
+    launch_apply_deaths(ctx->L, g->piles.as<uint2>(), g->dbuf.as<uint32_t>(), g->n_piles, g->cnt());
+    g->ovl_cur = 0;
+    g->inl_cur = 0;
+    g->slot_ovl = C_LIST0;
+    g->slot_inl = C_LIST0 + 1;
+    g->next_slot = C_LIST0 + 2;
+    scan_state(g, g->cap, &status, &ticket);
+    launch_list_pass(ctx->L, 0 /*kSplitAlive*/, g->P.view, g->cnt() + C_P, g->cap, g->piles.as<uint2>(), g->ovl[0].view,
+                     g->cnt() + g->slot_ovl, g->inl[0].view, g->cnt() + g->slot_inl, nullptr, g->cap, nullptr, g->n_piles,
+                     nullptr, g->cnt(), status, ticket);
+    CU(ctx, cudaGetLastError());
+    CU(ctx, end_stage(g, ST_CLASSIFY));
+    g->piles_dirty = false;   // lists are trimmed against the table as it stands (only liveness changed, and the split filtered on it)
+    g->state = 2;
+    g->retrim_passes = 0;
+    return RALA_B200_OK;
+}
+
+static int retrim_list(rala_b200_graph* g, ListBuf* bufs, int* cur, int* slot) {
+    rala_b200_ctx* ctx = g->ctx;
+    unsigned long long* status;
+    uint32_t* ticket;
+    scan_state(g, g->cap, &status, &ticket);
+    int out_slot = g->new_slot();
+    CU(ctx, zero_counter(g, out_slot));
+    List none{};
+    launch_list_pass(ctx->L, 1 /*kRetrim*/, bufs[*cur].view, g->cnt() + *slot, g->cap, g->piles.as<uint2>(), bufs[*cur ^ 1].view,
+                     g->cnt() + out_slot, none, nullptr, nullptr, g->cap, nullptr, g->n_piles, nullptr, g->cnt(), status, ticket);
+    *cur ^= 1;
+    *slot = out_slot;
+    return RALA_B200_OK;
+}
+
+// graph.cpp:722-736
+extern "C" int rala_b200_graph_retrim(rala_b200_graph* g) {
+    if (!g) return RALA_B200_ERR_ARG;
+    rala_b200_ctx* ctx = g->ctx;
+    if (g->state != 2) return fail(ctx, RALA_B200_ERR_STATE, "retrim: classify first");
+    if (!g->piles_dirty && g->skip_clean_retrim) return RALA_B200_OK;
+    CU(ctx, cudaSetDevice(ctx->device));
+    CU(ctx, begin_stage(g, ST_RETRIM));
+    int rc = retrim_list(g, g->ovl, &g->ovl_cur, &g->slot_ovl);
+    if (!rc) rc = retrim_list(g, g->inl, &g->inl_cur, &g->slot_inl);
+    if (rc) return rc;
+    CU(ctx, cudaGetLastError());
+    CU(ctx, end_stage(g, ST_RETRIM));
+    g->piles_dirty = false;
+    g->retrim_passes += 1;
+    return RALA_B200_OK;
+}
+
+// graph.cpp:801-824
+extern "C" int rala_b200_graph_retrim_promote(rala_b200_graph* g, int* is_changed) {
+    if (!g) return RALA_B200_ERR_ARG;
+    rala_b200_ctx* ctx = g->ctx;
+    if (g->state != 2) return fail(ctx, RALA_B200_ERR_STATE, "retrim_promote: classify first");
+    if (is_changed) *is_changed = 0;
+    // Against an unchanged pile table trim() is the identity and the internals keep their (non-dovetail) type.
+    if (!g->piles_dirty && g->skip_clean_retrim) return RALA_B200_OK;
+    CU(ctx, cudaSetDevice(ctx->device));
+    CU(ctx, begin_stage(g, ST_RETRIM));
+    int before_slot = g->slot_ovl;
+    int rc = retrim_list(g, g->ovl, &g->ovl_cur, &g->slot_ovl);
+    if (rc) return rc;
+    int after_slot = g->slot_ovl;
+    // internals: survivors stay (stream A), new dovetails are appended to `overlaps` (stream B)
+    unsigned long long* status;
+    uint32_t* ticket;
+    scan_state(g, g->cap, &status, &ticket);
+    int inl_out = g->new_slot(), ovl_out = g->new_slot();
+    CU(ctx, zero_counter(g, inl_out));
+    CU(ctx, cudaMemcpyAsync(g->cnt() + ovl_out, g->cnt() + after_slot, 4, cudaMemcpyDeviceToDevice, ctx->L.stream));
+    launch_list_pass(ctx->L, 2 /*kPromote*/, g->inl[g->inl_cur].view, g->cnt() + g->slot_inl, g->cap, g->piles.as<uint2>(),
+                     g->inl[g->inl_cur ^ 1].view, g->cnt() + inl_out, g->ovl[g->ovl_cur].view, g->cnt() + ovl_out,
+                     g->cnt() + after_slot, g->cap, nullptr, g->n_piles, nullptr, g->cnt(), status, ticket);
+    g->inl_cur ^= 1;
+    g->slot_inl = inl_out;
+    g->slot_ovl = ovl_out;
+    CU(ctx, cudaGetLastError());
+    CU(ctx, end_stage(g, ST_RETRIM));
+    g->piles_dirty = false;
+    g->retrim_passes += 1;
+    if (is_changed) {
+        uint32_t h[C_COUNT];
+        CU(ctx, cudaMemcpyAsync(h, g->counters.p, C_COUNT * 4, cudaMemcpyDeviceToHost, ctx->L.stream));
+        CU(ctx, cudaStreamSynchronize(ctx->L.stream));
+        *is_changed = h[after_slot] != h[before_slot];
+    }
+    return RALA_B200_OK;
+}
+
+// graph.cpp:831-877
+extern "C" int rala_b200_graph_finalize(rala_b200_graph* g) {
+    if (!g) return RALA_B200_ERR_ARG;
+    rala_b200_ctx* ctx = g->ctx;
+    if (g->state != 2) return fail(ctx, RALA_B200_ERR_STATE, "finalize: classify first");
+    CU(ctx, cudaSetDevice(ctx->device));
+    CU(ctx, begin_stage(g, ST_FINALIZE));
+    CU(ctx, zero_counter(g, C_EV));
+    launch_classify_final(ctx->L, g->ovl[g->ovl_cur].view, g->cnt() + g->slot_ovl, g->cap, nullptr, g->piles.as<uint2>(),
+                          g->events_view(), g->cap, g->cnt());
+    launch_classify_final(ctx->L, g->inl[g->inl_cur].view, g->cnt() + g->slot_inl, g->cap, g->cnt() + g->slot_ovl,
+                          g->piles.as<uint2>(), g->events_view(), g->cap, g->cnt());
+    int rc = resolve_containment(g);
+    if (rc) return rc;
+    unsigned long long* status;
+    uint32_t* ticket;
+    List none{};
+    // internals first: needs the death times against the table BEFORE the kills are applied
+    scan_state(g, g->cap, &status, &ticket);
+    int inl_out = g->new_slot();
+    CU(ctx, zero_counter(g, inl_out));
+    launch_list_pass(ctx->L, 4 /*kFinalInt*/, g->inl[g->inl_cur].view, g->cnt() + g->slot_inl, g->cap, g->piles.as<uint2>(),
+                     g->inl[g->inl_cur ^ 1].view, g->cnt() + inl_out, none, nullptr, nullptr, g->cap, g->dbuf.as<uint32_t>(),
+                     g->n_piles, g->cnt() + g->slot_ovl, g->cnt(), status, ticket);
+    g->inl_cur ^= 1;
+    g->slot_inl = inl_out;
+    launch_apply_deaths(ctx->L, g->piles.as<uint2>(), g->dbuf.as<uint32_t>(), g->n_piles, g->cnt());
+    scan_state(g, g->cap, &status, &ticket);
+    int ovl_out = g->new_slot();
+    CU(ctx, zero_counter(g, ovl_out));
+    launch_list_pass(ctx->L, 3 /*kFinalOvl*/, g->ovl[g->ovl_cur].view, g->cnt() + g->slot_ovl, g->cap, g->piles.as<uint2>(),
+                     g->ovl[g->ovl_cur ^ 1].view, g->cnt() + ovl_out, none, nullptr, nullptr, g->cap, nullptr, g->n_piles,
+                     nullptr, g->cnt(), status, ticket);
+    g->ovl_cur ^= 1;
+    g->slot_ovl = ovl_out;
+    CU(ctx, cudaGetLastError());
+    CU(ctx, end_stage(g, ST_FINALIZE));
+    g->state = 3;
+    return RALA_B200_OK;
+}
+
+// graph.cpp:552-632
+extern "C" int rala_b200_graph_build(rala_b200_graph* g) {
+    if (!g) return RALA_B200_ERR_ARG;
+    rala_b200_ctx* ctx = g->ctx;
+    if (g->state != 3) return fail(ctx, RALA_B200_ERR_STATE, "build: finalize first");
+    CU(ctx, cudaSetDevice(ctx->device));
+    CU(ctx, begin_stage(g, ST_BUILD));
+    CU(ctx, zero_counter(g, C_NODES, 4));   // C_NODES, C_ALIVE, C_DOVETAILS, C_EDGES
+    CU(ctx, cudaMemsetAsync(g->cursor.p, 0, ((size_t) g->n_nodes_max + 8) * 4, ctx->L.stream));
+    unsigned long long* status;
+    uint32_t* ticket;
+    scan_state(g, g->n_piles, &status, &ticket);
+    launch_node_ids(ctx->L, g->piles.as<uint2>(), g->n_piles, g->seq_to_node.as<uint32_t>(), g->cnt(), status, ticket);
+    scan_state(g, g->cap, &status, &ticket);
+    launch_emit_edges(ctx->L, g->ovl[g->ovl_cur].view, g->cnt() + g->slot_ovl, g->cap, g->piles.as<uint2>(), g->graph_view(),
+                      g->edge_cap, g->cnt(), status, ticket);
+    scan_state(g, (uint64_t) g->n_nodes_max + 1, &status, &ticket);
+    launch_build_csr(ctx->L, g->graph_view(), g->n_nodes_max, g->edge_cap, g->cnt(), status, ticket);
+    CU(ctx, cudaGetLastError());
+    CU(ctx, end_stage(g, ST_BUILD));
+    g->state = 4;
+    return RALA_B200_OK;
+}
+
+static int run_transitive(rala_b200_graph* g) {
+    rala_b200_ctx* ctx = g->ctx;
+    CU(ctx, zero_counter(g, C_PAIRS, 2));   // C_PAIRS, C_HEAVY
+    CU(ctx, zero_counter(g, C_HOP_LO, 2));
+    CU(ctx, cudaMemsetAsync(g->work_counter.p, 0, 64, ctx->L.stream));
+    CU(ctx, cudaMemsetAsync(g->T.p, 0, align_up(g->edge_cap, 256), ctx->L.stream));
+    CU(ctx, cudaEventRecord(g->ev_start[ST_K3_KERNELS], ctx->L.stream));
+    launch_transitive(ctx->L, g->graph_view(), g->n_nodes_max, g->edge_cap, g->heavy_view(), g->work_counter.as<uint32_t>(),
+                      g->cnt(), 0u, 0xFFFFFFFFu);
+    CU(ctx, end_stage(g, ST_K3_KERNELS));
+    launch_finalize_marks(ctx->L, g->graph_view(), g->edge_cap, g->cnt());
+    CU(ctx, cudaGetLastError());
+    return RALA_B200_OK;
+}
+
+// graph.cpp:1281-1318
+extern "C" int rala_b200_graph_transitive(rala_b200_graph* g) {
+    if (!g) return RALA_B200_ERR_ARG;
+    rala_b200_ctx* ctx = g->ctx;
+    if (g->state < 4) return fail(ctx, RALA_B200_ERR_STATE, "transitive: build first");
+    CU(ctx, cudaSetDevice(ctx->device));
+    CU(ctx, begin_stage(g, ST_TRANSITIVE));
+    int rc = run_transitive(g);
+    if (rc) return rc;
+    CU(ctx, end_stage(g, ST_TRANSITIVE));
+    g->state = 5;
+    return RALA_B200_OK;
+}
+
+extern "C" int rala_b200_graph_run(rala_b200_graph* g) {
+    int rc = rala_b200_graph_classify(g);
+    if (!rc) rc = rala_b200_graph_retrim(g);
+    if (!rc) rc = rala_b200_graph_retrim_promote(g, nullptr);
+    if (!rc) rc = rala_b200_graph_finalize(g);
+    if (!rc) rc = rala_b200_graph_build(g);
+    if (!rc) rc = rala_b200_graph_transitive(g);
+    return rc;
+}
+
+static int read_counters(rala_b200_graph* g, uint32_t* h) {
+    rala_b200_ctx* ctx = g->ctx;
+    CU(ctx, cudaSetDevice(ctx->device));
+    CU(ctx, cudaMemcpyAsync(h, g->counters.p, C_COUNT * 4, cudaMemcpyDeviceToHost, ctx->L.stream));
+    CU(ctx, cudaStreamSynchronize(ctx->L.stream));
+    if (h[C_OVERFLOW] || h[C_P] > g->cap || h[C_EV] > g->cap || h[C_HILL] > g->cap || h[C_HEAVY] > g->heavy_cap)
+        return fail(ctx, RALA_B200_ERR_LIMIT, "a device list overflowed its capacity (cap=%u P=%u events=%u hills=%u heavy=%u/%u)",
+                    g->cap, h[C_P], h[C_EV], h[C_HILL], h[C_HEAVY], g->heavy_cap);
+    return RALA_B200_OK;
+}
+
+extern "C" int rala_b200_graph_counts(rala_b200_graph* g, rala_b200_counts_t* out) {
+    if (!g || !out) return RALA_B200_ERR_ARG;
+    uint32_t h[C_COUNT];
+    int rc = read_counters(g, h);
+    if (rc) return rc;
+    memset(out, 0, sizeof(*out));
+    out->n_records = g->n_rec;
+    out->n_overlaps = g->state >= 2 ? h[g->slot_ovl] : 0;
+    out->n_internals = g->state >= 2 ? h[g->slot_inl] : 0;
+    out->n_candidates = h[C_EV];
+    out->n_rounds = h[C_ROUNDS];
+    out->n_piles = g->n_piles;
+    out->n_alive_piles = h[C_ALIVE];
+    out->n_nodes = h[C_NODES];
+    out->n_edges = h[C_EDGES];
+    out->n_two_hop = (uint64_t) h[C_HOP_LO] | ((uint64_t) h[C_HOP_HI] << 32);
+    out->n_transitive_pairs = h[C_PAIRS];
+    out->n_heavy_items = h[C_HEAVY];
+    return RALA_B200_OK;
+}
+
+extern "C" int rala_b200_graph_get_hill_coverage(rala_b200_graph* g, uint32_t* cov_out) {
+    if (!g || (g->n_hills && !cov_out)) return RALA_B200_ERR_ARG;
+    rala_b200_ctx* ctx = g->ctx;
+    CU(ctx, cudaSetDevice(ctx->device));
+    if (g->n_hills)
+        CU(ctx, cudaMemcpyAsync(cov_out, g->hills.as<uint32_t>() + 3 * (size_t) g->n_hills, (size_t) g->n_hills * 4,
+                                cudaMemcpyDeviceToHost, ctx->L.stream));
+    CU(ctx, cudaStreamSynchronize(ctx->L.stream));
+    return RALA_B200_OK;
+}
+
+extern "C" int rala_b200_graph_get_piles(rala_b200_graph* g, rala_pile_t* piles_out) {
+    if (!g || !piles_out) return RALA_B200_ERR_ARG;
+    rala_b200_ctx* ctx = g->ctx;
+    CU(ctx, cudaSetDevice(ctx->device));
+    launch_unpack_piles(ctx->L, g->piles.as<uint2>(), g->piles_raw.as<uint2>(), g->n_piles);
+    CU(ctx, cudaMemcpyAsync(piles_out, g->piles_raw.p, (size_t) g->n_piles * 8, cudaMemcpyDeviceToHost, ctx->L.stream));
+    CU(ctx, cudaStreamSynchronize(ctx->L.stream));
+    return RALA_B200_OK;
+}
+
+extern "C" int rala_b200_graph_get_connections(rala_b200_graph* g, uint32_t* ab_out) {
+    if (!g || !ab_out) return RALA_B200_ERR_ARG;
+    rala_b200_ctx* ctx = g->ctx;
+    if (g->state < 2) return fail(ctx, RALA_B200_ERR_STATE, "get_connections: classify first");
+    uint32_t h[C_COUNT];
+    int rc = read_counters(g, h);
+    if (rc) return rc;
+    uint32_t n = h[g->slot_ovl];
+    if (!n) return RALA_B200_OK;
+    DevBuf tmp;
+    CU(ctx, tmp.reserve((size_t) n * 8));
+    launch_list_connections(ctx->L, g->ovl[g->ovl_cur].view, g->cnt() + g->slot_ovl, g->cap, tmp.as<uint32_t>());
+    CU(ctx, cudaMemcpyAsync(ab_out, tmp.p, (size_t) n * 8, cudaMemcpyDeviceToHost, ctx->L.stream));
+    CU(ctx, cudaStreamSynchronize(ctx->L.stream));
+    tmp.release();
+    return RALA_B200_OK;
+}
+
+extern "C" int rala_b200_graph_get_lists(rala_b200_graph* g, rala_ovl_t* overlaps_out, rala_ovl_t* internals_out) {
+    if (!g) return RALA_B200_ERR_ARG;
+    rala_b200_ctx* ctx = g->ctx;
+    if (g->state < 2) return fail(ctx, RALA_B200_ERR_STATE, "get_lists: classify first");
+    uint32_t h[C_COUNT];
+    int rc = read_counters(g, h);
+    if (rc) return rc;
+    DevBuf tmp;
+    for (int which = 0; which < 2; ++which) {
+        rala_ovl_t* out = which ? internals_out : overlaps_out;
+        uint32_t n = which ? h[g->slot_inl] : h[g->slot_ovl];
+        if (!out || !n) continue;
+        CU(ctx, tmp.reserve((size_t) n * 28));
+        launch_list_to_aos(ctx->L, which ? g->inl[g->inl_cur].view : g->ovl[g->ovl_cur].view,
+                           g->cnt() + (which ? g->slot_inl : g->slot_ovl), g->cap, tmp.as<uint32_t>());
+        CU(ctx, cudaMemcpyAsync(out, tmp.p, (size_t) n * 28, cudaMemcpyDeviceToHost, ctx->L.stream));
+        CU(ctx, cudaStreamSynchronize(ctx->L.stream));
+    }
+    tmp.release();
+    return RALA_B200_OK;
+}
+
+extern "C" int rala_b200_graph_get_seq_to_node(rala_b200_graph* g, uint32_t* out) {
+    if (!g || !out) return RALA_B200_ERR_ARG;
+    rala_b200_ctx* ctx = g->ctx;
+    if (g->state < 4) return fail(ctx, RALA_B200_ERR_STATE, "get_seq_to_node: build first");
+    CU(ctx, cudaSetDevice(ctx->device));
+    CU(ctx, cudaMemcpyAsync(out, g->seq_to_node.p, (size_t) g->n_piles * 4, cudaMemcpyDeviceToHost, ctx->L.stream));
+    CU(ctx, cudaStreamSynchronize(ctx->L.stream));
+    return RALA_B200_OK;
+}
+
+extern "C" int rala_b200_graph_get_edges(rala_b200_graph* g, rala_edge_t* out) {
+    if (!g || !out) return RALA_B200_ERR_ARG;
+    rala_b200_ctx* ctx = g->ctx;
+    if (g->state < 4) return fail(ctx, RALA_B200_ERR_STATE, "get_edges: build first");
+    uint32_t h[C_COUNT];
+    int rc = read_counters(g, h);
+    if (rc) return rc;
+    uint32_t n = h[C_EDGES];
+    if (!n) return RALA_B200_OK;
+    // columns -> rows on the host side of the copy (three strided copies)
+    GraphArrays ga = g->graph_view();
+    CU(ctx, cudaMemcpy2DAsync(&out[0].src, 12, ga.src, 4, 4, n, cudaMemcpyDeviceToHost, ctx->L.stream));
+    CU(ctx, cudaMemcpy2DAsync(&out[0].dst, 12, ga.dst, 4, 4, n, cudaMemcpyDeviceToHost, ctx->L.stream));
+    CU(ctx, cudaMemcpy2DAsync(&out[0].len, 12, ga.len, 4, 4, n, cudaMemcpyDeviceToHost, ctx->L.stream));
+    CU(ctx, cudaStreamSynchronize(ctx->L.stream));
+    return RALA_B200_OK;
+}
+
+extern "C" int rala_b200_graph_get_marked(rala_b200_graph* g, uint8_t* out) {
+    if (!g || !out) return RALA_B200_ERR_ARG;
+    rala_b200_ctx* ctx = g->ctx;
+    if (g->state < 5) return fail(ctx, RALA_B200_ERR_STATE, "get_marked: transitive first");
+    uint32_t h[C_COUNT];
+    int rc = read_counters(g, h);
+    if (rc) return rc;
+    if (h[C_EDGES]) CU(ctx, cudaMemcpyAsync(out, g->marked.p, h[C_EDGES], cudaMemcpyDeviceToHost, ctx->L.stream));
+    CU(ctx, cudaStreamSynchronize(ctx->L.stream));
+    return RALA_B200_OK;
+}
+
+extern "C" int rala_b200_graph_stage_ms(rala_b200_graph* g, float* ms_out) {
+    if (!g || !ms_out) return RALA_B200_ERR_ARG;
+    rala_b200_ctx* ctx = g->ctx;
+    CU(ctx, cudaSetDevice(ctx->device));
+    CU(ctx, cudaStreamSynchronize(ctx->L.stream));
+    for (int i = 0; i < RALA_B200_N_STAGES; ++i) {
+        ms_out[i] = 0.f;
+        if (g->ev_valid[i]) CU(ctx, cudaEventElapsedTime(&ms_out[i], g->ev_start[i], g->ev_stop[i]));
+    }
+    return RALA_B200_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// stateless stages
+// ---------------------------------------------------------------------------------------------
+extern "C" int rala_b200_trim_classify(rala_b200_ctx* ctx, rala_ovl_t* ovl, uint64_t n, const rala_pile_t* piles,
+                                       uint32_t n_piles, uint8_t* type_out) {
+    if (!ctx || (n && (!ovl || !type_out)) || (n_piles && !piles)) return RALA_B200_ERR_ARG;
+    if (n >= (1ull << 31)) return fail(ctx, RALA_B200_ERR_LIMIT, "too many records");
+    if (n == 0) return RALA_B200_OK;
+    CU(ctx, cudaSetDevice(ctx->device));
+    DevBuf rec, praw, ppacked, types;
+    CU(ctx, rec.reserve((size_t) n * 28));
+    CU(ctx, praw.reserve((size_t) n_piles * 8 + 16));
+    CU(ctx, ppacked.reserve((size_t) n_piles * 8 + 16));
+    CU(ctx, types.reserve(n));
+    CU(ctx, cudaMemcpyAsync(rec.p, ovl, (size_t) n * 28, cudaMemcpyHostToDevice, ctx->L.stream));
+    CU(ctx, cudaMemcpyAsync(praw.p, piles, (size_t) n_piles * 8, cudaMemcpyHostToDevice, ctx->L.stream));
+    launch_pack_piles(ctx->L, praw.as<uint2>(), nullptr, ppacked.as<uint2>(), n_piles);
+    launch_trim_classify_aos(ctx->L, rec.as<uint32_t>(), (uint32_t) n, ppacked.as<uint2>(), n_piles, types.as<uint8_t>());
+    CU(ctx, cudaGetLastError());
+    CU(ctx, cudaMemcpyAsync(ovl, rec.p, (size_t) n * 28, cudaMemcpyDeviceToHost, ctx->L.stream));
+    CU(ctx, cudaMemcpyAsync(type_out, types.p, n, cudaMemcpyDeviceToHost, ctx->L.stream));
+    CU(ctx, cudaStreamSynchronize(ctx->L.stream));
+    rec.release(); praw.release(); ppacked.release(); types.release();
+    return RALA_B200_OK;
+}
+
+extern "C" int rala_b200_transitive_reduce(rala_b200_ctx* ctx, uint32_t n_nodes, uint64_t n_edges, const rala_edge_t* edges,
+                                           uint8_t* marked_out, uint64_t* n_pairs) {
+    if (!ctx || (n_edges && (!edges || !marked_out))) return RALA_B200_ERR_ARG;
+    if (n_edges >= (1ull << 31) || (n_edges & 1)) return fail(ctx, RALA_B200_ERR_ARG, "edge count must be even and < 2^31 (pair(e) = e ^ 1)");
+    if (n_pairs) *n_pairs = 0;
+    if (n_edges == 0) return RALA_B200_OK;
+    for (uint64_t i = 0; i < n_edges; ++i) {
+        if (edges[i].src >= n_nodes || edges[i].dst >= n_nodes) return fail(ctx, RALA_B200_ERR_ARG, "edge %llu references a node >= n_nodes", (unsigned long long) i);
+    }
+    CU(ctx, cudaSetDevice(ctx->device));
+    // a throw-away session provides the buffers
+    rala_b200_graph* g = nullptr;
+    int rc = rala_b200_graph_create(ctx, &g);
+    if (rc) return rc;
+    g->n_piles = (n_nodes + 1) / 2;
+    g->n_nodes_max = n_nodes;
+    g->edge_cap = (uint32_t) n_edges;
+    g->heavy_cap = g->edge_cap / 16 + 4096;
+    DevBuf rows;
+    cudaError_t e = rows.reserve((size_t) n_edges * 12);
+    if (e == cudaSuccess) e = g->edges.reserve(align_up((size_t) g->edge_cap * 4, 256) * 3);
+    if (e == cudaSuccess) e = g->col.reserve((size_t) g->edge_cap * 8);
+    if (e == cudaSuccess) e = g->col_eid.reserve((size_t) g->edge_cap * 4);
+    if (e == cudaSuccess) e = g->T.reserve(align_up(g->edge_cap, 256));
+    if (e == cudaSuccess) e = g->marked.reserve(align_up(g->edge_cap, 256));
+    if (e == cudaSuccess) e = g->heavy.reserve(align_up((size_t) g->heavy_cap * 4, 256) * 3);
+    if (e == cudaSuccess) e = g->row_ptr.reserve(((size_t) n_nodes + 8) * 4);
+    if (e == cudaSuccess) e = g->cursor.reserve(((size_t) n_nodes + 8) * 4);
+    g->scan_pool_words = 4 * (tiles_of((uint64_t) n_nodes + 1) + 8);
+    if (e == cudaSuccess) e = g->scan_pool.reserve(g->scan_pool_words * 8);
+    if (e != cudaSuccess) {
+        rows.release();
+        rala_b200_graph_destroy(g);
+        return fail(ctx, RALA_B200_ERR_CUDA, "transitive_reduce: %s", cudaGetErrorString(e));
+    }
+    auto cleanup = [&](int code) {
+        rows.release();
+        rala_b200_graph_destroy(g);
+        return code;
+    };
+    GraphArrays ga = g->graph_view();
+    cudaStream_t s = ctx->L.stream;
+#define CUX(call)                                                                                      \
+    do {                                                                                               \
+        cudaError_t err__ = (call);                                                                    \
+        if (err__ != cudaSuccess) return cleanup(fail(ctx, RALA_B200_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(err__))); \
+    } while (0)
+    CUX(cudaMemcpyAsync(rows.p, edges, (size_t) n_edges * 12, cudaMemcpyHostToDevice, s));
+    CUX(cudaMemcpy2DAsync(ga.src, 4, rows.as<char>(), 12, 4, n_edges, cudaMemcpyDeviceToDevice, s));
+    CUX(cudaMemcpy2DAsync(ga.dst, 4, rows.as<char>() + 4, 12, 4, n_edges, cudaMemcpyDeviceToDevice, s));
+    CUX(cudaMemcpy2DAsync(ga.len, 4, rows.as<char>() + 8, 12, 4, n_edges, cudaMemcpyDeviceToDevice, s));
+    uint32_t hc[C_COUNT];
+    memset(hc, 0, sizeof(hc));
+    hc[C_NODES] = n_nodes;
+    hc[C_EDGES] = (uint32_t) n_edges;
+    CUX(cudaMemcpyAsync(g->counters.p, hc, sizeof(hc), cudaMemcpyHostToDevice, s));
+    CUX(cudaMemsetAsync(g->cursor.p, 0, ((size_t) n_nodes + 8) * 4, s));
+    CUX(cudaMemsetAsync(g->scan_pool.p, 0, g->scan_pool_words * 8, s));
+    launch_degree_hist(ctx->L, ga.src, g->cnt() + C_EDGES, g->edge_cap, ga.cursor);
+    unsigned long long* status;
+    uint32_t* ticket;
+    scan_state(g, (uint64_t) n_nodes + 1, &status, &ticket);
+    launch_build_csr(ctx->L, ga, n_nodes, g->edge_cap, g->cnt(), status, ticket);
+    rc = run_transitive(g);
+    if (rc) return cleanup(rc);
+    uint32_t h[C_COUNT];
+    CUX(cudaMemcpyAsync(marked_out, g->marked.p, n_edges, cudaMemcpyDeviceToHost, s));
+    CUX(cudaMemcpyAsync(h, g->counters.p, sizeof(h), cudaMemcpyDeviceToHost, s));
+    CUX(cudaStreamSynchronize(s));
+#undef CUX
+    if (h[C_OVERFLOW] || h[C_HEAVY] > g->heavy_cap) return cleanup(fail(ctx, RALA_B200_ERR_LIMIT, "heavy work list overflow"));
+    if (n_pairs) *n_pairs = h[C_PAIRS];
+    return cleanup(RALA_B200_OK);
+}

@@ -1,0 +1,206 @@
+// common.cuh — device-side building blocks shared by the hot-path kernels (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace rb {
+
+constexpr uint32_t kInf = 0xFFFFFFFFu;         // "never dies" death time
+constexpr uint32_t kEndMask = 0x3FFFFFFFu;     // pile.y = end | flags << 30
+constexpr int kNumSMs = 148;
+
+enum : uint8_t { kX = 0, kA = 1, kB = 2, kAB = 3, kBA = 4, kRejected = 255 };
+
+// ---------------------------------------------------------------------------------------------
+// Pile table entry as stored on the device: x = begin, y = end | flags << 30 (end == 0: dead pile).
+// ---------------------------------------------------------------------------------------------
+struct Pile {
+    uint32_t begin, end, flags;
+    __device__ __forceinline__ bool alive() const { return end != 0; }
+};
+
+__device__ __forceinline__ Pile load_pile(const uint2* __restrict__ piles, uint32_t id) {
+    uint2 v = __ldg(piles + id);
+    Pile p;
+    p.begin = v.x;
+    p.end = v.y & kEndMask;
+    p.flags = v.y >> 30;
+    return p;
+}
+
+struct Coords {
+    uint32_t ab, ae, bb, be;
+};
+
+// Overlap::trim, /root/reference/src/overlap.cpp:117-192.  u32 wrap-around is part
+// of the contract.  Both piles are alive.
+__device__ __forceinline__ bool trim(Coords& c, uint32_t ori, const Pile& pa, const Pile& pb) {
+    if (c.ab >= pa.end || c.ae <= pa.begin || c.bb >= pb.end || c.be <= pb.begin) return false;   // :139-142
+    uint32_t cut_lb = c.bb < pb.begin ? pb.begin - c.bb : 0u, cut_rb = c.be > pb.end ? c.be - pb.end : 0u;
+    uint32_t cut_la = c.ab < pa.begin ? pa.begin - c.ab : 0u, cut_ra = c.ae > pa.end ? c.ae - pa.end : 0u;
+    uint32_t nab = c.ab + (ori ? cut_rb : cut_lb);                                                // :146-164
+    uint32_t nae = c.ae - (ori ? cut_lb : cut_rb);
+    uint32_t nbb = c.bb + (ori ? cut_ra : cut_la);
+    uint32_t nbe = c.be - (ori ? cut_la : cut_ra);
+    if (nab >= pa.end || nae <= pa.begin || nbb >= pb.end || nbe <= pb.begin) return false;       // :166-169
+    nab = max(nab, pa.begin); nae = min(nae, pa.end);                                             // :171-174
+    nbb = max(nbb, pb.begin); nbe = min(nbe, pb.end);
+    if (nab >= nae || nae - nab < 84u || nbb >= nbe || nbe - nbb < 84u) return false;             // :176-179
+    c.ab = nab; c.ae = nae; c.bb = nbb; c.be = nbe;
+    return true;
+}
+
+// Trimmed-read coordinates used by type() and by edge creation (overlap.cpp:206-216, graph.cpp:582-592).
+struct Rel {
+    uint32_t a0, a1, b0, b1, al, bl;
+};
+
+__device__ __forceinline__ Rel relative(const Coords& c, uint32_t ori, const Pile& pa, const Pile& pb) {
+    Rel r;
+    r.al = pa.end - pa.begin;
+    r.a0 = c.ab - pa.begin;
+    r.a1 = c.ae - pa.begin;
+    r.bl = pb.end - pb.begin;
+    r.b0 = ori ? r.bl - c.be + pb.begin : c.bb - pb.begin;
+    r.b1 = ori ? r.bl - c.bb + pb.begin : c.be - pb.begin;
+    return r;
+}
+
+__device__ __forceinline__ uint32_t absdiff(uint32_t a, uint32_t b) { return a > b ? a - b : b - a; }
+
+// Overlap::type, overlap.cpp:194-259.  The three double products are single IEEE
+// multiplications (__dmul_rn: no contraction), compared exactly as the reference compares them.
+__device__ __forceinline__ uint8_t classify(const Coords& c, const Rel& r) {
+    uint32_t overhang = min(r.a0, r.b0) + min(r.al - r.a1, r.bl - r.b1);                          // :218-219
+    uint32_t sa = r.a1 - r.a0, sb = r.b1 - r.b0;
+    if ((double) sa < __dmul_rn((double) (uint32_t) (sa + overhang), 0.875) ||
+        (double) sb < __dmul_rn((double) (uint32_t) (sb + overhang), 0.875)) return kX;           // :221-224
+    uint32_t ta = r.al - r.a1, tb = r.bl - r.b1;
+    if (r.a0 <= r.b0 && ta <= tb) return kB;                                                      // :225-227
+    if (r.a0 >= r.b0 && ta >= tb) return kA;                                                      // :228-230
+    uint32_t span_a = c.ae - c.ab, span_b = c.be - c.bb;
+    uint32_t length = max(span_a, span_b);                                                        // length_ (:189)
+    if ((double) absdiff(span_a, span_b) < __dmul_rn((double) length, 0.01)) {                    // :236
+        uint32_t min_ext = __double2uint_rz(__dmul_rn(0.05, (double) max(r.al, r.bl)));           // :237
+        if (absdiff(r.a0, r.b0) < min_ext) return ta >= tb ? kA : kB;                             // :239-245
+        if (absdiff(ta, tb) < min_ext) return r.a0 >= r.b0 ? kA : kB;                             // :246-252
+    }
+    return r.a0 > r.b0 ? kAB : kBA;                                                               // :255-258
+}
+
+// comparable(a, b, 0.12), graph.cpp:26-29; a = (double)(u32)(len_ab + len_bc), b = (double)len_ac.
+__device__ __forceinline__ bool comparable(uint32_t a_, uint32_t b_) {
+    const double lo = 1 - 0.12, hi = 1 + 0.12;
+    double a = (double) a_, b = (double) b_;
+    return (a >= __dmul_rn(b, lo) && a <= __dmul_rn(b, hi)) || (b >= __dmul_rn(a, lo) && b <= __dmul_rn(a, hi));
+}
+
+// ---------------------------------------------------------------------------------------------
+// Warp / block helpers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31u; }
+__device__ __forceinline__ uint32_t warp_id() { return threadIdx.x >> 5; }
+
+__device__ __forceinline__ uint32_t warp_inclusive_scan(uint32_t v) {
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        uint32_t t = __shfl_up_sync(0xFFFFFFFFu, v, d);
+        if ((int) lane_id() >= d) v += t;
+    }
+    return v;
+}
+
+__device__ __forceinline__ unsigned long long warp_sum64(unsigned long long v) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, d);
+    return v;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Single-pass ordered compaction: decoupled look-back over tile aggregates.
+// One 64-bit status word per tile: [63:62] state (0 empty, 1 aggregate, 2 inclusive prefix),
+// [61:31] count B, [30:0] count A.  Two independent 31-bit counters ride in one word so a kernel
+// can split its input into two ordered output lists in one pass.
+// Tiles are handed out through an atomic ticket, so a tile only ever waits on tiles that are
+// already resident or finished (forward progress without co-residency assumptions).
+// ---------------------------------------------------------------------------------------------
+constexpr unsigned long long kStateAgg = 1ull << 62, kStateInc = 2ull << 62, kStateMask = 3ull << 62;
+constexpr unsigned long long kCountMask = (1ull << 62) - 1;
+
+__device__ __forceinline__ unsigned long long pack_counts(uint32_t a, uint32_t b) {
+    return (unsigned long long) a | ((unsigned long long) b << 31);
+}
+__device__ __forceinline__ uint32_t count_a(unsigned long long v) { return (uint32_t) (v & 0x7FFFFFFFull); }
+__device__ __forceinline__ uint32_t count_b(unsigned long long v) { return (uint32_t) ((v >> 31) & 0x7FFFFFFFull); }
+
+__device__ __forceinline__ unsigned long long ld_status(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_status(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+// Called by ONE full warp of the block.  Returns the exclusive prefix (packed counts) of `tile`.
+__device__ __forceinline__ unsigned long long lookback_exclusive(unsigned long long* status, uint32_t tile,
+                                                                  unsigned long long aggregate) {
+    const uint32_t lane = lane_id();
+    if (tile == 0) {
+        if (lane == 0) st_status(status, kStateInc | aggregate);
+        return 0ull;
+    }
+    if (lane == 0) st_status(status + tile, kStateAgg | aggregate);
+    unsigned long long exclusive = 0ull;
+    int64_t look = (int64_t) tile - 1;
+    while (true) {
+        int64_t idx = look - (int64_t) lane;
+        unsigned long long s = kStateInc;  // virtual tile before tile 0: inclusive prefix 0
+        if (idx >= 0) {
+            s = ld_status(status + idx);
+            while ((s & kStateMask) == 0ull) s = ld_status(status + idx);
+        }
+        uint32_t inc_mask = __ballot_sync(0xFFFFFFFFu, (s & kStateMask) == kStateInc);
+        uint32_t first = inc_mask ? (uint32_t) (__ffs(inc_mask) - 1) : 32u;   // nearest tile holding an inclusive prefix
+        unsigned long long contrib = lane <= first ? (s & kCountMask) : 0ull;
+        exclusive += warp_sum64(contrib);
+        if (inc_mask) break;
+        look -= 32;
+    }
+    if (lane == 0) st_status(status + tile, kStateInc | ((exclusive + aggregate) & kCountMask));
+    return exclusive;
+}
+
+// ---------------------------------------------------------------------------------------------
+// TMA 1-D bulk copy global -> shared with mbarrier completion (cp.async.bulk; SASS: UBLKCP).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t) __cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_addr(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_addr(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_addr(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+}  // namespace rb

@@ -1,0 +1,224 @@
+// graph_build.cu — K2: node ids, edge list with reverse-complement twins, CSR adjacency.
+//
+// Replaces graph.cpp:552-632 (reference): sequence_id_to_node_id (:553-574), the two Edge objects per
+// dovetail overlap with their lengths (:576-632) and the implicit adjacency (suffix_edges_ vectors).
+#include "kernels.h"
+#include "lists.cuh"
+
+namespace rb {
+
+// sequence_id_to_node_id[i] = 2 * rank(i among alive piles)  (graph.cpp:553-561)
+__global__ void __launch_bounds__(kTileThreads) k_node_ids(const uint2* __restrict__ piles, uint32_t n_piles,
+                                                          uint32_t* __restrict__ seq_to_node,
+                                                          uint32_t* __restrict__ counters,
+                                                          unsigned long long* __restrict__ status,
+                                                          uint32_t* __restrict__ ticket) {
+    __shared__ TileShared sh;
+    const uint32_t tid = threadIdx.x;
+    const uint32_t num_tiles = (n_piles + kTile - 1) / kTile;
+    while (true) {
+        if (tid == 0) sh.tile = atomicAdd(ticket, 1u);
+        __syncthreads();
+        const uint32_t tile = sh.tile;
+        if (tile >= num_tiles) break;
+        int dest[kTileItems];
+#pragma unroll
+        for (int r = 0; r < kTileItems; ++r) {
+            const uint32_t idx = tile * kTile + r * kTileThreads + tid;
+            dest[r] = (idx < n_piles && (__ldg(piles + idx).y & kEndMask) != 0u) ? 1 : 0;
+        }
+        uint32_t pos[kTileItems];
+        unsigned long long inclusive = 0;
+        tile_rank(sh, status, tile, dest, pos, &inclusive);
+        if (tid == 0 && tile == num_tiles - 1) {
+            counters[C_ALIVE] = count_a(inclusive);
+            counters[C_NODES] = 2u * count_a(inclusive);
+        }
+#pragma unroll
+        for (int r = 0; r < kTileItems; ++r) {
+            const uint32_t idx = tile * kTile + r * kTileThreads + tid;
+            if (idx < n_piles) seq_to_node[idx] = dest[r] ? 2u * pos[r] : kInf;
+        }
+        __syncthreads();
+    }
+}
+
+// Two edges per dovetail overlap, ids 2j / 2j+1 in list order (graph.cpp:576-632), plus the
+// out-degree histogram the CSR build needs.
+__global__ void __launch_bounds__(kTileThreads) k_emit_edges(List ovl, const uint32_t* __restrict__ n_ptr, uint32_t cap,
+                                                            const uint2* __restrict__ piles,
+                                                            const uint32_t* __restrict__ seq_to_node,
+                                                            uint32_t* __restrict__ src, uint32_t* __restrict__ dst,
+                                                            uint32_t* __restrict__ len, uint32_t edge_cap,
+                                                            uint32_t* __restrict__ degree, uint32_t* __restrict__ counters,
+                                                            unsigned long long* __restrict__ status,
+                                                            uint32_t* __restrict__ ticket) {
+    __shared__ TileShared sh;
+    const uint32_t tid = threadIdx.x;
+    const uint32_t n = min(*n_ptr, cap);
+    const uint32_t num_tiles = (n + kTile - 1) / kTile;
+    while (true) {
+        if (tid == 0) sh.tile = atomicAdd(ticket, 1u);
+        __syncthreads();
+        const uint32_t tile = sh.tile;
+        if (tile >= num_tiles) break;
+        int dest[kTileItems];
+        uint32_t e_src[kTileItems], e_dst[kTileItems], e_len[kTileItems], c_len[kTileItems];
+#pragma unroll
+        for (int r = 0; r < kTileItems; ++r) {
+            const uint32_t idx = tile * kTile + r * kTileThreads + tid;
+            dest[r] = 0;
+            if (idx < n) {
+                Entry e = load_entry(ovl, idx);
+                const Pile pa = load_pile(piles, e.a), pb = load_pile(piles, e.b);
+                if (pa.alive() && pb.alive()) {
+                    const Rel q = relative(e.c, e.ori, pa, pb);
+                    const uint8_t t = classify(e.c, q);                      // it->type(piles_) at :594 / :612
+                    const uint32_t na = seq_to_node[e.a], nb = seq_to_node[e.b] + e.ori;   // :578-580
+                    if (t == kAB) {                                          // :594-610
+                        dest[r] = 1;
+                        e_src[r] = na; e_dst[r] = nb;
+                        e_len[r] = q.a0 - q.b0;
+                        c_len[r] = (q.bl - q.b1) - (q.al - q.a1);
+                    } else if (t == kBA) {                                   // :612-629
+                        dest[r] = 1;
+                        e_src[r] = nb; e_dst[r] = na;
+                        e_len[r] = q.b0 - q.a0;
+                        c_len[r] = (q.al - q.a1) - (q.bl - q.b1);
+                    }
+                }
+            }
+        }
+        uint32_t pos[kTileItems];
+        unsigned long long inclusive = 0;
+        tile_rank(sh, status, tile, dest, pos, &inclusive);
+        if (tid == 0 && tile == num_tiles - 1) {
+            counters[C_DOVETAILS] = count_a(inclusive);
+            counters[C_EDGES] = 2u * count_a(inclusive);
+            if (2ull * count_a(inclusive) > edge_cap) counters[C_OVERFLOW] = 1u;
+        }
+#pragma unroll
+        for (int r = 0; r < kTileItems; ++r) {
+            if (dest[r] && 2ull * pos[r] + 1 < edge_cap) {
+                const uint32_t j = pos[r];
+                // edge 2j = (from -> to), edge 2j+1 = (to^1 -> from^1): one 8-byte store per column
+                reinterpret_cast<uint2*>(src)[j] = make_uint2(e_src[r], e_dst[r] ^ 1u);
+                reinterpret_cast<uint2*>(dst)[j] = make_uint2(e_dst[r], e_src[r] ^ 1u);
+                reinterpret_cast<uint2*>(len)[j] = make_uint2(e_len[r], c_len[r]);
+                atomicAdd(&degree[e_src[r]], 1u);
+                atomicAdd(&degree[e_dst[r] ^ 1u], 1u);
+            }
+        }
+        __syncthreads();
+    }
+}
+
+__global__ void k_degree_hist(const uint32_t* __restrict__ src, const uint32_t* __restrict__ n_edges_ptr, uint32_t edge_cap,
+                              uint32_t* __restrict__ degree) {
+    const uint32_t n = min(*n_edges_ptr, edge_cap);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        atomicAdd(&degree[src[i]], 1u);
+    }
+}
+
+// Exclusive scan of the degree histogram into row_ptr (and a copy into the fill cursor), single pass.
+// Each thread owns 4 consecutive values (one 16-byte load).
+__global__ void __launch_bounds__(kTileThreads) k_scan_degrees(uint32_t* __restrict__ cursor, uint32_t* __restrict__ row_ptr,
+                                                              uint32_t n, unsigned long long* __restrict__ status,
+                                                              uint32_t* __restrict__ ticket) {
+    __shared__ uint32_t s_warp[kTileWarps];
+    __shared__ uint32_t s_tile;
+    __shared__ unsigned long long s_base;
+    const uint32_t tid = threadIdx.x, lane = lane_id(), warp = warp_id();
+    const uint32_t num_tiles = (n + kTile - 1) / kTile;
+    while (true) {
+        if (tid == 0) s_tile = atomicAdd(ticket, 1u);
+        __syncthreads();
+        const uint32_t tile = s_tile;
+        if (tile >= num_tiles) break;
+        const uint32_t i0 = tile * kTile + tid * 4;
+        uint32_t v[4] = {0u, 0u, 0u, 0u};
+        if (i0 + 3 < n) {
+            uint4 q = *reinterpret_cast<const uint4*>(cursor + i0);
+            v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+        } else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) if (i0 + k < n) v[k] = cursor[i0 + k];
+        }
+        const uint32_t tsum = v[0] + v[1] + v[2] + v[3];
+        const uint32_t inc = warp_inclusive_scan(tsum);
+        if (lane == 31) s_warp[warp] = inc;
+        __syncthreads();
+        if (warp == 0) {
+            uint32_t w = lane < kTileWarps ? s_warp[lane] : 0u;
+            uint32_t winc = warp_inclusive_scan(w);
+            uint32_t total = __shfl_sync(0xFFFFFFFFu, winc, kTileWarps - 1);
+            unsigned long long excl = lookback_exclusive(status, tile, (unsigned long long) total);
+            if (lane < kTileWarps) s_warp[lane] = winc - w;
+            if (lane == 0) s_base = excl;
+        }
+        __syncthreads();
+        uint32_t run = (uint32_t) s_base + s_warp[warp] + inc - tsum;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (i0 + k < n) {
+                row_ptr[i0 + k] = run;
+                cursor[i0 + k] = run;
+            }
+            run += v[k];
+        }
+        __syncthreads();
+    }
+}
+
+// Scatter every edge into its source row.  Slot order inside a row is arbitrary (atomic cursor);
+// nothing downstream depends on it: the transitive pass resolves parallel edges by edge id.
+__global__ void k_fill_csr(const uint32_t* __restrict__ src, const uint32_t* __restrict__ dst,
+                           const uint32_t* __restrict__ len, const uint32_t* __restrict__ n_edges_ptr, uint32_t edge_cap,
+                           uint32_t* __restrict__ cursor, uint2* __restrict__ col, uint32_t* __restrict__ col_eid) {
+    const uint32_t n = min(*n_edges_ptr, edge_cap);
+    for (uint32_t e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
+        const uint32_t p = atomicAdd(&cursor[src[e]], 1u);
+        col[p] = make_uint2(dst[e], len[e]);
+        col_eid[p] = e;
+    }
+}
+
+static inline int grid_for(uint64_t n, int per_block, int max_blocks) {
+    uint64_t b = (n + per_block - 1) / per_block;
+    if (b < 1) b = 1;
+    return (int) (b < (uint64_t) max_blocks ? b : (uint64_t) max_blocks);
+}
+
+void launch_node_ids(Launch& L, const uint2* piles, uint32_t n_piles, uint32_t* seq_to_node, uint32_t* counters,
+                     unsigned long long* status, uint32_t* ticket) {
+    if (n_piles == 0) return;
+    k_node_ids<<<grid_for(n_piles, kTile, kNumSMs * 8), kTileThreads, 0, L.stream>>>(piles, n_piles, seq_to_node, counters,
+                                                                                      status, ticket);
+    L.count++;
+}
+
+void launch_emit_edges(Launch& L, List ovl, const uint32_t* n_ptr, uint32_t cap, const uint2* piles, GraphArrays g,
+                       uint32_t edge_cap, uint32_t* counters, unsigned long long* status, uint32_t* ticket) {
+    k_emit_edges<<<grid_for(cap, kTile, kNumSMs * 8), kTileThreads, 0, L.stream>>>(
+        ovl, n_ptr, cap, piles, g.seq_to_node, g.src, g.dst, g.len, edge_cap, g.cursor, counters, status, ticket);
+    L.count++;
+}
+
+void launch_degree_hist(Launch& L, const uint32_t* src, const uint32_t* n_edges_ptr, uint32_t edge_cap, uint32_t* cursor) {
+    k_degree_hist<<<grid_for(edge_cap, 256, kNumSMs * 8), 256, 0, L.stream>>>(src, n_edges_ptr, edge_cap, cursor);
+    L.count++;
+}
+
+void launch_build_csr(Launch& L, GraphArrays g, uint32_t n_nodes_max, uint32_t edge_cap, uint32_t* counters,
+                      unsigned long long* status, uint32_t* ticket) {
+    // row_ptr has n_nodes_max + 1 entries; degrees beyond the live node count are zero
+    k_scan_degrees<<<grid_for(n_nodes_max + 1, kTile, kNumSMs * 8), kTileThreads, 0, L.stream>>>(
+        g.cursor, g.row_ptr, n_nodes_max + 1, status, ticket);
+    L.count++;
+    k_fill_csr<<<grid_for(edge_cap, 256, kNumSMs * 8), 256, 0, L.stream>>>(g.src, g.dst, g.len, counters + C_EDGES,
+                                                                            edge_cap, g.cursor, g.col, g.col_eid);
+    L.count++;
+}
+
+}  // namespace rb

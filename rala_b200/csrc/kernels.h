@@ -1,0 +1,90 @@
+// kernels.h — host-callable launchers of the hot-path kernels (internal to librala_b200.so).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace rb {
+
+struct List;
+struct Events;
+
+// slots of the device-side counter block (uint32 each)
+enum Counter {
+    C_P = 0,        // potential survivors of the first pass
+    C_EV,           // containment events of the current resolution
+    C_HILL,         // records touching a pile with hills
+    C_ROUNDS,       // fixed-point rounds
+    C_DSEL,         // which of the four death-time buffers holds the result
+    C_NODES,        // nodes_.size()
+    C_ALIVE,        // alive piles
+    C_DOVETAILS,    // dovetail overlaps = edges / 2
+    C_EDGES,        // edges_.size()
+    C_PAIRS,        // marked pairs
+    C_HEAVY,        // heavy work items of the transitive pass
+    C_OVERFLOW,     // some list hit its capacity
+    C_HOP_LO, C_HOP_HI,   // two-hop visits (64-bit)
+    C_LIST0,        // 16 rotating list-count slots follow
+    C_COUNT = C_LIST0 + 16
+};
+
+struct Launch {
+    cudaStream_t stream;
+    uint64_t count;   // kernels launched so far
+};
+
+// classify.cu
+void launch_classify_first(Launch& L, const uint32_t* rec, uint32_t n, uint32_t t0, const uint2* piles, uint32_t n_piles,
+                           List P, uint32_t p_cap, Events ev, uint32_t ev_cap, uint32_t* hill_rec, uint32_t hill_cap,
+                           uint32_t* counters, unsigned long long* status, uint32_t* ticket);
+void launch_fixpoint(Launch& L, Events ev, const uint32_t* n_events, uint32_t ev_cap, uint32_t* dbuf, uint32_t n_piles,
+                     uint32_t* flags, uint32_t* counters, int coop_blocks);
+int fixpoint_max_blocks();
+void launch_hill_coverage(Launch& L, const uint32_t* rec, uint32_t t0, const uint2* piles, const uint32_t* hill_rec,
+                          uint32_t hill_cap, const uint32_t* hill_pile, const uint32_t* hill_begin,
+                          const uint32_t* hill_end, uint32_t n_hills, uint32_t* hill_cov, const uint32_t* dbuf,
+                          uint32_t n_piles, const uint32_t* counters);
+void launch_apply_deaths(Launch& L, uint2* piles, const uint32_t* dbuf, uint32_t n_piles, const uint32_t* counters);
+void launch_list_pass(Launch& L, int mode, List in, const uint32_t* n_in, uint32_t in_cap, const uint2* piles, List out_a,
+                      uint32_t* n_out_a, List out_b, uint32_t* n_out_b, const uint32_t* b_base, uint32_t cap,
+                      const uint32_t* dbuf, uint32_t n_piles, const uint32_t* time_base, const uint32_t* counters,
+                      unsigned long long* status, uint32_t* ticket);
+void launch_classify_final(Launch& L, List lst, const uint32_t* n_ptr, uint32_t cap, const uint32_t* time_base,
+                           const uint2* piles, Events ev, uint32_t ev_cap, uint32_t* counters);
+void launch_trim_classify_aos(Launch& L, uint32_t* rec, uint32_t n, const uint2* piles, uint32_t n_piles, uint8_t* type_out);
+void launch_fill_u32(Launch& L, uint32_t* p, uint32_t v, size_t n);
+void launch_pack_piles(Launch& L, const uint2* in, const uint8_t* flags, uint2* out, uint32_t n);
+void launch_unpack_piles(Launch& L, const uint2* in, uint2* out, uint32_t n);
+void launch_list_to_aos(Launch& L, List l, const uint32_t* n_ptr, uint32_t cap, uint32_t* out);
+void launch_list_connections(Launch& L, List l, const uint32_t* n_ptr, uint32_t cap, uint32_t* out);
+
+// graph_build.cu
+struct GraphArrays {
+    uint32_t* seq_to_node;   // n_piles
+    uint32_t *src, *dst, *len;   // edge id order
+    uint32_t* row_ptr;       // n_nodes_max + 1
+    uint32_t* cursor;        // n_nodes_max + 1 (degree histogram, then fill cursor)
+    uint2* col;              // CSR (dst, len)
+    uint32_t* col_eid;       // CSR edge id
+    uint8_t* T;              // per edge: transitive test passed
+    uint8_t* marked;         // per edge: removed
+};
+void launch_node_ids(Launch& L, const uint2* piles, uint32_t n_piles, uint32_t* seq_to_node, uint32_t* counters,
+                     unsigned long long* status, uint32_t* ticket);
+void launch_emit_edges(Launch& L, List ovl, const uint32_t* n_ptr, uint32_t cap, const uint2* piles, GraphArrays g,
+                       uint32_t edge_cap, uint32_t* counters, unsigned long long* status, uint32_t* ticket);
+// degree histogram for an edge list that did not come from emit_edges (stateless transitive stage)
+void launch_degree_hist(Launch& L, const uint32_t* src, const uint32_t* n_edges_ptr, uint32_t edge_cap, uint32_t* cursor);
+void launch_build_csr(Launch& L, GraphArrays g, uint32_t n_nodes_max, uint32_t edge_cap, uint32_t* counters,
+                      unsigned long long* status, uint32_t* ticket);
+
+// transitive.cu
+struct HeavyItems {
+    uint32_t *node, *hash_chunk, *nbr_chunk;
+    uint32_t cap;
+};
+void launch_transitive(Launch& L, GraphArrays g, uint32_t n_nodes_max, uint32_t edge_cap, HeavyItems heavy,
+                       uint32_t* work_counter, uint32_t* counters, uint32_t node_begin, uint32_t node_end);
+void launch_finalize_marks(Launch& L, GraphArrays g, uint32_t edge_cap, uint32_t* counters);
+
+}  // namespace rb

@@ -1,0 +1,326 @@
+// transitive.cu — K3: transitive-edge reduction on the CSR adjacency.
+//
+// Replaces Graph::remove_transitive_edges, graph.cpp:1281-1318 (reference), in its order-free form
+// (SURVEY.md A.4):  cand(a,c) = highest-id edge a->c;  T(e = cand(a,c)) = exists a->b, b->c with
+// comparable(len_ab + len_bc, len_e, 0.12);  marked(e) = T(e) | T(e^1);  return = #{j : marked(2j)}.
+//
+// Per node a the neighbour set N+(a) is staged in shared memory as an open-addressing hash table
+// keyed by destination (value = edge id << 32 | length, merged with max => "highest id wins" for
+// parallel edges, graph.cpp:1291-1293).  The two-hop stream  { (b, j) : b in N+(a), j < deg(b) }  is
+// FLATTENED: lanes take consecutive flat indices, so several short rows N+(b) are in flight per
+// iteration and every load is an 8-byte (dst, len) element of a contiguous CSR row.
+//   light path : one warp per node      (deg <= 64 and <= 32768 two-hop visits)
+//   heavy path : one block per (node, hash chunk of 1024 neighbours, stream chunk of 256 neighbours)
+#include "kernels.h"
+#include "common.cuh"
+
+namespace rb {
+
+constexpr uint32_t kEmpty = 0xFFFFFFFFu;
+constexpr int kLightMaxDeg = 64;
+constexpr int kLightCap = 128;
+constexpr uint32_t kLightMaxVisits = 32768;
+constexpr int kLightWarps = 8;
+constexpr int kHeavyHashChunk = 1024;
+constexpr int kHeavyCap = 2048;
+constexpr int kHeavyNbrChunk = 256;
+constexpr int kHeavyThreads = 256;
+
+__device__ __forceinline__ uint32_t hash_slot(uint32_t key, uint32_t log2cap) {
+    return (key * 0x9E3779B1u) >> (32u - log2cap);
+}
+
+__device__ __forceinline__ void table_insert(uint32_t* keys, unsigned long long* vals, uint32_t mask, uint32_t log2cap,
+                                             uint32_t key, unsigned long long val) {
+    uint32_t s = hash_slot(key, log2cap);
+    while (true) {
+        uint32_t prev = atomicCAS(&keys[s], kEmpty, key);
+        if (prev == kEmpty || prev == key) {
+            atomicMax(&vals[s], val);
+            return;
+        }
+        s = (s + 1u) & mask;
+    }
+}
+
+// returns the slot of key or kEmpty
+__device__ __forceinline__ uint32_t table_find(const uint32_t* keys, uint32_t mask, uint32_t log2cap, uint32_t key) {
+    uint32_t s = hash_slot(key, log2cap);
+    while (true) {
+        uint32_t k = keys[s];
+        if (k == key) return s;
+        if (k == kEmpty) return kEmpty;
+        s = (s + 1u) & mask;
+    }
+}
+
+struct LightSmem {
+    unsigned long long vals[kLightCap];
+    uint32_t keys[kLightCap];
+    uint32_t nrow[kLightMaxDeg];
+    uint32_t nlen[kLightMaxDeg];
+    uint32_t noff[kLightMaxDeg + 1];
+    uint8_t hit[kLightCap];
+};
+
+__global__ void __launch_bounds__(kLightWarps * 32) k_transitive_light(
+    const uint32_t* __restrict__ row_ptr, const uint2* __restrict__ col, const uint32_t* __restrict__ col_eid,
+    uint8_t* __restrict__ T, uint32_t node_begin, uint32_t node_end, const uint32_t* __restrict__ n_nodes_ptr,
+    uint32_t* __restrict__ work_counter, HeavyItems heavy, uint32_t* __restrict__ counters) {
+    __shared__ LightSmem smem[kLightWarps];
+    LightSmem& S = smem[warp_id()];
+    const uint32_t lane = lane_id();
+    const uint32_t n_end = min(node_end, *n_nodes_ptr);
+    unsigned long long visits = 0;
+
+    while (true) {
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(work_counter, 32u);
+        base = node_begin + __shfl_sync(0xFFFFFFFFu, base, 0);
+        if (base >= n_end) break;
+        const uint32_t node = base + lane;
+        uint32_t r0 = 0, deg = 0;
+        if (node < n_end) {
+            r0 = row_ptr[node];
+            deg = row_ptr[node + 1] - r0;
+        }
+        uint32_t todo = __ballot_sync(0xFFFFFFFFu, deg >= 2u);   // < 2 neighbours: no two-hop witness can exist
+        while (todo) {
+            const uint32_t l = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const uint32_t a = base + l;
+            const uint32_t ra0 = __shfl_sync(0xFFFFFFFFu, r0, l);
+            const uint32_t d = __shfl_sync(0xFFFFFFFFu, deg, l);
+            if (d > (uint32_t) kLightMaxDeg) {
+                const uint32_t nca = (d + kHeavyHashChunk - 1) / kHeavyHashChunk, ncb = (d + kHeavyNbrChunk - 1) / kHeavyNbrChunk;
+                uint32_t hb = 0;
+                if (lane == 0) hb = atomicAdd(&counters[C_HEAVY], nca * ncb);
+                hb = __shfl_sync(0xFFFFFFFFu, hb, 0);
+                for (uint32_t i = lane; i < nca * ncb; i += 32) {
+                    if (hb + i < heavy.cap) {
+                        heavy.node[hb + i] = a;
+                        heavy.hash_chunk[hb + i] = i / ncb;
+                        heavy.nbr_chunk[hb + i] = i % ncb;
+                    } else {
+                        counters[C_OVERFLOW] = 1u;
+                    }
+                }
+                continue;
+            }
+            // table capacity: power of two >= 2d, at least 16
+            uint32_t log2cap = 4;
+            while ((1u << log2cap) < 2u * d) ++log2cap;
+            const uint32_t cap = 1u << log2cap, mask = cap - 1u;
+            for (uint32_t s = lane; s < cap; s += 32) {
+                S.keys[s] = kEmpty;
+                S.vals[s] = 0ull;
+                S.hit[s] = 0;
+            }
+            __syncwarp();
+            uint32_t carry = 0;
+            for (uint32_t i0 = 0; i0 < d; i0 += 32) {
+                const uint32_t i = i0 + lane;
+                uint32_t dg = 0;
+                if (i < d) {
+                    const uint2 e = col[ra0 + i];
+                    const uint32_t eid = col_eid[ra0 + i];
+                    table_insert(S.keys, S.vals, mask, log2cap, e.x, ((unsigned long long) eid << 32) | e.y);
+                    const uint32_t rs = row_ptr[e.x];
+                    dg = row_ptr[e.x + 1] - rs;
+                    S.nrow[i] = rs;
+                    S.nlen[i] = e.y;
+                }
+                const uint32_t inc = warp_inclusive_scan(dg);
+                if (i < d) S.noff[i] = carry + inc - dg;
+                carry += __shfl_sync(0xFFFFFFFFu, inc, 31);
+            }
+            const uint32_t W = carry;
+            if (lane == 0) S.noff[d] = W;
+            __syncwarp();
+            if (W > kLightMaxVisits) {   // few neighbours but very long rows behind them: give it to a block
+                const uint32_t ncb = (d + kHeavyNbrChunk - 1) / kHeavyNbrChunk;   // == 1
+                uint32_t hb = 0;
+                if (lane == 0) hb = atomicAdd(&counters[C_HEAVY], ncb);
+                hb = __shfl_sync(0xFFFFFFFFu, hb, 0);
+                if (lane < ncb) {
+                    if (hb + lane < heavy.cap) {
+                        heavy.node[hb + lane] = a;
+                        heavy.hash_chunk[hb + lane] = 0;
+                        heavy.nbr_chunk[hb + lane] = lane;
+                    } else {
+                        counters[C_OVERFLOW] = 1u;
+                    }
+                }
+                __syncwarp();
+                continue;
+            }
+            visits += W;
+
+            // flattened two-hop stream, 4 independent loads in flight per lane
+            uint32_t i = 0;
+            for (uint32_t f0 = 0; f0 < W; f0 += 128) {
+                uint2 e[4];
+                uint32_t lab[4];
+                bool ok[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const uint32_t f = f0 + u * 32 + lane;
+                    ok[u] = f < W;
+                    if (ok[u]) {
+                        while (f >= S.noff[i + 1]) ++i;
+                        e[u] = col[S.nrow[i] + (f - S.noff[i])];
+                        lab[u] = S.nlen[i];
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    if (ok[u]) {
+                        const uint32_t s = table_find(S.keys, mask, log2cap, e[u].x);
+                        if (s != kEmpty && !S.hit[s]) {
+                            if (comparable(lab[u] + e[u].y, (uint32_t) S.vals[s])) S.hit[s] = 1;   // graph.cpp:1301-1306
+                        }
+                    }
+                }
+            }
+            __syncwarp();
+            for (uint32_t s = lane; s < cap; s += 32) {
+                if (S.hit[s]) T[(uint32_t) (S.vals[s] >> 32)] = 1;
+            }
+            __syncwarp();
+        }
+    }
+    visits = warp_sum64(visits);
+    if (lane == 0 && visits) atomicAdd(reinterpret_cast<unsigned long long*>(counters + C_HOP_LO), visits);
+}
+
+struct HeavySmem {
+    unsigned long long vals[kHeavyCap];
+    uint32_t keys[kHeavyCap];
+    uint32_t nrow[kHeavyNbrChunk];
+    uint32_t nlen[kHeavyNbrChunk];
+    uint32_t noff[kHeavyNbrChunk + 1];
+    uint32_t warp_sums[kHeavyThreads / 32];
+    uint8_t hit[kHeavyCap];
+};
+
+__global__ void __launch_bounds__(kHeavyThreads) k_transitive_heavy(
+    const uint32_t* __restrict__ row_ptr, const uint2* __restrict__ col, const uint32_t* __restrict__ col_eid,
+    uint8_t* __restrict__ T, HeavyItems heavy, uint32_t* __restrict__ counters) {
+    __shared__ HeavySmem S;
+    const uint32_t tid = threadIdx.x, lane = lane_id(), warp = warp_id();
+    const uint32_t n_items = min(counters[C_HEAVY], heavy.cap);
+    unsigned long long visits = 0;
+    for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const uint32_t a = heavy.node[item], ca = heavy.hash_chunk[item], cb = heavy.nbr_chunk[item];
+        const uint32_t ra0 = row_ptr[a], d = row_ptr[a + 1] - ra0;
+        const uint32_t h0 = ca * kHeavyHashChunk, h1 = min(d, h0 + kHeavyHashChunk);
+        const uint32_t k0 = cb * kHeavyNbrChunk, k1 = min(d, k0 + kHeavyNbrChunk), nb = k1 - k0;
+        uint32_t log2cap = 4;
+        while ((1u << log2cap) < 2u * (h1 - h0)) ++log2cap;
+        const uint32_t cap = 1u << log2cap, mask = cap - 1u;
+        for (uint32_t s = tid; s < cap; s += kHeavyThreads) {
+            S.keys[s] = kEmpty;
+            S.vals[s] = 0ull;
+            S.hit[s] = 0;
+        }
+        __syncthreads();
+        for (uint32_t i = h0 + tid; i < h1; i += kHeavyThreads) {
+            const uint2 e = col[ra0 + i];
+            table_insert(S.keys, S.vals, mask, log2cap, e.x, ((unsigned long long) col_eid[ra0 + i] << 32) | e.y);
+        }
+        uint32_t dg = 0;
+        if (tid < nb) {
+            const uint2 e = col[ra0 + k0 + tid];
+            const uint32_t rs = row_ptr[e.x];
+            dg = row_ptr[e.x + 1] - rs;
+            S.nrow[tid] = rs;
+            S.nlen[tid] = e.y;
+        }
+        const uint32_t inc = warp_inclusive_scan(dg);
+        if (lane == 31) S.warp_sums[warp] = inc;
+        __syncthreads();
+        uint32_t woff = 0;
+        for (uint32_t w = 0; w < warp; ++w) woff += S.warp_sums[w];
+        if (tid < nb) S.noff[tid] = woff + inc - dg;
+        if (tid == kHeavyThreads - 1) S.noff[nb] = woff + inc;   // dg == 0 beyond nb, so this is the total
+        __syncthreads();
+        const uint32_t W = S.noff[nb];
+        if (ca == 0 && tid == 0) visits += W;
+
+        for (uint32_t f0 = 0; f0 < W; f0 += kHeavyThreads * 4) {
+            uint2 e[4];
+            uint32_t lab[4];
+            bool ok[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const uint32_t f = f0 + u * kHeavyThreads + tid;
+                ok[u] = f < W;
+                if (ok[u]) {
+                    uint32_t lo = 0, hi = nb;   // largest i with noff[i] <= f
+                    while (hi - lo > 1) {
+                        const uint32_t mid = (lo + hi) >> 1;
+                        if (S.noff[mid] <= f) lo = mid; else hi = mid;
+                    }
+                    e[u] = col[S.nrow[lo] + (f - S.noff[lo])];
+                    lab[u] = S.nlen[lo];
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (ok[u]) {
+                    const uint32_t s = table_find(S.keys, mask, log2cap, e[u].x);
+                    if (s != kEmpty && !S.hit[s]) {
+                        if (comparable(lab[u] + e[u].y, (uint32_t) S.vals[s])) S.hit[s] = 1;
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        for (uint32_t s = tid; s < cap; s += kHeavyThreads) {
+            if (S.hit[s]) T[(uint32_t) (S.vals[s] >> 32)] = 1;
+        }
+        __syncthreads();
+    }
+    if (tid == 0 && visits) atomicAdd(reinterpret_cast<unsigned long long*>(counters + C_HOP_LO), visits);
+}
+
+// marked(e) = T(e) | T(e^1); count of marked pairs = the reference's return value (graph.cpp:1305-1309, 1334)
+__global__ void k_finalize_marks(const uint8_t* __restrict__ T, uint8_t* __restrict__ marked,
+                                 const uint32_t* __restrict__ n_edges_ptr, uint32_t edge_cap, uint32_t* __restrict__ counters) {
+    const uint32_t n_pairs = min(*n_edges_ptr, edge_cap) / 2;
+    uint32_t local = 0;
+    for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n_pairs; j += gridDim.x * blockDim.x) {
+        const uchar2 t = reinterpret_cast<const uchar2*>(T)[j];
+        const uint8_t m = (t.x | t.y) ? 1 : 0;
+        reinterpret_cast<uchar2*>(marked)[j] = make_uchar2(m, m);
+        local += m;
+    }
+#pragma unroll
+    for (int dlt = 16; dlt > 0; dlt >>= 1) local += __shfl_xor_sync(0xFFFFFFFFu, local, dlt);
+    if (lane_id() == 0 && local) atomicAdd(&counters[C_PAIRS], local);
+}
+
+void launch_transitive(Launch& L, GraphArrays g, uint32_t n_nodes_max, uint32_t edge_cap, HeavyItems heavy,
+                       uint32_t* work_counter, uint32_t* counters, uint32_t node_begin, uint32_t node_end) {
+    (void) edge_cap;
+    uint64_t span = node_end > node_begin ? node_end - node_begin : 0;
+    if (span > n_nodes_max) span = n_nodes_max;
+    uint64_t blocks = (span + 32 * kLightWarps - 1) / (32 * kLightWarps);
+    if (blocks < 1) blocks = 1;
+    if (blocks > (uint64_t) kNumSMs * 8) blocks = kNumSMs * 8;
+    k_transitive_light<<<(int) blocks, kLightWarps * 32, 0, L.stream>>>(g.row_ptr, g.col, g.col_eid, g.T, node_begin, node_end,
+                                                                       counters + C_NODES, work_counter, heavy, counters);
+    L.count++;
+    k_transitive_heavy<<<kNumSMs * 4, kHeavyThreads, 0, L.stream>>>(g.row_ptr, g.col, g.col_eid, g.T, heavy, counters);
+    L.count++;
+}
+
+void launch_finalize_marks(Launch& L, GraphArrays g, uint32_t edge_cap, uint32_t* counters) {
+    uint64_t blocks = (edge_cap / 2 + 1023) / 1024;
+    if (blocks < 1) blocks = 1;
+    if (blocks > (uint64_t) kNumSMs * 8) blocks = kNumSMs * 8;
+    k_finalize_marks<<<(int) blocks, 256, 0, L.stream>>>(g.T, g.marked, counters + C_EDGES, edge_cap, counters);
+    L.count++;
+}
+
+}  // namespace rb

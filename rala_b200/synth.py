@@ -247,6 +247,6 @@ def hub_graph(n_hubs: int = 4, spokes: int = 2500, links_per_spoke: int = 6, see
                 if k + d < spokes:
                     t = base + 2 * (k + d + 1)
                     jitter = int(rng.integers(-4, 5))
-                    add(s, t, int(pos[k + d] - pos[k]) + jitter, int(pos[k + d] - pos[k]) + 7)
+                    add(s, t, max(1, int(pos[k + d] - pos[k]) + jitter), int(pos[k + d] - pos[k]) + 7)
     e = np.asarray(edges, dtype=np.uint32)
     return 2 * n_reads, e
