@@ -120,14 +120,16 @@ typedef struct {
     uint64_t n_records;      /* as set */
     uint64_t n_overlaps;     /* current `overlaps` list */
     uint64_t n_internals;    /* current `internals` list */
-    uint64_t n_candidates;   /* containment events fed to the last ordered-containment resolution */
-    uint32_t n_rounds;       /* fixed-point rounds it took */
+    uint64_t n_candidates;   /* containment events of the first pass (graph.cpp:469-480) */
+    uint32_t n_rounds;       /* fixed-point rounds their resolution took */
     uint32_t n_piles, n_alive_piles;
     uint32_t n_nodes;        /* nodes_.size() */
     uint64_t n_edges;        /* edges_.size() */
     uint64_t n_two_hop;      /* H = sum over edges (a->b) of outdegree(b): two-hop visits of the transitive pass */
     uint64_t n_transitive_pairs; /* return value of remove_transitive_edges */
     uint32_t n_heavy_items;  /* block-per-node work items of the last transitive pass */
+    uint32_t n_final_rounds; /* fixed-point rounds of the final containment pass (graph.cpp:831-866) */
+    uint64_t n_final_candidates; /* containment events of the final pass */
 } rala_b200_counts_t;
 
 int rala_b200_graph_create(rala_b200_ctx* ctx, rala_b200_graph** out);

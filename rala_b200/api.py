@@ -31,7 +31,8 @@ class Counts(C.Structure):
     _fields_ = [("n_records", C.c_uint64), ("n_overlaps", C.c_uint64), ("n_internals", C.c_uint64),
                 ("n_candidates", C.c_uint64), ("n_rounds", C.c_uint32), ("n_piles", C.c_uint32),
                 ("n_alive_piles", C.c_uint32), ("n_nodes", C.c_uint32), ("n_edges", C.c_uint64),
-                ("n_two_hop", C.c_uint64), ("n_transitive_pairs", C.c_uint64), ("n_heavy_items", C.c_uint32)]
+                ("n_two_hop", C.c_uint64), ("n_transitive_pairs", C.c_uint64), ("n_heavy_items", C.c_uint32),
+                ("n_final_rounds", C.c_uint32), ("n_final_candidates", C.c_uint64)]
 
     def as_dict(self):
         return {k: int(getattr(self, k)) for k, _ in self._fields_}

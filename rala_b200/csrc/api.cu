@@ -517,6 +517,8 @@ extern "C" int rala_b200_graph_finalize(rala_b200_graph* g) {
     if (g->state != 2) return fail(ctx, RALA_B200_ERR_STATE, "finalize: classify first");
     CU(ctx, cudaSetDevice(ctx->device));
     CU(ctx, begin_stage(g, ST_FINALIZE));
+    CU(ctx, cudaMemcpyAsync(g->cnt() + C_EV_FIRST, g->cnt() + C_EV, 4, cudaMemcpyDeviceToDevice, ctx->L.stream));
+    CU(ctx, cudaMemcpyAsync(g->cnt() + C_ROUNDS_FIRST, g->cnt() + C_ROUNDS, 4, cudaMemcpyDeviceToDevice, ctx->L.stream));
     CU(ctx, zero_counter(g, C_EV));
     launch_classify_final(ctx->L, g->ovl[g->ovl_cur].view, g->cnt() + g->slot_ovl, g->cap, nullptr, g->piles.as<uint2>(),
                           g->events_view(), g->cap, g->cnt());
@@ -634,8 +636,10 @@ extern "C" int rala_b200_graph_counts(rala_b200_graph* g, rala_b200_counts_t* ou
     out->n_records = g->n_rec;
     out->n_overlaps = g->state >= 2 ? h[g->slot_ovl] : 0;
     out->n_internals = g->state >= 2 ? h[g->slot_inl] : 0;
-    out->n_candidates = h[C_EV];
-    out->n_rounds = h[C_ROUNDS];
+    out->n_candidates = g->state >= 3 ? h[C_EV_FIRST] : h[C_EV];
+    out->n_rounds = g->state >= 3 ? h[C_ROUNDS_FIRST] : h[C_ROUNDS];
+    out->n_final_candidates = g->state >= 3 ? h[C_EV] : 0;
+    out->n_final_rounds = g->state >= 3 ? h[C_ROUNDS] : 0;
     out->n_piles = g->n_piles;
     out->n_alive_piles = h[C_ALIVE];
     out->n_nodes = h[C_NODES];

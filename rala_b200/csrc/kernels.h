@@ -24,6 +24,7 @@ enum Counter {
     C_HEAVY,        // heavy work items of the transitive pass
     C_OVERFLOW,     // some list hit its capacity
     C_HOP_LO, C_HOP_HI,   // two-hop visits (64-bit)
+    C_EV_FIRST, C_ROUNDS_FIRST,   // events / rounds of the first-pass resolution (C_EV / C_ROUNDS are reused by the final pass)
     C_LIST0,        // 16 rotating list-count slots follow
     C_COUNT = C_LIST0 + 16
 };

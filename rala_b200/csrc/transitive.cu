@@ -21,13 +21,24 @@ constexpr int kLightMaxDeg = 64;
 constexpr int kLightCap = 128;
 constexpr uint32_t kLightMaxVisits = 32768;
 constexpr int kLightWarps = 8;
-constexpr int kHeavyHashChunk = 1024;
+constexpr int kHeavyHashChunk = 1024;   // a node with more neighbours than this is split into hash chunks ...
+constexpr int kHeavyChunkFill = 768;    // ... of this expected size, assigned BY DESTINATION (see hash_chunk_of)
 constexpr int kHeavyCap = 2048;
 constexpr int kHeavyNbrChunk = 256;
 constexpr int kHeavyThreads = 256;
 
 __device__ __forceinline__ uint32_t hash_slot(uint32_t key, uint32_t log2cap) {
     return (key * 0x9E3779B1u) >> (32u - log2cap);
+}
+
+// Number of hash chunks of a node with d neighbours, and the chunk a destination belongs to.  Chunks
+// partition N+(a) by destination, not by position, so that parallel edges a->c always meet in the same
+// table and "highest id wins" stays a per-table decision.
+__host__ __device__ __forceinline__ uint32_t num_hash_chunks(uint32_t d) {
+    return d <= (uint32_t) kHeavyHashChunk ? 1u : (d + kHeavyChunkFill - 1) / kHeavyChunkFill;
+}
+__device__ __forceinline__ uint32_t hash_chunk_of(uint32_t key, uint32_t n_chunks) {
+    return n_chunks == 1 ? 0u : ((key * 0x85EBCA6Bu) >> 12) % n_chunks;
 }
 
 __device__ __forceinline__ void table_insert(uint32_t* keys, unsigned long long* vals, uint32_t mask, uint32_t log2cap,
@@ -41,6 +52,21 @@ __device__ __forceinline__ void table_insert(uint32_t* keys, unsigned long long*
         }
         s = (s + 1u) & mask;
     }
+}
+
+// same, but gives up (returns false) after probing the whole table
+__device__ __forceinline__ bool table_insert_bounded(uint32_t* keys, unsigned long long* vals, uint32_t mask, uint32_t log2cap,
+                                                     uint32_t key, unsigned long long val) {
+    uint32_t s = hash_slot(key, log2cap);
+    for (uint32_t probes = 0; probes <= mask; ++probes) {
+        uint32_t prev = atomicCAS(&keys[s], kEmpty, key);
+        if (prev == kEmpty || prev == key) {
+            atomicMax(&vals[s], val);
+            return true;
+        }
+        s = (s + 1u) & mask;
+    }
+    return false;
 }
 
 // returns the slot of key or kEmpty
@@ -92,7 +118,7 @@ __global__ void __launch_bounds__(kLightWarps * 32) k_transitive_light(
             const uint32_t ra0 = __shfl_sync(0xFFFFFFFFu, r0, l);
             const uint32_t d = __shfl_sync(0xFFFFFFFFu, deg, l);
             if (d > (uint32_t) kLightMaxDeg) {
-                const uint32_t nca = (d + kHeavyHashChunk - 1) / kHeavyHashChunk, ncb = (d + kHeavyNbrChunk - 1) / kHeavyNbrChunk;
+                const uint32_t nca = num_hash_chunks(d), ncb = (d + kHeavyNbrChunk - 1) / kHeavyNbrChunk;
                 uint32_t hb = 0;
                 if (lane == 0) hb = atomicAdd(&counters[C_HEAVY], nca * ncb);
                 hb = __shfl_sync(0xFFFFFFFFu, hb, 0);
@@ -154,7 +180,7 @@ __global__ void __launch_bounds__(kLightWarps * 32) k_transitive_light(
                 __syncwarp();
                 continue;
             }
-            visits += W;
+            if (lane == 0) visits += W;
 
             // flattened two-hop stream, 4 independent loads in flight per lane
             uint32_t i = 0;
@@ -213,10 +239,10 @@ __global__ void __launch_bounds__(kHeavyThreads) k_transitive_heavy(
     for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x) {
         const uint32_t a = heavy.node[item], ca = heavy.hash_chunk[item], cb = heavy.nbr_chunk[item];
         const uint32_t ra0 = row_ptr[a], d = row_ptr[a + 1] - ra0;
-        const uint32_t h0 = ca * kHeavyHashChunk, h1 = min(d, h0 + kHeavyHashChunk);
+        const uint32_t nca = num_hash_chunks(d);
         const uint32_t k0 = cb * kHeavyNbrChunk, k1 = min(d, k0 + kHeavyNbrChunk), nb = k1 - k0;
         uint32_t log2cap = 4;
-        while ((1u << log2cap) < 2u * (h1 - h0)) ++log2cap;
+        while ((1u << log2cap) < 2u * min(d, (uint32_t) kHeavyHashChunk)) ++log2cap;
         const uint32_t cap = 1u << log2cap, mask = cap - 1u;
         for (uint32_t s = tid; s < cap; s += kHeavyThreads) {
             S.keys[s] = kEmpty;
@@ -224,9 +250,11 @@ __global__ void __launch_bounds__(kHeavyThreads) k_transitive_heavy(
             S.hit[s] = 0;
         }
         __syncthreads();
-        for (uint32_t i = h0 + tid; i < h1; i += kHeavyThreads) {
+        for (uint32_t i = tid; i < d; i += kHeavyThreads) {
             const uint2 e = col[ra0 + i];
-            table_insert(S.keys, S.vals, mask, log2cap, e.x, ((unsigned long long) col_eid[ra0 + i] << 32) | e.y);
+            if (hash_chunk_of(e.x, nca) != ca) continue;
+            if (!table_insert_bounded(S.keys, S.vals, mask, log2cap, e.x, ((unsigned long long) col_eid[ra0 + i] << 32) | e.y))
+                counters[C_OVERFLOW] = 1u;   // > 2048 distinct destinations hashed into one chunk: reported as an error
         }
         uint32_t dg = 0;
         if (tid < nb) {
