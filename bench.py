@@ -179,7 +179,7 @@ def run_single(args):
     for _ in range(max(3, min(args.steps, 10))):
         G.run()
         s = G.stage_ms()
-        k1.append(s["k1_classify_kernel"])
+        k1.append(s["k1_classify_kernel"] + s["k1_survivors_kernel"])
         k3.append(s["k3_transitive_kernels"])
         for k, v in s.items():
             stage_acc.setdefault(k, []).append(v)

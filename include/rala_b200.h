@@ -163,9 +163,9 @@ int rala_b200_graph_get_marked(rala_b200_graph* g, uint8_t* out /* n_edges */);
 
 /* Device time of the last run of each stage, CUDA events on the context's stream (ms).
  * Order: classify, retrim, finalize, build, transitive (whole stages), then single kernels:
- * K1 first-pass classify kernel, K1b containment fixed point, K3 transitive kernels (light + heavy).
- * For bench.py's roofline object. */
-#define RALA_B200_N_STAGES 8
+ * K1 events kernel (first pass over the records), K1b containment fixed point, K3 transitive kernels
+ * (light + heavy), K1 survivors kernel (second pass over the records).  For bench.py's roofline object. */
+#define RALA_B200_N_STAGES 9
 int rala_b200_graph_stage_ms(rala_b200_graph* g, float* ms_out /* RALA_B200_N_STAGES */);
 
 #ifdef __cplusplus

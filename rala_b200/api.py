@@ -16,9 +16,9 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "librala_b200.so")
-N_STAGES = 8
+N_STAGES = 9
 STAGE_NAMES = ("classify", "retrim", "finalize", "build", "transitive", "k1_classify_kernel", "k1b_fixpoint_kernel",
-               "k3_transitive_kernels")
+               "k3_transitive_kernels", "k1_survivors_kernel")
 
 KX, KA, KB, KAB, KBA, REJECTED = 0, 1, 2, 3, 4, 255
 

@@ -56,7 +56,7 @@ extern "C" int rala_b200_create(rala_b200_ctx** out, int device) {
         delete ctx;
         return RALA_B200_ERR_CUDA;
     }
-    ctx->coop_blocks = fixpoint_max_blocks();
+    ctx->coop_blocks = resolve_max_blocks();
     cudaEventCreate(&ctx->ev[0]);
     cudaEventCreate(&ctx->ev[1]);
     *out = ctx;
@@ -139,7 +139,7 @@ struct ListBuf {
     }
 };
 
-enum Stage { ST_CLASSIFY = 0, ST_RETRIM, ST_FINALIZE, ST_BUILD, ST_TRANSITIVE, ST_K1_KERNEL, ST_K1B_KERNEL, ST_K3_KERNELS };
+enum Stage { ST_CLASSIFY = 0, ST_RETRIM, ST_FINALIZE, ST_BUILD, ST_TRANSITIVE, ST_K1_KERNEL, ST_K1B_KERNEL, ST_K3_KERNELS, ST_K1S_KERNEL };
 
 struct rala_b200_graph {
     rala_b200_ctx* ctx = nullptr;
@@ -153,15 +153,16 @@ struct rala_b200_graph {
     uint32_t n_hills = 0;
     // lists
     uint32_t cap = 0;   // capacity of every list / event array
-    ListBuf P, ovl[2], inl[2];
+    ListBuf ovl[2], inl[2];
     int ovl_cur = 0, inl_cur = 0;
     int slot_ovl = C_LIST0, slot_inl = C_LIST0 + 1, next_slot = C_LIST0 + 2;
     DevBuf events, hill_rec;
-    DevBuf dbuf, flags;
+    DevBuf dbuf, flags, segs, tiles;   // dbuf: S | vcursor | vstart | work0 | work1 ; segs: seg_c | seg_t ; tiles: info | off
     DevBuf counters;
     DevBuf scan_pool;
     size_t scan_pool_words = 0, scan_used = 0;
     // graph
+    DevBuf edges_aos;
     DevBuf seq_to_node, edges, row_ptr, cursor, col, col_eid, T, marked, heavy, work_counter;
     uint32_t edge_cap = 0, heavy_cap = 0, n_nodes_max = 0;
     // bookkeeping
@@ -267,10 +268,10 @@ extern "C" void rala_b200_graph_destroy(rala_b200_graph* g) {
     if (!g) return;
     cudaSetDevice(g->ctx->device);
     cudaStreamSynchronize(g->ctx->L.stream);
-    DevBuf* bufs[] = {&g->rec, &g->piles, &g->piles_raw, &g->pile_flags_raw, &g->piles_initial, &g->hills, &g->P.buf, &g->ovl[0].buf,
-                      &g->ovl[1].buf, &g->inl[0].buf, &g->inl[1].buf, &g->events, &g->hill_rec, &g->dbuf, &g->flags,
+    DevBuf* bufs[] = {&g->rec, &g->piles, &g->piles_raw, &g->pile_flags_raw, &g->piles_initial, &g->hills, &g->ovl[0].buf,
+                      &g->ovl[1].buf, &g->inl[0].buf, &g->inl[1].buf, &g->events, &g->hill_rec, &g->dbuf, &g->flags, &g->segs, &g->tiles,
                       &g->counters, &g->scan_pool, &g->seq_to_node, &g->edges, &g->row_ptr, &g->cursor, &g->col,
-                      &g->col_eid, &g->T, &g->marked, &g->heavy, &g->work_counter};
+                      &g->col_eid, &g->T, &g->marked, &g->heavy, &g->work_counter, &g->edges_aos};
     for (DevBuf* b : bufs) b->release();
     for (int i = 0; i < RALA_B200_N_STAGES; ++i) {
         cudaEventDestroy(g->ev_start[i]);
@@ -300,13 +301,13 @@ extern "C" int rala_b200_graph_set_overlaps(rala_b200_graph* g, const rala_ovl_t
     uint32_t cap = (uint32_t) (n <= (1ull << 27) ? n : n / 2);
     if (cap < 1024) cap = 1024;
     if (cap > g->cap) {
-        CU(ctx, g->P.reserve(cap));
         for (int i = 0; i < 2; ++i) {
             CU(ctx, g->ovl[i].reserve(cap));
             CU(ctx, g->inl[i].reserve(cap));
         }
         CU(ctx, g->events.reserve(align_up((size_t) cap * 4, 256) * 3));
         CU(ctx, g->hill_rec.reserve((size_t) cap * 4));
+        CU(ctx, g->segs.reserve(align_up((size_t) cap * 4, 256) * 2));
         g->cap = cap;
         g->edge_cap = 2 * cap;
         CU(ctx, g->edges.reserve(align_up((size_t) g->edge_cap * 4, 256) * 3));
@@ -319,6 +320,7 @@ extern "C" int rala_b200_graph_set_overlaps(rala_b200_graph* g, const rala_ovl_t
     } else {
         // views depend on cap: re-derive them for the (unchanged) capacity
     }
+    CU(ctx, g->tiles.reserve(align_up((size_t) classify_num_tiles((uint32_t) n) + 8, 64) * 4 * 6));
     int rc = reserve_scan_pool(g);
     if (rc) return rc;
     if (g->state < 1 && g->n_piles) g->state = 1;
@@ -343,7 +345,7 @@ extern "C" int rala_b200_graph_set_piles(rala_b200_graph* g, const rala_pile_t* 
     if (n_piles != g->n_piles) {
         g->n_piles = n_piles;
         g->n_nodes_max = 2 * n_piles;
-        CU(ctx, g->dbuf.reserve((size_t) n_piles * 16 + 16));
+        CU(ctx, g->dbuf.reserve(align_up((size_t) n_piles + 64, 64) * 4 * 5));
         CU(ctx, g->seq_to_node.reserve((size_t) n_piles * 4 + 16));
         CU(ctx, g->row_ptr.reserve(((size_t) g->n_nodes_max + 8) * 4));
         CU(ctx, g->cursor.reserve(((size_t) g->n_nodes_max + 8) * 4));
@@ -375,13 +377,33 @@ extern "C" int rala_b200_graph_set_hills(rala_b200_graph* g, const rala_hill_t* 
     return RALA_B200_OK;
 }
 
+static ResolveBufs resolve_bufs(const rala_b200_graph* g) {
+    ResolveBufs r;
+    const size_t stride = align_up((size_t) g->n_piles + 64, 64);   // 256-byte aligned sub-arrays (16-byte vector loads)
+    uint32_t* b = g->dbuf.as<uint32_t>();
+    r.S = b;
+    r.vcursor = b + stride;
+    r.vstart = b + 2 * stride;
+    r.work0 = b + 3 * stride;
+    r.work1 = b + 4 * stride;
+    r.n_work = g->flags.as<uint32_t>();
+    r.seg_c = g->segs.as<uint32_t>();
+    r.seg_t = (uint32_t*) (g->segs.as<char>() + align_up((size_t) g->cap * 4, 256));
+    return r;
+}
+
+// the classify kernels bump the per-victim histogram while they emit events: clear it first
+static cudaError_t clear_victim_histogram(rala_b200_graph* g) {
+    return cudaMemsetAsync(resolve_bufs(g).vcursor, 0, ((size_t) g->n_piles + 64) * 4, g->ctx->L.stream);
+}
+
 static int resolve_containment(rala_b200_graph* g) {
     rala_b200_ctx* ctx = g->ctx;
-    launch_fill_u32(ctx->L, g->dbuf.as<uint32_t>(), kInf, (size_t) g->n_piles * 4);
-    CU(ctx, cudaMemsetAsync(g->flags.p, 0, 64, ctx->L.stream));
-    int blocks = ctx->coop_blocks;
-    launch_fixpoint(ctx->L, g->events_view(), g->cnt() + C_EV, g->cap, g->dbuf.as<uint32_t>(), g->n_piles,
-                    g->flags.as<uint32_t>(), g->cnt(), blocks);
+    unsigned long long* status;
+    uint32_t* ticket;
+    scan_state(g, (uint64_t) g->n_piles + 1, &status, &ticket);
+    launch_resolve(ctx->L, g->events_view(), g->cnt() + C_EV, g->cap, resolve_bufs(g), g->n_piles, g->cnt(), status, ticket,
+                   ctx->coop_blocks);
     CU(ctx, cudaGetLastError());
     return RALA_B200_OK;
 }
@@ -404,10 +426,10 @@ extern "C" int rala_b200_graph_classify(rala_b200_graph* g) {
     if (g->n_hills) CU(ctx, cudaMemsetAsync(g->hills.as<uint32_t>() + 3 * (size_t) g->n_hills, 0, (size_t) g->n_hills * 4, ctx->L.stream));
     unsigned long long* status;
     uint32_t* ticket;
-    scan_state(g, g->n_rec, &status, &ticket);
+    CU(ctx, clear_victim_histogram(g));
     CU(ctx, cudaEventRecord(g->ev_start[ST_K1_KERNEL], ctx->L.stream));
-    launch_classify_first(ctx->L, g->rec.as<uint32_t>(), g->n_rec, 0u, g->piles.as<uint2>(), g->n_piles, g->P.view, g->cap,
-                          g->events_view(), g->cap, g->hill_rec.as<uint32_t>(), g->cap, g->cnt(), status, ticket);
+    launch_classify_events(ctx->L, g->rec.as<uint32_t>(), g->n_rec, 0u, g->piles.as<uint2>(), g->n_piles, g->events_view(),
+                           g->cap, resolve_bufs(g).vcursor, g->hill_rec.as<uint32_t>(), g->cap, g->cnt());
     CU(ctx, end_stage(g, ST_K1_KERNEL));
     CU(ctx, cudaEventRecord(g->ev_start[ST_K1B_KERNEL], ctx->L.stream));
     int rc = resolve_containment(g);
@@ -425,10 +447,21 @@ extern "C" int rala_b200_graph_classify(rala_b200_graph* g) {
     g->slot_ovl = C_LIST0;
     g->slot_inl = C_LIST0 + 1;
     g->next_slot = C_LIST0 + 2;
-    scan_state(g, g->cap, &status, &ticket);
-    launch_list_pass(ctx->L, 0 /*kSplitAlive*/, g->P.view, g->cnt() + C_P, g->cap, g->piles.as<uint2>(), g->ovl[0].view,
-                     g->cnt() + g->slot_ovl, g->inl[0].view, g->cnt() + g->slot_inl, nullptr, g->cap, nullptr, g->n_piles,
-                     nullptr, g->cnt(), status, ticket);
+    CU(ctx, cudaMemsetAsync(g->flags.as<uint32_t>() + 8, 0, 8, ctx->L.stream));   // scratch append counters
+    CU(ctx, cudaEventRecord(g->ev_start[ST_K1S_KERNEL], ctx->L.stream));
+    {
+        const size_t nt = align_up((size_t) classify_num_tiles(g->n_rec) + 8, 64);
+        uint32_t* t = g->tiles.as<uint32_t>();
+        TileRuns runs{t, t + nt, t + 2 * nt, t + 3 * nt, t + 4 * nt, t + 5 * nt};
+        unsigned long long* st2[2];
+        uint32_t* tk2[2];
+        scan_state(g, nt, &st2[0], &tk2[0]);
+        scan_state(g, nt, &st2[1], &tk2[1]);
+        launch_classify_survivors(ctx->L, g->rec.as<uint32_t>(), g->n_rec, g->piles.as<uint2>(), g->n_piles, g->ovl[1].view,
+                                  g->inl[1].view, g->ovl[0].view, g->cnt() + g->slot_ovl, g->inl[0].view,
+                                  g->cnt() + g->slot_inl, g->cap, runs, g->flags.as<uint32_t>() + 8, st2, tk2);
+    }
+    CU(ctx, end_stage(g, ST_K1S_KERNEL));
     CU(ctx, cudaGetLastError());
     CU(ctx, end_stage(g, ST_CLASSIFY));
     g->piles_dirty = false;   // lists are trimmed against the table as it stands (only liveness changed, and the split filtered on it)
@@ -520,10 +553,11 @@ extern "C" int rala_b200_graph_finalize(rala_b200_graph* g) {
     CU(ctx, cudaMemcpyAsync(g->cnt() + C_EV_FIRST, g->cnt() + C_EV, 4, cudaMemcpyDeviceToDevice, ctx->L.stream));
     CU(ctx, cudaMemcpyAsync(g->cnt() + C_ROUNDS_FIRST, g->cnt() + C_ROUNDS, 4, cudaMemcpyDeviceToDevice, ctx->L.stream));
     CU(ctx, zero_counter(g, C_EV));
+    CU(ctx, clear_victim_histogram(g));
     launch_classify_final(ctx->L, g->ovl[g->ovl_cur].view, g->cnt() + g->slot_ovl, g->cap, nullptr, g->piles.as<uint2>(),
-                          g->events_view(), g->cap, g->cnt());
+                          g->events_view(), g->cap, resolve_bufs(g).vcursor, g->cnt());
     launch_classify_final(ctx->L, g->inl[g->inl_cur].view, g->cnt() + g->slot_inl, g->cap, g->cnt() + g->slot_ovl,
-                          g->piles.as<uint2>(), g->events_view(), g->cap, g->cnt());
+                          g->piles.as<uint2>(), g->events_view(), g->cap, resolve_bufs(g).vcursor, g->cnt());
     int rc = resolve_containment(g);
     if (rc) return rc;
     unsigned long long* status;
@@ -621,9 +655,9 @@ static int read_counters(rala_b200_graph* g, uint32_t* h) {
     CU(ctx, cudaSetDevice(ctx->device));
     CU(ctx, cudaMemcpyAsync(h, g->counters.p, C_COUNT * 4, cudaMemcpyDeviceToHost, ctx->L.stream));
     CU(ctx, cudaStreamSynchronize(ctx->L.stream));
-    if (h[C_OVERFLOW] || h[C_P] > g->cap || h[C_EV] > g->cap || h[C_HILL] > g->cap || h[C_HEAVY] > g->heavy_cap)
-        return fail(ctx, RALA_B200_ERR_LIMIT, "a device list overflowed its capacity (cap=%u P=%u events=%u hills=%u heavy=%u/%u)",
-                    g->cap, h[C_P], h[C_EV], h[C_HILL], h[C_HEAVY], g->heavy_cap);
+    if (h[C_OVERFLOW] || (g->state >= 2 && (h[g->slot_ovl] > g->cap || h[g->slot_inl] > g->cap)) || h[C_EV] > g->cap || h[C_HILL] > g->cap || h[C_HEAVY] > g->heavy_cap)
+        return fail(ctx, RALA_B200_ERR_LIMIT, "a device list overflowed its capacity (cap=%u events=%u hills=%u heavy=%u/%u)",
+                    g->cap, h[C_EV], h[C_HILL], h[C_HEAVY], g->heavy_cap);
     return RALA_B200_OK;
 }
 
@@ -730,11 +764,10 @@ extern "C" int rala_b200_graph_get_edges(rala_b200_graph* g, rala_edge_t* out) {
     if (rc) return rc;
     uint32_t n = h[C_EDGES];
     if (!n) return RALA_B200_OK;
-    // columns -> rows on the host side of the copy (three strided copies)
-    GraphArrays ga = g->graph_view();
-    CU(ctx, cudaMemcpy2DAsync(&out[0].src, 12, ga.src, 4, 4, n, cudaMemcpyDeviceToHost, ctx->L.stream));
-    CU(ctx, cudaMemcpy2DAsync(&out[0].dst, 12, ga.dst, 4, 4, n, cudaMemcpyDeviceToHost, ctx->L.stream));
-    CU(ctx, cudaMemcpy2DAsync(&out[0].len, 12, ga.len, 4, 4, n, cudaMemcpyDeviceToHost, ctx->L.stream));
+    // columns -> rows on the device, then one contiguous copy
+    CU(ctx, g->edges_aos.reserve((size_t) g->edge_cap * 12));
+    launch_pack_edges(ctx->L, g->graph_view(), g->edge_cap, g->cnt() + C_EDGES, g->edges_aos.as<uint32_t>());
+    CU(ctx, cudaMemcpyAsync(out, g->edges_aos.p, (size_t) n * 12, cudaMemcpyDeviceToHost, ctx->L.stream));
     CU(ctx, cudaStreamSynchronize(ctx->L.stream));
     return RALA_B200_OK;
 }

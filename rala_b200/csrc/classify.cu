@@ -4,192 +4,264 @@
 // Replaces (reference file:line): Overlap::trim / Overlap::type overlap.cpp:117-259 as driven by
 // graph.cpp:443-518 (classify loop), 722-736 and 801-824 (re-trim, promotion of internals),
 // 831-877 (final containment), and Pile::check_chimeric_hills pile.cpp:457-469.
-#include <cooperative_groups.h>
-
 #include "kernels.h"
 #include "lists.cuh"
-
-namespace cg = cooperative_groups;
 
 namespace rb {
 
 // =============================================================================================
-// K1 first pass (graph.cpp:448-488): one thread per record.  Records arrive as the 28-byte AoS the
-// host marshals (rala_ovl_t); a tile of 1024 records (28 KiB, contiguous) is staged into shared
-// memory by one TMA bulk copy and read back with a 7-word stride (odd => conflict free).
-// Outputs, all in one pass over the records:
-//   P      records that can still survive (kX, dovetails, kA/kB whose container is chimeric), trimmed,
-//          in FILE ORDER (single-pass decoupled look-back compaction)            -> 25 B each
-//   events (victim, container, time) of every kA/kB that may kill                -> 12 B each, any order
-//   hills  indices of records that touch a pile with chimeric hills (rare)       ->  4 B each, any order
+// K1 (graph.cpp:443-518) runs as two streaming kernels over the 28-byte AoS records the host
+// marshals (rala_ovl_t), with the containment fixed point between them:
+//   k_classify_events    every record: static gates, trim, type; emits only what the ORDER-DEPENDENT
+//                        part needs: the containment events (victim, container, time) of kA/kB records
+//                        and the indices of records touching a pile with chimeric hills.
+//   k_classify_survivors every record again, once the final pile liveness is known: records whose two
+//                        piles are still alive are trimmed, typed and written, in FILE ORDER, to
+//                        `overlaps` (kA/kB with a chimeric container, kAB, kBA) or `internals` (kX).
+// No intermediate list: on clean data ~95 % of the records are dovetails at classification time but
+// only ~7 % survive the dead-pile filter, so materialising the "potential survivors" costs more than
+// re-reading the records.
+// Both kernels stage tiles of 512 records (14 KiB, contiguous) into shared memory with TMA bulk
+// copies (cp.async.bulk + mbarrier), double buffered, and read them back with a 7-word stride
+// (odd => bank-conflict free).
 // =============================================================================================
-__global__ void __launch_bounds__(kTileThreads) k_classify_first(
-    const uint32_t* __restrict__ rec, uint32_t n, uint32_t t0, const uint2* __restrict__ piles, uint32_t n_piles,
-    List P, uint32_t p_cap, Events ev, uint32_t ev_cap, uint32_t* __restrict__ hill_rec, uint32_t hill_cap,
-    uint32_t* __restrict__ counters, unsigned long long* __restrict__ status, uint32_t* __restrict__ ticket) {
-    __shared__ __align__(128) uint32_t s_rec[kTile * 7];
-    __shared__ __align__(8) uint64_t s_bar;
-    __shared__ TileShared sh;
-    __shared__ uint32_t s_ev_cnt[kTileItems * kTileWarps];
-    __shared__ uint32_t s_ev_base;
+constexpr int kRecItems = 2;
+constexpr int kRecTile = kTileThreads * kRecItems;       // 512 records
+constexpr uint32_t kRecTileWords = kRecTile * 7;
 
+struct RecStage {
+    __align__(128) uint32_t rec[2][kRecTileWords];
+    __align__(8) uint64_t bar[2];
+};
+
+// issue the TMA load of `tile` into buffer b (one thread)
+__device__ __forceinline__ void issue_tile(RecStage& st, int b, const uint32_t* __restrict__ rec, uint32_t n, uint32_t tile) {
+    const uint32_t base = tile * kRecTile;
+    const uint32_t cnt = min((uint32_t) kRecTile, n - base);
+    const uint32_t bytes = (cnt * 28u + 15u) & ~15u;   // the record buffer is padded by 16 B past its end
+    fence_proxy_async();                               // earlier generic-proxy reads of this buffer come first
+    mbar_expect_tx(&st.bar[b], bytes);
+    bulk_g2s(st.rec[b], rec + (size_t) base * 7, bytes, &st.bar[b]);
+}
+
+struct RecFields {
+    Entry e;
+    uint32_t flags;
+};
+
+__device__ __forceinline__ RecFields read_record(const uint32_t* q) {
+    RecFields r;
+    r.e.a = q[0];
+    r.e.b = q[1];
+    r.e.c.ab = q[2];
+    r.e.c.ae = q[3];
+    r.e.c.bb = q[4];
+    r.e.c.be = q[5];
+    r.flags = q[6];
+    r.e.ori = r.flags & 1u;
+    return r;
+}
+
+constexpr int kEvStage = 64;   // per-warp staging of events before one aggregated global append
+
+__global__ void __launch_bounds__(kTileThreads) k_classify_events(
+    const uint32_t* __restrict__ rec, uint32_t n, uint32_t t0, const uint2* __restrict__ piles, uint32_t n_piles,
+    Events ev, uint32_t ev_cap, uint32_t* __restrict__ vcount, uint32_t* __restrict__ hill_rec, uint32_t hill_cap,
+    uint32_t* __restrict__ counters) {
+    __shared__ RecStage st;
+    __shared__ uint32_t s_ev[kTileWarps][3][kEvStage];
     const uint32_t tid = threadIdx.x, lane = lane_id(), warp = warp_id();
-    const uint32_t num_tiles = (n + kTile - 1) / kTile;
+    const uint32_t num_tiles = (n + kRecTile - 1) / kRecTile;
     if (tid == 0) {
-        mbar_init(&s_bar, 1);
+        mbar_init(&st.bar[0], 1);
+        mbar_init(&st.bar[1], 1);
         fence_mbar_init();
     }
     __syncthreads();
-    uint32_t parity = 0;
+    uint32_t parity[2] = {0u, 0u};
+    uint32_t staged = 0;   // warp-uniform
 
-    while (true) {
-        if (tid == 0) sh.tile = atomicAdd(ticket, 1u);
-        __syncthreads();
-        const uint32_t tile = sh.tile;
-        if (tile >= num_tiles) break;
-        const uint32_t base = tile * kTile;
-        const uint32_t cnt = min((uint32_t) kTile, n - base);
-        if (cnt == kTile) {
-            if (tid == 0) {
-                fence_proxy_async();   // earlier generic-proxy reads of s_rec are ordered before the async write
-                mbar_expect_tx(&s_bar, kTile * 28u);
-                bulk_g2s(s_rec, rec + (size_t) base * 7, kTile * 28u, &s_bar);
+    auto flush = [&]() {
+        uint32_t gbase = 0;
+        if (lane == 0) gbase = atomicAdd(&counters[C_EV], staged);
+        gbase = __shfl_sync(0xFFFFFFFFu, gbase, 0);
+        for (uint32_t i = lane; i < staged; i += 32) {
+            if (gbase + i < ev_cap) {
+                ev.v[gbase + i] = s_ev[warp][0][i];
+                ev.c[gbase + i] = s_ev[warp][1][i];
+                ev.t[gbase + i] = s_ev[warp][2][i];
             }
-            mbar_wait(&s_bar, parity);
-            parity ^= 1u;
-        } else {
-            for (uint32_t i = tid; i < cnt * 7; i += kTileThreads) s_rec[i] = rec[(size_t) base * 7 + i];
-            __syncthreads();
         }
+        __syncwarp();
+        staged = 0;
+    };
 
-        Entry e[kTileItems];
-        uint8_t tag[kTileItems];
-        int dest[kTileItems];
-        uint32_t evv[kTileItems], evc[kTileItems];
-        bool is_ev[kTileItems];
+    uint32_t tile = blockIdx.x;
+    if (tid == 0 && tile < num_tiles) issue_tile(st, 0, rec, n, tile);
+    for (uint32_t it = 0; tile < num_tiles; ++it, tile += gridDim.x) {
+        const int b = it & 1;
+        if (tid == 0 && tile + gridDim.x < num_tiles) issue_tile(st, b ^ 1, rec, n, tile + gridDim.x);
+        mbar_wait(&st.bar[b], parity[b]);
+        parity[b] ^= 1u;
+        const uint32_t base = tile * kRecTile;
+        const uint32_t cnt = min((uint32_t) kRecTile, n - base);
 #pragma unroll
-        for (int r = 0; r < kTileItems; ++r) {
+        for (int r = 0; r < kRecItems; ++r) {
             const uint32_t idx = r * kTileThreads + tid;
-            dest[r] = 0;
-            is_ev[r] = false;
-            tag[r] = kRejected;
+            bool is_ev = false;
+            uint32_t evv = 0, evc = 0;
             if (idx < cnt) {
-                const uint32_t* q = s_rec + idx * 7;
-                e[r].a = q[0];
-                e[r].b = q[1];
-                e[r].c.ab = q[2];
-                e[r].c.ae = q[3];
-                e[r].c.bb = q[4];
-                e[r].c.be = q[5];
-                const uint32_t flags = q[6];
-                e[r].ori = flags & 1u;
-                if (!(flags & 2u) && e[r].a < n_piles && e[r].b < n_piles) {          // graph.cpp:450-451
-                    const Pile pa = load_pile(piles, e[r].a), pb = load_pile(piles, e[r].b);
-                    if (pa.alive() && pb.alive() && trim(e[r].c, e[r].ori, pa, pb)) {   // :451-452
-                        if ((pa.flags | pb.flags) & 1u) {                               // :457-462, resolved later
+                RecFields f = read_record(st.rec[b] + idx * 7);
+                if (!(f.flags & 2u) && f.e.a < n_piles && f.e.b < n_piles) {                 // graph.cpp:450-451
+                    const Pile pa = load_pile(piles, f.e.a), pb = load_pile(piles, f.e.b);
+                    if (pa.alive() && pb.alive() && trim(f.e.c, f.e.ori, pa, pb)) {           // :451-452
+                        if ((pa.flags | pb.flags) & 1u) {                                    // :457-462, resolved by k_hill_coverage
                             uint32_t slot = atomicAdd(&counters[C_HILL], 1u);
                             if (slot < hill_cap) hill_rec[slot] = base + idx;
                         }
-                        const uint8_t t = classify(e[r].c, relative(e[r].c, e[r].ori, pa, pb));
-                        tag[r] = t;
-                        if (t == kB && !(pb.flags & 2u)) {                              // :469-474
-                            is_ev[r] = true; evv[r] = e[r].a; evc[r] = e[r].b;
-                        } else if (t == kA && !(pa.flags & 2u)) {                       // :475-480
-                            is_ev[r] = true; evv[r] = e[r].b; evc[r] = e[r].a;
-                        } else {
-                            dest[r] = 1;
+                        const uint8_t t = classify(f.e.c, relative(f.e.c, f.e.ori, pa, pb));
+                        if (t == kB && !(pb.flags & 2u)) {                                   // :469-474
+                            is_ev = true; evv = f.e.a; evc = f.e.b;
+                        } else if (t == kA && !(pa.flags & 2u)) {                            // :475-480
+                            is_ev = true; evv = f.e.b; evc = f.e.a;
                         }
                     }
                 }
             }
+            const uint32_t m = __ballot_sync(0xFFFFFFFFu, is_ev);
+            if (m) {
+                if (is_ev) {
+                    atomicAdd(&vcount[evv], 1u);   // per-victim histogram for the resolution's counting sort
+                    const uint32_t p = staged + __popc(m & ((1u << lane) - 1u));
+                    s_ev[warp][0][p] = evv;
+                    s_ev[warp][1][p] = evc;
+                    s_ev[warp][2][p] = t0 + base + idx;
+                }
+                staged += __popc(m);
+                __syncwarp();
+                if (staged > kEvStage - 32) flush();
+            }
         }
+        __syncthreads();   // everyone is done with buffer b before it is refilled
+    }
+    if (staged) flush();
+}
 
-        // events: unordered, one global atomic per tile
-        uint32_t ev_rank[kTileItems];
+// Survivors pass.  Tiles are independent: a tile appends its survivors (in record order) to scratch
+// lists at a base claimed with one atomic, and records (base, count) per tile; k_tile_offsets turns the
+// counts into file-order offsets and k_relocate moves each tile's run to its final place.  (A single-pass
+// look-back compaction was measured 2.5x slower here: a tile's aggregate is only known after its TMA load
+// and two dependent pile gathers, so the look-back chain serialised the waves.)
+__global__ void __launch_bounds__(kTileThreads) k_classify_survivors(
+    const uint32_t* __restrict__ rec, uint32_t n, const uint2* __restrict__ piles, uint32_t n_piles,
+    List tmp_ovl, List tmp_inl, uint32_t cap, TileRuns runs, uint32_t* __restrict__ tmp_counts) {
+    __shared__ RecStage st;
+    __shared__ uint32_t s_cnt_a[kRecItems * kTileWarps], s_cnt_b[kRecItems * kTileWarps];
+    __shared__ uint32_t s_base_a, s_base_b;
+    const uint32_t tid = threadIdx.x, lane = lane_id(), warp = warp_id();
+    const uint32_t num_tiles = (n + kRecTile - 1) / kRecTile;
+    if (tid == 0) {
+        mbar_init(&st.bar[0], 1);
+        mbar_init(&st.bar[1], 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+    uint32_t parity[2] = {0u, 0u};
+    uint32_t tile = blockIdx.x;
+    if (tid == 0 && tile < num_tiles) issue_tile(st, 0, rec, n, tile);
+    for (uint32_t it = 0; tile < num_tiles; ++it, tile += gridDim.x) {
+        const int b = it & 1;
+        if (tid == 0 && tile + gridDim.x < num_tiles) issue_tile(st, b ^ 1, rec, n, tile + gridDim.x);
+        mbar_wait(&st.bar[b], parity[b]);
+        parity[b] ^= 1u;
+        const uint32_t base = tile * kRecTile;
+        const uint32_t cnt = min((uint32_t) kRecTile, n - base);
+        int dest[kRecItems];
+        Entry e[kRecItems];
+        uint8_t tag[kRecItems];
+        uint32_t lrank[kRecItems];
 #pragma unroll
-        for (int r = 0; r < kTileItems; ++r) {
-            uint32_t m = __ballot_sync(0xFFFFFFFFu, is_ev[r]);
-            ev_rank[r] = __popc(m & ((1u << lane) - 1u));
-            if (lane == 0) s_ev_cnt[r * kTileWarps + warp] = __popc(m);
+        for (int r = 0; r < kRecItems; ++r) {
+            const uint32_t idx = r * kTileThreads + tid;
+            dest[r] = 0;
+            tag[r] = kRejected;
+            if (idx < cnt) {
+                RecFields f = read_record(st.rec[b] + idx * 7);
+                if (!(f.flags & 2u) && f.e.a < n_piles && f.e.b < n_piles) {
+                    // the table already carries the kills: both piles alive at the end (graph.cpp:493-515)
+                    const Pile pa = load_pile(piles, f.e.a);
+                    if (pa.alive()) {
+                        const Pile pb = load_pile(piles, f.e.b);
+                        if (pb.alive() && trim(f.e.c, f.e.ori, pa, pb)) {
+                            tag[r] = classify(f.e.c, relative(f.e.c, f.e.ori, pa, pb));
+                            dest[r] = tag[r] == kX ? 2 : 1;   // a surviving kA/kB has a chimeric container (:470, :476)
+                            e[r] = f.e;
+                        }
+                    }
+                }
+            }
+            const uint32_t ma = __ballot_sync(0xFFFFFFFFu, dest[r] == 1), mb = __ballot_sync(0xFFFFFFFFu, dest[r] == 2);
+            const uint32_t below = (1u << lane) - 1u;
+            lrank[r] = dest[r] == 1 ? __popc(ma & below) : __popc(mb & below);
+            if (lane == 0) {
+                s_cnt_a[r * kTileWarps + warp] = __popc(ma);
+                s_cnt_b[r * kTileWarps + warp] = __popc(mb);
+            }
         }
-        uint32_t pos[kTileItems];
-        unsigned long long inclusive = 0;
-        tile_rank(sh, status, tile, dest, pos, &inclusive);   // (first __syncthreads inside publishes s_ev_cnt)
+        __syncthreads();   // counts visible; everyone is done reading buffer b
         if (warp == 0) {
-            uint32_t c = s_ev_cnt[lane];
-            uint32_t inc = warp_inclusive_scan(c);
-            uint32_t total = __shfl_sync(0xFFFFFFFFu, inc, 31);
-            uint32_t gbase = 0;
-            if (lane == 0 && total) gbase = atomicAdd(&counters[C_EV], total);
-            gbase = __shfl_sync(0xFFFFFFFFu, gbase, 0);
-            s_ev_cnt[lane] = gbase + inc - c;
-            if (lane == 0 && tile == num_tiles - 1) counters[C_P] = count_a(inclusive);
+            const uint32_t ca = lane < kRecItems * kTileWarps ? s_cnt_a[lane] : 0u, cb = lane < kRecItems * kTileWarps ? s_cnt_b[lane] : 0u;
+            const uint32_t ia = warp_inclusive_scan(ca), ib = warp_inclusive_scan(cb);
+            const uint32_t ta = __shfl_sync(0xFFFFFFFFu, ia, 31), tb = __shfl_sync(0xFFFFFFFFu, ib, 31);
+            if (lane < kRecItems * kTileWarps) {
+                s_cnt_a[lane] = ia - ca;
+                s_cnt_b[lane] = ib - cb;
+            }
+            if (lane == 0) {
+                const uint32_t ga = ta ? atomicAdd(&tmp_counts[0], ta) : 0u, gb = tb ? atomicAdd(&tmp_counts[1], tb) : 0u;
+                s_base_a = ga;
+                s_base_b = gb;
+                runs.base_a[tile] = ga;
+                runs.cnt_a[tile] = ta;
+                runs.base_b[tile] = gb;
+                runs.cnt_b[tile] = tb;
+            }
         }
         __syncthreads();
 #pragma unroll
-        for (int r = 0; r < kTileItems; ++r) {
-            if (dest[r] == 1 && pos[r] < p_cap) store_entry(P, pos[r], e[r], tag[r]);
-            if (is_ev[r]) {
-                uint32_t p = s_ev_cnt[r * kTileWarps + warp] + ev_rank[r];
-                if (p < ev_cap) {
-                    ev.v[p] = evv[r];
-                    ev.c[p] = evc[r];
-                    ev.t[p] = t0 + base + r * kTileThreads + tid;
-                }
+        for (int r = 0; r < kRecItems; ++r) {
+            if (dest[r] == 1) {
+                const uint32_t p = s_base_a + s_cnt_a[r * kTileWarps + warp] + lrank[r];
+                if (p < cap) store_entry(tmp_ovl, p, e[r], tag[r]);
+            } else if (dest[r] == 2) {
+                const uint32_t p = s_base_b + s_cnt_b[r * kTileWarps + warp] + lrank[r];
+                if (p < cap) store_entry(tmp_inl, p, e[r], tag[r]);
             }
         }
-        __syncthreads();   // s_rec, sh and s_ev_cnt are reused by the next tile
+        // s_cnt / s_base are rewritten only after the next tile's first barrier... which every thread reaches
+        // after these reads; buffer b is refilled by the TMA issued at the top of the NEXT-next iteration
+        __syncthreads();
     }
 }
 
-// =============================================================================================
-// K1b: ordered containment as a death-time fixed point.
-//   D_{r+1}[x] = min{ t_i : victim_i = x and D_r[container_i] > t_i },  D_0 = +inf.
-// One cooperative persistent kernel; four rotating D buffers make a round ONE pass over the events
-// and ONE grid barrier:  in round r the pass (1) builds D_{r+1} with atomicMin, (2) checks
-// D_r == D_{r-1} on the victims (only victims ever change), (3) resets the victims' slots of the
-// buffer round r+1 will build.  When the check finds no difference D_r is the answer.
-// =============================================================================================
-__global__ void __launch_bounds__(256) k_containment_fixpoint(Events ev, const uint32_t* __restrict__ n_events,
-                                                             uint32_t ev_cap, uint32_t* __restrict__ dbuf,
-                                                             uint32_t n_piles, uint32_t* __restrict__ flags,
-                                                             uint32_t* __restrict__ counters) {
-    cg::grid_group grid = cg::this_grid();
-    const uint32_t n = min(*n_events, ev_cap);
-    const uint32_t stride = gridDim.x * blockDim.x, gtid = blockIdx.x * blockDim.x + threadIdx.x;
-    uint32_t* D[4] = {dbuf, dbuf + n_piles, dbuf + 2 * (size_t) n_piles, dbuf + 3 * (size_t) n_piles};
-    // buffers arrive filled with +inf; D[0] = D_0.  flags[r % 3] is the "changed" flag of round r (three slots:
-    // slot (r+1)%3 is cleared during round r, after every thread has finished reading it for round r-2).
-    uint32_t round = 0;
-    uint32_t result = 0;
-    if (n == 0) {
-        if (gtid == 0) { counters[C_ROUNDS] = 0; counters[C_DSEL] = 0; }
-        return;
-    }
-    while (true) {
-        const uint32_t* cur = D[round & 3];                 // D_r
-        const uint32_t* prev = D[(round + 3) & 3];          // D_{r-1}
-        uint32_t* next = D[(round + 1) & 3];                // D_{r+1}, pre-reset
-        uint32_t* next2 = D[(round + 2) & 3];               // buffer of round r+1, reset now
-        bool changed = false;
-        for (uint32_t i = gtid; i < n; i += stride) {
-            const uint32_t v = ev.v[i], c = ev.c[i], t = ev.t[i];
-            if (cur[c] > t) atomicMin(&next[v], t);
-            if (round > 0 && cur[v] != prev[v]) changed = true;
-            next2[v] = kInf;
+// scratch run -> final position, one thread per output entry: the tile of entry j is found by binary
+// search in the scanned offsets (off[t] <= j < off[t+1]); writes are fully coalesced
+__global__ void k_relocate(List tmp, List out, uint32_t cap, const uint32_t* __restrict__ base, const uint32_t* __restrict__ off,
+                           uint32_t num_tiles) {
+    const uint32_t total = min(off[num_tiles], cap);
+    for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < total; j += gridDim.x * blockDim.x) {
+        uint32_t lo = 0, hi = num_tiles;   // largest t with off[t] <= j
+        while (hi - lo > 1) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (off[mid] <= j) lo = mid; else hi = mid;
         }
-        if (round > 0 && changed) flags[round % 3] = 1u;
-        if (gtid == 0) flags[(round + 1) % 3] = 0u;
-        grid.sync();
-        if (round > 0 && flags[round % 3] == 0u) {
-            result = round & 3;
-            break;
+        const uint32_t src = base[lo] + (j - off[lo]);
+        if (src < cap) {
+            out.a[j] = tmp.a[src]; out.b[j] = tmp.b[src];
+            out.ab[j] = tmp.ab[src]; out.ae[j] = tmp.ae[src];
+            out.bb[j] = tmp.bb[src]; out.be[j] = tmp.be[src];
+            out.tag[j] = tmp.tag[src];
         }
-        ++round;
-    }
-    if (gtid == 0) {
-        counters[C_ROUNDS] = round;
-        counters[C_DSEL] = result;
     }
 }
 
@@ -304,7 +376,7 @@ __global__ void __launch_bounds__(kTileThreads) k_list_pass(
         }
         uint32_t pos[kTileItems];
         unsigned long long inclusive = 0;
-        tile_rank(sh, status, tile, dest, pos, &inclusive);
+        tile_rank<kTileItems>(sh, status, tile, dest, pos, &inclusive);
         if (tid == 0 && tile == num_tiles - 1) {
             *n_out_a = count_a(inclusive);
             if (n_out_b) *n_out_b = b_off + count_b(inclusive);
@@ -323,7 +395,7 @@ __global__ void __launch_bounds__(kTileThreads) k_list_pass(
 // concatenation.  No chimeric gating in this pass.
 __global__ void k_classify_final(List lst, const uint32_t* __restrict__ n_ptr, uint32_t cap,
                                  const uint32_t* __restrict__ time_base_ptr, const uint2* __restrict__ piles, Events ev,
-                                 uint32_t ev_cap, uint32_t* __restrict__ counters) {
+                                 uint32_t ev_cap, uint32_t* __restrict__ vcount, uint32_t* __restrict__ counters) {
     const uint32_t n = min(*n_ptr, cap);
     const uint32_t time_base = time_base_ptr ? *time_base_ptr : 0u;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
@@ -346,6 +418,7 @@ __global__ void k_classify_final(List lst, const uint32_t* __restrict__ n_ptr, u
                     ev.c[p] = t == kA ? e.a : e.b;
                     ev.t[p] = time_base + i;
                 }
+                atomicAdd(&vcount[t == kA ? e.b : e.a], 1u);
             }
         }
         lst.tag[i] = t;
@@ -419,33 +492,35 @@ static inline int grid_for(uint64_t n, int per_block, int max_blocks) {
     return (int) (b < (uint64_t) max_blocks ? b : (uint64_t) max_blocks);
 }
 
-void launch_classify_first(Launch& L, const uint32_t* rec, uint32_t n, uint32_t t0, const uint2* piles, uint32_t n_piles,
-                           List P, uint32_t p_cap, Events ev, uint32_t ev_cap, uint32_t* hill_rec, uint32_t hill_cap,
-                           uint32_t* counters, unsigned long long* status, uint32_t* ticket) {
+void launch_classify_events(Launch& L, const uint32_t* rec, uint32_t n, uint32_t t0, const uint2* piles, uint32_t n_piles,
+                            Events ev, uint32_t ev_cap, uint32_t* vcount, uint32_t* hill_rec, uint32_t hill_cap, uint32_t* counters) {
     if (n == 0) return;
-    int grid = grid_for(n, kTile, kNumSMs * 6);
-    k_classify_first<<<grid, kTileThreads, 0, L.stream>>>(rec, n, t0, piles, n_piles, P, p_cap, ev, ev_cap, hill_rec,
-                                                          hill_cap, counters, status, ticket);
+    int grid = grid_for(n, kRecTile, kNumSMs * 6);
+    k_classify_events<<<grid, kTileThreads, 0, L.stream>>>(rec, n, t0, piles, n_piles, ev, ev_cap, vcount, hill_rec, hill_cap, counters);
     L.count++;
 }
 
-void launch_fixpoint(Launch& L, Events ev, const uint32_t* n_events, uint32_t ev_cap, uint32_t* dbuf, uint32_t n_piles,
-                     uint32_t* flags, uint32_t* counters, int coop_blocks) {
-    void* args[] = {&ev, &n_events, &ev_cap, &dbuf, &n_piles, &flags, &counters};
-    cudaLaunchCooperativeKernel((void*) k_containment_fixpoint, dim3(coop_blocks), dim3(256), args, 0, L.stream);
+void launch_classify_survivors(Launch& L, const uint32_t* rec, uint32_t n, const uint2* piles, uint32_t n_piles, List tmp_ovl,
+                               List tmp_inl, List ovl, uint32_t* n_ovl, List inl, uint32_t* n_inl, uint32_t cap, TileRuns runs,
+                               uint32_t* tmp_counts, unsigned long long* status[2], uint32_t* ticket[2]) {
+    if (n == 0) return;   // n_ovl / n_inl were zeroed by the caller
+    const uint32_t num_tiles = (n + kRecTile - 1) / kRecTile;
+    // counts of the sentinel tile [num_tiles] must be zero so that the scans end with the totals
+    cudaMemsetAsync(runs.cnt_a + num_tiles, 0, 4, L.stream);
+    cudaMemsetAsync(runs.cnt_b + num_tiles, 0, 4, L.stream);
+    int grid = grid_for(n, kRecTile, kNumSMs * 6);
+    k_classify_survivors<<<grid, kTileThreads, 0, L.stream>>>(rec, n, piles, n_piles, tmp_ovl, tmp_inl, cap, runs, tmp_counts);
     L.count++;
+    launch_scan_u32(L, runs.cnt_a, runs.off_a, num_tiles + 1, status[0], ticket[0]);
+    launch_scan_u32(L, runs.cnt_b, runs.off_b, num_tiles + 1, status[1], ticket[1]);
+    cudaMemcpyAsync(n_ovl, runs.off_a + num_tiles, 4, cudaMemcpyDeviceToDevice, L.stream);
+    cudaMemcpyAsync(n_inl, runs.off_b + num_tiles, 4, cudaMemcpyDeviceToDevice, L.stream);
+    k_relocate<<<grid_for(cap, 256, kNumSMs * 8), 256, 0, L.stream>>>(tmp_ovl, ovl, cap, runs.base_a, runs.off_a, num_tiles);
+    k_relocate<<<grid_for(cap, 256, kNumSMs * 8), 256, 0, L.stream>>>(tmp_inl, inl, cap, runs.base_b, runs.off_b, num_tiles);
+    L.count += 2;
 }
 
-int fixpoint_max_blocks() {
-    int per_sm = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_containment_fixpoint, 256, 0);
-    if (per_sm < 1) per_sm = 1;
-    if (per_sm > 4) per_sm = 4;
-    int dev = 0, sms = kNumSMs;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    return per_sm * sms;
-}
+uint32_t classify_num_tiles(uint32_t n) { return (n + kRecTile - 1) / kRecTile; }
 
 void launch_hill_coverage(Launch& L, const uint32_t* rec, uint32_t t0, const uint2* piles, const uint32_t* hill_rec,
                           uint32_t hill_cap, const uint32_t* hill_pile, const uint32_t* hill_begin,
@@ -481,9 +556,9 @@ void launch_list_pass(Launch& L, int mode, List in, const uint32_t* n_in, uint32
 }
 
 void launch_classify_final(Launch& L, List lst, const uint32_t* n_ptr, uint32_t cap, const uint32_t* time_base,
-                           const uint2* piles, Events ev, uint32_t ev_cap, uint32_t* counters) {
+                           const uint2* piles, Events ev, uint32_t ev_cap, uint32_t* vcount, uint32_t* counters) {
     k_classify_final<<<grid_for(cap, 256, kNumSMs * 8), 256, 0, L.stream>>>(lst, n_ptr, cap, time_base, piles, ev, ev_cap,
-                                                                            counters);
+                                                                            vcount, counters);
     L.count++;
 }
 

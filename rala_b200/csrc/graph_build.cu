@@ -29,7 +29,7 @@ __global__ void __launch_bounds__(kTileThreads) k_node_ids(const uint2* __restri
         }
         uint32_t pos[kTileItems];
         unsigned long long inclusive = 0;
-        tile_rank(sh, status, tile, dest, pos, &inclusive);
+        tile_rank<kTileItems>(sh, status, tile, dest, pos, &inclusive);
         if (tid == 0 && tile == num_tiles - 1) {
             counters[C_ALIVE] = count_a(inclusive);
             counters[C_NODES] = 2u * count_a(inclusive);
@@ -91,7 +91,7 @@ __global__ void __launch_bounds__(kTileThreads) k_emit_edges(List ovl, const uin
         }
         uint32_t pos[kTileItems];
         unsigned long long inclusive = 0;
-        tile_rank(sh, status, tile, dest, pos, &inclusive);
+        tile_rank<kTileItems>(sh, status, tile, dest, pos, &inclusive);
         if (tid == 0 && tile == num_tiles - 1) {
             counters[C_DOVETAILS] = count_a(inclusive);
             counters[C_EDGES] = 2u * count_a(inclusive);
@@ -184,6 +184,17 @@ __global__ void k_fill_csr(const uint32_t* __restrict__ src, const uint32_t* __r
     }
 }
 
+// edge columns -> rala_edge_t rows (download path)
+__global__ void k_pack_edges(const uint32_t* __restrict__ src, const uint32_t* __restrict__ dst, const uint32_t* __restrict__ len,
+                             const uint32_t* __restrict__ n_edges_ptr, uint32_t edge_cap, uint32_t* __restrict__ out) {
+    const uint32_t n = min(*n_edges_ptr, edge_cap);
+    for (uint32_t e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
+        out[3 * (size_t) e] = src[e];
+        out[3 * (size_t) e + 1] = dst[e];
+        out[3 * (size_t) e + 2] = len[e];
+    }
+}
+
 static inline int grid_for(uint64_t n, int per_block, int max_blocks) {
     uint64_t b = (n + per_block - 1) / per_block;
     if (b < 1) b = 1;
@@ -205,8 +216,20 @@ void launch_emit_edges(Launch& L, List ovl, const uint32_t* n_ptr, uint32_t cap,
     L.count++;
 }
 
+void launch_pack_edges(Launch& L, GraphArrays g, uint32_t edge_cap, const uint32_t* n_edges_ptr, uint32_t* out) {
+    k_pack_edges<<<grid_for(edge_cap, 256, kNumSMs * 8), 256, 0, L.stream>>>(g.src, g.dst, g.len, n_edges_ptr, edge_cap, out);
+    L.count++;
+}
+
 void launch_degree_hist(Launch& L, const uint32_t* src, const uint32_t* n_edges_ptr, uint32_t edge_cap, uint32_t* cursor) {
     k_degree_hist<<<grid_for(edge_cap, 256, kNumSMs * 8), 256, 0, L.stream>>>(src, n_edges_ptr, edge_cap, cursor);
+    L.count++;
+}
+
+// exclusive scan of n values: exclusive_out[i] and values_inout[i] both receive the prefix
+void launch_scan_u32(Launch& L, uint32_t* values_inout, uint32_t* exclusive_out, uint32_t n, unsigned long long* status,
+                     uint32_t* ticket) {
+    k_scan_degrees<<<grid_for(n, kTile, kNumSMs * 8), kTileThreads, 0, L.stream>>>(values_inout, exclusive_out, n, status, ticket);
     L.count++;
 }
 

@@ -11,7 +11,7 @@ struct Events;
 
 // slots of the device-side counter block (uint32 each)
 enum Counter {
-    C_P = 0,        // potential survivors of the first pass
+    C_P = 0,        // (unused)
     C_EV,           // containment events of the current resolution
     C_HILL,         // records touching a pile with hills
     C_ROUNDS,       // fixed-point rounds
@@ -35,12 +35,16 @@ struct Launch {
 };
 
 // classify.cu
-void launch_classify_first(Launch& L, const uint32_t* rec, uint32_t n, uint32_t t0, const uint2* piles, uint32_t n_piles,
-                           List P, uint32_t p_cap, Events ev, uint32_t ev_cap, uint32_t* hill_rec, uint32_t hill_cap,
-                           uint32_t* counters, unsigned long long* status, uint32_t* ticket);
-void launch_fixpoint(Launch& L, Events ev, const uint32_t* n_events, uint32_t ev_cap, uint32_t* dbuf, uint32_t n_piles,
-                     uint32_t* flags, uint32_t* counters, int coop_blocks);
-int fixpoint_max_blocks();
+void launch_classify_events(Launch& L, const uint32_t* rec, uint32_t n, uint32_t t0, const uint2* piles, uint32_t n_piles,
+                            Events ev, uint32_t ev_cap, uint32_t* vcount, uint32_t* hill_rec, uint32_t hill_cap, uint32_t* counters);
+// per-tile survivor runs of the survivors pass: scratch base + count (scanned in place into file-order offsets)
+struct TileRuns {
+    uint32_t *base_a, *cnt_a, *off_a, *base_b, *cnt_b, *off_b;   // num_tiles + 1 each
+};
+void launch_classify_survivors(Launch& L, const uint32_t* rec, uint32_t n, const uint2* piles, uint32_t n_piles, List tmp_ovl,
+                               List tmp_inl, List ovl, uint32_t* n_ovl, List inl, uint32_t* n_inl, uint32_t cap, TileRuns runs,
+                               uint32_t* tmp_counts, unsigned long long* status[2], uint32_t* ticket[2]);
+uint32_t classify_num_tiles(uint32_t n);
 void launch_hill_coverage(Launch& L, const uint32_t* rec, uint32_t t0, const uint2* piles, const uint32_t* hill_rec,
                           uint32_t hill_cap, const uint32_t* hill_pile, const uint32_t* hill_begin,
                           const uint32_t* hill_end, uint32_t n_hills, uint32_t* hill_cov, const uint32_t* dbuf,
@@ -51,7 +55,7 @@ void launch_list_pass(Launch& L, int mode, List in, const uint32_t* n_in, uint32
                       const uint32_t* dbuf, uint32_t n_piles, const uint32_t* time_base, const uint32_t* counters,
                       unsigned long long* status, uint32_t* ticket);
 void launch_classify_final(Launch& L, List lst, const uint32_t* n_ptr, uint32_t cap, const uint32_t* time_base,
-                           const uint2* piles, Events ev, uint32_t ev_cap, uint32_t* counters);
+                           const uint2* piles, Events ev, uint32_t ev_cap, uint32_t* vcount, uint32_t* counters);
 void launch_trim_classify_aos(Launch& L, uint32_t* rec, uint32_t n, const uint2* piles, uint32_t n_piles, uint8_t* type_out);
 void launch_fill_u32(Launch& L, uint32_t* p, uint32_t v, size_t n);
 void launch_pack_piles(Launch& L, const uint2* in, const uint8_t* flags, uint2* out, uint32_t n);
@@ -59,7 +63,22 @@ void launch_unpack_piles(Launch& L, const uint2* in, uint2* out, uint32_t n);
 void launch_list_to_aos(Launch& L, List l, const uint32_t* n_ptr, uint32_t cap, uint32_t* out);
 void launch_list_connections(Launch& L, List l, const uint32_t* n_ptr, uint32_t cap, uint32_t* out);
 
+// containment.cu
+struct ResolveBufs {
+    uint32_t* S;         // n_piles: state during the resolution, death times (kInf = never) afterwards
+    uint32_t* vcursor;   // n_piles + 1: per-victim event histogram on entry, scatter cursor inside
+    uint32_t* vstart;    // n_piles + 1
+    uint32_t *work0, *work1;   // n_piles each
+    uint32_t* n_work;    // 4 words
+    uint32_t *seg_c, *seg_t;   // event capacity each
+};
+int resolve_max_blocks();
+void launch_resolve(Launch& L, Events ev, const uint32_t* n_events, uint32_t ev_cap, ResolveBufs rb, uint32_t n_piles,
+                    uint32_t* counters, unsigned long long* status, uint32_t* ticket, int coop_blocks);
+
 // graph_build.cu
+void launch_scan_u32(Launch& L, uint32_t* values_inout, uint32_t* exclusive_out, uint32_t n, unsigned long long* status,
+                     uint32_t* ticket);
 struct GraphArrays {
     uint32_t* seq_to_node;   // n_piles
     uint32_t *src, *dst, *len;   // edge id order
@@ -74,6 +93,7 @@ void launch_node_ids(Launch& L, const uint2* piles, uint32_t n_piles, uint32_t* 
                      unsigned long long* status, uint32_t* ticket);
 void launch_emit_edges(Launch& L, List ovl, const uint32_t* n_ptr, uint32_t cap, const uint2* piles, GraphArrays g,
                        uint32_t edge_cap, uint32_t* counters, unsigned long long* status, uint32_t* ticket);
+void launch_pack_edges(Launch& L, GraphArrays g, uint32_t edge_cap, const uint32_t* n_edges_ptr, uint32_t* out);
 // degree histogram for an edge list that did not come from emit_edges (stateless transitive stage)
 void launch_degree_hist(Launch& L, const uint32_t* src, const uint32_t* n_edges_ptr, uint32_t edge_cap, uint32_t* cursor);
 void launch_build_csr(Launch& L, GraphArrays g, uint32_t n_nodes_max, uint32_t edge_cap, uint32_t* counters,

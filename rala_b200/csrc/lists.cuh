@@ -60,14 +60,17 @@ struct TileShared {
 // Ordered positions for up to two output streams.  dest[r] in {0 drop, 1 stream A, 2 stream B}.
 // On return pos[r] is the global rank of item r inside its stream (exclusive prefix over all
 // earlier entries in entry order).  Returns the packed inclusive totals through *inclusive
-// (meaningful for every tile; the last tile's value is the grand total).  Contains __syncthreads.
+// (meaningful in warp 0 for every tile; the last tile's value is the grand total).  Contains two
+// __syncthreads.  ITEMS * 8 warps <= 32 partial counts: one warp scans them.
+template <int ITEMS>
 __device__ __forceinline__ void tile_rank(TileShared& sh, unsigned long long* status, uint32_t tile,
-                                          const int (&dest)[kTileItems], uint32_t (&pos)[kTileItems],
+                                          const int (&dest)[ITEMS], uint32_t (&pos)[ITEMS],
                                           unsigned long long* inclusive) {
+    static_assert(ITEMS * kTileWarps <= 32, "partials must fit one warp");
     const uint32_t lane = lane_id(), warp = warp_id();
-    uint32_t lane_rank[kTileItems];
+    uint32_t lane_rank[ITEMS];
 #pragma unroll
-    for (int r = 0; r < kTileItems; ++r) {
+    for (int r = 0; r < ITEMS; ++r) {
         uint32_t ma = __ballot_sync(0xFFFFFFFFu, dest[r] == 1);
         uint32_t mb = __ballot_sync(0xFFFFFFFFu, dest[r] == 2);
         uint32_t below = (1u << lane) - 1u;
@@ -79,13 +82,15 @@ __device__ __forceinline__ void tile_rank(TileShared& sh, unsigned long long* st
     }
     __syncthreads();
     if (warp == 0) {
-        uint32_t ca = sh.cnt_a[lane], cb = sh.cnt_b[lane];
+        uint32_t ca = lane < ITEMS * kTileWarps ? sh.cnt_a[lane] : 0u, cb = lane < ITEMS * kTileWarps ? sh.cnt_b[lane] : 0u;
         uint32_t ia = warp_inclusive_scan(ca), ib = warp_inclusive_scan(cb);
         uint32_t ta = __shfl_sync(0xFFFFFFFFu, ia, 31), tb = __shfl_sync(0xFFFFFFFFu, ib, 31);
         unsigned long long agg = pack_counts(ta, tb);
         unsigned long long excl = lookback_exclusive(status, tile, agg);
-        sh.cnt_a[lane] = ia - ca;
-        sh.cnt_b[lane] = ib - cb;
+        if (lane < ITEMS * kTileWarps) {
+            sh.cnt_a[lane] = ia - ca;
+            sh.cnt_b[lane] = ib - cb;
+        }
         if (lane == 0) {
             sh.base_a = count_a(excl);
             sh.base_b = count_b(excl);
@@ -94,7 +99,7 @@ __device__ __forceinline__ void tile_rank(TileShared& sh, unsigned long long* st
     }
     __syncthreads();
 #pragma unroll
-    for (int r = 0; r < kTileItems; ++r) {
+    for (int r = 0; r < ITEMS; ++r) {
         uint32_t base = dest[r] == 1 ? sh.base_a + sh.cnt_a[r * kTileWarps + warp]
                                      : sh.base_b + sh.cnt_b[r * kTileWarps + warp];
         pos[r] = base + lane_rank[r];
