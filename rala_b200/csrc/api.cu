@@ -152,7 +152,9 @@ struct rala_b200_graph {
     DevBuf hills;   // 4 columns of n_hills: pile begin end cov
     uint32_t n_hills = 0;
     // lists
-    uint32_t cap = 0;   // capacity of every list / event array
+    uint32_t cap = 0;      // capacity of every overlap list
+    uint32_t ev_cap = 0;   // capacity of the event arrays and victim segments (multi-GPU: events of ALL ranks)
+    uint32_t t0 = 0;       // global time (file position) of the first local record (multi-GPU shards)
     ListBuf ovl[2], inl[2];
     int ovl_cur = 0, inl_cur = 0;
     int slot_ovl = C_LIST0, slot_inl = C_LIST0 + 1, next_slot = C_LIST0 + 2;
@@ -166,6 +168,7 @@ struct rala_b200_graph {
     DevBuf seq_to_node, edges, row_ptr, cursor, col, col_eid, T, marked, heavy, work_counter;
     uint32_t edge_cap = 0, heavy_cap = 0, n_nodes_max = 0;
     // bookkeeping
+    bool final_lists_ready = true;  // after finalize: have the filtered lists of graph.cpp:867-877 been written out?
     bool piles_dirty = true;        // pile table changed since the lists were last trimmed against it
     bool skip_clean_retrim = true;  // re-trimming against an unchanged table is the identity: skip the pass
     int state = 0;                  // 0 empty, 1 inputs set, 2 classified, 3 finalized, 4 built, 5 reduced
@@ -176,7 +179,7 @@ struct rala_b200_graph {
     uint32_t* cnt() const { return counters.as<uint32_t>(); }
     Events events_view() const {
         Events e;
-        size_t col = align_up((size_t) cap * 4, 256);
+        size_t col = align_up((size_t) ev_cap * 4, 256);
         char* b = events.as<char>();
         e.v = (uint32_t*) b;
         e.c = (uint32_t*) (b + col);
@@ -280,6 +283,30 @@ extern "C" void rala_b200_graph_destroy(rala_b200_graph* g) {
     delete g;
 }
 
+static int reserve_events(rala_b200_graph* g, uint32_t ev_cap) {
+    if (ev_cap <= g->ev_cap) return RALA_B200_OK;
+    rala_b200_ctx* ctx = g->ctx;
+    // growing re-allocates: contents are not preserved (callers grow before they fill)
+    g->ev_cap = ev_cap;
+    CU(ctx, g->events.reserve(align_up((size_t) ev_cap * 4, 256) * 3));
+    CU(ctx, g->segs.reserve(align_up((size_t) ev_cap * 4, 256) * 2));
+    return RALA_B200_OK;
+}
+
+static int reserve_edges(rala_b200_graph* g, uint32_t edge_cap) {
+    if (edge_cap <= g->edge_cap) return RALA_B200_OK;
+    rala_b200_ctx* ctx = g->ctx;
+    g->edge_cap = edge_cap;
+    CU(ctx, g->edges.reserve(align_up((size_t) edge_cap * 4, 256) * 3));
+    CU(ctx, g->col.reserve((size_t) edge_cap * 8));
+    CU(ctx, g->col_eid.reserve((size_t) edge_cap * 4));
+    CU(ctx, g->T.reserve(align_up(edge_cap, 256)));
+    CU(ctx, g->marked.reserve(align_up(edge_cap, 256)));
+    g->heavy_cap = edge_cap / 16 + 4096;
+    CU(ctx, g->heavy.reserve(align_up((size_t) g->heavy_cap * 4, 256) * 3));
+    return RALA_B200_OK;
+}
+
 static int reserve_scan_pool(rala_b200_graph* g) {
     size_t words = 8 * (tiles_of(g->n_rec) + tiles_of(2ull * g->n_piles + 8) + 8);
     if (words > g->scan_pool_words) {
@@ -305,18 +332,11 @@ extern "C" int rala_b200_graph_set_overlaps(rala_b200_graph* g, const rala_ovl_t
             CU(ctx, g->ovl[i].reserve(cap));
             CU(ctx, g->inl[i].reserve(cap));
         }
-        CU(ctx, g->events.reserve(align_up((size_t) cap * 4, 256) * 3));
         CU(ctx, g->hill_rec.reserve((size_t) cap * 4));
-        CU(ctx, g->segs.reserve(align_up((size_t) cap * 4, 256) * 2));
         g->cap = cap;
-        g->edge_cap = 2 * cap;
-        CU(ctx, g->edges.reserve(align_up((size_t) g->edge_cap * 4, 256) * 3));
-        CU(ctx, g->col.reserve((size_t) g->edge_cap * 8));
-        CU(ctx, g->col_eid.reserve((size_t) g->edge_cap * 4));
-        CU(ctx, g->T.reserve(align_up(g->edge_cap, 256)));
-        CU(ctx, g->marked.reserve(align_up(g->edge_cap, 256)));
-        g->heavy_cap = g->edge_cap / 16 + 4096;
-        CU(ctx, g->heavy.reserve(align_up((size_t) g->heavy_cap * 4, 256) * 3));
+        int rc2 = reserve_events(g, cap);
+        if (!rc2) rc2 = reserve_edges(g, 2 * cap);
+        if (rc2) return rc2;
     } else {
         // views depend on cap: re-derive them for the (unchanged) capacity
     }
@@ -388,7 +408,7 @@ static ResolveBufs resolve_bufs(const rala_b200_graph* g) {
     r.work1 = b + 4 * stride;
     r.n_work = g->flags.as<uint32_t>();
     r.seg_c = g->segs.as<uint32_t>();
-    r.seg_t = (uint32_t*) (g->segs.as<char>() + align_up((size_t) g->cap * 4, 256));
+    r.seg_t = (uint32_t*) (g->segs.as<char>() + align_up((size_t) g->ev_cap * 4, 256));
     return r;
 }
 
@@ -402,7 +422,7 @@ static int resolve_containment(rala_b200_graph* g) {
     unsigned long long* status;
     uint32_t* ticket;
     scan_state(g, (uint64_t) g->n_piles + 1, &status, &ticket);
-    launch_resolve(ctx->L, g->events_view(), g->cnt() + C_EV, g->cap, resolve_bufs(g), g->n_piles, g->cnt(), status, ticket,
+    launch_resolve(ctx->L, g->events_view(), g->cnt() + C_EV, g->ev_cap, resolve_bufs(g), g->n_piles, g->cnt(), status, ticket,
                    ctx->coop_blocks);
     CU(ctx, cudaGetLastError());
     return RALA_B200_OK;
@@ -428,8 +448,8 @@ extern "C" int rala_b200_graph_classify(rala_b200_graph* g) {
     uint32_t* ticket;
     CU(ctx, clear_victim_histogram(g));
     CU(ctx, cudaEventRecord(g->ev_start[ST_K1_KERNEL], ctx->L.stream));
-    launch_classify_events(ctx->L, g->rec.as<uint32_t>(), g->n_rec, 0u, g->piles.as<uint2>(), g->n_piles, g->events_view(),
-                           g->cap, resolve_bufs(g).vcursor, g->hill_rec.as<uint32_t>(), g->cap, g->cnt());
+    launch_classify_events(ctx->L, g->rec.as<uint32_t>(), g->n_rec, g->t0, g->piles.as<uint2>(), g->n_piles, g->events_view(),
+                           g->ev_cap, resolve_bufs(g).vcursor, g->hill_rec.as<uint32_t>(), g->cap, g->cnt());
     CU(ctx, end_stage(g, ST_K1_KERNEL));
     CU(ctx, cudaEventRecord(g->ev_start[ST_K1B_KERNEL], ctx->L.stream));
     int rc = resolve_containment(g);
@@ -437,7 +457,7 @@ extern "C" int rala_b200_graph_classify(rala_b200_graph* g) {
     CU(ctx, end_stage(g, ST_K1B_KERNEL));
     if (g->n_hills) {
         const uint32_t* h = g->hills.as<uint32_t>();
-        launch_hill_coverage(ctx->L, g->rec.as<uint32_t>(), 0u, g->piles.as<uint2>(), g->hill_rec.as<uint32_t>(), g->cap, h,
+        launch_hill_coverage(ctx->L, g->rec.as<uint32_t>(), g->t0, g->piles.as<uint2>(), g->hill_rec.as<uint32_t>(), g->cap, h,
                              h + g->n_hills, h + 2 * (size_t) g->n_hills, g->n_hills,
                              g->hills.as<uint32_t>() + 3 * (size_t) g->n_hills, g->dbuf.as<uint32_t>(), g->n_piles, g->cnt());
     }
@@ -466,6 +486,7 @@ extern "C" int rala_b200_graph_classify(rala_b200_graph* g) {
     CU(ctx, end_stage(g, ST_CLASSIFY));
     g->piles_dirty = false;   // lists are trimmed against the table as it stands (only liveness changed, and the split filtered on it)
     g->state = 2;
+    g->final_lists_ready = true;
     g->retrim_passes = 0;
     return RALA_B200_OK;
 }
@@ -543,6 +564,37 @@ extern "C" int rala_b200_graph_retrim_promote(rala_b200_graph* g, int* is_change
     return RALA_B200_OK;
 }
 
+// graph.cpp:849-877 on demand: the final `internals` (alive at their own time, not kA/kB) and `overlaps`
+// (both piles alive at the end, not kA/kB)
+static int materialize_final_lists(rala_b200_graph* g) {
+    if (g->final_lists_ready || g->state < 3) return RALA_B200_OK;
+    rala_b200_ctx* ctx = g->ctx;
+    unsigned long long* status;
+    uint32_t* ticket;
+    List none{};
+    g->scan_used = 0;
+    CU(ctx, cudaMemsetAsync(g->scan_pool.p, 0, g->scan_pool_words * 8, ctx->L.stream));
+    scan_state(g, g->cap, &status, &ticket);
+    int inl_out = g->new_slot();
+    CU(ctx, zero_counter(g, inl_out));
+    launch_list_pass(ctx->L, 4 /*kFinalInt*/, g->inl[g->inl_cur].view, g->cnt() + g->slot_inl, g->cap, g->piles.as<uint2>(),
+                     g->inl[g->inl_cur ^ 1].view, g->cnt() + inl_out, none, nullptr, nullptr, g->cap, g->dbuf.as<uint32_t>(),
+                     g->n_piles, g->cnt() + g->slot_ovl, g->cnt(), status, ticket);
+    g->inl_cur ^= 1;
+    g->slot_inl = inl_out;
+    scan_state(g, g->cap, &status, &ticket);
+    int ovl_out = g->new_slot();
+    CU(ctx, zero_counter(g, ovl_out));
+    launch_list_pass(ctx->L, 3 /*kFinalOvl*/, g->ovl[g->ovl_cur].view, g->cnt() + g->slot_ovl, g->cap, g->piles.as<uint2>(),
+                     g->ovl[g->ovl_cur ^ 1].view, g->cnt() + ovl_out, none, nullptr, nullptr, g->cap, nullptr, g->n_piles,
+                     nullptr, g->cnt(), status, ticket);
+    g->ovl_cur ^= 1;
+    g->slot_ovl = ovl_out;
+    CU(ctx, cudaGetLastError());
+    g->final_lists_ready = true;
+    return RALA_B200_OK;
+}
+
 // graph.cpp:831-877
 extern "C" int rala_b200_graph_finalize(rala_b200_graph* g) {
     if (!g) return RALA_B200_ERR_ARG;
@@ -555,32 +607,16 @@ extern "C" int rala_b200_graph_finalize(rala_b200_graph* g) {
     CU(ctx, zero_counter(g, C_EV));
     CU(ctx, clear_victim_histogram(g));
     launch_classify_final(ctx->L, g->ovl[g->ovl_cur].view, g->cnt() + g->slot_ovl, g->cap, nullptr, g->piles.as<uint2>(),
-                          g->events_view(), g->cap, resolve_bufs(g).vcursor, g->cnt());
+                          g->events_view(), g->ev_cap, resolve_bufs(g).vcursor, g->cnt());
     launch_classify_final(ctx->L, g->inl[g->inl_cur].view, g->cnt() + g->slot_inl, g->cap, g->cnt() + g->slot_ovl,
-                          g->piles.as<uint2>(), g->events_view(), g->cap, resolve_bufs(g).vcursor, g->cnt());
+                          g->piles.as<uint2>(), g->events_view(), g->ev_cap, resolve_bufs(g).vcursor, g->cnt());
     int rc = resolve_containment(g);
     if (rc) return rc;
-    unsigned long long* status;
-    uint32_t* ticket;
-    List none{};
-    // internals first: needs the death times against the table BEFORE the kills are applied
-    scan_state(g, g->cap, &status, &ticket);
-    int inl_out = g->new_slot();
-    CU(ctx, zero_counter(g, inl_out));
-    launch_list_pass(ctx->L, 4 /*kFinalInt*/, g->inl[g->inl_cur].view, g->cnt() + g->slot_inl, g->cap, g->piles.as<uint2>(),
-                     g->inl[g->inl_cur ^ 1].view, g->cnt() + inl_out, none, nullptr, nullptr, g->cap, g->dbuf.as<uint32_t>(),
-                     g->n_piles, g->cnt() + g->slot_ovl, g->cnt(), status, ticket);
-    g->inl_cur ^= 1;
-    g->slot_inl = inl_out;
     launch_apply_deaths(ctx->L, g->piles.as<uint2>(), g->dbuf.as<uint32_t>(), g->n_piles, g->cnt());
-    scan_state(g, g->cap, &status, &ticket);
-    int ovl_out = g->new_slot();
-    CU(ctx, zero_counter(g, ovl_out));
-    launch_list_pass(ctx->L, 3 /*kFinalOvl*/, g->ovl[g->ovl_cur].view, g->cnt() + g->slot_ovl, g->cap, g->piles.as<uint2>(),
-                     g->ovl[g->ovl_cur ^ 1].view, g->cnt() + ovl_out, none, nullptr, nullptr, g->cap, nullptr, g->n_piles,
-                     nullptr, g->cnt(), status, ticket);
-    g->ovl_cur ^= 1;
-    g->slot_ovl = ovl_out;
+    // The filtered `overlaps` / `internals` vectors of graph.cpp:867-877 are NOT materialised here: edge creation
+    // (build) applies the same filter on the fly (both piles alive, type kAB/kBA), and nothing else on the path
+    // reads them.  get_lists / counts materialise them on demand (materialize_final_lists).
+    g->final_lists_ready = false;
     CU(ctx, cudaGetLastError());
     CU(ctx, end_stage(g, ST_FINALIZE));
     g->state = 3;
@@ -655,7 +691,7 @@ static int read_counters(rala_b200_graph* g, uint32_t* h) {
     CU(ctx, cudaSetDevice(ctx->device));
     CU(ctx, cudaMemcpyAsync(h, g->counters.p, C_COUNT * 4, cudaMemcpyDeviceToHost, ctx->L.stream));
     CU(ctx, cudaStreamSynchronize(ctx->L.stream));
-    if (h[C_OVERFLOW] || (g->state >= 2 && (h[g->slot_ovl] > g->cap || h[g->slot_inl] > g->cap)) || h[C_EV] > g->cap || h[C_HILL] > g->cap || h[C_HEAVY] > g->heavy_cap)
+    if (h[C_OVERFLOW] || (g->state >= 2 && (h[g->slot_ovl] > g->cap || h[g->slot_inl] > g->cap)) || h[C_EV] > g->ev_cap || h[C_HILL] > g->cap || h[C_HEAVY] > g->heavy_cap)
         return fail(ctx, RALA_B200_ERR_LIMIT, "a device list overflowed its capacity (cap=%u events=%u hills=%u heavy=%u/%u)",
                     g->cap, h[C_EV], h[C_HILL], h[C_HEAVY], g->heavy_cap);
     return RALA_B200_OK;
@@ -664,7 +700,8 @@ static int read_counters(rala_b200_graph* g, uint32_t* h) {
 extern "C" int rala_b200_graph_counts(rala_b200_graph* g, rala_b200_counts_t* out) {
     if (!g || !out) return RALA_B200_ERR_ARG;
     uint32_t h[C_COUNT];
-    int rc = read_counters(g, h);
+    int rc = materialize_final_lists(g);
+    if (!rc) rc = read_counters(g, h);
     if (rc) return rc;
     memset(out, 0, sizeof(*out));
     out->n_records = g->n_rec;
@@ -728,7 +765,8 @@ extern "C" int rala_b200_graph_get_lists(rala_b200_graph* g, rala_ovl_t* overlap
     rala_b200_ctx* ctx = g->ctx;
     if (g->state < 2) return fail(ctx, RALA_B200_ERR_STATE, "get_lists: classify first");
     uint32_t h[C_COUNT];
-    int rc = read_counters(g, h);
+    int rc = materialize_final_lists(g);
+    if (!rc) rc = read_counters(g, h);
     if (rc) return rc;
     DevBuf tmp;
     for (int which = 0; which < 2; ++which) {

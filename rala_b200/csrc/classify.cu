@@ -156,8 +156,9 @@ __global__ void __launch_bounds__(kTileThreads) k_classify_survivors(
     const uint32_t* __restrict__ rec, uint32_t n, const uint2* __restrict__ piles, uint32_t n_piles,
     List tmp_ovl, List tmp_inl, uint32_t cap, TileRuns runs, uint32_t* __restrict__ tmp_counts) {
     __shared__ RecStage st;
-    __shared__ uint32_t s_cnt_a[kRecItems * kTileWarps], s_cnt_b[kRecItems * kTileWarps];
-    __shared__ uint32_t s_base_a, s_base_b;
+    // scratch indexed by the iteration's parity: two barriers per tile suffice (see the end of the loop)
+    __shared__ uint32_t s_cnt_a2[2][kRecItems * kTileWarps], s_cnt_b2[2][kRecItems * kTileWarps];
+    __shared__ uint32_t s_base_a2[2], s_base_b2[2];
     const uint32_t tid = threadIdx.x, lane = lane_id(), warp = warp_id();
     const uint32_t num_tiles = (n + kRecTile - 1) / kRecTile;
     if (tid == 0) {
@@ -171,6 +172,10 @@ __global__ void __launch_bounds__(kTileThreads) k_classify_survivors(
     if (tid == 0 && tile < num_tiles) issue_tile(st, 0, rec, n, tile);
     for (uint32_t it = 0; tile < num_tiles; ++it, tile += gridDim.x) {
         const int b = it & 1;
+        uint32_t* s_cnt_a = s_cnt_a2[b];
+        uint32_t* s_cnt_b = s_cnt_b2[b];
+        uint32_t& s_base_a = s_base_a2[b];
+        uint32_t& s_base_b = s_base_b2[b];
         if (tid == 0 && tile + gridDim.x < num_tiles) issue_tile(st, b ^ 1, rec, n, tile + gridDim.x);
         mbar_wait(&st.bar[b], parity[b]);
         parity[b] ^= 1u;
@@ -189,14 +194,11 @@ __global__ void __launch_bounds__(kTileThreads) k_classify_survivors(
                 RecFields f = read_record(st.rec[b] + idx * 7);
                 if (!(f.flags & 2u) && f.e.a < n_piles && f.e.b < n_piles) {
                     // the table already carries the kills: both piles alive at the end (graph.cpp:493-515)
-                    const Pile pa = load_pile(piles, f.e.a);
-                    if (pa.alive()) {
-                        const Pile pb = load_pile(piles, f.e.b);
-                        if (pb.alive() && trim(f.e.c, f.e.ori, pa, pb)) {
-                            tag[r] = classify(f.e.c, relative(f.e.c, f.e.ori, pa, pb));
-                            dest[r] = tag[r] == kX ? 2 : 1;   // a surviving kA/kB has a chimeric container (:470, :476)
-                            e[r] = f.e;
-                        }
+                    const Pile pa = load_pile(piles, f.e.a), pb = load_pile(piles, f.e.b);   // independent gathers
+                    if (pa.alive() && pb.alive() && trim(f.e.c, f.e.ori, pa, pb)) {
+                        tag[r] = classify(f.e.c, relative(f.e.c, f.e.ori, pa, pb));
+                        dest[r] = tag[r] == kX ? 2 : 1;   // a surviving kA/kB has a chimeric container (:470, :476)
+                        e[r] = f.e;
                     }
                 }
             }
@@ -238,9 +240,9 @@ __global__ void __launch_bounds__(kTileThreads) k_classify_survivors(
                 if (p < cap) store_entry(tmp_inl, p, e[r], tag[r]);
             }
         }
-        // s_cnt / s_base are rewritten only after the next tile's first barrier... which every thread reaches
-        // after these reads; buffer b is refilled by the TMA issued at the top of the NEXT-next iteration
-        __syncthreads();
+        // no trailing barrier: this parity's scratch is next written two iterations from now (two barriers away),
+        // and staging buffer b is refilled by the TMA thread 0 issues at the top of the next iteration, i.e. after
+        // it passed this iteration's second barrier, which every thread reaches only after reading buffer b
     }
 }
 
@@ -367,9 +369,11 @@ __global__ void __launch_bounds__(kTileThreads) k_list_pass(
                     }
                 } else if (MODE == kFinalOvl) {
                     if (pa.alive() && pb.alive() && tag[r] != kA && tag[r] != kB) dest[r] = 1;
-                } else {   // kFinalInt: piles here are the table BEFORE the final kills were applied
+                } else {   // kFinalInt: alive before the pass (alive now, or killed by it) and still alive at its own time
                     const uint32_t t = time_base + idx;
-                    if (pa.alive() && pb.alive() && D[e[r].a] > t && D[e[r].b] > t && tag[r] != kA && tag[r] != kB)
+                    const uint32_t da = D[e[r].a], db = D[e[r].b];
+                    if ((pa.alive() || da != kInf) && (pb.alive() || db != kInf) && da > t && db > t && tag[r] != kA &&
+                        tag[r] != kB)
                         dest[r] = 1;
                 }
             }
