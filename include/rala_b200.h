@@ -168,6 +168,49 @@ int rala_b200_graph_get_marked(rala_b200_graph* g, uint8_t* out /* n_edges */);
 #define RALA_B200_N_STAGES 9
 int rala_b200_graph_stage_ms(rala_b200_graph* g, float* ms_out /* RALA_B200_N_STAGES */);
 
+/* ------------------------------------------------------------------------------------------------
+ * Multi-GPU phases: one process per GPU, records sharded by contiguous FILE RANGE (shard r holds
+ * records [t0_r, t0_r + n_r)), pile table replicated.  The reference has no distributed code; this
+ * is the partition BASELINE.json's north_star asks for: work split by overlap range (classify) and
+ * by source-node range (transitive), the event lists and the edge list all-gathered, the marks
+ * merged with an all-reduce(max) (= OR on 0/1 bytes).  The collectives are the caller's
+ * (rala_b200/multi.py uses torch.distributed / NCCL); every pointer below is a DEVICE pointer of
+ * the caller's exchange buffer, laid out as three columns of `stride` 32-bit words
+ * (events: victim | container | time;  edges: src | dst | len).
+ *
+ *   set_shard; set_piles; set_overlaps(local records)
+ *   phase_events              -> events_count, export_events, [all-gather], import_events (all ranks' blocks)
+ *   phase_resolve(1)          ordered containment of graph.cpp:469-480 on the union of the events (replicated)
+ *   phase_survivors           -> list_counts, [all-gather counts]
+ *   phase_final_events(ovl_base, int_base)  time = global position in overlaps ++ internals (graph.cpp:831-866)
+ *                             -> events_count, export_events, [all-gather], import_events
+ *   phase_resolve(0)
+ *   phase_emit_edges          -> export_edges, [all-gather], import_edges (global edge-id order = rank order)
+ *   phase_csr                 CSR of the whole graph, replicated (two-hop lookups cross shards)
+ *   phase_transitive          T(e) for candidate edges whose source node this rank owns
+ *   export_marks, [all-reduce(max)], phase_marks     marked(e) = T(e) | T(e^1)
+ * ---------------------------------------------------------------------------------------------- */
+/* a context that enqueues on the caller's CUDA stream (cudaStream_t), e.g. torch's current stream */
+int rala_b200_create_on_stream(rala_b200_ctx** out, int device, void* cuda_stream);
+int rala_b200_graph_set_shard(rala_b200_graph* g, uint32_t t0, int rank, int world);
+int rala_b200_graph_phase_events(rala_b200_graph* g);
+int rala_b200_graph_events_count(rala_b200_graph* g, uint32_t* n);
+int rala_b200_graph_export_events(rala_b200_graph* g, uint32_t* d_cols, uint32_t stride, uint32_t n);
+int rala_b200_graph_import_events(rala_b200_graph* g, const uint32_t* d_cols, uint32_t stride, uint32_t n,
+                                  uint32_t offset, uint32_t total);
+int rala_b200_graph_phase_resolve(rala_b200_graph* g, int first_pass);
+int rala_b200_graph_phase_survivors(rala_b200_graph* g);
+int rala_b200_graph_list_counts(rala_b200_graph* g, uint32_t* n_ovl, uint32_t* n_int);
+int rala_b200_graph_phase_final_events(rala_b200_graph* g, uint32_t ovl_base, uint32_t int_base);
+int rala_b200_graph_phase_emit_edges(rala_b200_graph* g, uint32_t* n_local_edges);
+int rala_b200_graph_export_edges(rala_b200_graph* g, uint32_t* d_cols, uint32_t stride, uint32_t n);
+int rala_b200_graph_import_edges(rala_b200_graph* g, const uint32_t* d_cols, uint32_t stride, uint32_t n,
+                                 uint32_t offset, uint32_t total);
+int rala_b200_graph_phase_csr(rala_b200_graph* g);
+int rala_b200_graph_phase_transitive(rala_b200_graph* g);
+int rala_b200_graph_export_marks(rala_b200_graph* g, uint8_t* d_T, uint32_t n);
+int rala_b200_graph_phase_marks(rala_b200_graph* g, const uint8_t* d_T, uint32_t n);
+
 #ifdef __cplusplus
 }
 #endif

@@ -49,6 +49,13 @@ EXPORTS = [
     "rala_b200_graph_get_hill_coverage", "rala_b200_graph_get_piles", "rala_b200_graph_get_connections",
     "rala_b200_graph_get_lists", "rala_b200_graph_get_seq_to_node", "rala_b200_graph_get_edges",
     "rala_b200_graph_get_marked", "rala_b200_graph_stage_ms",
+    # multi-GPU phases
+    "rala_b200_create_on_stream", "rala_b200_graph_set_shard", "rala_b200_graph_phase_events",
+    "rala_b200_graph_events_count", "rala_b200_graph_export_events", "rala_b200_graph_import_events",
+    "rala_b200_graph_phase_resolve", "rala_b200_graph_phase_survivors", "rala_b200_graph_list_counts",
+    "rala_b200_graph_phase_final_events", "rala_b200_graph_phase_emit_edges", "rala_b200_graph_export_edges",
+    "rala_b200_graph_import_edges", "rala_b200_graph_phase_csr", "rala_b200_graph_phase_transitive",
+    "rala_b200_graph_export_marks", "rala_b200_graph_phase_marks",
 ]
 
 _LIB = None

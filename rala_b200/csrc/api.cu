@@ -14,6 +14,7 @@
 using namespace rb;
 
 struct rala_b200_ctx {
+    bool owns_stream = true;
     cudaEvent_t ev[2]{};
     int device = 0;
     Launch L{nullptr, 0};
@@ -63,10 +64,19 @@ extern "C" int rala_b200_create(rala_b200_ctx** out, int device) {
     return RALA_B200_OK;
 }
 
+extern "C" int rala_b200_create_on_stream(rala_b200_ctx** out, int device, void* cuda_stream) {
+    int rc = rala_b200_create(out, device);
+    if (rc) return rc;
+    cudaStreamDestroy((*out)->L.stream);
+    (*out)->L.stream = reinterpret_cast<cudaStream_t>(cuda_stream);
+    (*out)->owns_stream = false;
+    return RALA_B200_OK;
+}
+
 extern "C" void rala_b200_destroy(rala_b200_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
-    if (ctx->L.stream) cudaStreamDestroy(ctx->L.stream);
+    if (ctx->L.stream && ctx->owns_stream) cudaStreamDestroy(ctx->L.stream);
     delete ctx;
 }
 
@@ -154,6 +164,7 @@ struct rala_b200_graph {
     // lists
     uint32_t cap = 0;      // capacity of every overlap list
     uint32_t ev_cap = 0;   // capacity of the event arrays and victim segments (multi-GPU: events of ALL ranks)
+    int rank = 0, world = 1;   // multi-GPU: which share of the source nodes the transitive phase takes
     uint32_t t0 = 0;       // global time (file position) of the first local record (multi-GPU shards)
     ListBuf ovl[2], inl[2];
     int ovl_cur = 0, inl_cur = 0;
@@ -168,6 +179,7 @@ struct rala_b200_graph {
     DevBuf seq_to_node, edges, row_ptr, cursor, col, col_eid, T, marked, heavy, work_counter;
     uint32_t edge_cap = 0, heavy_cap = 0, n_nodes_max = 0;
     // bookkeeping
+    int final_time_base_slot = C_LIST0;   // counter slot holding the time base of `internals` in the final pass
     bool final_lists_ready = true;  // after finalize: have the filtered lists of graph.cpp:867-877 been written out?
     bool piles_dirty = true;        // pile table changed since the lists were last trimmed against it
     bool skip_clean_retrim = true;  // re-trimming against an unchanged table is the identity: skip the pass
@@ -428,9 +440,8 @@ static int resolve_containment(rala_b200_graph* g) {
     return RALA_B200_OK;
 }
 
-// graph.cpp:443-518
-extern "C" int rala_b200_graph_classify(rala_b200_graph* g) {
-    if (!g) return RALA_B200_ERR_ARG;
+// ---- graph.cpp:443-518 in three phases (the multi-GPU path exchanges events between them) ----------------
+static int phase_events(rala_b200_graph* g) {
     rala_b200_ctx* ctx = g->ctx;
     if (g->state < 1) return fail(ctx, RALA_B200_ERR_STATE, "classify: set_overlaps and set_piles first");
     CU(ctx, cudaSetDevice(ctx->device));
@@ -444,29 +455,40 @@ extern "C" int rala_b200_graph_classify(rala_b200_graph* g) {
     CU(ctx, begin_stage(g, ST_CLASSIFY));
     CU(ctx, cudaMemsetAsync(g->counters.p, 0, C_COUNT * 4, ctx->L.stream));
     if (g->n_hills) CU(ctx, cudaMemsetAsync(g->hills.as<uint32_t>() + 3 * (size_t) g->n_hills, 0, (size_t) g->n_hills * 4, ctx->L.stream));
-    unsigned long long* status;
-    uint32_t* ticket;
     CU(ctx, clear_victim_histogram(g));
     CU(ctx, cudaEventRecord(g->ev_start[ST_K1_KERNEL], ctx->L.stream));
     launch_classify_events(ctx->L, g->rec.as<uint32_t>(), g->n_rec, g->t0, g->piles.as<uint2>(), g->n_piles, g->events_view(),
                            g->ev_cap, resolve_bufs(g).vcursor, g->hill_rec.as<uint32_t>(), g->cap, g->cnt());
     CU(ctx, end_stage(g, ST_K1_KERNEL));
+    CU(ctx, cudaGetLastError());
+    return RALA_B200_OK;
+}
+
+static int phase_resolve(rala_b200_graph* g, bool first_pass) {
+    rala_b200_ctx* ctx = g->ctx;
     CU(ctx, cudaEventRecord(g->ev_start[ST_K1B_KERNEL], ctx->L.stream));
     int rc = resolve_containment(g);
     if (rc) return rc;
     CU(ctx, end_stage(g, ST_K1B_KERNEL));
-    if (g->n_hills) {
+    if (first_pass && g->n_hills) {
         const uint32_t* h = g->hills.as<uint32_t>();
         launch_hill_coverage(ctx->L, g->rec.as<uint32_t>(), g->t0, g->piles.as<uint2>(), g->hill_rec.as<uint32_t>(), g->cap, h,
                              h + g->n_hills, h + 2 * (size_t) g->n_hills, g->n_hills,
                              g->hills.as<uint32_t>() + 3 * (size_t) g->n_hills, g->dbuf.as<uint32_t>(), g->n_piles, g->cnt());
     }
     launch_apply_deaths(ctx->L, g->piles.as<uint2>(), g->dbuf.as<uint32_t>(), g->n_piles, g->cnt());
+    CU(ctx, cudaGetLastError());
+    return RALA_B200_OK;
+}
+
+static int phase_survivors(rala_b200_graph* g) {
+    rala_b200_ctx* ctx = g->ctx;
     g->ovl_cur = 0;
     g->inl_cur = 0;
     g->slot_ovl = C_LIST0;
     g->slot_inl = C_LIST0 + 1;
     g->next_slot = C_LIST0 + 2;
+    CU(ctx, zero_counter(g, C_LIST0, 2));
     CU(ctx, cudaMemsetAsync(g->flags.as<uint32_t>() + 8, 0, 8, ctx->L.stream));   // scratch append counters
     CU(ctx, cudaEventRecord(g->ev_start[ST_K1S_KERNEL], ctx->L.stream));
     {
@@ -489,6 +511,14 @@ extern "C" int rala_b200_graph_classify(rala_b200_graph* g) {
     g->final_lists_ready = true;
     g->retrim_passes = 0;
     return RALA_B200_OK;
+}
+
+extern "C" int rala_b200_graph_classify(rala_b200_graph* g) {
+    if (!g) return RALA_B200_ERR_ARG;
+    int rc = phase_events(g);
+    if (!rc) rc = phase_resolve(g, true);
+    if (!rc) rc = phase_survivors(g);
+    return rc;
 }
 
 static int retrim_list(rala_b200_graph* g, ListBuf* bufs, int* cur, int* slot) {
@@ -579,7 +609,7 @@ static int materialize_final_lists(rala_b200_graph* g) {
     CU(ctx, zero_counter(g, inl_out));
     launch_list_pass(ctx->L, 4 /*kFinalInt*/, g->inl[g->inl_cur].view, g->cnt() + g->slot_inl, g->cap, g->piles.as<uint2>(),
                      g->inl[g->inl_cur ^ 1].view, g->cnt() + inl_out, none, nullptr, nullptr, g->cap, g->dbuf.as<uint32_t>(),
-                     g->n_piles, g->cnt() + g->slot_ovl, g->cnt(), status, ticket);
+                     g->n_piles, g->cnt() + g->final_time_base_slot, g->cnt(), status, ticket);
     g->inl_cur ^= 1;
     g->slot_inl = inl_out;
     scan_state(g, g->cap, &status, &ticket);
@@ -595,9 +625,9 @@ static int materialize_final_lists(rala_b200_graph* g) {
     return RALA_B200_OK;
 }
 
-// graph.cpp:831-877
-extern "C" int rala_b200_graph_finalize(rala_b200_graph* g) {
-    if (!g) return RALA_B200_ERR_ARG;
+// ---- graph.cpp:831-877 in two phases ---------------------------------------------------------------------
+static int phase_final_events(rala_b200_graph* g, const uint32_t* ovl_base /* device, nullable */,
+                              const uint32_t* inl_base /* device */) {
     rala_b200_ctx* ctx = g->ctx;
     if (g->state != 2) return fail(ctx, RALA_B200_ERR_STATE, "finalize: classify first");
     CU(ctx, cudaSetDevice(ctx->device));
@@ -606,21 +636,33 @@ extern "C" int rala_b200_graph_finalize(rala_b200_graph* g) {
     CU(ctx, cudaMemcpyAsync(g->cnt() + C_ROUNDS_FIRST, g->cnt() + C_ROUNDS, 4, cudaMemcpyDeviceToDevice, ctx->L.stream));
     CU(ctx, zero_counter(g, C_EV));
     CU(ctx, clear_victim_histogram(g));
-    launch_classify_final(ctx->L, g->ovl[g->ovl_cur].view, g->cnt() + g->slot_ovl, g->cap, nullptr, g->piles.as<uint2>(),
+    launch_classify_final(ctx->L, g->ovl[g->ovl_cur].view, g->cnt() + g->slot_ovl, g->cap, ovl_base, g->piles.as<uint2>(),
                           g->events_view(), g->ev_cap, resolve_bufs(g).vcursor, g->cnt());
-    launch_classify_final(ctx->L, g->inl[g->inl_cur].view, g->cnt() + g->slot_inl, g->cap, g->cnt() + g->slot_ovl,
+    launch_classify_final(ctx->L, g->inl[g->inl_cur].view, g->cnt() + g->slot_inl, g->cap, inl_base,
                           g->piles.as<uint2>(), g->events_view(), g->ev_cap, resolve_bufs(g).vcursor, g->cnt());
-    int rc = resolve_containment(g);
+    CU(ctx, cudaGetLastError());
+    return RALA_B200_OK;
+}
+
+static int phase_final_resolve(rala_b200_graph* g) {
+    rala_b200_ctx* ctx = g->ctx;
+    int rc = phase_resolve(g, false);
     if (rc) return rc;
-    launch_apply_deaths(ctx->L, g->piles.as<uint2>(), g->dbuf.as<uint32_t>(), g->n_piles, g->cnt());
     // The filtered `overlaps` / `internals` vectors of graph.cpp:867-877 are NOT materialised here: edge creation
     // (build) applies the same filter on the fly (both piles alive, type kAB/kBA), and nothing else on the path
     // reads them.  get_lists / counts materialise them on demand (materialize_final_lists).
     g->final_lists_ready = false;
-    CU(ctx, cudaGetLastError());
     CU(ctx, end_stage(g, ST_FINALIZE));
     g->state = 3;
     return RALA_B200_OK;
+}
+
+extern "C" int rala_b200_graph_finalize(rala_b200_graph* g) {
+    if (!g) return RALA_B200_ERR_ARG;
+    g->final_time_base_slot = g->slot_ovl;   // internals are timed after every entry of `overlaps`
+    int rc = phase_final_events(g, nullptr, g->cnt() + g->slot_ovl);
+    if (!rc) rc = phase_final_resolve(g);
+    return rc;
 }
 
 // graph.cpp:552-632
@@ -655,7 +697,7 @@ static int run_transitive(rala_b200_graph* g) {
     CU(ctx, cudaMemsetAsync(g->T.p, 0, align_up(g->edge_cap, 256), ctx->L.stream));
     CU(ctx, cudaEventRecord(g->ev_start[ST_K3_KERNELS], ctx->L.stream));
     launch_transitive(ctx->L, g->graph_view(), g->n_nodes_max, g->edge_cap, g->heavy_view(), g->work_counter.as<uint32_t>(),
-                      g->cnt(), 0u, 0xFFFFFFFFu);
+                      g->cnt(), 0u, 0xFFFFFFFFu, g->world > 1 ? g->work_counter.as<uint32_t>() + 4 : nullptr);
     CU(ctx, end_stage(g, ST_K3_KERNELS));
     launch_finalize_marks(ctx->L, g->graph_view(), g->edge_cap, g->cnt());
     CU(ctx, cudaGetLastError());
@@ -933,4 +975,220 @@ extern "C" int rala_b200_transitive_reduce(rala_b200_ctx* ctx, uint32_t n_nodes,
     if (h[C_OVERFLOW] || h[C_HEAVY] > g->heavy_cap) return cleanup(fail(ctx, RALA_B200_ERR_LIMIT, "heavy work list overflow"));
     if (n_pairs) *n_pairs = h[C_PAIRS];
     return cleanup(RALA_B200_OK);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Multi-GPU phases (one process per GPU).  The records are sharded by contiguous file range, the pile
+// table is replicated; the collectives between the phases belong to the caller (NCCL through
+// torch.distributed in rala_b200/multi.py), which passes DEVICE pointers of its exchange buffers:
+//   phase_events -> [all-gather events] -> import_events -> phase_resolve(1) -> phase_survivors
+//   -> [all-gather list counts] -> phase_final_events -> [all-gather events] -> import_events
+//   -> phase_final_resolve -> phase_emit_edges -> [all-gather edges] -> import_edges -> phase_csr
+//   -> phase_transitive(rank, world) -> [all-reduce(max) marks] -> phase_marks
+// Exchange blocks are three columns of `stride` words: events v | c | t, edges src | dst | len.
+// ---------------------------------------------------------------------------------------------
+extern "C" int rala_b200_graph_set_shard(rala_b200_graph* g, uint32_t t0, int rank, int world) {
+    if (!g || world < 1 || rank < 0 || rank >= world) return RALA_B200_ERR_ARG;
+    g->t0 = t0;
+    g->rank = rank;
+    g->world = world;
+    return RALA_B200_OK;
+}
+
+extern "C" int rala_b200_graph_phase_events(rala_b200_graph* g) { return g ? phase_events(g) : RALA_B200_ERR_ARG; }
+
+static int read_counter(rala_b200_graph* g, int slot, uint32_t* out) {
+    rala_b200_ctx* ctx = g->ctx;
+    CU(ctx, cudaSetDevice(ctx->device));
+    CU(ctx, cudaMemcpyAsync(out, g->cnt() + slot, 4, cudaMemcpyDeviceToHost, ctx->L.stream));
+    CU(ctx, cudaStreamSynchronize(ctx->L.stream));
+    return RALA_B200_OK;
+}
+
+extern "C" int rala_b200_graph_events_count(rala_b200_graph* g, uint32_t* n) {
+    if (!g || !n) return RALA_B200_ERR_ARG;
+    int rc = read_counter(g, C_EV, n);
+    if (!rc && *n > g->ev_cap) return fail(g->ctx, RALA_B200_ERR_LIMIT, "event list overflow (%u > %u)", *n, g->ev_cap);
+    return rc;
+}
+
+extern "C" int rala_b200_graph_export_events(rala_b200_graph* g, uint32_t* d_cols, uint32_t stride, uint32_t n) {
+    if (!g || (n && !d_cols) || n > stride) return RALA_B200_ERR_ARG;
+    rala_b200_ctx* ctx = g->ctx;
+    CU(ctx, cudaSetDevice(ctx->device));
+    Events ev = g->events_view();
+    if (n) {
+        CU(ctx, cudaMemcpyAsync(d_cols, ev.v, (size_t) n * 4, cudaMemcpyDeviceToDevice, ctx->L.stream));
+        CU(ctx, cudaMemcpyAsync(d_cols + stride, ev.c, (size_t) n * 4, cudaMemcpyDeviceToDevice, ctx->L.stream));
+        CU(ctx, cudaMemcpyAsync(d_cols + 2 * (size_t) stride, ev.t, (size_t) n * 4, cudaMemcpyDeviceToDevice, ctx->L.stream));
+    }
+    return RALA_B200_OK;
+}
+
+extern "C" int rala_b200_graph_import_events(rala_b200_graph* g, const uint32_t* d_cols, uint32_t stride, uint32_t n,
+                                             uint32_t offset, uint32_t total) {
+    if (!g || (n && !d_cols) || (uint64_t) offset + n > total) return RALA_B200_ERR_ARG;
+    rala_b200_ctx* ctx = g->ctx;
+    CU(ctx, cudaSetDevice(ctx->device));
+    if (offset == 0) {
+        int rc = reserve_events(g, total);   // the local events were exported before the first import
+        if (rc) return rc;
+    }
+    Events ev = g->events_view();
+    if (n) {
+        CU(ctx, cudaMemcpyAsync(ev.v + offset, d_cols, (size_t) n * 4, cudaMemcpyDeviceToDevice, ctx->L.stream));
+        CU(ctx, cudaMemcpyAsync(ev.c + offset, d_cols + stride, (size_t) n * 4, cudaMemcpyDeviceToDevice, ctx->L.stream));
+        CU(ctx, cudaMemcpyAsync(ev.t + offset, d_cols + 2 * (size_t) stride, (size_t) n * 4, cudaMemcpyDeviceToDevice, ctx->L.stream));
+    }
+    if ((uint64_t) offset + n == total) {
+        CU(ctx, cudaMemcpyAsync(g->cnt() + C_EV, &total, 4, cudaMemcpyHostToDevice, ctx->L.stream));
+        CU(ctx, cudaStreamSynchronize(ctx->L.stream));   // `total` lives on this stack frame
+        CU(ctx, clear_victim_histogram(g));
+        launch_events_hist(ctx->L, g->events_view(), g->cnt() + C_EV, g->ev_cap, resolve_bufs(g).vcursor);
+        CU(ctx, cudaGetLastError());
+    }
+    return RALA_B200_OK;
+}
+
+extern "C" int rala_b200_graph_phase_resolve(rala_b200_graph* g, int first_pass) {
+    if (!g) return RALA_B200_ERR_ARG;
+    return first_pass ? phase_resolve(g, true) : phase_final_resolve(g);
+}
+
+extern "C" int rala_b200_graph_phase_survivors(rala_b200_graph* g) { return g ? phase_survivors(g) : RALA_B200_ERR_ARG; }
+
+extern "C" int rala_b200_graph_list_counts(rala_b200_graph* g, uint32_t* n_ovl, uint32_t* n_int) {
+    if (!g || !n_ovl || !n_int) return RALA_B200_ERR_ARG;
+    if (g->state < 2) return fail(g->ctx, RALA_B200_ERR_STATE, "list_counts: classify first");
+    uint32_t h[C_COUNT];
+    int rc = read_counters(g, h);
+    if (rc) return rc;
+    *n_ovl = h[g->slot_ovl];
+    *n_int = h[g->slot_inl];
+    return RALA_B200_OK;
+}
+
+extern "C" int rala_b200_graph_phase_final_events(rala_b200_graph* g, uint32_t ovl_base, uint32_t int_base) {
+    if (!g) return RALA_B200_ERR_ARG;
+    rala_b200_ctx* ctx = g->ctx;
+    CU(ctx, cudaSetDevice(ctx->device));
+    uint32_t bases[2] = {ovl_base, int_base};
+    CU(ctx, cudaMemcpyAsync(g->cnt() + C_TBASE_OVL, bases, 8, cudaMemcpyHostToDevice, ctx->L.stream));
+    CU(ctx, cudaStreamSynchronize(ctx->L.stream));
+    g->final_time_base_slot = C_TBASE_INL;
+    return phase_final_events(g, g->cnt() + C_TBASE_OVL, g->cnt() + C_TBASE_INL);
+}
+
+// node ids (replicated) + the edges of the LOCAL overlaps, in local list order, with global node ids
+extern "C" int rala_b200_graph_phase_emit_edges(rala_b200_graph* g, uint32_t* n_local_edges) {
+    if (!g || !n_local_edges) return RALA_B200_ERR_ARG;
+    rala_b200_ctx* ctx = g->ctx;
+    if (g->state != 3) return fail(ctx, RALA_B200_ERR_STATE, "emit_edges: finalize first");
+    CU(ctx, cudaSetDevice(ctx->device));
+    CU(ctx, begin_stage(g, ST_BUILD));
+    CU(ctx, zero_counter(g, C_NODES, 4));
+    CU(ctx, cudaMemsetAsync(g->cursor.p, 0, ((size_t) g->n_nodes_max + 8) * 4, ctx->L.stream));
+    unsigned long long* status;
+    uint32_t* ticket;
+    scan_state(g, g->n_piles, &status, &ticket);
+    launch_node_ids(ctx->L, g->piles.as<uint2>(), g->n_piles, g->seq_to_node.as<uint32_t>(), g->cnt(), status, ticket);
+    scan_state(g, g->cap, &status, &ticket);
+    launch_emit_edges(ctx->L, g->ovl[g->ovl_cur].view, g->cnt() + g->slot_ovl, g->cap, g->piles.as<uint2>(), g->graph_view(),
+                      g->edge_cap, g->cnt(), status, ticket);
+    CU(ctx, cudaGetLastError());
+    return read_counter(g, C_EDGES, n_local_edges);
+}
+
+extern "C" int rala_b200_graph_export_edges(rala_b200_graph* g, uint32_t* d_cols, uint32_t stride, uint32_t n) {
+    if (!g || (n && !d_cols) || n > stride) return RALA_B200_ERR_ARG;
+    rala_b200_ctx* ctx = g->ctx;
+    CU(ctx, cudaSetDevice(ctx->device));
+    GraphArrays ga = g->graph_view();
+    if (n) {
+        CU(ctx, cudaMemcpyAsync(d_cols, ga.src, (size_t) n * 4, cudaMemcpyDeviceToDevice, ctx->L.stream));
+        CU(ctx, cudaMemcpyAsync(d_cols + stride, ga.dst, (size_t) n * 4, cudaMemcpyDeviceToDevice, ctx->L.stream));
+        CU(ctx, cudaMemcpyAsync(d_cols + 2 * (size_t) stride, ga.len, (size_t) n * 4, cudaMemcpyDeviceToDevice, ctx->L.stream));
+    }
+    return RALA_B200_OK;
+}
+
+extern "C" int rala_b200_graph_import_edges(rala_b200_graph* g, const uint32_t* d_cols, uint32_t stride, uint32_t n,
+                                            uint32_t offset, uint32_t total) {
+    if (!g || (n && !d_cols) || (uint64_t) offset + n > total) return RALA_B200_ERR_ARG;
+    rala_b200_ctx* ctx = g->ctx;
+    CU(ctx, cudaSetDevice(ctx->device));
+    if (offset == 0) {
+        int rc = reserve_edges(g, total);   // the local edges were exported before the first import
+        if (rc) return rc;
+    }
+    GraphArrays ga = g->graph_view();
+    if (n) {
+        CU(ctx, cudaMemcpyAsync(ga.src + offset, d_cols, (size_t) n * 4, cudaMemcpyDeviceToDevice, ctx->L.stream));
+        CU(ctx, cudaMemcpyAsync(ga.dst + offset, d_cols + stride, (size_t) n * 4, cudaMemcpyDeviceToDevice, ctx->L.stream));
+        CU(ctx, cudaMemcpyAsync(ga.len + offset, d_cols + 2 * (size_t) stride, (size_t) n * 4, cudaMemcpyDeviceToDevice, ctx->L.stream));
+    }
+    if ((uint64_t) offset + n == total) {
+        CU(ctx, cudaMemcpyAsync(g->cnt() + C_EDGES, &total, 4, cudaMemcpyHostToDevice, ctx->L.stream));
+        CU(ctx, cudaStreamSynchronize(ctx->L.stream));
+    }
+    return RALA_B200_OK;
+}
+
+// CSR over ALL edges (replicated on every rank)
+extern "C" int rala_b200_graph_phase_csr(rala_b200_graph* g) {
+    if (!g) return RALA_B200_ERR_ARG;
+    rala_b200_ctx* ctx = g->ctx;
+    CU(ctx, cudaSetDevice(ctx->device));
+    CU(ctx, cudaMemsetAsync(g->cursor.p, 0, ((size_t) g->n_nodes_max + 8) * 4, ctx->L.stream));
+    GraphArrays ga = g->graph_view();
+    launch_degree_hist(ctx->L, ga.src, g->cnt() + C_EDGES, g->edge_cap, ga.cursor);
+    unsigned long long* status;
+    uint32_t* ticket;
+    scan_state(g, (uint64_t) g->n_nodes_max + 1, &status, &ticket);
+    launch_build_csr(ctx->L, ga, g->n_nodes_max, g->edge_cap, g->cnt(), status, ticket);
+    CU(ctx, cudaGetLastError());
+    CU(ctx, end_stage(g, ST_BUILD));
+    g->state = 4;
+    return RALA_B200_OK;
+}
+
+// T(e) for the candidate edges whose source node this rank owns
+extern "C" int rala_b200_graph_phase_transitive(rala_b200_graph* g) {
+    if (!g) return RALA_B200_ERR_ARG;
+    rala_b200_ctx* ctx = g->ctx;
+    if (g->state < 4) return fail(ctx, RALA_B200_ERR_STATE, "transitive: build first");
+    CU(ctx, cudaSetDevice(ctx->device));
+    CU(ctx, begin_stage(g, ST_TRANSITIVE));
+    CU(ctx, zero_counter(g, C_PAIRS, 2));
+    CU(ctx, zero_counter(g, C_HOP_LO, 2));
+    CU(ctx, cudaMemsetAsync(g->work_counter.p, 0, 64, ctx->L.stream));
+    CU(ctx, cudaMemsetAsync(g->T.p, 0, align_up(g->edge_cap, 256), ctx->L.stream));
+    launch_node_range(ctx->L, g->graph_view(), g->cnt(), (uint32_t) g->rank, (uint32_t) g->world, g->work_counter.as<uint32_t>() + 4);
+    CU(ctx, cudaEventRecord(g->ev_start[ST_K3_KERNELS], ctx->L.stream));
+    launch_transitive(ctx->L, g->graph_view(), g->n_nodes_max, g->edge_cap, g->heavy_view(), g->work_counter.as<uint32_t>(),
+                      g->cnt(), 0u, 0xFFFFFFFFu, g->work_counter.as<uint32_t>() + 4);
+    CU(ctx, end_stage(g, ST_K3_KERNELS));
+    CU(ctx, cudaGetLastError());
+    return RALA_B200_OK;
+}
+
+extern "C" int rala_b200_graph_export_marks(rala_b200_graph* g, uint8_t* d_T, uint32_t n) {
+    if (!g || (n && !d_T)) return RALA_B200_ERR_ARG;
+    rala_b200_ctx* ctx = g->ctx;
+    CU(ctx, cudaSetDevice(ctx->device));
+    if (n) CU(ctx, cudaMemcpyAsync(d_T, g->T.p, n, cudaMemcpyDeviceToDevice, ctx->L.stream));
+    return RALA_B200_OK;
+}
+
+// merged T in, marked(e) = T(e) | T(e^1) out
+extern "C" int rala_b200_graph_phase_marks(rala_b200_graph* g, const uint8_t* d_T, uint32_t n) {
+    if (!g || (n && !d_T)) return RALA_B200_ERR_ARG;
+    rala_b200_ctx* ctx = g->ctx;
+    CU(ctx, cudaSetDevice(ctx->device));
+    if (n) CU(ctx, cudaMemcpyAsync(g->T.p, d_T, n, cudaMemcpyDeviceToDevice, ctx->L.stream));
+    launch_finalize_marks(ctx->L, g->graph_view(), g->edge_cap, g->cnt());
+    CU(ctx, cudaGetLastError());
+    CU(ctx, end_stage(g, ST_TRANSITIVE));
+    g->state = 5;
+    return RALA_B200_OK;
 }

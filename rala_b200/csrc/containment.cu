@@ -48,6 +48,11 @@ __global__ void k_events_fill(Events ev, const uint32_t* __restrict__ n_events, 
     }
 }
 
+__global__ void k_events_hist(Events ev, const uint32_t* __restrict__ n_events, uint32_t ev_cap, uint32_t* __restrict__ vcount) {
+    const uint32_t n = min(*n_events, ev_cap);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) atomicAdd(&vcount[ev.v[i]], 1u);
+}
+
 __global__ void k_resolve_init(const uint32_t* __restrict__ vstart, uint32_t n_piles, uint32_t* __restrict__ S,
                                uint32_t* __restrict__ work, uint32_t* __restrict__ n_work) {
     for (uint32_t base = blockIdx.x * blockDim.x; base < n_piles; base += gridDim.x * blockDim.x) {
@@ -192,6 +197,11 @@ static inline int grid_for(uint64_t n, int per_block, int max_blocks) {
     uint64_t b = (n + per_block - 1) / per_block;
     if (b < 1) b = 1;
     return (int) (b < (uint64_t) max_blocks ? b : (uint64_t) max_blocks);
+}
+
+void launch_events_hist(Launch& L, Events ev, const uint32_t* n_events, uint32_t ev_cap, uint32_t* vcount) {
+    k_events_hist<<<grid_for(ev_cap, 256, kNumSMs * 8), 256, 0, L.stream>>>(ev, n_events, ev_cap, vcount);
+    L.count++;
 }
 
 int resolve_max_blocks() {

@@ -24,6 +24,7 @@ enum Counter {
     C_HEAVY,        // heavy work items of the transitive pass
     C_OVERFLOW,     // some list hit its capacity
     C_HOP_LO, C_HOP_HI,   // two-hop visits (64-bit)
+    C_TBASE_OVL, C_TBASE_INL,     // multi-GPU: global time bases of the local lists in the final pass
     C_EV_FIRST, C_ROUNDS_FIRST,   // events / rounds of the first-pass resolution (C_EV / C_ROUNDS are reused by the final pass)
     C_LIST0,        // 16 rotating list-count slots follow
     C_COUNT = C_LIST0 + 16
@@ -73,6 +74,8 @@ struct ResolveBufs {
     uint32_t *seg_c, *seg_t;   // event capacity each
 };
 int resolve_max_blocks();
+// per-victim histogram of an imported event list (the classify kernels build it on the fly otherwise)
+void launch_events_hist(Launch& L, Events ev, const uint32_t* n_events, uint32_t ev_cap, uint32_t* vcount);
 void launch_resolve(Launch& L, Events ev, const uint32_t* n_events, uint32_t ev_cap, ResolveBufs rb, uint32_t n_piles,
                     uint32_t* counters, unsigned long long* status, uint32_t* ticket, int coop_blocks);
 
@@ -105,7 +108,9 @@ struct HeavyItems {
     uint32_t cap;
 };
 void launch_transitive(Launch& L, GraphArrays g, uint32_t n_nodes_max, uint32_t edge_cap, HeavyItems heavy,
-                       uint32_t* work_counter, uint32_t* counters, uint32_t node_begin, uint32_t node_end);
+                       uint32_t* work_counter, uint32_t* counters, uint32_t node_begin, uint32_t node_end,
+                       const uint32_t* node_range /* device {begin, end}, nullable */);
+void launch_node_range(Launch& L, GraphArrays g, const uint32_t* counters, uint32_t rank, uint32_t world, uint32_t* out);
 void launch_finalize_marks(Launch& L, GraphArrays g, uint32_t edge_cap, uint32_t* counters);
 
 }  // namespace rb

@@ -91,11 +91,16 @@ struct LightSmem {
 
 __global__ void __launch_bounds__(kLightWarps * 32) k_transitive_light(
     const uint32_t* __restrict__ row_ptr, const uint2* __restrict__ col, const uint32_t* __restrict__ col_eid,
-    uint8_t* __restrict__ T, uint32_t node_begin, uint32_t node_end, const uint32_t* __restrict__ n_nodes_ptr,
-    uint32_t* __restrict__ work_counter, HeavyItems heavy, uint32_t* __restrict__ counters) {
+    uint8_t* __restrict__ T, uint32_t node_begin, uint32_t node_end, const uint32_t* __restrict__ node_range,
+    const uint32_t* __restrict__ n_nodes_ptr, uint32_t* __restrict__ work_counter, HeavyItems heavy,
+    uint32_t* __restrict__ counters) {
     __shared__ LightSmem smem[kLightWarps];
     LightSmem& S = smem[warp_id()];
     const uint32_t lane = lane_id();
+    if (node_range) {   // multi-GPU: this rank's share of the source nodes, computed on the device
+        node_begin = node_range[0];
+        node_end = node_range[1];
+    }
     const uint32_t n_end = min(node_end, *n_nodes_ptr);
     unsigned long long visits = 0;
 
@@ -328,8 +333,36 @@ __global__ void k_finalize_marks(const uint8_t* __restrict__ T, uint8_t* __restr
     if (lane_id() == 0 && local) atomicAdd(&counters[C_PAIRS], local);
 }
 
+// Source-node range of `rank`: nodes are split so that every rank owns about the same number of edges
+// (begin(r) = first node whose row starts at or after E * r / world).
+__global__ void k_node_range(const uint32_t* __restrict__ row_ptr, const uint32_t* __restrict__ n_nodes_ptr,
+                             const uint32_t* __restrict__ n_edges_ptr, uint32_t rank, uint32_t world, uint32_t* __restrict__ out) {
+    if (threadIdx.x >= 2) return;
+    const uint32_t n_nodes = *n_nodes_ptr;
+    const unsigned long long E = *n_edges_ptr;
+    const uint32_t r = rank + threadIdx.x;   // thread 0: begin(rank), thread 1: begin(rank + 1)
+    uint32_t result = n_nodes;
+    if (r == 0) result = 0;
+    else if (r < world) {
+        const uint32_t target = (uint32_t) (E * r / world);
+        uint32_t lo = 0, hi = n_nodes;   // first node with row_ptr[node] >= target
+        while (lo < hi) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (row_ptr[mid] < target) lo = mid + 1; else hi = mid;
+        }
+        result = lo;
+    }
+    out[threadIdx.x] = result;
+}
+
+void launch_node_range(Launch& L, GraphArrays g, const uint32_t* counters, uint32_t rank, uint32_t world, uint32_t* out) {
+    k_node_range<<<1, 32, 0, L.stream>>>(g.row_ptr, counters + C_NODES, counters + C_EDGES, rank, world, out);
+    L.count++;
+}
+
 void launch_transitive(Launch& L, GraphArrays g, uint32_t n_nodes_max, uint32_t edge_cap, HeavyItems heavy,
-                       uint32_t* work_counter, uint32_t* counters, uint32_t node_begin, uint32_t node_end) {
+                       uint32_t* work_counter, uint32_t* counters, uint32_t node_begin, uint32_t node_end,
+                       const uint32_t* node_range) {
     (void) edge_cap;
     uint64_t span = node_end > node_begin ? node_end - node_begin : 0;
     if (span > n_nodes_max) span = n_nodes_max;
@@ -337,7 +370,7 @@ void launch_transitive(Launch& L, GraphArrays g, uint32_t n_nodes_max, uint32_t 
     if (blocks < 1) blocks = 1;
     if (blocks > (uint64_t) kNumSMs * 8) blocks = kNumSMs * 8;
     k_transitive_light<<<(int) blocks, kLightWarps * 32, 0, L.stream>>>(g.row_ptr, g.col, g.col_eid, g.T, node_begin, node_end,
-                                                                       counters + C_NODES, work_counter, heavy, counters);
+                                                                       node_range, counters + C_NODES, work_counter, heavy, counters);
     L.count++;
     k_transitive_heavy<<<kNumSMs * 4, kHeavyThreads, 0, L.stream>>>(g.row_ptr, g.col, g.col_eid, g.T, heavy, counters);
     L.count++;

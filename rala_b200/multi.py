@@ -1,0 +1,341 @@
+"""Multi-GPU hot path: one process per GPU, torch.distributed (NCCL over NVLink / NVSwitch) for the
+exchange steps, the CUDA phases of librala_b200.so for everything else.
+
+Partition (BASELINE.json north_star):
+  * overlap records are sharded by contiguous FILE RANGE (rank r holds records [t0_r, t0_r + n_r)); the
+    pile table is replicated;
+  * the containment events of all shards are all-gathered and the ordered-containment resolution runs
+    replicated (its result, the set of dead piles, is needed by every rank);
+  * every rank emits the edges of its own surviving overlaps; the edge lists are all-gathered in rank
+    order (= global edge-id order) and the CSR of the whole graph is built on every rank, because the
+    two-hop lookups of the transitive pass cross shards;
+  * the transitive pass is split by source-node range (equal edge share per rank); the per-edge marks are
+    merged with an all-reduce(max), which is OR on 0/1 bytes.
+
+`DistributedGraph` is written against the small `ShardSession` interface so that the orchestration
+(sharding arithmetic, padding, offsets, collectives) is testable on CPU with the gloo backend and a
+stand-in session (tests/test_multi_gloo.py); the product session is `CudaShardSession`.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import time
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import api
+
+
+class CudaShardSession:
+    """The CUDA phases of one rank (include/rala_b200.h, "Multi-GPU phases").  Enqueues on torch's current
+    stream, so NCCL collectives issued through torch.distributed are ordered with the kernels."""
+
+    def __init__(self, device_index: int):
+        self.device = torch.device("cuda", device_index)
+        torch.cuda.set_device(self.device)
+        lib = api.load()
+        self.ctx = api.Context.__new__(api.Context)
+        self.ctx.lib = lib
+        self.ctx.handle = C.c_void_p()
+        self.ctx.device = device_index
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        rc = lib.rala_b200_create_on_stream(C.byref(self.ctx.handle), C.c_int(device_index), C.c_void_p(stream))
+        if rc != 0:
+            raise api.RalaB200Error(f"rala_b200_create_on_stream failed with status {rc} (no CPU fallback)")
+        self.G = api.Graph(self.ctx)
+
+    # ---- inputs -------------------------------------------------------------------------------------------
+    def set_inputs(self, records, piles, flags, t0: int, rank: int, world: int):
+        self.G.set_piles(piles, flags).set_hills(None).set_overlaps(records)
+        self.G._call("rala_b200_graph_set_shard", C.c_uint32(t0), C.c_int(rank), C.c_int(world))
+
+    def _u32(self, name, *args):
+        out = C.c_uint32(0)
+        self.G._call(name, *args, C.byref(out))
+        return int(out.value)
+
+    @staticmethod
+    def _dp(t: torch.Tensor):
+        return C.c_void_p(t.data_ptr())
+
+    # ---- phases -------------------------------------------------------------------------------------------
+    def phase_events(self) -> int:
+        self.G._call("rala_b200_graph_phase_events")
+        return self._u32("rala_b200_graph_events_count")
+
+    def export_events(self, block: torch.Tensor, n: int):
+        self.G._call("rala_b200_graph_export_events", self._dp(block), C.c_uint32(block.shape[1]), C.c_uint32(n))
+
+    def import_events(self, block: torch.Tensor, n: int, offset: int, total: int):
+        self.G._call("rala_b200_graph_import_events", self._dp(block), C.c_uint32(block.shape[1]), C.c_uint32(n),
+                     C.c_uint32(offset), C.c_uint32(total))
+
+    def phase_resolve(self, first: bool):
+        self.G._call("rala_b200_graph_phase_resolve", C.c_int(1 if first else 0))
+
+    def phase_survivors(self):
+        self.G._call("rala_b200_graph_phase_survivors")
+        a, b = C.c_uint32(0), C.c_uint32(0)
+        self.G._call("rala_b200_graph_list_counts", C.byref(a), C.byref(b))
+        return int(a.value), int(b.value)
+
+    def phase_final_events(self, ovl_base: int, int_base: int) -> int:
+        self.G._call("rala_b200_graph_phase_final_events", C.c_uint32(ovl_base), C.c_uint32(int_base))
+        return self._u32("rala_b200_graph_events_count")
+
+    def phase_emit_edges(self) -> int:
+        return self._u32("rala_b200_graph_phase_emit_edges")
+
+    def export_edges(self, block: torch.Tensor, n: int):
+        self.G._call("rala_b200_graph_export_edges", self._dp(block), C.c_uint32(block.shape[1]), C.c_uint32(n))
+
+    def import_edges(self, block: torch.Tensor, n: int, offset: int, total: int):
+        self.G._call("rala_b200_graph_import_edges", self._dp(block), C.c_uint32(block.shape[1]), C.c_uint32(n),
+                     C.c_uint32(offset), C.c_uint32(total))
+
+    def phase_csr(self):
+        self.G._call("rala_b200_graph_phase_csr")
+
+    def phase_transitive(self):
+        self.G._call("rala_b200_graph_phase_transitive")
+
+    def export_marks(self, t: torch.Tensor):
+        self.G._call("rala_b200_graph_export_marks", self._dp(t), C.c_uint32(t.shape[0]))
+
+    def phase_marks(self, t: torch.Tensor):
+        self.G._call("rala_b200_graph_phase_marks", self._dp(t), C.c_uint32(t.shape[0]))
+
+    # ---- results (replicated on every rank) ------------------------------------------------------------------
+    def counts(self):
+        return self.G.counts()
+
+    def edges(self):
+        return self.G.edges()
+
+    def marked(self):
+        return self.G.marked()
+
+    def close(self):
+        self.G.close()
+        self.ctx.close()
+
+
+class DistributedGraph:
+    """Drives one ShardSession per rank through the phases, with the collectives in between."""
+
+    def __init__(self, session, rank: int, world: int, group=None):
+        self.s, self.rank, self.world, self.group = session, rank, world, group
+        self.device = session.device
+        self.comm_bytes = 0   # bytes this rank received through collectives in the last run
+
+    def _gather_counts(self, values):
+        t = torch.tensor(values, dtype=torch.int64, device=self.device)
+        out = [torch.empty_like(t) for _ in range(self.world)]
+        dist.all_gather(out, t, group=self.group)
+        return torch.stack(out).cpu().numpy()   # (world, len(values))
+
+    def _exchange(self, n_local: int, export_fn, import_fn):
+        """All-gather of variable-length 3-column blocks; imports them in rank order. Returns the total."""
+        counts = self._gather_counts([n_local])[:, 0]
+        total, stride = int(counts.sum()), max(int(counts.max()), 1)
+        block = torch.zeros((3, stride), dtype=torch.int32, device=self.device)
+        export_fn(block, n_local)
+        gathered = [torch.empty_like(block) for _ in range(self.world)]
+        dist.all_gather(gathered, block, group=self.group)
+        self.comm_bytes += block.numel() * 4 * (self.world - 1)
+        off = 0
+        for k in range(self.world):
+            n_k = int(counts[k])
+            if n_k or k == self.world - 1:
+                import_fn(gathered[k], n_k, off, total)   # the last import publishes the total
+            off += n_k
+        return total
+
+    def run(self):
+        s = self.s
+        self.comm_bytes = 0
+        # graph.cpp:443-518
+        n_ev = s.phase_events()
+        n_events = self._exchange(n_ev, s.export_events, s.import_events)
+        s.phase_resolve(True)
+        n_ovl, n_int = s.phase_survivors()
+        # graph.cpp:831-877 — time of a list entry = its position in the GLOBAL overlaps ++ internals order
+        counts = self._gather_counts([n_ovl, n_int])
+        total_ovl = int(counts[:, 0].sum())
+        ovl_base = int(counts[:self.rank, 0].sum())
+        int_base = total_ovl + int(counts[:self.rank, 1].sum())
+        n_ev2 = s.phase_final_events(ovl_base, int_base)
+        n_final_events = self._exchange(n_ev2, s.export_events, s.import_events)
+        s.phase_resolve(False)
+        # graph.cpp:552-632 — edge ids follow the global list order = rank order of the shards
+        n_e = s.phase_emit_edges()
+        n_edges = self._exchange(n_e, s.export_edges, s.import_edges)
+        s.phase_csr()
+        # graph.cpp:1281-1318 — split by source node; marks merged with all-reduce(max)
+        s.phase_transitive()
+        marks = torch.zeros(max(n_edges, 1), dtype=torch.uint8, device=self.device)
+        s.export_marks(marks[:n_edges])
+        dist.all_reduce(marks, op=dist.ReduceOp.MAX, group=self.group)
+        self.comm_bytes += marks.numel() * 2 * (self.world - 1) // self.world
+        s.phase_marks(marks[:n_edges])
+        return dict(n_events=n_events, n_final_events=n_final_events, n_edges=n_edges, n_overlaps=total_ovl)
+
+
+def shard_bounds(n_records: int, world: int):
+    """Contiguous, 4-record aligned shards of a file of n_records (the reference's own chunking is by
+    bytes, graph.cpp:24; alignment keeps every shard start 16-byte aligned for the TMA tile loads)."""
+    per = (n_records + world - 1) // world
+    per = (per + 3) // 4 * 4
+    return [(min(n_records, r * per), min(n_records, (r + 1) * per)) for r in range(world)]
+
+
+# -------------------------------------------------------------------------------------------------------------
+# bench entry (python -m torch.distributed.run ... bench.py --gpus N)
+# -------------------------------------------------------------------------------------------------------------
+def _global_dataset(args, rank, world, device):
+    """Weak scaling: `world` chromosomes of the single-GPU workload; read ids are shuffled GLOBALLY, so every
+    shard's records reference piles (and later CSR rows) owned by all the other shards.  Each rank generates
+    one chromosome, then the records are redistributed by query-id range with an all-to-all (setup, untimed)."""
+    import bench
+    from . import synth
+    genome, cov, rl, _ = bench.WORKLOADS[args.workload]
+    ds = synth.generate(genome, cov, rl, seed=3 + rank)
+    n_chr = ds.n_reads
+    n_total = n_chr * world
+    perm = np.random.Generator(np.random.PCG64(12345)).permutation(n_total).astype(np.uint32)   # same on all ranks
+    gid = perm[rank * n_chr:(rank + 1) * n_chr]
+    rec = ds.records.copy()
+    a, b = gid[rec[:, 0]], gid[rec[:, 1]]
+    swap = a > b                                     # keep "listed once under the lower id as query"
+    rec[:, 0], rec[:, 1] = np.where(swap, b, a), np.where(swap, a, b)
+    ab, ae, bb, be = rec[:, 2].copy(), rec[:, 3].copy(), rec[:, 4].copy(), rec[:, 5].copy()
+    rec[:, 2], rec[:, 3] = np.where(swap, bb, ab), np.where(swap, be, ae)
+    rec[:, 4], rec[:, 5] = np.where(swap, ab, bb), np.where(swap, ae, be)
+    # destination rank = owner of the query id range
+    per = (n_total + world - 1) // world
+    dest = (rec[:, 0] // per).astype(np.int64)
+    order = np.argsort(dest, kind="stable")
+    rec = rec[order]
+    send_counts = np.bincount(dest, minlength=world).astype(np.int64)
+    sc = torch.tensor(send_counts, device=device)
+    rc = torch.empty_like(sc)
+    dist.all_to_all_single(rc, sc)
+    send = torch.from_numpy(rec.view(np.int32)).to(device)
+    recv = torch.empty((int(rc.sum().item()), 7), dtype=torch.int32, device=device)
+    dist.all_to_all_single(recv, send, output_split_sizes=rc.tolist(), input_split_sizes=sc.tolist())
+    local = recv.cpu().numpy().view(np.uint32)
+    local = local[np.lexsort((local[:, 2], local[:, 1], local[:, 0]))]     # grouped by query, ascending
+    # replicated pile table: read lengths of every chromosome (fixed-length reads here) at their global ids
+    lens = torch.zeros(n_total, dtype=torch.int32, device=device)
+    lens[torch.from_numpy(gid.astype(np.int64)).to(device)] = torch.from_numpy(ds.read_len.astype(np.int32)).to(device)
+    dist.all_reduce(lens, op=dist.ReduceOp.SUM)
+    read_len = lens.cpu().numpy().astype(np.uint32)
+    piles = np.empty((n_total, 2), dtype=np.uint32)
+    piles[:, 0] = 15
+    piles[:, 1] = read_len - 15
+    counts = torch.tensor([local.shape[0]], dtype=torch.int64, device=device)
+    allc = [torch.empty_like(counts) for _ in range(world)]
+    dist.all_gather(allc, counts)
+    allc = [int(c.item()) for c in allc]
+    t0 = sum(allc[:rank])
+    return np.ascontiguousarray(local), piles, t0, sum(allc)
+
+
+def bench_main(args):
+    import json
+    import bench
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", str(rank)))
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    dist.init_process_group("nccl", device_id=device)
+    records, piles, t0, n_total_records = _global_dataset(args, rank, world, device)
+
+    sess = CudaShardSession(local_rank)
+    sess.set_inputs(records, piles, None, t0, rank, world)
+    dg = DistributedGraph(sess, rank, world)
+    for _ in range(max(args.warmup, 3)):
+        info = dg.run()
+    torch.cuda.synchronize()
+    sampler = bench.ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    launches0 = sess.ctx.launch_count
+    dist.barrier()
+    torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_wall = time.perf_counter()
+    ev0.record()
+    for _ in range(args.steps):
+        info = dg.run()
+    ev1.record()
+    torch.cuda.synchronize()
+    dist.barrier()
+    wall_ms = 1e3 * (time.perf_counter() - t_wall)
+    dev_ms = ev0.elapsed_time(ev1)
+    launches = sess.ctx.launch_count - launches0
+    t = torch.tensor([dev_ms, wall_ms], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)           # max over ranks
+    ms_per_step = float(t[0].item()) / args.steps
+    stage = sess.G.stage_ms()
+    clocks = sampler.stop() if sampler else None
+    c = sess.counts()
+    E = info["n_edges"]
+
+    # end to end: host (pinned) shard -> device, full pipeline, edges + marks back to the host on every rank
+    rec_pin = torch.from_numpy(records).pin_memory()
+    piles_pin = torch.from_numpy(piles).pin_memory()
+    e2e_steps = max(3, min(args.steps, 5))
+    edges_pin = torch.empty((max(E, 1), 3), dtype=torch.int32).pin_memory()
+    marked_pin = torch.empty(max(E, 1), dtype=torch.uint8).pin_memory()
+
+    def e2e_step():
+        sess.G.set_piles(piles_pin).set_overlaps(rec_pin)
+        dg.run()
+        sess.G.edges(out=edges_pin)
+        sess.G.marked(out=marked_pin)
+
+    e2e_step()
+    dist.barrier()
+    torch.cuda.synchronize()
+    t1 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    torch.cuda.synchronize()
+    dist.barrier()
+    e2e_s = torch.tensor([(time.perf_counter() - t1) / e2e_steps], dtype=torch.float64, device=device)
+    dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    e2e_s = float(e2e_s.item())
+
+    if rank == 0:
+        peak, peak_src = bench.measured_peaks()
+        k1_ms = stage["k1_classify_kernel"]
+        k1_gbs = bench.K1_BYTES_PER_OVERLAP * records.shape[0] / (k1_ms * 1e-3) / 1e9 if k1_ms > 0 else 0.0
+        print(json.dumps({
+            "metric": "graph_edges_per_sec", "value": E / (ms_per_step * 1e-3), "unit": "edges/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "u32+f64", "data": "synthetic",
+            "config": {"workload": f"{world} x ({bench.WORKLOADS[args.workload][3]}), read ids shuffled globally",
+                       "n_overlaps": n_total_records, "n_overlaps_per_gpu": int(records.shape[0]), "n_reads": int(piles.shape[0]),
+                       "edges": E, "nodes": c["n_nodes"], "containment_events": info["n_events"],
+                       "parallelism": f"{world} GPUs: records by file range, CSR replicated (all-gather), "
+                                      "transitive by source-node range, marks all-reduce(max)",
+                       "l2": "inputs larger than L2 (each rank streams its 400 MB record shard per step)",
+                       "collective_bytes_received_per_rank_per_step": dg.comm_bytes},
+            "wall_ms_per_step": float(t[1].item()) / args.steps,
+            "e2e": {"value": E / e2e_s, "unit": "edges/s", "h2d_bytes_per_step": int((records.nbytes + piles.nbytes) * world),
+                    "d2h_bytes_per_step": int(13 * E * world), "ms_per_step": 1e3 * e2e_s},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "kernel": "k_classify_events", "achieved": k1_gbs, "peak": peak, "unit": "GB/s",
+                         "frac": k1_gbs / peak, "traffic": None, "peak_source": peak_src,
+                         "note": "rank 0's first pass over its record shard; stage_ms are rank 0's last step",
+                         "stage_ms": stage},
+            "cpu_baseline": None, "clocks": clocks,
+        }))
+    sess.close()
+    dist.destroy_process_group()

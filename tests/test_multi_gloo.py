@@ -1,0 +1,213 @@
+"""CPU suite, world_size 2 and 3 over gloo: the multi-GPU ORCHESTRATION (rala_b200/multi.py: sharding,
+padding, offsets, time bases, exchange order) driven with a stand-in session whose phases are computed
+with the oracle.  The product session (CudaShardSession) has the same interface; its kernels are covered
+by tests/test_gpu_parity.py and tests/test_multi_gpu.py."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from oracle import oracle as O  # noqa: E402
+from rala_b200 import multi, synth  # noqa: E402
+
+INF = 0xFFFFFFFF
+
+
+class OracleShardSession:
+    """ShardSession stand-in: every phase computed on the host with the oracle's trim / type."""
+
+    def __init__(self, records, piles, flags, t0, rank, world):
+        self.device = torch.device("cpu")
+        self.rec = np.ascontiguousarray(records, dtype=np.uint32).reshape(-1, 7)
+        self.piles = np.ascontiguousarray(piles, dtype=np.uint32).copy()
+        self.flags = np.zeros(len(piles), np.uint8) if flags is None else np.asarray(flags, np.uint8)
+        self.t0, self.rank, self.world = t0, rank, world
+        self.events = np.zeros((0, 3), np.uint32)
+        self.edges_all = np.zeros((0, 3), np.uint32)
+
+    def _trim_type(self, r):
+        a, b = int(r[0]), int(r[1])
+        if r[6] & 2 or a >= len(self.piles) or b >= len(self.piles) or self.piles[a, 1] == 0 or self.piles[b, 1] == 0:
+            return False, r, O.REJECT
+        return O.trim_type(r, self.piles[a], self.piles[b])
+
+    @staticmethod
+    def _to_block(arr, block, n):
+        if n:
+            block[:, :n] = torch.from_numpy(np.ascontiguousarray(arr[:n].T).view(np.int32))
+
+    @staticmethod
+    def _from_block(block, n):
+        return block[:, :n].numpy().view(np.uint32).T.copy()
+
+    def phase_events(self):
+        ev = []
+        for i, r in enumerate(self.rec):
+            ok, tr, t = self._trim_type(r)
+            if not ok:
+                continue
+            a, b = int(r[0]), int(r[1])
+            if t == O.KB and not (self.flags[b] & 2):
+                ev.append((a, b, self.t0 + i))
+            elif t == O.KA and not (self.flags[a] & 2):
+                ev.append((b, a, self.t0 + i))
+        self.events = np.asarray(ev, np.uint32).reshape(-1, 3)
+        return len(ev)
+
+    def export_events(self, block, n):
+        self._to_block(self.events, block, n)
+
+    def import_events(self, block, n, offset, total):
+        if offset == 0:
+            self.events_all = np.zeros((total, 3), np.uint32)
+        self.events_all[offset:offset + n] = self._from_block(block, n)
+
+    def phase_resolve(self, first):
+        # the reference's sequential semantics: in time order, an event fires iff both piles are still alive
+        ev = self.events_all[np.argsort(self.events_all[:, 2], kind="stable")] if len(self.events_all) else self.events_all
+        alive = self.piles[:, 1] != 0
+        self.death = np.full(len(self.piles), INF, np.uint64)
+        for v, c, t in ev.tolist():
+            if alive[v] and alive[c]:
+                alive[v] = False
+                self.death[v] = t
+        self.pre_final_alive = self.piles[:, 1] != 0
+        self.piles[~alive] = 0
+
+    def phase_survivors(self):
+        ovl, inl = [], []
+        for r in self.rec:
+            ok, tr, t = self._trim_type(r)
+            if ok:
+                tr[0], tr[1] = r[0], r[1]   # O.trim_type works on a two-pile table and renumbers the ids
+                (inl if t == O.KX else ovl).append(tr)
+        self.ovl = np.asarray(ovl, np.uint32).reshape(-1, 7)
+        self.inl = np.asarray(inl, np.uint32).reshape(-1, 7)
+        return len(ovl), len(inl)
+
+    def phase_final_events(self, ovl_base, int_base):
+        ev = []
+        for base, lst in ((ovl_base, self.ovl), (int_base, self.inl)):
+            for i, r in enumerate(lst):
+                piles2 = np.ascontiguousarray(self.piles[[r[0], r[1]]])
+                rr = r.copy(); rr[0], rr[1] = 0, 1
+                t = O.lib().ora_type(O._p(rr), O._p(piles2))
+                if t == O.KA:
+                    ev.append((int(r[1]), int(r[0]), base + i))
+                elif t == O.KB:
+                    ev.append((int(r[0]), int(r[1]), base + i))
+        self.events = np.asarray(ev, np.uint32).reshape(-1, 3)
+        return len(ev)
+
+    def phase_emit_edges(self):
+        alive = self.piles[:, 1] != 0
+        s2n = np.full(len(self.piles), INF, np.uint64)
+        s2n[alive] = 2 * np.arange(int(alive.sum()))
+        self.n_nodes = 2 * int(alive.sum())
+        keep = [r for r in self.ovl if alive[r[0]] and alive[r[1]]]
+        P = O.Pipeline(np.zeros((0, 7), np.uint32), self.piles)
+        P.ovl = np.asarray(keep, np.uint32).reshape(-1, 7)
+        P.build_edges()      # local node numbering == global: the pile table is replicated
+        self.edges = P.edges
+        return len(self.edges)
+
+    def export_edges(self, block, n):
+        self._to_block(self.edges, block, n)
+
+    def import_edges(self, block, n, offset, total):
+        if offset == 0:
+            self.edges_all = np.zeros((total, 3), np.uint32)
+        self.edges_all[offset:offset + n] = self._from_block(block, n)
+
+    def phase_csr(self):
+        pass
+
+    def phase_transitive(self):
+        e = self.edges_all
+        E = len(e)
+        row_start = np.searchsorted(np.sort(e[:, 0]), np.arange(self.n_nodes + 1)) if E else np.zeros(self.n_nodes + 1, int)
+
+        def begin(r):
+            if r == 0:
+                return 0
+            if r >= self.world:
+                return self.n_nodes
+            return int(np.searchsorted(row_start[:self.n_nodes], E * r // self.world, side="left"))
+
+        lo, hi = begin(self.rank), begin(self.rank + 1)
+        out = {}
+        for i, (s, d, l) in enumerate(e.tolist()):
+            out.setdefault(s, []).append((d, l, i))
+        T = np.zeros(E, np.uint8)
+        for a in range(lo, hi):
+            cand = {}
+            for d, l, i in out.get(a, []):
+                if d not in cand or cand[d][1] < i:
+                    cand[d] = (l, i)
+            for b, lab, _ in out.get(a, []):
+                for c, lbc, _ in out.get(b, []):
+                    if c in cand and O.comparable((lab + lbc) & 0xFFFFFFFF, cand[c][0]):
+                        T[cand[c][1]] = 1
+        self.T = T
+
+    def export_marks(self, t):
+        t[:] = torch.from_numpy(self.T)
+
+    def phase_marks(self, t):
+        T = t.numpy()
+        m = (T[0::2] | T[1::2])
+        self.marked = np.repeat(m, 2).astype(np.uint8)
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, kw, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        ds = synth.generate(**kw)
+        piles = ds.flat_piles()
+        flags = (np.random.Generator(np.random.PCG64(1)).random(ds.n_reads) < 0.05).astype(np.uint8) * 2
+        lo, hi = multi.shard_bounds(ds.n_overlaps, world)[rank]
+        sess = OracleShardSession(ds.records[lo:hi], piles, flags, lo, rank, world)
+        info = multi.DistributedGraph(sess, rank, world).run()
+        np.savez(os.path.join(out_dir, f"r{rank}.npz"), edges=sess.edges_all, marked=sess.marked, piles=sess.piles,
+                 n_events=info["n_events"])
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_orchestration_matches_single_process_oracle(world, tmp_path):
+    kw = dict(genome_len=150_000, coverage=30, read_len=6000, len_sd=1500, seed=61, noise=60, dual=True, min_ovl=800)
+    ds = synth.generate(**kw)
+    flags = (np.random.Generator(np.random.PCG64(1)).random(ds.n_reads) < 0.05).astype(np.uint8) * 2
+    want = O.Pipeline(ds.records, ds.flat_piles(), flags).run()
+    assert want.edges.shape[0] > 200 and want.n_pairs > 20
+    mp.spawn(_worker, args=(world, _free_port(), kw, str(tmp_path)), nprocs=world, join=True)
+    for r in range(world):
+        z = np.load(tmp_path / f"r{r}.npz")
+        assert np.array_equal(z["edges"], want.edges), f"rank {r}: edge list"
+        assert np.array_equal(z["marked"], want.marked), f"rank {r}: removed-edge set"
+        assert np.array_equal(z["piles"], want.piles), f"rank {r}: pile liveness"
+
+
+def test_shard_bounds():
+    for n, w in ((0, 2), (5, 2), (1000, 3), (1001, 8), (14403721, 8)):
+        b = multi.shard_bounds(n, w)
+        assert b[0][0] == 0 and b[-1][1] == n
+        assert all(b[i][1] == b[i + 1][0] for i in range(w - 1))
+        assert all(lo % 4 == 0 for lo, hi in b if lo < n)

@@ -1,0 +1,67 @@
+"""GPU suite: the multi-GPU phases of the C ABI (CudaShardSession) under the real orchestrator over NCCL,
+against the single-process oracle.  world = 1 runs on any GPU box; world = 2 / 4 need that many GPUs."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from oracle import oracle as O  # noqa: E402
+from rala_b200 import multi, synth  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+
+KW = dict(genome_len=3_000_000, coverage=30, read_len=9000, len_sd=2500, seed=71, noise=50, dual=True, min_ovl=900)
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        ds = synth.generate(**KW)
+        piles = ds.flat_piles()
+        flags = (np.random.Generator(np.random.PCG64(1)).random(ds.n_reads) < 0.05).astype(np.uint8) * 2
+        lo, hi = multi.shard_bounds(ds.n_overlaps, world)[rank]
+        sess = multi.CudaShardSession(rank)
+        sess.set_inputs(np.ascontiguousarray(ds.records[lo:hi]), piles, flags, lo, rank, world)
+        dg = multi.DistributedGraph(sess, rank, world)
+        for _ in range(2):   # twice: the session must be re-runnable (bench loop)
+            info = dg.run()
+        c = sess.counts()
+        np.savez(os.path.join(out_dir, f"r{rank}.npz"), edges=sess.edges(), marked=sess.marked(), piles=sess.G.piles(),
+                 n_pairs=c["n_transitive_pairs"], n_nodes=c["n_nodes"], n_events=info["n_events"])
+        sess.close()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [1, 2, 4])
+def test_multi_gpu_matches_oracle(world, tmp_path):
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    ds = synth.generate(**KW)
+    flags = (np.random.Generator(np.random.PCG64(1)).random(ds.n_reads) < 0.05).astype(np.uint8) * 2
+    want = O.Pipeline(ds.records, ds.flat_piles(), flags).run()
+    assert want.edges.shape[0] > 5000
+    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    for r in range(world):
+        z = np.load(tmp_path / f"r{r}.npz")
+        assert np.array_equal(z["edges"], want.edges), f"rank {r}: edge list"
+        assert np.array_equal(z["marked"], want.marked), f"rank {r}: removed-edge set"
+        assert np.array_equal(z["piles"], want.piles), f"rank {r}: pile liveness"
+        assert int(z["n_pairs"]) == want.n_pairs and int(z["n_nodes"]) == want.n_nodes
