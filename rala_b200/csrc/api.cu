@@ -154,7 +154,9 @@ enum Stage { ST_CLASSIFY = 0, ST_RETRIM, ST_FINALIZE, ST_BUILD, ST_TRANSITIVE, S
 struct rala_b200_graph {
     rala_b200_ctx* ctx = nullptr;
     // inputs
-    DevBuf rec;
+    DevBuf rec;        // the host's rala_ovl_t rows as uploaded (staging of the transpose)
+    ListBuf recs;      // device-resident records: six columns, 24 B / record (classify.cu)
+    DevBuf alive_bits; // one bit per pile: alive after the last containment resolution
     uint32_t n_rec = 0;
     DevBuf piles, piles_raw, pile_flags_raw, piles_initial;
     bool piles_fresh = false;       // set_piles since the last classify
@@ -283,7 +285,7 @@ extern "C" void rala_b200_graph_destroy(rala_b200_graph* g) {
     if (!g) return;
     cudaSetDevice(g->ctx->device);
     cudaStreamSynchronize(g->ctx->L.stream);
-    DevBuf* bufs[] = {&g->rec, &g->piles, &g->piles_raw, &g->pile_flags_raw, &g->piles_initial, &g->hills, &g->ovl[0].buf,
+    DevBuf* bufs[] = {&g->rec, &g->recs.buf, &g->alive_bits, &g->piles, &g->piles_raw, &g->pile_flags_raw, &g->piles_initial, &g->hills, &g->ovl[0].buf,
                       &g->ovl[1].buf, &g->inl[0].buf, &g->inl[1].buf, &g->events, &g->hill_rec, &g->dbuf, &g->flags, &g->segs, &g->tiles,
                       &g->counters, &g->scan_pool, &g->seq_to_node, &g->edges, &g->row_ptr, &g->cursor, &g->col,
                       &g->col_eid, &g->T, &g->marked, &g->heavy, &g->work_counter, &g->edges_aos};
@@ -336,8 +338,12 @@ extern "C" int rala_b200_graph_set_overlaps(rala_b200_graph* g, const rala_ovl_t
     CU(ctx, g->rec.reserve(align_up((size_t) n * sizeof(rala_ovl_t) + 16, 256)));
     if (n) CU(ctx, cudaMemcpyAsync(g->rec.p, ovl, (size_t) n * sizeof(rala_ovl_t), cudaMemcpyHostToDevice, ctx->L.stream));
     g->n_rec = (uint32_t) n;
-    // worst case every record survives; very large inputs get half and rely on the overflow check
-    uint32_t cap = (uint32_t) (n <= (1ull << 27) ? n : n / 2);
+    // layout in HBM: rows -> six columns, once per upload (the kernels read 16 bytes per column and thread)
+    CU(ctx, g->recs.reserve((uint32_t) ((n + 3) / 4 * 4 + 4)));
+    launch_records_to_soa(ctx->L, g->rec.as<uint32_t>(), (uint32_t) n, g->recs.view);
+    CU(ctx, cudaGetLastError());
+    // worst case every record survives; the scratch lists of the survivors pass are indexed by record position
+    uint32_t cap = (uint32_t) align_up((size_t) n, 128);
     if (cap < 1024) cap = 1024;
     if (cap > g->cap) {
         for (int i = 0; i < 2; ++i) {
@@ -352,7 +358,7 @@ extern "C" int rala_b200_graph_set_overlaps(rala_b200_graph* g, const rala_ovl_t
     } else {
         // views depend on cap: re-derive them for the (unchanged) capacity
     }
-    CU(ctx, g->tiles.reserve(align_up((size_t) classify_num_tiles((uint32_t) n) + 8, 64) * 4 * 6));
+    CU(ctx, g->tiles.reserve(align_up((size_t) classify_num_runs((uint32_t) n) + 8, 64) * 4 * 3));
     int rc = reserve_scan_pool(g);
     if (rc) return rc;
     if (g->state < 1 && g->n_piles) g->state = 1;
@@ -378,6 +384,7 @@ extern "C" int rala_b200_graph_set_piles(rala_b200_graph* g, const rala_pile_t* 
         g->n_piles = n_piles;
         g->n_nodes_max = 2 * n_piles;
         CU(ctx, g->dbuf.reserve(align_up((size_t) n_piles + 64, 64) * 4 * 5));
+        CU(ctx, g->alive_bits.reserve(((size_t) n_piles / 32 + 2) * 4));
         CU(ctx, g->seq_to_node.reserve((size_t) n_piles * 4 + 16));
         CU(ctx, g->row_ptr.reserve(((size_t) g->n_nodes_max + 8) * 4));
         CU(ctx, g->cursor.reserve(((size_t) g->n_nodes_max + 8) * 4));
@@ -457,7 +464,7 @@ static int phase_events(rala_b200_graph* g) {
     if (g->n_hills) CU(ctx, cudaMemsetAsync(g->hills.as<uint32_t>() + 3 * (size_t) g->n_hills, 0, (size_t) g->n_hills * 4, ctx->L.stream));
     CU(ctx, clear_victim_histogram(g));
     CU(ctx, cudaEventRecord(g->ev_start[ST_K1_KERNEL], ctx->L.stream));
-    launch_classify_events(ctx->L, g->rec.as<uint32_t>(), g->n_rec, g->t0, g->piles.as<uint2>(), g->n_piles, g->events_view(),
+    launch_classify_events(ctx->L, g->recs.view, g->n_rec, g->t0, g->piles.as<uint2>(), g->n_piles, g->events_view(),
                            g->ev_cap, resolve_bufs(g).vcursor, g->hill_rec.as<uint32_t>(), g->cap, g->cnt());
     CU(ctx, end_stage(g, ST_K1_KERNEL));
     CU(ctx, cudaGetLastError());
@@ -472,11 +479,11 @@ static int phase_resolve(rala_b200_graph* g, bool first_pass) {
     CU(ctx, end_stage(g, ST_K1B_KERNEL));
     if (first_pass && g->n_hills) {
         const uint32_t* h = g->hills.as<uint32_t>();
-        launch_hill_coverage(ctx->L, g->rec.as<uint32_t>(), g->t0, g->piles.as<uint2>(), g->hill_rec.as<uint32_t>(), g->cap, h,
+        launch_hill_coverage(ctx->L, g->recs.view, g->t0, g->piles.as<uint2>(), g->hill_rec.as<uint32_t>(), g->cap, h,
                              h + g->n_hills, h + 2 * (size_t) g->n_hills, g->n_hills,
                              g->hills.as<uint32_t>() + 3 * (size_t) g->n_hills, g->dbuf.as<uint32_t>(), g->n_piles, g->cnt());
     }
-    launch_apply_deaths(ctx->L, g->piles.as<uint2>(), g->dbuf.as<uint32_t>(), g->n_piles, g->cnt());
+    launch_apply_deaths(ctx->L, g->piles.as<uint2>(), g->dbuf.as<uint32_t>(), g->n_piles, g->cnt(), g->alive_bits.as<uint32_t>());
     CU(ctx, cudaGetLastError());
     return RALA_B200_OK;
 }
@@ -489,19 +496,17 @@ static int phase_survivors(rala_b200_graph* g) {
     g->slot_inl = C_LIST0 + 1;
     g->next_slot = C_LIST0 + 2;
     CU(ctx, zero_counter(g, C_LIST0, 2));
-    CU(ctx, cudaMemsetAsync(g->flags.as<uint32_t>() + 8, 0, 8, ctx->L.stream));   // scratch append counters
     CU(ctx, cudaEventRecord(g->ev_start[ST_K1S_KERNEL], ctx->L.stream));
     {
-        const size_t nt = align_up((size_t) classify_num_tiles(g->n_rec) + 8, 64);
+        const size_t nr = align_up((size_t) classify_num_runs(g->n_rec) + 8, 64);
         uint32_t* t = g->tiles.as<uint32_t>();
-        TileRuns runs{t, t + nt, t + 2 * nt, t + 3 * nt, t + 4 * nt, t + 5 * nt};
-        unsigned long long* st2[2];
-        uint32_t* tk2[2];
-        scan_state(g, nt, &st2[0], &tk2[0]);
-        scan_state(g, nt, &st2[1], &tk2[1]);
-        launch_classify_survivors(ctx->L, g->rec.as<uint32_t>(), g->n_rec, g->piles.as<uint2>(), g->n_piles, g->ovl[1].view,
-                                  g->inl[1].view, g->ovl[0].view, g->cnt() + g->slot_ovl, g->inl[0].view,
-                                  g->cnt() + g->slot_inl, g->cap, runs, g->flags.as<uint32_t>() + 8, st2, tk2);
+        RunBufs runs{t, t + nr, t + 2 * nr};
+        unsigned long long* status;
+        uint32_t* ticket;
+        scan_state(g, nr, &status, &ticket);
+        launch_classify_survivors(ctx->L, g->recs.view, g->n_rec, g->piles.as<uint2>(), g->alive_bits.as<uint32_t>(), g->n_piles,
+                                  g->ovl[1].view, g->inl[1].view, g->ovl[0].view, g->cnt() + g->slot_ovl, g->inl[0].view,
+                                  g->cnt() + g->slot_inl, g->cap, runs, status, ticket);
     }
     CU(ctx, end_stage(g, ST_K1S_KERNEL));
     CU(ctx, cudaGetLastError());

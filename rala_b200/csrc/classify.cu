@@ -4,14 +4,16 @@
 // Replaces (reference file:line): Overlap::trim / Overlap::type overlap.cpp:117-259 as driven by
 // graph.cpp:443-518 (classify loop), 722-736 and 801-824 (re-trim, promotion of internals),
 // 831-877 (final containment), and Pile::check_chimeric_hills pile.cpp:457-469.
+#include <cstdlib>
+
 #include "kernels.h"
 #include "lists.cuh"
 
 namespace rb {
 
 // =============================================================================================
-// K1 (graph.cpp:443-518) runs as two streaming kernels over the 28-byte AoS records the host
-// marshals (rala_ovl_t), with the containment fixed point between them:
+// K1 (graph.cpp:443-518) runs as two streaming kernels over the device-resident records, with the
+// containment resolution between them:
 //   k_classify_events    every record: static gates, trim, type; emits only what the ORDER-DEPENDENT
 //                        part needs: the containment events (victim, container, time) of kA/kB records
 //                        and the indices of records touching a pile with chimeric hills.
@@ -21,64 +23,48 @@ namespace rb {
 // No intermediate list: on clean data ~95 % of the records are dovetails at classification time but
 // only ~7 % survive the dead-pile filter, so materialising the "potential survivors" costs more than
 // re-reading the records.
-// Both kernels stage tiles of 512 records (14 KiB, contiguous) into shared memory with TMA bulk
-// copies (cp.async.bulk + mbarrier), double buffered, and read them back with a 7-word stride
-// (odd => bank-conflict free).
+//
+// Layout in HBM: the 28-byte rala_ovl_t rows the host marshals are transposed ONCE, at upload
+// (k_records_to_soa), into six 4-byte columns (a | invalid << 31, b | orientation << 31, a_begin, a_end,
+// b_begin, b_end: 24 B / record).  Each thread owns 4 consecutive records and reads every column with
+// one 16-byte load, so a warp touches 512 contiguous bytes per column: fully coalesced, no staging, no
+// barriers in the first pass.  The second pass reads only the two id columns (8 B / record) plus one
+// bit per pile of an L1-resident liveness bitmap, and gathers the coordinates of the few survivors.
 // =============================================================================================
-constexpr int kRecItems = 2;
-constexpr int kRecTile = kTileThreads * kRecItems;       // 512 records
-constexpr uint32_t kRecTileWords = kRecTile * 7;
+constexpr int kRecItems = 4;                              // consecutive records per thread (one uint4 per column)
+constexpr int kRecTile = kTileThreads * kRecItems;        // records per block iteration
+constexpr uint32_t kInvalidBit = 0x80000000u;             // in column a
+constexpr uint32_t kRunRecords = 128;                     // survivors pass: records per warp iteration = one run
 
-struct RecStage {
-    __align__(128) uint32_t rec[2][kRecTileWords];
-    __align__(8) uint64_t bar[2];
-};
-
-// issue the TMA load of `tile` into buffer b (one thread)
-__device__ __forceinline__ void issue_tile(RecStage& st, int b, const uint32_t* __restrict__ rec, uint32_t n, uint32_t tile) {
-    const uint32_t base = tile * kRecTile;
-    const uint32_t cnt = min((uint32_t) kRecTile, n - base);
-    const uint32_t bytes = (cnt * 28u + 15u) & ~15u;   // the record buffer is padded by 16 B past its end
-    fence_proxy_async();                               // earlier generic-proxy reads of this buffer come first
-    mbar_expect_tx(&st.bar[b], bytes);
-    bulk_g2s(st.rec[b], rec + (size_t) base * 7, bytes, &st.bar[b]);
+__global__ void k_records_to_soa(const uint32_t* __restrict__ aos, uint32_t n, List recs) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint32_t* q = aos + (size_t) i * 7;
+        const uint32_t flags = q[6];
+        // ids beyond 2^31 cannot name a pile (rala_b200.h limits): such a record is invalid
+        const bool bad = (flags & 2u) || (q[0] & kInvalidBit) || (q[1] & kInvalidBit);
+        recs.a[i] = (q[0] & ~kInvalidBit) | (bad ? kInvalidBit : 0u);
+        recs.b[i] = (q[1] & ~kInvalidBit) | ((flags & 1u) << 31);
+        recs.ab[i] = q[2];
+        recs.ae[i] = q[3];
+        recs.bb[i] = q[4];
+        recs.be[i] = q[5];
+    }
 }
 
-struct RecFields {
-    Entry e;
-    uint32_t flags;
-};
-
-__device__ __forceinline__ RecFields read_record(const uint32_t* q) {
-    RecFields r;
-    r.e.a = q[0];
-    r.e.b = q[1];
-    r.e.c.ab = q[2];
-    r.e.c.ae = q[3];
-    r.e.c.bb = q[4];
-    r.e.c.be = q[5];
-    r.flags = q[6];
-    r.e.ori = r.flags & 1u;
-    return r;
+__device__ __forceinline__ void unpack4(const uint4 v, uint32_t (&out)[4]) {
+    out[0] = v.x; out[1] = v.y; out[2] = v.z; out[3] = v.w;
 }
 
-constexpr int kEvStage = 64;   // per-warp staging of events before one aggregated global append
+constexpr int kEvStage = 96;   // per-warp staging of events before one aggregated global append
 
-__global__ void __launch_bounds__(kTileThreads) k_classify_events(
-    const uint32_t* __restrict__ rec, uint32_t n, uint32_t t0, const uint2* __restrict__ piles, uint32_t n_piles,
+template <int MINB>
+__global__ void __launch_bounds__(kTileThreads, MINB) k_classify_events(
+    List recs, uint32_t n, uint32_t t0, const uint2* __restrict__ piles, uint32_t n_piles,
     Events ev, uint32_t ev_cap, uint32_t* __restrict__ vcount, uint32_t* __restrict__ hill_rec, uint32_t hill_cap,
     uint32_t* __restrict__ counters) {
-    __shared__ RecStage st;
     __shared__ uint32_t s_ev[kTileWarps][3][kEvStage];
-    const uint32_t tid = threadIdx.x, lane = lane_id(), warp = warp_id();
-    const uint32_t num_tiles = (n + kRecTile - 1) / kRecTile;
-    if (tid == 0) {
-        mbar_init(&st.bar[0], 1);
-        mbar_init(&st.bar[1], 1);
-        fence_mbar_init();
-    }
-    __syncthreads();
-    uint32_t parity[2] = {0u, 0u};
+    const uint32_t lane = lane_id(), warp = warp_id();
+    const uint32_t n4 = (n + 3u) / 4u;
     uint32_t staged = 0;   // warp-uniform
 
     auto flush = [&]() {
@@ -96,35 +82,49 @@ __global__ void __launch_bounds__(kTileThreads) k_classify_events(
         staged = 0;
     };
 
-    uint32_t tile = blockIdx.x;
-    if (tid == 0 && tile < num_tiles) issue_tile(st, 0, rec, n, tile);
-    for (uint32_t it = 0; tile < num_tiles; ++it, tile += gridDim.x) {
-        const int b = it & 1;
-        if (tid == 0 && tile + gridDim.x < num_tiles) issue_tile(st, b ^ 1, rec, n, tile + gridDim.x);
-        mbar_wait(&st.bar[b], parity[b]);
-        parity[b] ^= 1u;
-        const uint32_t base = tile * kRecTile;
-        const uint32_t cnt = min((uint32_t) kRecTile, n - base);
+    for (uint32_t qbase = blockIdx.x * kTileThreads; qbase < n4; qbase += gridDim.x * kTileThreads) {
+        const uint32_t q = qbase + threadIdx.x;
+        uint32_t a[4], b[4], ab[4], ae[4], bb[4], be[4];
+        uint2 pa[4], pb[4];
+        bool live[4];
+        if (q < n4) {
+            unpack4(reinterpret_cast<const uint4*>(recs.a)[q], a);
+            unpack4(reinterpret_cast<const uint4*>(recs.b)[q], b);
+            unpack4(reinterpret_cast<const uint4*>(recs.ab)[q], ab);
+            unpack4(reinterpret_cast<const uint4*>(recs.ae)[q], ae);
+            unpack4(reinterpret_cast<const uint4*>(recs.bb)[q], bb);
+            unpack4(reinterpret_cast<const uint4*>(recs.be)[q], be);
+        }
+        // all eight pile gathers of the thread's records are in flight before the first one is used
 #pragma unroll
         for (int r = 0; r < kRecItems; ++r) {
-            const uint32_t idx = r * kTileThreads + tid;
+            const uint32_t idb = b[r] & 0x7FFFFFFFu;
+            live[r] = q < n4 && 4u * q + r < n && !(a[r] & kInvalidBit) && a[r] < n_piles && idb < n_piles;   // graph.cpp:450-451
+            if (live[r]) {
+                pa[r] = __ldg(piles + a[r]);
+                pb[r] = __ldg(piles + idb);
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < kRecItems; ++r) {
             bool is_ev = false;
             uint32_t evv = 0, evc = 0;
-            if (idx < cnt) {
-                RecFields f = read_record(st.rec[b] + idx * 7);
-                if (!(f.flags & 2u) && f.e.a < n_piles && f.e.b < n_piles) {                 // graph.cpp:450-451
-                    const Pile pa = load_pile(piles, f.e.a), pb = load_pile(piles, f.e.b);
-                    if (pa.alive() && pb.alive() && trim(f.e.c, f.e.ori, pa, pb)) {           // :451-452
-                        if ((pa.flags | pb.flags) & 1u) {                                    // :457-462, resolved by k_hill_coverage
-                            uint32_t slot = atomicAdd(&counters[C_HILL], 1u);
-                            if (slot < hill_cap) hill_rec[slot] = base + idx;
-                        }
-                        const uint8_t t = classify(f.e.c, relative(f.e.c, f.e.ori, pa, pb));
-                        if (t == kB && !(pb.flags & 2u)) {                                   // :469-474
-                            is_ev = true; evv = f.e.a; evc = f.e.b;
-                        } else if (t == kA && !(pa.flags & 2u)) {                            // :475-480
-                            is_ev = true; evv = f.e.b; evc = f.e.a;
-                        }
+            if (live[r]) {
+                Pile A, B;
+                A.begin = pa[r].x; A.end = pa[r].y & kEndMask; A.flags = pa[r].y >> 30;
+                B.begin = pb[r].x; B.end = pb[r].y & kEndMask; B.flags = pb[r].y >> 30;
+                const uint32_t idb = b[r] & 0x7FFFFFFFu, ori = b[r] >> 31;
+                Coords c{ab[r], ae[r], bb[r], be[r]};
+                if (A.alive() && B.alive() && trim(c, ori, A, B)) {                          // :451-452
+                    if ((A.flags | B.flags) & 1u) {                                          // :457-462, resolved by k_hill_coverage
+                        uint32_t slot = atomicAdd(&counters[C_HILL], 1u);
+                        if (slot < hill_cap) hill_rec[slot] = 4u * q + r;
+                    }
+                    const uint8_t t = classify(c, relative(c, ori, A, B));
+                    if (t == kB && !(B.flags & 2u)) {                                        // :469-474
+                        is_ev = true; evv = a[r]; evc = idb;
+                    } else if (t == kA && !(A.flags & 2u)) {                                 // :475-480
+                        is_ev = true; evv = idb; evc = a[r];
                     }
                 }
             }
@@ -135,141 +135,177 @@ __global__ void __launch_bounds__(kTileThreads) k_classify_events(
                     const uint32_t p = staged + __popc(m & ((1u << lane) - 1u));
                     s_ev[warp][0][p] = evv;
                     s_ev[warp][1][p] = evc;
-                    s_ev[warp][2][p] = t0 + base + idx;
+                    s_ev[warp][2][p] = t0 + 4u * q + r;
                 }
                 staged += __popc(m);
                 __syncwarp();
                 if (staged > kEvStage - 32) flush();
             }
         }
-        __syncthreads();   // everyone is done with buffer b before it is refilled
     }
     if (staged) flush();
 }
 
-// Survivors pass.  Tiles are independent: a tile appends its survivors (in record order) to scratch
-// lists at a base claimed with one atomic, and records (base, count) per tile; k_tile_offsets turns the
-// counts into file-order offsets and k_relocate moves each tile's run to its final place.  (A single-pass
-// look-back compaction was measured 2.5x slower here: a tile's aggregate is only known after its TMA load
-// and two dependent pile gathers, so the look-back chain serialised the waves.)
+// Survivors pass.  Every warp owns RUNS of 128 consecutive records (4 per lane): it writes the survivors of a
+// run, in record order, to the run's own slot range of the scratch lists (slot = record index of the run's
+// first record: the scratch lists are as long as the record set) and stores the run's two counts.  No atomics,
+// no block barriers, no dependence between runs.  k_scan_runs turns the counts into file-order offsets
+// (single-pass look-back scan) and k_relocate moves each run to its final place.
 __global__ void __launch_bounds__(kTileThreads) k_classify_survivors(
-    const uint32_t* __restrict__ rec, uint32_t n, const uint2* __restrict__ piles, uint32_t n_piles,
-    List tmp_ovl, List tmp_inl, uint32_t cap, TileRuns runs, uint32_t* __restrict__ tmp_counts) {
-    __shared__ RecStage st;
-    // scratch indexed by the iteration's parity: two barriers per tile suffice (see the end of the loop)
-    __shared__ uint32_t s_cnt_a2[2][kRecItems * kTileWarps], s_cnt_b2[2][kRecItems * kTileWarps];
-    __shared__ uint32_t s_base_a2[2], s_base_b2[2];
-    const uint32_t tid = threadIdx.x, lane = lane_id(), warp = warp_id();
-    const uint32_t num_tiles = (n + kRecTile - 1) / kRecTile;
-    if (tid == 0) {
-        mbar_init(&st.bar[0], 1);
-        mbar_init(&st.bar[1], 1);
-        fence_mbar_init();
-    }
-    __syncthreads();
-    uint32_t parity[2] = {0u, 0u};
-    uint32_t tile = blockIdx.x;
-    if (tid == 0 && tile < num_tiles) issue_tile(st, 0, rec, n, tile);
-    for (uint32_t it = 0; tile < num_tiles; ++it, tile += gridDim.x) {
-        const int b = it & 1;
-        uint32_t* s_cnt_a = s_cnt_a2[b];
-        uint32_t* s_cnt_b = s_cnt_b2[b];
-        uint32_t& s_base_a = s_base_a2[b];
-        uint32_t& s_base_b = s_base_b2[b];
-        if (tid == 0 && tile + gridDim.x < num_tiles) issue_tile(st, b ^ 1, rec, n, tile + gridDim.x);
-        mbar_wait(&st.bar[b], parity[b]);
-        parity[b] ^= 1u;
-        const uint32_t base = tile * kRecTile;
-        const uint32_t cnt = min((uint32_t) kRecTile, n - base);
+    List recs, uint32_t n, const uint2* __restrict__ piles, const uint32_t* __restrict__ alive_bits, uint32_t n_piles,
+    List tmp_ovl, List tmp_inl, uint32_t cap, uint32_t* __restrict__ run_cnt) {
+    const uint32_t lane = lane_id();
+    const uint32_t num_runs = (n + kRunRecords - 1) / kRunRecords;
+    const uint32_t warps = gridDim.x * kTileWarps;
+    for (uint32_t run = blockIdx.x * kTileWarps + warp_id(); run < num_runs; run += warps) {
+        const uint32_t q = run * 32u + lane;     // this lane's group of 4 records
+        uint32_t a[4] = {kInvalidBit, kInvalidBit, kInvalidBit, kInvalidBit}, b[4] = {0u, 0u, 0u, 0u};
+        if (4u * q < n) {
+            unpack4(reinterpret_cast<const uint4*>(recs.a)[q], a);
+            unpack4(reinterpret_cast<const uint4*>(recs.b)[q], b);
+        }
+        bool cand[kRecItems];
+#pragma unroll
+        for (int r = 0; r < kRecItems; ++r) {   // both piles alive at the end (graph.cpp:493-515)?  one L1-resident bit each
+            const uint32_t i = 4u * q + r, idb = b[r] & 0x7FFFFFFFu;
+            cand[r] = i < n && !(a[r] & kInvalidBit) && a[r] < n_piles && idb < n_piles &&
+                      ((__ldg(alive_bits + (a[r] >> 5)) >> (a[r] & 31u)) & 1u) && ((__ldg(alive_bits + (idb >> 5)) >> (idb & 31u)) & 1u);
+        }
         int dest[kRecItems];
         Entry e[kRecItems];
         uint8_t tag[kRecItems];
-        uint32_t lrank[kRecItems];
+        uint32_t packed = 0;   // survivors of this lane: `overlaps` in the low half, `internals` in the high half
 #pragma unroll
         for (int r = 0; r < kRecItems; ++r) {
-            const uint32_t idx = r * kTileThreads + tid;
             dest[r] = 0;
             tag[r] = kRejected;
-            if (idx < cnt) {
-                RecFields f = read_record(st.rec[b] + idx * 7);
-                if (!(f.flags & 2u) && f.e.a < n_piles && f.e.b < n_piles) {
-                    // the table already carries the kills: both piles alive at the end (graph.cpp:493-515)
-                    const Pile pa = load_pile(piles, f.e.a), pb = load_pile(piles, f.e.b);   // independent gathers
-                    if (pa.alive() && pb.alive() && trim(f.e.c, f.e.ori, pa, pb)) {
-                        tag[r] = classify(f.e.c, relative(f.e.c, f.e.ori, pa, pb));
-                        dest[r] = tag[r] == kX ? 2 : 1;   // a surviving kA/kB has a chimeric container (:470, :476)
-                        e[r] = f.e;
-                    }
+            if (cand[r]) {   // only now fetch the coordinates and the two piles
+                const uint32_t i = 4u * q + r;
+                e[r].a = a[r];
+                e[r].b = b[r] & 0x7FFFFFFFu;
+                e[r].ori = b[r] >> 31;
+                e[r].c.ab = recs.ab[i]; e[r].c.ae = recs.ae[i]; e[r].c.bb = recs.bb[i]; e[r].c.be = recs.be[i];
+                const Pile pa = load_pile(piles, e[r].a), pb = load_pile(piles, e[r].b);
+                if (trim(e[r].c, e[r].ori, pa, pb)) {
+                    tag[r] = classify(e[r].c, relative(e[r].c, e[r].ori, pa, pb));
+                    dest[r] = tag[r] == kX ? 2 : 1;   // a surviving kA/kB has a chimeric container (:470, :476)
+                    packed += dest[r] == 1 ? 1u : 0x10000u;
                 }
             }
-            const uint32_t ma = __ballot_sync(0xFFFFFFFFu, dest[r] == 1), mb = __ballot_sync(0xFFFFFFFFu, dest[r] == 2);
-            const uint32_t below = (1u << lane) - 1u;
-            lrank[r] = dest[r] == 1 ? __popc(ma & below) : __popc(mb & below);
-            if (lane == 0) {
-                s_cnt_a[r * kTileWarps + warp] = __popc(ma);
-                s_cnt_b[r * kTileWarps + warp] = __popc(mb);
-            }
         }
-        __syncthreads();   // counts visible; everyone is done reading buffer b
-        if (warp == 0) {
-            const uint32_t ca = lane < kRecItems * kTileWarps ? s_cnt_a[lane] : 0u, cb = lane < kRecItems * kTileWarps ? s_cnt_b[lane] : 0u;
-            const uint32_t ia = warp_inclusive_scan(ca), ib = warp_inclusive_scan(cb);
-            const uint32_t ta = __shfl_sync(0xFFFFFFFFu, ia, 31), tb = __shfl_sync(0xFFFFFFFFu, ib, 31);
-            if (lane < kRecItems * kTileWarps) {
-                s_cnt_a[lane] = ia - ca;
-                s_cnt_b[lane] = ib - cb;
-            }
-            if (lane == 0) {
-                const uint32_t ga = ta ? atomicAdd(&tmp_counts[0], ta) : 0u, gb = tb ? atomicAdd(&tmp_counts[1], tb) : 0u;
-                s_base_a = ga;
-                s_base_b = gb;
-                runs.base_a[tile] = ga;
-                runs.cnt_a[tile] = ta;
-                runs.base_b[tile] = gb;
-                runs.cnt_b[tile] = tb;
-            }
-        }
-        __syncthreads();
+        const uint32_t inc = warp_inclusive_scan(packed);
+        if (lane == 31) run_cnt[run] = inc;
+        if (packed) {
+            const uint32_t before = inc - packed;
+            uint32_t pa_ = run * kRunRecords + (before & 0xFFFFu), pb_ = run * kRunRecords + (before >> 16);
 #pragma unroll
-        for (int r = 0; r < kRecItems; ++r) {
-            if (dest[r] == 1) {
-                const uint32_t p = s_base_a + s_cnt_a[r * kTileWarps + warp] + lrank[r];
-                if (p < cap) store_entry(tmp_ovl, p, e[r], tag[r]);
-            } else if (dest[r] == 2) {
-                const uint32_t p = s_base_b + s_cnt_b[r * kTileWarps + warp] + lrank[r];
-                if (p < cap) store_entry(tmp_inl, p, e[r], tag[r]);
+            for (int r = 0; r < kRecItems; ++r) {
+                if (dest[r] == 1) {
+                    if (pa_ < cap) store_entry(tmp_ovl, pa_, e[r], tag[r]);
+                    ++pa_;
+                } else if (dest[r] == 2) {
+                    if (pb_ < cap) store_entry(tmp_inl, pb_, e[r], tag[r]);
+                    ++pb_;
+                }
             }
         }
-        // no trailing barrier: this parity's scratch is next written two iterations from now (two barriers away),
-        // and staging buffer b is refilled by the TMA thread 0 issues at the top of the next iteration, i.e. after
-        // it passed this iteration's second barrier, which every thread reaches only after reading buffer b
     }
 }
 
-// scratch run -> final position, one thread per output entry: the tile of entry j is found by binary
-// search in the scanned offsets (off[t] <= j < off[t+1]); writes are fully coalesced
-__global__ void k_relocate(List tmp, List out, uint32_t cap, const uint32_t* __restrict__ base, const uint32_t* __restrict__ off,
-                           uint32_t num_tiles) {
-    const uint32_t total = min(off[num_tiles], cap);
-    for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < total; j += gridDim.x * blockDim.x) {
-        uint32_t lo = 0, hi = num_tiles;   // largest t with off[t] <= j
+// per-run survivor counts (A | B << 16) -> file-order offsets of both lists; single pass, decoupled look-back
+__global__ void __launch_bounds__(kTileThreads) k_scan_runs(const uint32_t* __restrict__ run_cnt, uint32_t num_runs,
+                                                           uint32_t* __restrict__ off_a, uint32_t* __restrict__ off_b,
+                                                           uint32_t* __restrict__ n_a, uint32_t* __restrict__ n_b,
+                                                           unsigned long long* __restrict__ status, uint32_t* __restrict__ ticket) {
+    __shared__ unsigned long long s_warp[kTileWarps];
+    __shared__ unsigned long long s_base;
+    __shared__ uint32_t s_tile;
+    const uint32_t tid = threadIdx.x, lane = lane_id(), warp = warp_id();
+    const uint32_t num_tiles = (num_runs + kTile - 1) / kTile;
+    while (true) {
+        if (tid == 0) s_tile = atomicAdd(ticket, 1u);
+        __syncthreads();
+        const uint32_t tile = s_tile;
+        if (tile >= num_tiles) break;
+        const uint32_t i0 = tile * kTile + tid * 4;
+        unsigned long long v[4];
+        unsigned long long tsum = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const uint32_t c = i0 + k < num_runs ? run_cnt[i0 + k] : 0u;
+            v[k] = pack_counts(c & 0xFFFFu, c >> 16);
+            tsum += v[k];
+        }
+        unsigned long long inc = tsum;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const unsigned long long x = __shfl_up_sync(0xFFFFFFFFu, inc, d);
+            if ((int) lane >= d) inc += x;
+        }
+        if (lane == 31) s_warp[warp] = inc;
+        __syncthreads();
+        if (warp == 0) {
+            const unsigned long long w = lane < kTileWarps ? s_warp[lane] : 0ull;
+            unsigned long long winc = w;
+#pragma unroll
+            for (int d = 1; d < kTileWarps; d <<= 1) {
+                const unsigned long long x = __shfl_up_sync(0xFFFFFFFFu, winc, d);
+                if ((int) lane >= d) winc += x;
+            }
+            const unsigned long long total = __shfl_sync(0xFFFFFFFFu, winc, kTileWarps - 1);
+            const unsigned long long excl = lookback_exclusive(status, tile, total);
+            if (lane < kTileWarps) s_warp[lane] = winc - w;
+            if (lane == 0) s_base = excl;
+        }
+        __syncthreads();
+        unsigned long long runv = s_base + s_warp[warp] + inc - tsum;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (i0 + k < num_runs) {
+                off_a[i0 + k] = count_a(runv);
+                off_b[i0 + k] = count_b(runv);
+            }
+            runv += v[k];
+        }
+        if (tile == num_tiles - 1 && tid == kTileThreads - 1) {
+            *n_a = count_a(runv);
+            *n_b = count_b(runv);
+        }
+        __syncthreads();
+    }
+}
+
+// scratch run -> final position, one thread per OUTPUT entry (stores fully coalesced, gathers contiguous inside a
+// run).  The run of entry j satisfies off[run] <= j < off[run + 1]: lane 0 finds it by binary search, the other
+// lanes walk forward from there (32 consecutive entries span a handful of runs).
+__global__ void k_relocate(List tmp, List out, uint32_t cap, const uint32_t* __restrict__ off, const uint32_t* __restrict__ total_ptr,
+                           uint32_t num_runs) {
+    const uint32_t total = min(*total_ptr, cap);
+    for (uint32_t base = blockIdx.x * blockDim.x; base < total; base += gridDim.x * blockDim.x) {
+        const uint32_t j = base + threadIdx.x;
+        const uint32_t j0 = base + (threadIdx.x & ~31u);   // lane 0's entry
+        uint32_t lo = 0, hi = num_runs;                    // largest run with off[run] <= j0
         while (hi - lo > 1) {
             const uint32_t mid = (lo + hi) >> 1;
-            if (off[mid] <= j) lo = mid; else hi = mid;
+            if (__ldg(off + mid) <= j0) lo = mid; else hi = mid;
         }
-        const uint32_t src = base[lo] + (j - off[lo]);
-        if (src < cap) {
-            out.a[j] = tmp.a[src]; out.b[j] = tmp.b[src];
-            out.ab[j] = tmp.ab[src]; out.ae[j] = tmp.ae[src];
-            out.bb[j] = tmp.bb[src]; out.be[j] = tmp.be[src];
-            out.tag[j] = tmp.tag[src];
+        if (j < total) {
+            uint32_t run = lo;
+            while (run + 1 < num_runs && __ldg(off + run + 1) <= j) ++run;
+            const uint32_t s = run * kRunRecords + (j - __ldg(off + run));
+            if (s < cap) {
+                out.a[j] = tmp.a[s]; out.b[j] = tmp.b[s];
+                out.ab[j] = tmp.ab[s]; out.ae[j] = tmp.ae[s];
+                out.bb[j] = tmp.bb[s]; out.be[j] = tmp.be[s];
+                out.tag[j] = tmp.tag[s];
+            }
         }
     }
 }
 
 // K1c: Pile::check_chimeric_hills (pile.cpp:457-469) for every PROCESSED record that touches a pile
 // with hills.  Processed = passed the static gates and both piles were still alive at its time.
-__global__ void k_hill_coverage(const uint32_t* __restrict__ rec, uint32_t t0, const uint2* __restrict__ piles,
+__global__ void k_hill_coverage(List recs, uint32_t t0, const uint2* __restrict__ piles,
                                 const uint32_t* __restrict__ hill_rec, uint32_t hill_cap,
                                 const uint32_t* __restrict__ hill_pile, const uint32_t* __restrict__ hill_begin,
                                 const uint32_t* __restrict__ hill_end, uint32_t n_hills, uint32_t* __restrict__ hill_cov,
@@ -278,9 +314,7 @@ __global__ void k_hill_coverage(const uint32_t* __restrict__ rec, uint32_t t0, c
     const uint32_t* D = dbuf + (size_t) counters[C_DSEL] * n_piles;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const uint32_t idx = hill_rec[i];
-        const uint32_t* q = rec + (size_t) idx * 7;
-        Entry e;
-        e.a = q[0]; e.b = q[1]; e.c.ab = q[2]; e.c.ae = q[3]; e.c.bb = q[4]; e.c.be = q[5]; e.ori = q[6] & 1u;
+        Entry e = load_entry(recs, idx);   // the record passed the static gates: the invalid bit of column a is clear
         const uint32_t t = t0 + idx;
         if (D[e.a] < t || D[e.b] < t) continue;   // a pile was already dead: transmute() rejected it (overlap.cpp:51,70)
         const Pile pa = load_pile(piles, e.a), pb = load_pile(piles, e.b);
@@ -305,11 +339,19 @@ __global__ void k_hill_coverage(const uint32_t* __restrict__ rec, uint32_t t0, c
 }
 
 // Piles with a finite death time die (piles_[x].reset(), graph.cpp:471,477,838,842).
+// Also refreshes the one-bit-per-pile liveness bitmap the survivors pass tests first.
 __global__ void k_apply_deaths(uint2* __restrict__ piles, const uint32_t* __restrict__ dbuf, uint32_t n_piles,
-                               const uint32_t* __restrict__ counters) {
+                               const uint32_t* __restrict__ counters, uint32_t* __restrict__ alive_bits) {
     const uint32_t* D = dbuf + (size_t) counters[C_DSEL] * n_piles;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_piles; i += gridDim.x * blockDim.x) {
-        if (D[i] != kInf) piles[i] = make_uint2(0u, 0u);
+    for (uint32_t base = blockIdx.x * blockDim.x; base < n_piles; base += gridDim.x * blockDim.x) {
+        const uint32_t i = base + threadIdx.x;
+        bool alive = false;
+        if (i < n_piles) {
+            if (D[i] != kInf) piles[i] = make_uint2(0u, 0u);
+            else alive = (piles[i].y & kEndMask) != 0u;
+        }
+        const uint32_t m = __ballot_sync(0xFFFFFFFFu, alive);
+        if (lane_id() == 0 && i < n_piles) alive_bits[i >> 5] = m;
     }
 }
 
@@ -496,48 +538,59 @@ static inline int grid_for(uint64_t n, int per_block, int max_blocks) {
     return (int) (b < (uint64_t) max_blocks ? b : (uint64_t) max_blocks);
 }
 
-void launch_classify_events(Launch& L, const uint32_t* rec, uint32_t n, uint32_t t0, const uint2* piles, uint32_t n_piles,
-                            Events ev, uint32_t ev_cap, uint32_t* vcount, uint32_t* hill_rec, uint32_t hill_cap, uint32_t* counters) {
+void launch_records_to_soa(Launch& L, const uint32_t* aos, uint32_t n, List recs) {
     if (n == 0) return;
-    int grid = grid_for(n, kRecTile, kNumSMs * 6);
-    k_classify_events<<<grid, kTileThreads, 0, L.stream>>>(rec, n, t0, piles, n_piles, ev, ev_cap, vcount, hill_rec, hill_cap, counters);
+    k_records_to_soa<<<grid_for(n, 256, kNumSMs * 8), 256, 0, L.stream>>>(aos, n, recs);
     L.count++;
 }
 
-void launch_classify_survivors(Launch& L, const uint32_t* rec, uint32_t n, const uint2* piles, uint32_t n_piles, List tmp_ovl,
-                               List tmp_inl, List ovl, uint32_t* n_ovl, List inl, uint32_t* n_inl, uint32_t cap, TileRuns runs,
-                               uint32_t* tmp_counts, unsigned long long* status[2], uint32_t* ticket[2]) {
-    if (n == 0) return;   // n_ovl / n_inl were zeroed by the caller
-    const uint32_t num_tiles = (n + kRecTile - 1) / kRecTile;
-    // counts of the sentinel tile [num_tiles] must be zero so that the scans end with the totals
-    cudaMemsetAsync(runs.cnt_a + num_tiles, 0, 4, L.stream);
-    cudaMemsetAsync(runs.cnt_b + num_tiles, 0, 4, L.stream);
-    int grid = grid_for(n, kRecTile, kNumSMs * 6);
-    k_classify_survivors<<<grid, kTileThreads, 0, L.stream>>>(rec, n, piles, n_piles, tmp_ovl, tmp_inl, cap, runs, tmp_counts);
+void launch_classify_events(Launch& L, List recs, uint32_t n, uint32_t t0, const uint2* piles, uint32_t n_piles,
+                            Events ev, uint32_t ev_cap, uint32_t* vcount, uint32_t* hill_rec, uint32_t hill_cap, uint32_t* counters) {
+    if (n == 0) return;
+    static const int minb = getenv("RALA_B200_EV_MINB") ? atoi(getenv("RALA_B200_EV_MINB")) : 3;   // tuning knob (blocks / SM)
+    int grid = grid_for(n, kRecTile, kNumSMs * minb);
+    if (minb == 4)
+        k_classify_events<4><<<grid, kTileThreads, 0, L.stream>>>(recs, n, t0, piles, n_piles, ev, ev_cap, vcount, hill_rec, hill_cap, counters);
+    else if (minb == 5)
+        k_classify_events<5><<<grid, kTileThreads, 0, L.stream>>>(recs, n, t0, piles, n_piles, ev, ev_cap, vcount, hill_rec, hill_cap, counters);
+    else if (minb == 6)
+        k_classify_events<6><<<grid, kTileThreads, 0, L.stream>>>(recs, n, t0, piles, n_piles, ev, ev_cap, vcount, hill_rec, hill_cap, counters);
+    else
+        k_classify_events<3><<<grid, kTileThreads, 0, L.stream>>>(recs, n, t0, piles, n_piles, ev, ev_cap, vcount, hill_rec, hill_cap, counters);
     L.count++;
-    launch_scan_u32(L, runs.cnt_a, runs.off_a, num_tiles + 1, status[0], ticket[0]);
-    launch_scan_u32(L, runs.cnt_b, runs.off_b, num_tiles + 1, status[1], ticket[1]);
-    cudaMemcpyAsync(n_ovl, runs.off_a + num_tiles, 4, cudaMemcpyDeviceToDevice, L.stream);
-    cudaMemcpyAsync(n_inl, runs.off_b + num_tiles, 4, cudaMemcpyDeviceToDevice, L.stream);
-    k_relocate<<<grid_for(cap, 256, kNumSMs * 8), 256, 0, L.stream>>>(tmp_ovl, ovl, cap, runs.base_a, runs.off_a, num_tiles);
-    k_relocate<<<grid_for(cap, 256, kNumSMs * 8), 256, 0, L.stream>>>(tmp_inl, inl, cap, runs.base_b, runs.off_b, num_tiles);
+}
+
+void launch_classify_survivors(Launch& L, List recs, uint32_t n, const uint2* piles, const uint32_t* alive_bits, uint32_t n_piles,
+                               List tmp_ovl, List tmp_inl, List ovl, uint32_t* n_ovl, List inl, uint32_t* n_inl, uint32_t cap,
+                               RunBufs runs, unsigned long long* status, uint32_t* ticket) {
+    if (n == 0) return;   // n_ovl / n_inl were zeroed by the caller
+    const uint32_t num_runs = (n + kRunRecords - 1) / kRunRecords;
+    k_classify_survivors<<<grid_for(num_runs, kTileWarps, kNumSMs * 8), kTileThreads, 0, L.stream>>>(
+        recs, n, piles, alive_bits, n_piles, tmp_ovl, tmp_inl, cap, runs.cnt);
+    L.count++;
+    k_scan_runs<<<grid_for(num_runs, kTile, kNumSMs * 4), kTileThreads, 0, L.stream>>>(runs.cnt, num_runs, runs.off_a, runs.off_b, n_ovl,
+                                                                                       n_inl, status, ticket);
+    L.count++;
+    k_relocate<<<grid_for(cap, 256, kNumSMs * 8), 256, 0, L.stream>>>(tmp_ovl, ovl, cap, runs.off_a, n_ovl, num_runs);
+    k_relocate<<<grid_for(cap, 256, kNumSMs * 8), 256, 0, L.stream>>>(tmp_inl, inl, cap, runs.off_b, n_inl, num_runs);
     L.count += 2;
 }
 
-uint32_t classify_num_tiles(uint32_t n) { return (n + kRecTile - 1) / kRecTile; }
+uint32_t classify_num_runs(uint32_t n) { return (n + kRunRecords - 1) / kRunRecords; }
 
-void launch_hill_coverage(Launch& L, const uint32_t* rec, uint32_t t0, const uint2* piles, const uint32_t* hill_rec,
+void launch_hill_coverage(Launch& L, List recs, uint32_t t0, const uint2* piles, const uint32_t* hill_rec,
                           uint32_t hill_cap, const uint32_t* hill_pile, const uint32_t* hill_begin,
                           const uint32_t* hill_end, uint32_t n_hills, uint32_t* hill_cov, const uint32_t* dbuf,
                           uint32_t n_piles, const uint32_t* counters) {
-    k_hill_coverage<<<kNumSMs * 2, 256, 0, L.stream>>>(rec, t0, piles, hill_rec, hill_cap, hill_pile, hill_begin, hill_end,
+    k_hill_coverage<<<kNumSMs * 2, 256, 0, L.stream>>>(recs, t0, piles, hill_rec, hill_cap, hill_pile, hill_begin, hill_end,
                                                        n_hills, hill_cov, dbuf, n_piles, counters);
     L.count++;
 }
 
-void launch_apply_deaths(Launch& L, uint2* piles, const uint32_t* dbuf, uint32_t n_piles, const uint32_t* counters) {
+void launch_apply_deaths(Launch& L, uint2* piles, const uint32_t* dbuf, uint32_t n_piles, const uint32_t* counters,
+                         uint32_t* alive_bits) {
     if (n_piles == 0) return;
-    k_apply_deaths<<<grid_for(n_piles, 256, kNumSMs * 8), 256, 0, L.stream>>>(piles, dbuf, n_piles, counters);
+    k_apply_deaths<<<grid_for(n_piles, 256, kNumSMs * 8), 256, 0, L.stream>>>(piles, dbuf, n_piles, counters, alive_bits);
     L.count++;
 }
 

@@ -69,31 +69,56 @@ __device__ __forceinline__ Rel relative(const Coords& c, uint32_t ori, const Pil
 
 __device__ __forceinline__ uint32_t absdiff(uint32_t a, uint32_t b) { return a > b ? a - b : b - a; }
 
-// Overlap::type, overlap.cpp:194-259.  The three double products are single IEEE
-// multiplications (__dmul_rn: no contraction), compared exactly as the reference compares them.
+// ---------------------------------------------------------------------------------------------
+// The reference's floating point on this path is three IEEE double products compared with integers
+// (overlap.cpp:221-222, 236-237; graph.cpp:26-29).  u32 -> f64 conversions run on the XU pipe
+// (16 lanes / clk / SM) and made K1 and K3 XU-bound (profiles/r01a_pipes_stalls.txt), so each
+// comparison is evaluated in EXACT integer arithmetic instead.  Bit-identical for every u32 input
+// (proofs in DESIGN.md "Exact integer forms"; tests/test_exact_arith.py checks every boundary case
+// of the u32 range against IEEE doubles):
+//   (double)s <  (double)t * 0.875        <=>  8 s < 7 t            (0.875 = 7/8, product exact)
+//   (double)d <  (double)L * 0.01         <=>  100 d < L            (RN(L * 0.01) == L / 100 when 100 | L)
+//   (u32)(0.05 * (double)M)                ==  M / 20               (RN(M * 0.05) == M / 20 when 20 | M)
+//   a >= b * (1 - 0.12), a <= b * (1 + 0.12)  <=>  25 a >= 22 b,  25 a <= 28 b
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool lt_7_8(uint32_t s, uint32_t t) {   // (double)s < (double)t * 0.875
+    return (unsigned long long) s * 8ull < (unsigned long long) t * 7ull;
+}
+
+// Overlap::type, overlap.cpp:194-259.
 __device__ __forceinline__ uint8_t classify(const Coords& c, const Rel& r) {
     uint32_t overhang = min(r.a0, r.b0) + min(r.al - r.a1, r.bl - r.b1);                          // :218-219
     uint32_t sa = r.a1 - r.a0, sb = r.b1 - r.b0;
-    if ((double) sa < __dmul_rn((double) (uint32_t) (sa + overhang), 0.875) ||
-        (double) sb < __dmul_rn((double) (uint32_t) (sb + overhang), 0.875)) return kX;           // :221-224
+    if (lt_7_8(sa, sa + overhang) || lt_7_8(sb, sb + overhang)) return kX;                        // :221-224
     uint32_t ta = r.al - r.a1, tb = r.bl - r.b1;
     if (r.a0 <= r.b0 && ta <= tb) return kB;                                                      // :225-227
     if (r.a0 >= r.b0 && ta >= tb) return kA;                                                      // :228-230
     uint32_t span_a = c.ae - c.ab, span_b = c.be - c.bb;
     uint32_t length = max(span_a, span_b);                                                        // length_ (:189)
-    if ((double) absdiff(span_a, span_b) < __dmul_rn((double) length, 0.01)) {                    // :236
-        uint32_t min_ext = __double2uint_rz(__dmul_rn(0.05, (double) max(r.al, r.bl)));           // :237
+    if ((unsigned long long) absdiff(span_a, span_b) * 100ull < (unsigned long long) length) {    // :236
+        uint32_t min_ext = max(r.al, r.bl) / 20u;                                                 // :237
         if (absdiff(r.a0, r.b0) < min_ext) return ta >= tb ? kA : kB;                             // :239-245
         if (absdiff(ta, tb) < min_ext) return r.a0 >= r.b0 ? kA : kB;                             // :246-252
     }
     return r.a0 > r.b0 ? kAB : kBA;                                                               // :255-258
 }
 
-// comparable(a, b, 0.12), graph.cpp:26-29; a = (double)(u32)(len_ab + len_bc), b = (double)len_ac.
-__device__ __forceinline__ bool comparable(uint32_t a_, uint32_t b_) {
-    const double lo = 1 - 0.12, hi = 1 + 0.12;
-    double a = (double) a_, b = (double) b_;
-    return (a >= __dmul_rn(b, lo) && a <= __dmul_rn(b, hi)) || (b >= __dmul_rn(a, lo) && b <= __dmul_rn(a, hi));
+// comparable(a, b, 0.12), graph.cpp:26-29; a = (double)(u32)(len_ab + len_bc), b = (double)len_ac:
+//   (a >= 0.88 b && a <= 1.12 b) || (b >= 0.88 a && b <= 1.12 a)
+// In exact arithmetic the two clauses are the intervals [22b/25, 28b/25] and [25b/28, 25b/22] for a; they
+// overlap (25/28 < 28/25), so their union is the hull:  25 a >= 22 b  &&  22 a <= 25 b.
+__device__ __forceinline__ bool comparable(uint32_t a, uint32_t b) {
+    return (unsigned long long) a * 25ull >= (unsigned long long) b * 22ull &&
+           (unsigned long long) a * 22ull <= (unsigned long long) b * 25ull;
+}
+
+// The same test as an interval of a for a fixed b: comparable(a, b) <=> a - lo <= range (unsigned),
+// lo = ceil(22 b / 25), range = min(floor(25 b / 22), 2^32 - 1) - lo.
+__device__ __forceinline__ uint2 comparable_interval(uint32_t b) {
+    const unsigned long long lo = ((unsigned long long) b * 22ull + 24ull) / 25ull;
+    unsigned long long hi = (unsigned long long) b * 25ull / 22ull;
+    if (hi > 0xFFFFFFFFull) hi = 0xFFFFFFFFull;
+    return make_uint2((uint32_t) lo, (uint32_t) (hi - lo));   // lo <= b <= hi always
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -4,10 +4,10 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "lists.cuh"
+
 namespace rb {
 
-struct List;
-struct Events;
 
 // slots of the device-side counter block (uint32 each)
 enum Counter {
@@ -36,21 +36,23 @@ struct Launch {
 };
 
 // classify.cu
-void launch_classify_events(Launch& L, const uint32_t* rec, uint32_t n, uint32_t t0, const uint2* piles, uint32_t n_piles,
+void launch_records_to_soa(Launch& L, const uint32_t* aos, uint32_t n, List recs);
+void launch_classify_events(Launch& L, List recs, uint32_t n, uint32_t t0, const uint2* piles, uint32_t n_piles,
                             Events ev, uint32_t ev_cap, uint32_t* vcount, uint32_t* hill_rec, uint32_t hill_cap, uint32_t* counters);
-// per-tile survivor runs of the survivors pass: scratch base + count (scanned in place into file-order offsets)
-struct TileRuns {
-    uint32_t *base_a, *cnt_a, *off_a, *base_b, *cnt_b, *off_b;   // num_tiles + 1 each
+// runs of the survivors pass (128 records each): packed counts (overlaps | internals << 16) and the scanned offsets
+struct RunBufs {
+    uint32_t *cnt, *off_a, *off_b;   // num_runs each
 };
-void launch_classify_survivors(Launch& L, const uint32_t* rec, uint32_t n, const uint2* piles, uint32_t n_piles, List tmp_ovl,
-                               List tmp_inl, List ovl, uint32_t* n_ovl, List inl, uint32_t* n_inl, uint32_t cap, TileRuns runs,
-                               uint32_t* tmp_counts, unsigned long long* status[2], uint32_t* ticket[2]);
-uint32_t classify_num_tiles(uint32_t n);
-void launch_hill_coverage(Launch& L, const uint32_t* rec, uint32_t t0, const uint2* piles, const uint32_t* hill_rec,
+void launch_classify_survivors(Launch& L, List recs, uint32_t n, const uint2* piles, const uint32_t* alive_bits, uint32_t n_piles,
+                               List tmp_ovl, List tmp_inl, List ovl, uint32_t* n_ovl, List inl, uint32_t* n_inl, uint32_t cap,
+                               RunBufs runs, unsigned long long* status, uint32_t* ticket);
+uint32_t classify_num_runs(uint32_t n);
+void launch_hill_coverage(Launch& L, List recs, uint32_t t0, const uint2* piles, const uint32_t* hill_rec,
                           uint32_t hill_cap, const uint32_t* hill_pile, const uint32_t* hill_begin,
                           const uint32_t* hill_end, uint32_t n_hills, uint32_t* hill_cov, const uint32_t* dbuf,
                           uint32_t n_piles, const uint32_t* counters);
-void launch_apply_deaths(Launch& L, uint2* piles, const uint32_t* dbuf, uint32_t n_piles, const uint32_t* counters);
+void launch_apply_deaths(Launch& L, uint2* piles, const uint32_t* dbuf, uint32_t n_piles, const uint32_t* counters,
+                         uint32_t* alive_bits);
 void launch_list_pass(Launch& L, int mode, List in, const uint32_t* n_in, uint32_t in_cap, const uint2* piles, List out_a,
                       uint32_t* n_out_a, List out_b, uint32_t* n_out_b, const uint32_t* b_base, uint32_t cap,
                       const uint32_t* dbuf, uint32_t n_piles, const uint32_t* time_base, const uint32_t* counters,

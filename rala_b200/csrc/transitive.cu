@@ -9,14 +9,26 @@
 // parallel edges, graph.cpp:1291-1293).  The two-hop stream  { (b, j) : b in N+(a), j < deg(b) }  is
 // FLATTENED: lanes take consecutive flat indices, so several short rows N+(b) are in flight per
 // iteration and every load is an 8-byte (dst, len) element of a contiguous CSR row.
-//   light path : one warp per node      (deg <= 64 and <= 32768 two-hop visits)
+//   group path : 8 lanes per node, 4 nodes per warp   (2 <= deg <= 16 and <= 4096 two-hop visits: almost every
+//                node of an overlap graph, mean out-degree ~9; a full warp per such node leaves 3/4 of
+//                the lanes idle during set-up and pays the per-node overhead four times as often)
+//   light path : one warp per node      (16 < deg <= 64 and <= 32768 two-hop visits)
 //   heavy path : one block per (node, hash chunk of 1024 neighbours, stream chunk of 256 neighbours)
+// Measured alternatives that lost (profiles/README.md): one thread per edge with a linear or (rows sorted)
+// binary-search membership test, and the group path streaming one row N+(b) at a time: both expose the
+// latency of dependent L2 gathers; the flattened stream keeps 4 independent gathers in flight per lane.
 #include "kernels.h"
 #include "common.cuh"
 
 namespace rb {
 
 constexpr uint32_t kEmpty = 0xFFFFFFFFu;
+constexpr int kGroupLanes = 8;
+constexpr int kGroupsPerWarp = 32 / kGroupLanes;
+constexpr int kGroupMaxDeg = 16;
+constexpr int kGroupLog2Cap = 5;                    // 32 slots per group: load factor <= 0.5
+constexpr int kGroupCap = 1 << kGroupLog2Cap;
+constexpr uint32_t kGroupMaxVisits = 4096;
 constexpr int kLightMaxDeg = 64;
 constexpr int kLightCap = 128;
 constexpr uint32_t kLightMaxVisits = 32768;
@@ -80,6 +92,176 @@ __device__ __forceinline__ uint32_t table_find(const uint32_t* keys, uint32_t ma
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// group path: 8 lanes per node
+// ---------------------------------------------------------------------------------------------
+struct GroupSmem {
+    uint32_t keys[kGroupCap];
+    uint32_t eid[kGroupCap];    // highest edge id a->key (graph.cpp:1291-1293)
+    uint32_t lo[kGroupCap];     // comparable(sum, len of that edge)  <=>  sum - lo <= rng
+    uint32_t rng[kGroupCap];
+    uint32_t nrow[kGroupMaxDeg];
+    uint32_t nlen[kGroupMaxDeg];
+    uint32_t noff[kGroupMaxDeg + 1];
+    uint32_t hit;               // bit s: the candidate in slot s passed the test
+};
+
+__device__ __forceinline__ uint32_t group_inclusive_scan(uint32_t v, uint32_t gl) {
+#pragma unroll
+    for (int d = 1; d < kGroupLanes; d <<= 1) {
+        uint32_t t = __shfl_up_sync(0xFFFFFFFFu, v, d, kGroupLanes);
+        if ((int) gl >= d) v += t;
+    }
+    return v;
+}
+
+__global__ void __launch_bounds__(kLightWarps * 32, 6) k_transitive_group(
+    const uint32_t* __restrict__ row_ptr, const uint2* __restrict__ col, const uint32_t* __restrict__ col_eid,
+    uint8_t* __restrict__ T, uint32_t node_begin, uint32_t node_end, const uint32_t* __restrict__ node_range,
+    const uint32_t* __restrict__ n_nodes_ptr, uint32_t* __restrict__ work_counter, HeavyItems heavy,
+    uint32_t* __restrict__ counters) {
+    __shared__ GroupSmem smem[kLightWarps][kGroupsPerWarp];
+    const uint32_t lane = lane_id(), gl = lane & (kGroupLanes - 1), grp = lane / kGroupLanes;
+    GroupSmem& S = smem[warp_id()][grp];
+    if (node_range) {
+        node_begin = node_range[0];
+        node_end = node_range[1];
+    }
+    const uint32_t n_end = min(node_end, *n_nodes_ptr);
+    unsigned long long visits = 0;
+
+    while (true) {
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(work_counter, 32u);
+        base = node_begin + __shfl_sync(0xFFFFFFFFu, base, 0);
+        if (base >= n_end) break;
+        uint32_t r0 = 0, deg = 0;
+        if (base + lane < n_end) {
+            r0 = row_ptr[base + lane];
+            deg = row_ptr[base + lane + 1] - r0;
+        }
+#pragma unroll 1
+        for (uint32_t round = 0; round < 32 / kGroupsPerWarp; ++round) {
+            const uint32_t from = round * kGroupsPerWarp + grp;
+            const uint32_t a = base + from;
+            const uint32_t ra0 = __shfl_sync(0xFFFFFFFFu, r0, from);
+            const uint32_t d = __shfl_sync(0xFFFFFFFFu, deg, from);
+            bool act = d >= 2u && d <= (uint32_t) kGroupMaxDeg;   // < 2 neighbours: no two-hop witness can exist
+            if (!__any_sync(0xFFFFFFFFu, act)) continue;
+            if (act) {
+#pragma unroll
+                for (uint32_t s = gl; s < (uint32_t) kGroupCap; s += kGroupLanes) {
+                    S.keys[s] = kEmpty;
+                    S.eid[s] = 0u;
+                }
+                if (gl == 0) S.hit = 0u;
+            }
+            __syncwarp();
+            uint32_t dg[2] = {0u, 0u}, my_slot[2] = {kEmpty, kEmpty}, my_eid[2] = {0u, 0u}, my_len[2] = {0u, 0u};
+            if (act) {
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const uint32_t i = gl + h * kGroupLanes;
+                    if (i < d) {
+                        const uint2 e = col[ra0 + i];
+                        my_eid[h] = col_eid[ra0 + i];
+                        my_len[h] = e.y;
+                        uint32_t sl = hash_slot(e.x, kGroupLog2Cap);
+                        while (true) {
+                            const uint32_t prev = atomicCAS(&S.keys[sl], kEmpty, e.x);
+                            if (prev == kEmpty || prev == e.x) break;
+                            sl = (sl + 1u) & (kGroupCap - 1);
+                        }
+                        atomicMax(&S.eid[sl], my_eid[h]);
+                        my_slot[h] = sl;
+                        const uint32_t rs = row_ptr[e.x];
+                        dg[h] = row_ptr[e.x + 1] - rs;
+                        S.nrow[i] = rs;
+                        S.nlen[i] = e.y;
+                    }
+                }
+            }
+            const uint32_t inc0 = group_inclusive_scan(dg[0], gl), inc1 = group_inclusive_scan(dg[1], gl);
+            const uint32_t tot0 = __shfl_sync(0xFFFFFFFFu, inc0, kGroupLanes - 1, kGroupLanes);
+            const uint32_t W = tot0 + __shfl_sync(0xFFFFFFFFu, inc1, kGroupLanes - 1, kGroupLanes);
+            if (act) {
+                if (gl < d) S.noff[gl] = inc0 - dg[0];
+                if (gl + kGroupLanes < d) S.noff[gl + kGroupLanes] = tot0 + inc1 - dg[1];
+                if (gl == 0) S.noff[d] = W;
+            }
+            __syncwarp();
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {   // the winner of each slot publishes its acceptance interval
+                if (my_slot[h] != kEmpty && S.eid[my_slot[h]] == my_eid[h]) {
+                    const uint2 iv = comparable_interval(my_len[h]);
+                    S.lo[my_slot[h]] = iv.x;
+                    S.rng[my_slot[h]] = iv.y;
+                }
+            }
+            __syncwarp();
+            if (act && W > kGroupMaxVisits) {   // short row, very long rows behind it: give the node to a block
+                if (gl == 0) {
+                    const uint32_t hb = atomicAdd(&counters[C_HEAVY], 1u);
+                    if (hb < heavy.cap) {
+                        heavy.node[hb] = a;
+                        heavy.hash_chunk[hb] = 0;
+                        heavy.nbr_chunk[hb] = 0;
+                    } else {
+                        counters[C_OVERFLOW] = 1u;
+                    }
+                }
+                act = false;
+            }
+            if (act) {
+                if (gl == 0) visits += W;
+                uint32_t i = 0;
+                for (uint32_t f0 = 0; f0 < W; f0 += 4 * kGroupLanes) {
+                    uint2 e[4];
+                    uint32_t lab[4];
+                    bool ok[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const uint32_t f = f0 + u * kGroupLanes + gl;
+                        ok[u] = f < W;
+                        if (ok[u]) {
+                            while (f >= S.noff[i + 1]) ++i;
+                            e[u] = col[S.nrow[i] + (f - S.noff[i])];
+                            lab[u] = S.nlen[i];
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        if (ok[u]) {
+                            uint32_t s = hash_slot(e[u].x, kGroupLog2Cap);
+                            while (true) {
+                                const uint32_t k = S.keys[s];
+                                if (k == e[u].x) {
+                                    if (!((S.hit >> s) & 1u) && lab[u] + e[u].y - S.lo[s] <= S.rng[s]) atomicOr(&S.hit, 1u << s);   // graph.cpp:1301-1306
+                                    break;
+                                }
+                                if (k == kEmpty) break;
+                                s = (s + 1u) & (kGroupCap - 1);
+                            }
+                        }
+                    }
+                }
+            }
+            __syncwarp();
+            if (act) {
+                const uint32_t h = S.hit;
+#pragma unroll
+                for (uint32_t s = gl; s < (uint32_t) kGroupCap; s += kGroupLanes) {
+                    if ((h >> s) & 1u) T[S.eid[s]] = 1;
+                }
+            }
+            __syncwarp();
+        }
+    }
+    visits = warp_sum64(visits);
+    if (lane == 0 && visits) atomicAdd(reinterpret_cast<unsigned long long*>(counters + C_HOP_LO), visits);
+}
+
 struct LightSmem {
     unsigned long long vals[kLightCap];
     uint32_t keys[kLightCap];
@@ -115,7 +297,7 @@ __global__ void __launch_bounds__(kLightWarps * 32) k_transitive_light(
             r0 = row_ptr[node];
             deg = row_ptr[node + 1] - r0;
         }
-        uint32_t todo = __ballot_sync(0xFFFFFFFFu, deg >= 2u);   // < 2 neighbours: no two-hop witness can exist
+        uint32_t todo = __ballot_sync(0xFFFFFFFFu, deg > (uint32_t) kGroupMaxDeg);   // smaller nodes: k_transitive_group
         while (todo) {
             const uint32_t l = __ffs(todo) - 1;
             todo &= todo - 1;
@@ -369,6 +551,9 @@ void launch_transitive(Launch& L, GraphArrays g, uint32_t n_nodes_max, uint32_t 
     uint64_t blocks = (span + 32 * kLightWarps - 1) / (32 * kLightWarps);
     if (blocks < 1) blocks = 1;
     if (blocks > (uint64_t) kNumSMs * 8) blocks = kNumSMs * 8;
+    k_transitive_group<<<(int) blocks, kLightWarps * 32, 0, L.stream>>>(g.row_ptr, g.col, g.col_eid, g.T, node_begin, node_end,
+                                                                       node_range, counters + C_NODES, work_counter + 1, heavy, counters);
+    L.count++;
     k_transitive_light<<<(int) blocks, kLightWarps * 32, 0, L.stream>>>(g.row_ptr, g.col, g.col_eid, g.T, node_begin, node_end,
                                                                        node_range, counters + C_NODES, work_counter, heavy, counters);
     L.count++;
