@@ -1,0 +1,437 @@
+// host/graph_b200.cpp — the drop-in: rala's own CLI and front end with the hot path on the B200.
+//
+// Builds (host/Makefile) into host/_build/rala_b200 together with the UNMODIFIED reference sources
+// where they lie under /root/reference: nothing of the reference is copied into this repository.
+// Its graph.cpp and main.cpp are pulled in with #include; `#define private public` gives this
+// translation unit the access a member function of rala::Graph has (the state the two replaced
+// functions own is private, /root/reference/src/graph.hpp:118-177).
+//
+//   rala::Graph::construct               graph.cpp:427-640    ->  rala_b200::construct(graph, path)
+//   rala::Graph::remove_transitive_edges graph.cpp:1281-1335  ->  rala_b200::remove_transitive_edges(graph)
+//
+// What stays on the host, by the reference's own code: Graph::initialize (names, piles, duplicate
+// filter, pile analysis), bioparser, thread_pool, logger, every Pile method, Sequence trimming and
+// reverse complements, Graph::preprocess(overlaps, sensitive_path), remove_marked_objects, tips,
+// bubbles, layout, unitigs, contig extraction, and the CLI (src/main.cpp, included below unchanged).
+// What moves to the device: the classify loop with its order-dependent containment removal
+// (:443-518), the re-trim / promote / final containment passes of preprocess (:722-736, :801-877),
+// node ids and the edge list (:553-632), and the transitive marks (:1281-1318).
+//
+// In a fork of the reference the same code lives INSIDE the two member functions (INTEGRATION.md shows
+// that patch); here, because the reference tree is read-only, the two call sites of main.cpp are
+// redirected with two macros instead, and Graph::simplify's driver loop (:642-697) is re-stated around
+// the reference's own remove_tips / remove_bubbles / shrink / postprocess / remove_long_edges.
+#include <algorithm>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <deque>
+#include <future>
+#include <memory>
+#include <numeric>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#define private public
+#include "graph.cpp"   // -I$(REF)/src: the unmodified reference
+#undef private
+
+#include "rala_b200.hpp"
+
+namespace rala_b200 {
+
+namespace {
+
+using rala::Graph;
+using rala::Overlap;
+using rala::Pile;
+
+// rala::Graph has no room for a new member: sessions are keyed by the graph they belong to.
+struct Attached {
+    std::unique_ptr<Session> session;
+    uint64_t n_nodes = 0, n_edges = 0;
+};
+std::unordered_map<const Graph*, Attached>& attached() {
+    static std::unordered_map<const Graph*, Attached> a;
+    return a;
+}
+
+// pile table as the C ABI wants it (include/rala_b200.h): end == 0 <=> piles_[i] == nullptr
+void export_piles(const Graph& g, std::vector<rala_pile_t>& table, std::vector<uint8_t>& flags) {
+    table.resize(g.piles_.size());
+    flags.resize(g.piles_.size());
+    for (size_t i = 0; i < g.piles_.size(); ++i) {
+        const auto& p = g.piles_[i];
+        if (p == nullptr) {
+            table[i] = rala_pile_t{0u, 0u};
+            flags[i] = 0;
+        } else {
+            table[i] = rala_pile_t{p->begin(), p->end()};
+            flags[i] = (p->has_chimeric_hill() ? RALA_PILE_HAS_HILL : 0u) | (p->has_chimeric_region() ? RALA_PILE_HAS_REGION : 0u);
+        }
+    }
+}
+
+void upload_piles(const Graph& g, Session& s) {
+    std::vector<rala_pile_t> table;
+    std::vector<uint8_t> flags;
+    export_piles(g, table, flags);
+    s.set_piles(table, flags);
+}
+
+// piles the device killed (containment, graph.cpp:471, 477, 838, 842) die on the host too
+void apply_kills(Graph& g, Session& s) {
+    const auto table = s.piles();
+    for (size_t i = 0; i < g.piles_.size(); ++i) {
+        if (g.piles_[i] != nullptr && table[i].end == 0u) g.piles_[i].reset();
+    }
+}
+
+rala_ovl_t marshal(const Overlap& o, bool valid) {
+    rala_ovl_t r;
+    r.a_id = valid ? static_cast<uint32_t>(o.a_id_) : 0u;
+    r.b_id = valid ? static_cast<uint32_t>(o.b_id_) : 0u;
+    r.a_begin = o.a_begin_;
+    r.a_end = o.a_end_;
+    r.b_begin = o.b_begin_;
+    r.b_end = o.b_end_;
+    r.flags = (o.orientation_ & 1u) | (valid ? 0u : RALA_OVL_INVALID);
+    return r;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+// Graph::construct, graph.cpp:427-640
+// ------------------------------------------------------------------------------------------------
+void construct(Graph& g, const std::string& sensitive_overlaps_path) {
+    if (!g.piles_.empty()) {
+        fprintf(stderr, "[rala::Graph::construct] warning: object already constructed!\n");
+        return;
+    }
+
+    g.initialize();   // unchanged front end: name_to_id_, piles_, is_valid_overlap_ (graph.cpp:244-425)
+
+    (*g.logger_)();
+
+    if (g.piles_.size() >= (1ull << 31)) {
+        fprintf(stderr, "[rala::Graph::construct] error: too many sequences for 32-bit device ids!\n");
+        exit(1);
+    }
+
+    // second pass over the overlap file (:446-448): parse, name -> id, marshal 28 bytes per record, free the objects
+    std::vector<rala_ovl_t> records;
+    records.reserve(g.is_valid_overlap_.size());
+    {
+        std::vector<std::unique_ptr<Overlap>> chunk;
+        uint64_t num_overlaps = 0;
+        g.oparser_->reset();
+        while (true) {
+            auto status = g.oparser_->parse_objects(chunk, rala::kChunkSize);
+            for (uint64_t i = 0; i < chunk.size(); ++i) {
+                // :450-451; transmute() sees the piles as initialize() left them: its "pile is already dead" gate for
+                // piles killed LATER in the loop is what the device resolves
+                bool valid = g.is_valid_overlap_[num_overlaps + i] && chunk[i]->transmute(g.piles_, g.name_to_id_);
+                records.emplace_back(marshal(*chunk[i], valid));
+            }
+            num_overlaps += chunk.size();
+            chunk.clear();
+            if (!status) break;
+        }
+    }
+
+    auto& slot = attached()[&g];
+    slot.session.reset(new Session("rala::Graph::construct"));
+    Session& s = *slot.session;
+
+    std::vector<rala_hill_t> hills;
+    for (const auto& p : g.piles_) {
+        if (p == nullptr) continue;
+        for (const auto& h : p->chimeric_hills_) hills.push_back(rala_hill_t{static_cast<uint32_t>(p->id()), h.first, h.second});
+    }
+    upload_piles(g, s);
+    s.set_hills(hills);
+    s.set_overlaps(records);
+    std::vector<rala_ovl_t>().swap(records);
+
+    s.classify();   // :448-517 on the device: trim, type, hill counters, ordered containment, dead-pile filter
+
+    {   // Pile::check_chimeric_hills (pile.cpp:457-469) ran on the device: hand the counters back
+        const auto cov = s.hill_coverage();
+        size_t k = 0;
+        for (const auto& p : g.piles_) {
+            if (p == nullptr) continue;
+            for (size_t j = 0; j < p->chimeric_hills_.size(); ++j, ++k) p->chimeric_hill_coverage_[j] += cov[k];
+        }
+    }
+    apply_kills(g, s);
+
+    (*g.logger_)("[rala::Graph::construct] loaded overlaps");
+
+    // ---- Graph::preprocess(overlaps, internals), graph.cpp:699-880 ----------------------------------
+    (*g.logger_)();
+    {
+        std::vector<std::future<void>> thread_futures;
+        for (const auto& it : g.piles_) {   // :704-720, host (Pile)
+            if (it == nullptr) continue;
+            thread_futures.emplace_back(g.thread_pool_->submit_task(
+                [&](uint64_t i) -> void {
+                    if (g.piles_[i]->has_chimeric_hill() && g.piles_[i]->break_over_chimeric_hills() == false) {
+                        g.piles_[i].reset();
+                    }
+                }, it->id()));
+        }
+        for (const auto& it : thread_futures) it.wait();
+        thread_futures.clear();
+
+        upload_piles(g, s);
+        s.retrim();   // :722-736
+
+        while (true) {
+            // :740-783: connected components over `overlaps`; only the component's median matters, so any labelling does
+            const auto conn = s.connections();
+            std::vector<uint32_t> parent(g.piles_.size());
+            std::iota(parent.begin(), parent.end(), 0u);
+            auto find = [&](uint32_t x) {
+                while (parent[x] != x) {
+                    parent[x] = parent[parent[x]];
+                    x = parent[x];
+                }
+                return x;
+            };
+            std::vector<bool> touched(g.piles_.size(), false);
+            for (size_t i = 0; i + 1 < conn.size(); i += 2) {
+                uint32_t a = find(conn[i]), b = find(conn[i + 1]);
+                touched[conn[i]] = touched[conn[i + 1]] = true;
+                if (a != b) parent[std::max(a, b)] = std::min(a, b);
+            }
+            std::unordered_map<uint32_t, std::vector<uint32_t>> components;
+            for (uint32_t i = 0; i < g.piles_.size(); ++i) {
+                if (touched[i]) components[find(i)].emplace_back(i);
+            }
+            for (const auto& kv : components) {   // :774-797, host (Pile)
+                const auto& component = kv.second;
+                std::vector<uint16_t> medians;
+                for (const auto& it : component) medians.emplace_back(g.piles_[it]->median());
+                std::nth_element(medians.begin(), medians.begin() + medians.size() / 2, medians.end());
+                uint16_t component_median = medians[medians.size() / 2];
+                for (const auto& it : component) {
+                    thread_futures.emplace_back(g.thread_pool_->submit_task(
+                        [&](uint64_t i) -> void {
+                            if (g.piles_[i]->break_over_chimeric_pits(component_median) == false) g.piles_[i].reset();
+                        }, it));
+                }
+                for (const auto& it : thread_futures) it.wait();
+                thread_futures.clear();
+            }
+
+            upload_piles(g, s);
+            if (!s.retrim_promote()) break;   // :799-828
+        }
+
+        s.finalize();   // :831-877
+        apply_kills(g, s);
+    }
+    (*g.logger_)("[rala::Graph::preprocess]");
+
+    // ---- Graph::preprocess(overlaps, sensitive_overlaps_path), :523 / :882-1054: host, unchanged -------
+    if (!sensitive_overlaps_path.empty()) {
+        std::vector<std::unique_ptr<Overlap>> overlaps;
+        for (const auto& r : s.overlaps()) {
+            // numeric constructor (overlap.cpp:12-20): ids are 1-based there, orientation = a_rc != b_rc
+            overlaps.emplace_back(new Overlap(static_cast<uint64_t>(r.a_id) + 1, static_cast<uint64_t>(r.b_id) + 1, 0.0, 0,
+                0, r.a_begin, r.a_end, 0, r.flags & 1u, r.b_begin, r.b_end, 0));
+            overlaps.back()->is_transmuted_ = true;
+        }
+        g.preprocess(overlaps, sensitive_overlaps_path);
+        std::vector<rala_ovl_t> kept;
+        kept.reserve(overlaps.size());
+        for (const auto& it : overlaps) kept.emplace_back(marshal(*it, true));
+        s.replace_overlaps(kept);
+    }
+
+    (*g.logger_)();
+
+    // store reads (:527-547), host, unchanged
+    std::vector<std::unique_ptr<rala::Sequence>> sequences;
+    g.sparser_->reset();
+    while (true) {
+        uint64_t l = sequences.size();
+        auto status = g.sparser_->parse_objects(sequences, rala::kChunkSize);
+        for (uint64_t i = l; i < sequences.size(); ++i) {
+            if (g.piles_[i] == nullptr) {
+                sequences[i].reset();
+                continue;
+            }
+            sequences[i]->trim(g.piles_[i]->begin(), g.piles_[i]->end());
+        }
+        if (!status) break;
+    }
+
+    (*g.logger_)("[rala::Graph::construct] loaded sequences");
+    (*g.logger_)();
+
+    // ---- assembly graph: ids, lengths and adjacency from the device (:553-632) -------------------------
+    s.build();
+    const auto counts = s.counts();
+    const auto seq_to_node = s.seq_to_node();
+    const auto edges = s.edges();
+
+    uint64_t node_id = 0;
+    for (uint64_t i = 0; i < sequences.size(); ++i) {   // :555-574: strings stay host work
+        if (sequences[i] == nullptr) continue;
+        const auto& it = sequences[i];
+        if (seq_to_node[i] != node_id) {
+            fprintf(stderr, "[rala::Graph::construct] error: device node id %u != %lu for sequence %lu!\n", seq_to_node[i], node_id, i);
+            exit(1);
+        }
+        std::unique_ptr<Graph::Node> node(new Graph::Node(node_id++, i, it->name(), it->data()));
+        std::unique_ptr<Graph::Node> node_complement(new Graph::Node(node_id++, i, it->name(), it->reverse_complement()));
+        node->pair_ = node_complement.get();
+        node_complement->pair_ = node.get();
+        g.nodes_.emplace_back(std::move(node));
+        g.nodes_.emplace_back(std::move(node_complement));
+        sequences[i].reset();
+    }
+    if (g.nodes_.size() != counts.n_nodes) {
+        fprintf(stderr, "[rala::Graph::construct] error: %zu nodes on the host, %u on the device!\n", g.nodes_.size(), counts.n_nodes);
+        exit(1);
+    }
+
+    // Edge objects in edge-id order: 2j = (from -> to), 2j+1 = (to^1 -> from^1); the four adjacency pushes in the
+    // reference's order (:603-606 / :622-625) keep every suffix_edges_ / prefix_edges_ vector ascending in edge id
+    g.edges_.reserve(edges.size());
+    for (uint64_t j = 0; j + 1 < edges.size(); j += 2) {
+        Graph::Node* from = g.nodes_[edges[j].src].get();
+        Graph::Node* to = g.nodes_[edges[j].dst].get();
+        std::unique_ptr<Graph::Edge> edge(new Graph::Edge(j, from, to, edges[j].len));
+        std::unique_ptr<Graph::Edge> edge_complement(new Graph::Edge(j + 1, to->pair_, from->pair_, edges[j + 1].len));
+        edge->pair_ = edge_complement.get();
+        edge_complement->pair_ = edge.get();
+        from->suffix_edges_.emplace_back(edge.get());
+        from->pair_->prefix_edges_.emplace_back(edge_complement.get());
+        to->prefix_edges_.emplace_back(edge.get());
+        to->pair_->suffix_edges_.emplace_back(edge_complement.get());
+        g.edges_.emplace_back(std::move(edge));
+        g.edges_.emplace_back(std::move(edge_complement));
+    }
+    slot.n_nodes = g.nodes_.size();
+    slot.n_edges = g.edges_.size();
+
+    (*g.logger_)("[rala::Graph::construct] created assembly graph");
+
+    fprintf(stderr, "[rala::Graph::construct] number of nodes = %zu\n", g.nodes_.size());
+    fprintf(stderr, "[rala::Graph::construct] number of edges = %zu\n", g.edges_.size());
+}
+
+// ------------------------------------------------------------------------------------------------
+// Graph::remove_transitive_edges, graph.cpp:1281-1335
+// ------------------------------------------------------------------------------------------------
+uint32_t remove_transitive_edges(Graph& g) {
+    std::vector<uint8_t> marked;
+    uint64_t n_pairs = 0;
+
+    bool untouched = false;   // is the device-resident graph still the host's graph?
+    auto it = attached().find(&g);
+    if (it != attached().end() && it->second.session != nullptr && it->second.n_edges == g.edges_.size() &&
+        it->second.n_nodes == g.nodes_.size()) {
+        untouched = true;
+        for (const auto& e : g.edges_) {
+            if (e == nullptr || e->is_marked_) { untouched = false; break; }
+        }
+    }
+    if (untouched) {
+        Session& s = *it->second.session;
+        s.where("rala::Graph::remove_transitive_edges");
+        s.transitive();   // :1283-1318 on the CSR left by construct
+        marked = s.marked();
+        n_pairs = s.counts().n_transitive_pairs;
+    } else {
+        // the graph was edited since construct (or built elsewhere): marshal the live edges; pairs stay adjacent
+        std::vector<rala_edge_t> live;
+        std::vector<uint64_t> ids;
+        for (uint64_t j = 0; j + 1 < g.edges_.size(); j += 2) {
+            if (g.edges_[j] == nullptr || g.edges_[j + 1] == nullptr) continue;
+            for (uint64_t k = j; k < j + 2; ++k) {
+                const auto& e = g.edges_[k];
+                live.push_back(rala_edge_t{static_cast<uint32_t>(e->begin_node_->id_), static_cast<uint32_t>(e->end_node_->id_), e->length_});
+                ids.push_back(k);
+            }
+        }
+        Session s("rala::Graph::remove_transitive_edges");
+        std::vector<uint8_t> m;
+        n_pairs = s.transitive_reduce(static_cast<uint32_t>(g.nodes_.size()), live, m);
+        marked.assign(g.edges_.size(), 0);
+        for (size_t k = 0; k < ids.size(); ++k) marked[ids[k]] = m[k];
+    }
+    if (it != attached().end()) attached().erase(it);   // frees the device memory of the session
+
+    for (uint64_t i = 0; i < marked.size(); ++i) {   // :1305-1308
+        if (marked[i]) {
+            g.edges_[i]->is_marked_ = true;
+            g.marked_edges_.emplace(i);
+        }
+    }
+    for (uint64_t i = 1; i < marked.size(); i += 2) {   // :1320-1330 (the set is unordered there; the vector is sorted next)
+        if (!marked[i]) continue;
+        g.transitive_edges_.emplace_back((g.edges_[i]->begin_node_->id_ >> 1) << 1, (g.edges_[i]->end_node_->id_ >> 1) << 1);
+        g.transitive_edges_.emplace_back(g.transitive_edges_.back().second, g.transitive_edges_.back().first);
+    }
+    std::sort(g.transitive_edges_.begin(), g.transitive_edges_.end());
+
+    g.remove_marked_objects();   // :1332, host, unchanged (stable adjacency compaction)
+
+    return static_cast<uint32_t>(n_pairs);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Graph::simplify's driver, graph.cpp:642-697, around the reference's own members.  (In a fork this
+// function does not exist: Graph::simplify calls the patched member.)
+// ------------------------------------------------------------------------------------------------
+void simplify(Graph& g) {
+    (*g.logger_)();
+
+    uint32_t num_transitive_edges = remove_transitive_edges(g);
+    uint32_t num_tips = 0, num_bubbles = 0, num_long_edges = 0;
+
+    auto tips_and_bubbles = [&]() {
+        while (true) {
+            uint32_t num_changes = g.remove_tips();
+            num_tips += num_changes;
+            uint32_t num_changes_part = g.remove_bubbles();
+            num_bubbles += num_changes_part;
+            if (num_changes + num_changes_part == 0) break;   // :654 doubles num_changes first; zero stays zero
+        }
+    };
+
+    tips_and_bubbles();
+    g.shrink(42);
+    for (uint32_t i = 0; i < 5; ++i) {
+        g.postprocess();
+        num_long_edges += g.remove_long_edges();
+        num_tips += g.remove_tips();
+    }
+    tips_and_bubbles();
+
+    (*g.logger_)("[rala::Graph::simplify]");
+
+    fprintf(stderr, "[rala::Graph::simplify] number of transitive edges = %u\n", num_transitive_edges);
+    fprintf(stderr, "[rala::Graph::simplify] number of tips = %u\n", num_tips);
+    fprintf(stderr, "[rala::Graph::simplify] number of bubbles = %u\n", num_bubbles);
+    fprintf(stderr, "[rala::Graph::simplify] number of long edges = %u\n", num_long_edges);
+}
+
+}  // namespace rala_b200
+
+// ------------------------------------------------------------------------------------------------
+// The reference's CLI, unchanged: its two calls `graph->construct(path)` and `graph->simplify()`
+// (src/main.cpp:74, 86) are redirected; everything else in main.cpp compiles as it stands.
+// ------------------------------------------------------------------------------------------------
+#ifndef RALA_B200_NO_MAIN
+#define construct(path) piles_.size(), rala_b200::construct(*graph, path)
+#define simplify() piles_.size(), rala_b200::simplify(*graph)
+#include "main.cpp"
+#undef construct
+#undef simplify
+#endif

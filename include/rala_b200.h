@@ -157,6 +157,9 @@ int rala_b200_graph_get_piles(rala_b200_graph* g, rala_pile_t* piles_out /* n_pi
 int rala_b200_graph_get_connections(rala_b200_graph* g, uint32_t* ab_out /* 2 * n_overlaps */);
 int rala_b200_graph_get_lists(rala_b200_graph* g, rala_ovl_t* overlaps_out /* nullable */,
                               rala_ovl_t* internals_out /* nullable */);
+/* Replaces the device `overlaps` list after finalize by a host-filtered copy of it, same order: what
+ * Graph::preprocess(overlaps, sensitive_overlaps_path) (graph.cpp:523, 882-1054, the -s option) leaves. */
+int rala_b200_graph_set_kept_overlaps(rala_b200_graph* g, const rala_ovl_t* kept, uint64_t n);
 int rala_b200_graph_get_seq_to_node(rala_b200_graph* g, uint32_t* out /* n_piles; 0xFFFFFFFF = dead */);
 int rala_b200_graph_get_edges(rala_b200_graph* g, rala_edge_t* out /* n_edges */);
 int rala_b200_graph_get_marked(rala_b200_graph* g, uint8_t* out /* n_edges */);

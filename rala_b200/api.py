@@ -48,7 +48,7 @@ EXPORTS = [
     "rala_b200_graph_build", "rala_b200_graph_transitive", "rala_b200_graph_run", "rala_b200_graph_counts",
     "rala_b200_graph_get_hill_coverage", "rala_b200_graph_get_piles", "rala_b200_graph_get_connections",
     "rala_b200_graph_get_lists", "rala_b200_graph_get_seq_to_node", "rala_b200_graph_get_edges",
-    "rala_b200_graph_get_marked", "rala_b200_graph_stage_ms",
+    "rala_b200_graph_get_marked", "rala_b200_graph_stage_ms", "rala_b200_graph_set_kept_overlaps",
     # multi-GPU phases
     "rala_b200_create_on_stream", "rala_b200_graph_set_shard", "rala_b200_graph_phase_events",
     "rala_b200_graph_events_count", "rala_b200_graph_export_events", "rala_b200_graph_import_events",
@@ -273,6 +273,12 @@ class Graph:
         inl = np.zeros((c["n_internals"], 7), dtype=np.uint32)
         self._call("rala_b200_graph_get_lists", _ptr(ovl), _ptr(inl))
         return ovl, inl
+
+    def set_kept_overlaps(self, kept):
+        """graph.cpp:523: replace `overlaps` by the host-filtered list (the -s repeat filter only drops entries)"""
+        k = _np(kept, np.uint32, 7)
+        self._call("rala_b200_graph_set_kept_overlaps", _ptr(k), C.c_uint64(k.shape[0]))
+        return self
 
     def seq_to_node(self):
         out = np.zeros(self.n_piles, dtype=np.uint32)

@@ -830,6 +830,27 @@ extern "C" int rala_b200_graph_get_lists(rala_b200_graph* g, rala_ovl_t* overlap
     return RALA_B200_OK;
 }
 
+// graph.cpp:523 / 882-1054: the host filtered `overlaps` (Graph::preprocess(overlaps, sensitive_path) only ever drops
+// entries); the device list is replaced by what is left, in the same order.
+extern "C" int rala_b200_graph_set_kept_overlaps(rala_b200_graph* g, const rala_ovl_t* kept, uint64_t n) {
+    if (!g || (n && !kept)) return RALA_B200_ERR_ARG;
+    rala_b200_ctx* ctx = g->ctx;
+    if (g->state != 3) return fail(ctx, RALA_B200_ERR_STATE, "set_kept_overlaps: finalize first");
+    if (n > g->cap) return fail(ctx, RALA_B200_ERR_LIMIT, "set_kept_overlaps: %llu entries exceed the list capacity %u", (unsigned long long) n, g->cap);
+    CU(ctx, cudaSetDevice(ctx->device));
+    int rc = materialize_final_lists(g);   // `internals` keeps its final form
+    if (rc) return rc;
+    DevBuf tmp;
+    CU(ctx, tmp.reserve((size_t) n * 28 + 16));
+    if (n) CU(ctx, cudaMemcpyAsync(tmp.p, kept, (size_t) n * 28, cudaMemcpyHostToDevice, ctx->L.stream));
+    launch_aos_to_list(ctx->L, tmp.as<uint32_t>(), (uint32_t) n, g->ovl[g->ovl_cur].view);
+    const uint32_t n32 = (uint32_t) n;
+    CU(ctx, cudaMemcpyAsync(g->cnt() + g->slot_ovl, &n32, 4, cudaMemcpyHostToDevice, ctx->L.stream));
+    CU(ctx, cudaStreamSynchronize(ctx->L.stream));
+    tmp.release();
+    return RALA_B200_OK;
+}
+
 extern "C" int rala_b200_graph_get_seq_to_node(rala_b200_graph* g, uint32_t* out) {
     if (!g || !out) return RALA_B200_ERR_ARG;
     rala_b200_ctx* ctx = g->ctx;

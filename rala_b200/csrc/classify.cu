@@ -521,6 +521,16 @@ __global__ void k_list_to_aos(List l, const uint32_t* __restrict__ n_ptr, uint32
     }
 }
 
+// rala_ovl_t rows -> SoA list (upload of a host-filtered `overlaps`, C ABI rala_b200_graph_set_kept_overlaps)
+__global__ void k_aos_to_list(const uint32_t* __restrict__ aos, uint32_t n, List l) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint32_t* q = aos + (size_t) i * 7;
+        Entry e;
+        e.a = q[0]; e.b = q[1] & 0x7FFFFFFFu; e.c.ab = q[2]; e.c.ae = q[3]; e.c.bb = q[4]; e.c.be = q[5]; e.ori = q[6] & 1u;
+        store_entry(l, i, e, kRejected);   // the type is recomputed by whoever needs it (edge creation, graph.cpp:594)
+    }
+}
+
 __global__ void k_list_connections(List l, const uint32_t* __restrict__ n_ptr, uint32_t cap, uint32_t* __restrict__ out) {
     const uint32_t n = min(*n_ptr, cap);
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
@@ -645,6 +655,12 @@ void launch_unpack_piles(Launch& L, const uint2* in, uint2* out, uint32_t n) {
 
 void launch_list_to_aos(Launch& L, List l, const uint32_t* n_ptr, uint32_t cap, uint32_t* out) {
     k_list_to_aos<<<grid_for(cap, 256, kNumSMs * 8), 256, 0, L.stream>>>(l, n_ptr, cap, out);
+    L.count++;
+}
+
+void launch_aos_to_list(Launch& L, const uint32_t* aos, uint32_t n, List l) {
+    if (n == 0) return;
+    k_aos_to_list<<<grid_for(n, 256, kNumSMs * 8), 256, 0, L.stream>>>(aos, n, l);
     L.count++;
 }
 

@@ -64,6 +64,7 @@ void launch_fill_u32(Launch& L, uint32_t* p, uint32_t v, size_t n);
 void launch_pack_piles(Launch& L, const uint2* in, const uint8_t* flags, uint2* out, uint32_t n);
 void launch_unpack_piles(Launch& L, const uint2* in, uint2* out, uint32_t n);
 void launch_list_to_aos(Launch& L, List l, const uint32_t* n_ptr, uint32_t cap, uint32_t* out);
+void launch_aos_to_list(Launch& L, const uint32_t* aos, uint32_t n, List l);
 void launch_list_connections(Launch& L, List l, const uint32_t* n_ptr, uint32_t cap, uint32_t* out);
 
 // containment.cu

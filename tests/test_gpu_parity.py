@@ -162,6 +162,36 @@ def test_run_frozen_piles_vs_oracle(ctx, kw):
     G.close()
 
 
+def test_host_filtered_overlaps_before_build(ctx):
+    """The -s option (Graph::preprocess(overlaps, path), graph.cpp:523, 882-1054) stays host code that only DROPS
+    entries of `overlaps`; the kept list goes back to the device (rala_b200_graph_set_kept_overlaps) and edge creation
+    plus the transitive pass run on it.  (The reference CLI itself crashes with -s outside its two-pass workflow, so this
+    is checked at the boundary: drop a random subset, compare with the oracle's edge creation on the same subset.)"""
+    ds = synth.generate(1_500_000, 30, 10000, len_sd=2000, seed=61, noise=40)
+    piles = ds.flat_piles()
+    P = O.Pipeline(ds.records, piles)
+    P.classify().retrim()
+    while P.retrim_promote():
+        pass
+    P.final_containment()
+    G = api.Graph(ctx)
+    G.set_piles(piles).set_hills(None).set_overlaps(ds.records)
+    G.classify().retrim()
+    G.retrim_promote()
+    G.finalize()
+    ovl, _ = G.lists()
+    assert_same(ovl, P.ovl, "final overlaps")
+    keep = np.random.Generator(np.random.PCG64(61)).random(ovl.shape[0]) < 0.8
+    P.ovl = np.ascontiguousarray(P.ovl[keep])
+    P.build_edges().transitive()
+    G.set_kept_overlaps(ovl[keep]).build().transitive()
+    assert_same(G.lists()[0], P.ovl, "kept overlaps")
+    assert_same(G.edges(), P.edges, "edges of the kept overlaps")
+    assert_same(G.marked(), P.marked, "marks of the kept overlaps")
+    assert G.counts()["n_transitive_pairs"] == P.n_pairs > 0
+    G.close()
+
+
 def test_empty_and_ragged_inputs(ctx):
     G = api.Graph(ctx)
     piles = np.array([[15, 9985], [15, 9985], [0, 0]], np.uint32)
