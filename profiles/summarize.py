@@ -55,7 +55,7 @@ def launches(tag: str):
         f.write(f"{'kernel':40s} {'launches':>8s} {'mean_us':>10s} {'share_%':>8s}\n")
         for k, v in sorted(agg.items(), key=lambda kv: -sum(kv[1])):
             f.write(f"{k[:40]:40s} {len(v):8d} {sum(v) / len(v) / 1e3:10.1f} {100 * sum(v) / tot:8.1f}\n")
-    first = [i for i, x in enumerate(rows) if x["Kernel Name"].startswith("k_classify_events")]
+    first = [i for i, x in enumerate(rows) if "k_classify_events" in x["Kernel Name"]]
     if len(first) >= 6:
         s, e = first[4], first[5]
         with open(os.path.join(DST, f"{tag}_step_sequence.txt"), "w") as f:
