@@ -50,26 +50,59 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons sampled DURING the timed region."""
+    """SM clocks + throttle reasons sampled DURING the timed region: NVML every 5 ms (nvidia_ml_py), else one
+    nvidia-smi query every 100 ms."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, index: int):
         self.index, self.samples, self.stop_flag, self.th = index, [], threading.Event(), None
+        self.nvml, self.handle, self.max_mhz = None, None, None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(visible.split(",")[index]) if visible and visible.split(",")[index].isdigit() else index
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
 
-    def _run(self):
+    def _run_nvml(self):
+        n = self.nvml
+        bits = [getattr(n, "nvmlClocksEventReasonHwSlowdown", getattr(n, "nvmlClocksThrottleReasonHwSlowdown", 0x8)),
+                getattr(n, "nvmlClocksEventReasonHwThermalSlowdown", getattr(n, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40)),
+                getattr(n, "nvmlClocksEventReasonSwThermalSlowdown", getattr(n, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20)),
+                getattr(n, "nvmlClocksEventReasonSwPowerCap", getattr(n, "nvmlClocksThrottleReasonSwPowerCap", 0x4))]
+        while not self.stop_flag.is_set():
+            try:
+                mhz = float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM))
+                try:
+                    r = n.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
+                except Exception:
+                    r = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+                watts = n.nvmlDeviceGetPowerUsage(self.handle) / 1e3
+                self.samples.append([mhz, self.max_mhz, watts] + [bool(r & b) for b in bits])
+            except Exception:
+                pass
+            self.stop_flag.wait(0.005)
+
+    def _run_smi(self):
         while not self.stop_flag.is_set():
             try:
                 out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
                                      capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.samples.append([x.strip() for x in out.split(",")])
+                f = [x.strip() for x in out.split(",")]
+                if len(f) >= 7:
+                    self.samples.append([float(f[0]), float(f[1]), float(f[2])] + [x.lower().startswith("active") for x in f[3:7]])
             except Exception:
                 pass
             self.stop_flag.wait(0.1)
 
     def start(self):
-        self.th = threading.Thread(target=self._run, daemon=True)
+        self.th = threading.Thread(target=self._run_nvml if self.nvml else self._run_smi, daemon=True)
         self.th.start()
 
     def stop(self) -> dict:
@@ -78,11 +111,23 @@ class ClockSampler:
             self.th.join(timeout=6)
         if not self.samples:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"], "samples": 0}
-        sm = sorted(float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit())
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(s[3 + i].lower().startswith("active") for s in self.samples)]
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(self.samples[0][1]),
-                "power_w_max": max(float(s[2]) for s in self.samples), "reasons": reasons, "samples": len(self.samples)}
+        sm = sorted(s[0] for s in self.samples)
+        reasons = [n for i, n in enumerate(self.NAMES) if any(s[3 + i] for s in self.samples)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self.samples[0][1], "power_w_max": max(s[2] for s in self.samples),
+                "reasons": reasons, "samples": len(self.samples), "source": "nvml" if self.nvml else "nvidia-smi"}
+
+
+def ncu_traffic(kernels):
+    """dram__bytes_read + write per launch of the named kernels, from the committed `ncu --set full` summary
+    (profiles/traffic.json, written by profiles/summarize.py); None when no capture has them."""
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    if not os.path.exists(path):
+        return None, None
+    with open(path) as f:
+        t = json.load(f)
+    if not all(k in t["kernels"] for k in kernels):
+        return None, t.get("tag")
+    return sum(t["kernels"][k]["dram_bytes"] for k in kernels), t.get("tag")
 
 
 def make_dataset(workload: str, n_gpus: int, seed: int = 3):
@@ -91,15 +136,25 @@ def make_dataset(workload: str, n_gpus: int, seed: int = 3):
     return synth.generate(genome * n_gpus, cov, rl, seed=seed)
 
 
-def cpu_reference_run(ds, piles, repeat: int = 1) -> dict:
-    """The reference's own CPU path on in-memory inputs (oracle/_ref), else the plain-C oracle port."""
+def cpu_reference_prepare(ds, piles, tmpdir: str):
+    """Write the batch once in the form oracle/_ref/rala_ref reads (binary records + pile table)."""
+    from oracle import oracle as O
+    if not O.have_ref():
+        return None
+    prefix = os.path.join(tmpdir, "w")
+    O.write_hotpath_inputs(prefix, ds.records, piles, None, None, ds.read_len)
+    return prefix
+
+
+def cpu_reference_run(ds, piles, prefix=None) -> dict:
+    """One pass of the reference's own CPU path on in-memory inputs (oracle/_ref), else the plain-C oracle port."""
     from oracle import oracle as O
     cores_used = 1   # the reference runs this path on its main thread whatever -t is (SURVEY.md finding 1)
     if O.have_ref():
         with tempfile.TemporaryDirectory() as tmp:
-            prefix = os.path.join(tmp, "w")
-            O.write_hotpath_inputs(prefix, ds.records, piles, None, None, ds.read_len)
-            r = json.loads(O.ref_run(["hotpath", prefix, "-", repeat]).strip().splitlines()[-1])
+            if prefix is None:
+                prefix = cpu_reference_prepare(ds, piles, tmp)
+            r = json.loads(O.ref_run(["hotpath", prefix, "-", 1]).strip().splitlines()[-1])
         t = r["t_classify"] + r["t_preprocess"] + r["t_nodes"] + r["t_edges"] + r["t_transitive"]
         return {"kind": "reference", "edges": r["edges"], "seconds": t, "cores": cores_used, "phases": r}
     t0 = time.perf_counter()
@@ -108,26 +163,45 @@ def cpu_reference_run(ds, piles, repeat: int = 1) -> dict:
     return {"kind": "port", "edges": int(P.edges.shape[0]), "seconds": t, "cores": cores_used, "phases": {}}
 
 
+REFERENCE_ARM_BUDGET_S = 150.0   # wall-clock budget of one `--impl reference` run
+
+
 def run_reference_arm(args):
+    """The reference's own CPU implementation of the path, timed on this box's host cores.  Each step is one pass
+    over a BOUNDED sample of the workload: a genome of the same coverage and read length, sized from a probe run
+    so that warmup + steps passes fit REFERENCE_ARM_BUDGET_S (the whole batch when that fits)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    ds = make_dataset(args.workload, 1)
-    piles = ds.flat_piles()
-    times, edges, kind = [], 0, "port"
-    for i in range(args.warmup + args.steps):
-        r = cpu_reference_run(ds, piles)
-        edges, kind = r["edges"], r["kind"]
-        if i >= args.warmup:
-            times.append(r["seconds"])
+    from rala_b200 import synth
+    genome, cov, rl, desc = WORKLOADS[args.workload]
+    passes = max(args.steps + args.warmup, 1)
+    with tempfile.TemporaryDirectory() as tmp:
+        probe_g = min(genome, 5_000_000)
+        probe = synth.generate(probe_g, cov, rl, seed=3)
+        ppre = cpu_reference_prepare(probe, probe.flat_piles(), tmp)
+        t0 = time.perf_counter()
+        cpu_reference_run(probe, probe.flat_piles(), ppre)
+        wall_per_bp = (time.perf_counter() - t0) / probe_g
+        sample_g = int(min(genome, max(probe_g, REFERENCE_ARM_BUDGET_S / passes / wall_per_bp)))
+        ds = probe if sample_g == probe_g else synth.generate(sample_g, cov, rl, seed=3)
+        piles = ds.flat_piles()
+        prefix = ppre if ds is probe else cpu_reference_prepare(ds, piles, tmp)
+        times, edges, kind = [], 0, "port"
+        for i in range(args.warmup + args.steps):
+            r = cpu_reference_run(ds, piles, prefix)
+            edges, kind = r["edges"], r["kind"]
+            if i >= args.warmup:
+                times.append(r["seconds"])
     t = sum(times) / len(times)
     value = edges / t
-    sample = f"full {args.workload} batch: {ds.n_overlaps} overlap records, {ds.n_reads} reads, {edges} edges"
+    sample = (f"{'full batch' if sample_g == genome else 'bounded sample'}: {sample_g / 1e6:.1f} Mbp genome of the same coverage / read length "
+              f"({ds.n_overlaps} overlap records, {ds.n_reads} reads, {edges} edges) per step; workload genome {genome / 1e6:.0f} Mbp")
     print(json.dumps({
         "impl": "reference", "metric": "graph_edges_per_sec", "value": value, "unit": "edges/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u32+f64", "data": "synthetic",
-        "config": {"workload": WORKLOADS[args.workload][3], "n_overlaps": ds.n_overlaps, "n_reads": ds.n_reads, "edges": edges},
+        "config": {"workload": desc, "n_overlaps": ds.n_overlaps, "n_reads": ds.n_reads, "edges": edges},
         "cpu_baseline": {"value": value, "unit": "edges/s", "cores": 1, "kind": kind, "sample": sample,
                          "host_cores_available": os.cpu_count(),
                          "note": "the reference runs this path single-threaded regardless of -t (graph.cpp:443-518, 576-632, 1281-1335)"},
@@ -190,9 +264,18 @@ def run_single(args):
     k3_bytes = K3_BYTES_PER_VISIT * counts["n_two_hop"] + 9 * E + 8 * counts["n_nodes"]
     k1_gbs = k1_bytes / (k1_ms * 1e-3) / 1e9
     k3_gbs = k3_bytes / (k3_ms * 1e-3) / 1e9 if k3_ms > 0 else 0.0
-    dominant = "k_classify_first" if k1_ms >= k3_ms else "k_transitive_light+heavy"
+    dominant = "k_classify_first" if k1_ms >= k3_ms else "k_transitive"
+    traffic, traffic_tag = ncu_traffic(["k_classify_events", "k_classify_survivors"] if k1_ms >= k3_ms
+                                       else ["k_transitive_group", "k_transitive_light", "k_transitive_heavy"])
+    step_bytes = k1_bytes + k3_bytes + 20 * counts["n_candidates"] + 4 * n_reads + 25 * counts["n_overlaps"] + 48 * E
     roof = {"bound": "hbm", "kernel": dominant, "achieved": k1_gbs if k1_ms >= k3_ms else k3_gbs, "peak": peak,
-            "unit": "GB/s", "frac": (k1_gbs if k1_ms >= k3_ms else k3_gbs) / peak, "traffic": None, "peak_source": peak_src,
+            "unit": "GB/s", "frac": (k1_gbs if k1_ms >= k3_ms else k3_gbs) / peak, "traffic": traffic,
+            "traffic_source": f"profiles/{traffic_tag}_kernels.csv (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch)" if traffic else None,
+            "peak_source": peak_src,
+            "kernel_members": ["k_classify_events", "k_classify_survivors (+ k_scan_runs, k_relocate)"] if k1_ms >= k3_ms
+                              else ["k_transitive_group", "k_transitive_light", "k_transitive_heavy"],
+            "whole_step": {"algorithmic_bytes": int(step_bytes), "gbs": step_bytes / (ms_per_step * 1e-3) / 1e9,
+                           "frac": step_bytes / (ms_per_step * 1e-3) / 1e9 / peak},
             "kernels": {"k_classify_first": {"ms": k1_ms, "algorithmic_bytes": k1_bytes, "gbs": k1_gbs, "frac": k1_gbs / peak},
                         "k_transitive": {"ms": k3_ms, "algorithmic_bytes": k3_bytes, "gbs": k3_gbs, "frac": k3_gbs / peak}},
             "stage_ms": {k: float(np.mean(v)) for k, v in stage_acc.items()}}
@@ -230,7 +313,7 @@ def run_single(args):
     line = {
         "metric": "graph_edges_per_sec", "value": value, "unit": "edges/s", "n_gpus": 1, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "u32+f64", "data": "synthetic",
+        "vs_baseline": None, "dtype": "u32", "data": "synthetic",
         "config": {"workload": WORKLOADS[args.workload][3], "n_overlaps": n_ovl, "n_reads": n_reads, "edges": E,
                    "nodes": counts["n_nodes"], "two_hop_visits": counts["n_two_hop"], "transitive_pairs": counts["n_transitive_pairs"],
                    "containment_events": counts["n_candidates"], "fixpoint_rounds": counts["n_rounds"],
@@ -251,7 +334,7 @@ def run_single(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c3", choices=list(WORKLOADS))

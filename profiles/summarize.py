@@ -82,6 +82,24 @@ def full(tag: str):
         w.writerow(["kernel"] + [f"{m} [{units[idx[m]]}]" for m in cols])
         for d in data:
             w.writerow([d[idx["Kernel Name"]].split("(")[0]] + [d[idx[m]] for m in cols])
+    # per-launch DRAM traffic of every captured kernel, for bench.py's roofline.traffic
+    import json
+    tpath = os.path.join(DST, "traffic.json")
+    traffic = {"tag": tag, "kernels": {}}
+    if os.path.exists(tpath):
+        with open(tpath) as f:
+            traffic = json.load(f)
+        traffic["tag"] = tag
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    for d in data:
+        name = d[idx["Kernel Name"]].split("(")[0].replace("void ", "").split("<")[0]
+        rd = float(d[idx["dram__bytes_read.sum"]]) * scale[units[idx["dram__bytes_read.sum"]]]
+        wr = float(d[idx["dram__bytes_write.sum"]]) * scale[units[idx["dram__bytes_write.sum"]]]
+        prev = traffic["kernels"].get(name)
+        if prev is None or prev.get("tag") != tag or rd + wr > prev["dram_bytes"]:   # keep the largest launch of a capture
+            traffic["kernels"][name] = {"dram_bytes": rd + wr, "read": rd, "write": wr, "tag": tag}
+    with open(tpath, "w") as f:
+        json.dump(traffic, f, indent=1, sort_keys=True)
     pipe_keys = [h for h in hdr if "pipe" in h and h.endswith(".avg.pct_of_peak_sustained_active")] + \
                 [h for h in hdr if "pipe_xu" in h or h.startswith("l1tex__data_pipe_lsu_wavefronts.avg")]
     stall_keys = [h for h in hdr if h.startswith("smsp__average_warps_issue_stalled") and h.endswith("per_issue_active.ratio")]
