@@ -210,6 +210,16 @@ int rala_b200_graph_export_edges(rala_b200_graph* g, uint32_t* d_cols, uint32_t 
 int rala_b200_graph_import_edges(rala_b200_graph* g, const uint32_t* d_cols, uint32_t stride, uint32_t n,
                                  uint32_t offset, uint32_t total);
 int rala_b200_graph_phase_csr(rala_b200_graph* g);
+/* Capacity-bounded variants of the exchange steps: element counts travel inside the blocks and the time bases are
+ * computed on the device, so no call below synchronises with the host (the sized variants above read counts back).
+ *   block (3 * cap + 4 words) = [n clamped to cap | overflow flag | 0 | 0 | column 0 [cap] | column 1 [cap] | column 2 [cap]]
+ *   kind: 0 = containment events, 1 = edges.  d_gathered = the `world` blocks of an all-gather, in rank order.
+ * A count beyond `cap` raises the session's overflow flag (reported by rala_b200_graph_counts): re-run sized.
+ * rala_b200_graph_phase_emit_edges accepts n_local_edges == NULL (no read-back). */
+int rala_b200_graph_export_padded(rala_b200_graph* g, int kind, uint32_t* d_block, uint32_t cap);
+int rala_b200_graph_import_gathered(rala_b200_graph* g, int kind, const uint32_t* d_gathered, uint32_t cap, int world);
+int rala_b200_graph_export_list_counts(rala_b200_graph* g, uint32_t* d_pair /* n_overlaps, n_internals */);
+int rala_b200_graph_phase_final_events_gathered(rala_b200_graph* g, const uint32_t* d_counts /* world x 2 */, int world);
 int rala_b200_graph_phase_transitive(rala_b200_graph* g);
 int rala_b200_graph_export_marks(rala_b200_graph* g, uint8_t* d_T, uint32_t n);
 int rala_b200_graph_phase_marks(rala_b200_graph* g, const uint8_t* d_T, uint32_t n);

@@ -56,6 +56,8 @@ EXPORTS = [
     "rala_b200_graph_phase_final_events", "rala_b200_graph_phase_emit_edges", "rala_b200_graph_export_edges",
     "rala_b200_graph_import_edges", "rala_b200_graph_phase_csr", "rala_b200_graph_phase_transitive",
     "rala_b200_graph_export_marks", "rala_b200_graph_phase_marks",
+    "rala_b200_graph_export_padded", "rala_b200_graph_import_gathered", "rala_b200_graph_export_list_counts",
+    "rala_b200_graph_phase_final_events_gathered",
 ]
 
 _LIB = None

@@ -1107,7 +1107,7 @@ extern "C" int rala_b200_graph_phase_final_events(rala_b200_graph* g, uint32_t o
 
 // node ids (replicated) + the edges of the LOCAL overlaps, in local list order, with global node ids
 extern "C" int rala_b200_graph_phase_emit_edges(rala_b200_graph* g, uint32_t* n_local_edges) {
-    if (!g || !n_local_edges) return RALA_B200_ERR_ARG;
+    if (!g) return RALA_B200_ERR_ARG;
     rala_b200_ctx* ctx = g->ctx;
     if (g->state != 3) return fail(ctx, RALA_B200_ERR_STATE, "emit_edges: finalize first");
     CU(ctx, cudaSetDevice(ctx->device));
@@ -1122,7 +1122,7 @@ extern "C" int rala_b200_graph_phase_emit_edges(rala_b200_graph* g, uint32_t* n_
     launch_emit_edges(ctx->L, g->ovl[g->ovl_cur].view, g->cnt() + g->slot_ovl, g->cap, g->piles.as<uint2>(), g->graph_view(),
                       g->edge_cap, g->cnt(), status, ticket);
     CU(ctx, cudaGetLastError());
-    return read_counter(g, C_EDGES, n_local_edges);
+    return n_local_edges ? read_counter(g, C_EDGES, n_local_edges) : RALA_B200_OK;   // NULL: no host synchronisation
 }
 
 extern "C" int rala_b200_graph_export_edges(rala_b200_graph* g, uint32_t* d_cols, uint32_t stride, uint32_t n) {
@@ -1158,6 +1158,64 @@ extern "C" int rala_b200_graph_import_edges(rala_b200_graph* g, const uint32_t* 
         CU(ctx, cudaStreamSynchronize(ctx->L.stream));
     }
     return RALA_B200_OK;
+}
+
+// ---- capacity-bounded exchange: counts travel inside the blocks, nothing is read back by the host ------------------------
+extern "C" int rala_b200_graph_export_padded(rala_b200_graph* g, int kind, uint32_t* d_block, uint32_t cap) {
+    if (!g || !d_block || cap == 0 || (kind != 0 && kind != 1)) return RALA_B200_ERR_ARG;
+    rala_b200_ctx* ctx = g->ctx;
+    CU(ctx, cudaSetDevice(ctx->device));
+    if (kind == 0) {
+        Events ev = g->events_view();
+        launch_export_padded(ctx->L, ev.v, ev.c, ev.t, g->cnt() + C_EV, g->ev_cap, cap, d_block);
+    } else {
+        GraphArrays ga = g->graph_view();
+        launch_export_padded(ctx->L, ga.src, ga.dst, ga.len, g->cnt() + C_EDGES, g->edge_cap, cap, d_block);
+    }
+    CU(ctx, cudaGetLastError());
+    return RALA_B200_OK;
+}
+
+extern "C" int rala_b200_graph_import_gathered(rala_b200_graph* g, int kind, const uint32_t* d_gathered, uint32_t cap, int world) {
+    if (!g || !d_gathered || cap == 0 || world < 1 || (kind != 0 && kind != 1)) return RALA_B200_ERR_ARG;
+    rala_b200_ctx* ctx = g->ctx;
+    CU(ctx, cudaSetDevice(ctx->device));
+    const uint64_t total_cap = (uint64_t) cap * world;
+    if (total_cap >= (1ull << 31)) return fail(ctx, RALA_B200_ERR_LIMIT, "exchange capacity too large");
+    if (kind == 0) {
+        int rc = reserve_events(g, (uint32_t) total_cap);   // the local events were exported before
+        if (rc) return rc;
+        Events ev = g->events_view();
+        launch_import_gathered(ctx->L, d_gathered, cap, (uint32_t) world, ev.v, ev.c, ev.t, g->ev_cap, g->cnt() + C_EV, g->cnt() + C_OVERFLOW);
+        CU(ctx, clear_victim_histogram(g));
+        launch_events_hist(ctx->L, g->events_view(), g->cnt() + C_EV, g->ev_cap, resolve_bufs(g).vcursor);
+    } else {
+        int rc = reserve_edges(g, (uint32_t) total_cap);     // the local edges were exported before
+        if (rc) return rc;
+        GraphArrays ga = g->graph_view();
+        launch_import_gathered(ctx->L, d_gathered, cap, (uint32_t) world, ga.src, ga.dst, ga.len, g->edge_cap, g->cnt() + C_EDGES, g->cnt() + C_OVERFLOW);
+    }
+    CU(ctx, cudaGetLastError());
+    return RALA_B200_OK;
+}
+
+extern "C" int rala_b200_graph_export_list_counts(rala_b200_graph* g, uint32_t* d_pair) {
+    if (!g || !d_pair) return RALA_B200_ERR_ARG;
+    rala_b200_ctx* ctx = g->ctx;
+    if (g->state < 2) return fail(ctx, RALA_B200_ERR_STATE, "export_list_counts: classify first");
+    CU(ctx, cudaSetDevice(ctx->device));
+    CU(ctx, cudaMemcpyAsync(d_pair, g->cnt() + g->slot_ovl, 4, cudaMemcpyDeviceToDevice, ctx->L.stream));
+    CU(ctx, cudaMemcpyAsync(d_pair + 1, g->cnt() + g->slot_inl, 4, cudaMemcpyDeviceToDevice, ctx->L.stream));
+    return RALA_B200_OK;
+}
+
+extern "C" int rala_b200_graph_phase_final_events_gathered(rala_b200_graph* g, const uint32_t* d_counts, int world) {
+    if (!g || !d_counts || world < 1) return RALA_B200_ERR_ARG;
+    rala_b200_ctx* ctx = g->ctx;
+    CU(ctx, cudaSetDevice(ctx->device));
+    launch_time_bases(ctx->L, d_counts, (uint32_t) g->rank, (uint32_t) world, g->cnt() + C_TBASE_OVL);
+    g->final_time_base_slot = C_TBASE_INL;
+    return phase_final_events(g, g->cnt() + C_TBASE_OVL, g->cnt() + C_TBASE_INL);
 }
 
 // CSR over ALL edges (replicated on every rank)

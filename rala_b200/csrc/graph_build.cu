@@ -195,6 +195,61 @@ __global__ void k_pack_edges(const uint32_t* __restrict__ src, const uint32_t* _
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Capacity-bounded exchange blocks of the multi-GPU path: the element count travels INSIDE the block, so the
+// host never has to read it (no synchronisation around the collectives).
+//   block = [n (clamped to cap) | overflow flag | 0 | 0 | column 0 [cap] | column 1 [cap] | column 2 [cap]]
+// ---------------------------------------------------------------------------------------------
+__global__ void k_export_padded(const uint32_t* __restrict__ c0, const uint32_t* __restrict__ c1, const uint32_t* __restrict__ c2,
+                                const uint32_t* __restrict__ n_ptr, uint32_t src_cap, uint32_t cap, uint32_t* __restrict__ block) {
+    const uint32_t n = min(*n_ptr, src_cap), m = min(n, cap);
+    if (blockIdx.x == 0 && threadIdx.x < 4) block[threadIdx.x] = threadIdx.x == 0 ? m : (threadIdx.x == 1 ? (n > cap ? 1u : 0u) : 0u);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += gridDim.x * blockDim.x) {
+        block[4 + i] = c0[i];
+        block[4 + (size_t) cap + i] = c1[i];
+        block[4 + 2 * (size_t) cap + i] = c2[i];
+    }
+}
+
+// gathered = `world` blocks back to back; rank r's elements land behind those of ranks < r (blockIdx.y = r)
+__global__ void k_import_gathered(const uint32_t* __restrict__ gathered, uint32_t cap, uint32_t world, uint32_t* __restrict__ d0,
+                                  uint32_t* __restrict__ d1, uint32_t* __restrict__ d2, uint32_t dst_cap, uint32_t* __restrict__ n_out,
+                                  uint32_t* __restrict__ overflow) {
+    const size_t stride = 3 * (size_t) cap + 4;
+    const uint32_t r = blockIdx.y;
+    uint32_t offset = 0;
+    for (uint32_t q = 0; q < r; ++q) offset += gathered[q * stride];
+    const uint32_t* blk = gathered + r * stride;
+    const uint32_t n = blk[0];
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        if (blk[1] || offset + n > dst_cap) *overflow = 1u;
+        if (r == world - 1) *n_out = min(offset + n, dst_cap);
+    }
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        if (offset + i < dst_cap) {
+            d0[offset + i] = blk[4 + i];
+            d1[offset + i] = blk[4 + (size_t) cap + i];
+            d2[offset + i] = blk[4 + 2 * (size_t) cap + i];
+        }
+    }
+}
+
+// time bases of the local lists in the final containment pass (graph.cpp:831-866): position in the GLOBAL
+// overlaps ++ internals order.  counts = (n_overlaps, n_internals) of every rank.
+__global__ void k_time_bases(const uint32_t* __restrict__ counts, uint32_t rank, uint32_t world, uint32_t* __restrict__ bases) {
+    if (blockIdx.x || threadIdx.x) return;
+    uint32_t total_ovl = 0, ovl_before = 0, int_before = 0;
+    for (uint32_t q = 0; q < world; ++q) {
+        if (q < rank) {
+            ovl_before += counts[2 * q];
+            int_before += counts[2 * q + 1];
+        }
+        total_ovl += counts[2 * q];
+    }
+    bases[0] = ovl_before;
+    bases[1] = total_ovl + int_before;
+}
+
 static inline int grid_for(uint64_t n, int per_block, int max_blocks) {
     uint64_t b = (n + per_block - 1) / per_block;
     if (b < 1) b = 1;
@@ -223,6 +278,24 @@ void launch_pack_edges(Launch& L, GraphArrays g, uint32_t edge_cap, const uint32
 
 void launch_degree_hist(Launch& L, const uint32_t* src, const uint32_t* n_edges_ptr, uint32_t edge_cap, uint32_t* cursor) {
     k_degree_hist<<<grid_for(edge_cap, 256, kNumSMs * 8), 256, 0, L.stream>>>(src, n_edges_ptr, edge_cap, cursor);
+    L.count++;
+}
+
+void launch_export_padded(Launch& L, const uint32_t* c0, const uint32_t* c1, const uint32_t* c2, const uint32_t* n_ptr,
+                          uint32_t src_cap, uint32_t cap, uint32_t* block) {
+    k_export_padded<<<grid_for(cap, 256, kNumSMs * 4), 256, 0, L.stream>>>(c0, c1, c2, n_ptr, src_cap, cap, block);
+    L.count++;
+}
+
+void launch_import_gathered(Launch& L, const uint32_t* gathered, uint32_t cap, uint32_t world, uint32_t* d0, uint32_t* d1,
+                            uint32_t* d2, uint32_t dst_cap, uint32_t* n_out, uint32_t* overflow) {
+    dim3 grid(grid_for(cap, 256, kNumSMs * 2), world);
+    k_import_gathered<<<grid, 256, 0, L.stream>>>(gathered, cap, world, d0, d1, d2, dst_cap, n_out, overflow);
+    L.count++;
+}
+
+void launch_time_bases(Launch& L, const uint32_t* counts, uint32_t rank, uint32_t world, uint32_t* bases) {
+    k_time_bases<<<1, 32, 0, L.stream>>>(counts, rank, world, bases);
     L.count++;
 }
 

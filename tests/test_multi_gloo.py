@@ -28,7 +28,9 @@ class OracleShardSession:
     def __init__(self, records, piles, flags, t0, rank, world):
         self.device = torch.device("cpu")
         self.rec = np.ascontiguousarray(records, dtype=np.uint32).reshape(-1, 7)
-        self.piles = np.ascontiguousarray(piles, dtype=np.uint32).copy()
+        self.piles0 = np.ascontiguousarray(piles, dtype=np.uint32).copy()
+        self.piles = self.piles0.copy()
+        self._overflow = False
         self.flags = np.zeros(len(piles), np.uint8) if flags is None else np.asarray(flags, np.uint8)
         self.t0, self.rank, self.world = t0, rank, world
         self.events = np.zeros((0, 3), np.uint32)
@@ -50,6 +52,8 @@ class OracleShardSession:
         return block[:, :n].numpy().view(np.uint32).T.copy()
 
     def phase_events(self):
+        self.piles = self.piles0.copy()   # re-runnable, like the CUDA session
+        self._overflow = False
         ev = []
         for i, r in enumerate(self.rec):
             ok, tr, t = self._trim_type(r)
@@ -160,12 +164,56 @@ class OracleShardSession:
         self.T = T
 
     def export_marks(self, t):
-        t[:] = torch.from_numpy(self.T)
+        t.zero_()
+        t[:len(self.T)] = torch.from_numpy(self.T)
 
     def phase_marks(self, t):
-        T = t.numpy()
+        T = t.numpy()[:len(self.edges_all)]
         m = (T[0::2] | T[1::2])
         self.marked = np.repeat(m, 2).astype(np.uint8)
+
+
+    # ---- capacity-bounded interface (counts travel inside the blocks) ---------------------------------------
+    def phase_events_async(self):
+        self.phase_events()
+
+    def phase_survivors_async(self):
+        self.phase_survivors()
+
+    def phase_emit_edges_async(self):
+        self.phase_emit_edges()
+
+    def export_padded(self, kind, block, cap):
+        arr = self.events if kind == 0 else self.edges
+        n = len(arr)
+        m = min(n, cap)
+        b = block.numpy().view(np.uint32)
+        b[:4] = (m, int(n > cap), 0, 0)
+        for k in range(3):
+            b[4 + k * cap: 4 + k * cap + m] = arr[:m, k]
+
+    def import_gathered(self, kind, gathered, cap, world):
+        g = gathered.numpy().view(np.uint32)
+        parts = []
+        for r in range(world):
+            n = int(g[r, 0])
+            self._overflow |= bool(g[r, 1])
+            parts.append(np.stack([g[r, 4 + k * cap: 4 + k * cap + n] for k in range(3)], 1))
+        merged = np.concatenate(parts).astype(np.uint32)
+        if kind == 0:
+            self.events_all = merged
+        else:
+            self.edges_all = merged
+
+    def export_list_counts(self, pair):
+        pair[0], pair[1] = len(self.ovl), len(self.inl)
+
+    def phase_final_events_gathered(self, counts, world):
+        c = counts.numpy().astype(np.int64)
+        self.phase_final_events(int(c[:self.rank, 0].sum()), int(c[:, 0].sum() + c[:self.rank, 1].sum()))
+
+    def overflowed(self):
+        return self._overflow
 
 
 def _free_port():
@@ -183,7 +231,19 @@ def _worker(rank, world, port, kw, out_dir):
         flags = (np.random.Generator(np.random.PCG64(1)).random(ds.n_reads) < 0.05).astype(np.uint8) * 2
         lo, hi = multi.shard_bounds(ds.n_overlaps, world)[rank]
         sess = OracleShardSession(ds.records[lo:hi], piles, flags, lo, rank, world)
-        info = multi.DistributedGraph(sess, rank, world).run()
+        dg = multi.DistributedGraph(sess, rank, world)
+        info = dg.run()                                   # sized: every exchange is counted on the host first
+        first = (sess.edges_all.copy(), sess.marked.copy(), sess.piles.copy())
+        again = dg.run()                                  # bounded: counts travel inside the blocks
+        assert again.get("bounded") and dg.check()
+        for x, y in zip(first, (sess.edges_all, sess.marked, sess.piles)):
+            assert np.array_equal(x, y)
+        dg.caps = {k: 8 for k in dg.caps}                 # far too small: must be detected, and the next run sized again
+        dg._bufs = {}
+        dg.run()
+        assert not dg.check() and dg.caps is None
+        info = dg.run()
+        assert "bounded" not in info
         np.savez(os.path.join(out_dir, f"r{rank}.npz"), edges=sess.edges_all, marked=sess.marked, piles=sess.piles,
                  n_events=info["n_events"])
     finally:
