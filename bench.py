@@ -244,11 +244,12 @@ def run_single(args):
     ctx.synchronize()
     wall_ms = 1e3 * (time.perf_counter() - t0)
     launches = ctx.launch_count - launches0
-    stage_ms = G.stage_ms()            # last step's per-stage / per-kernel device times
     ms_per_step = dev_ms / args.steps
     value = E / (ms_per_step * 1e-3)
 
-    # per-kernel durations averaged over a few extra (untimed) steps for the roofline object
+    # per-kernel durations averaged over a few extra (untimed) steps for the roofline object; the stage timers are
+    # CUDA events between the kernels, which only exist in the eager chain (the timed steps replay a CUDA graph)
+    G.use_cuda_graph(False)
     k1, k3 = [], []
     for _ in range(max(3, min(args.steps, 10))):
         G.run()
@@ -257,6 +258,7 @@ def run_single(args):
         k3.append(s["k3_transitive_kernels"])
         for k, v in s.items():
             stage_acc.setdefault(k, []).append(v)
+    G.use_cuda_graph(True)
     clocks = sampler.stop()
     k1_ms, k3_ms = float(np.mean(k1)), float(np.mean(k3))
     peak, peak_src = measured_peaks()

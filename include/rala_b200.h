@@ -147,6 +147,11 @@ int rala_b200_graph_finalize(rala_b200_graph* g);
 int rala_b200_graph_build(rala_b200_graph* g);
 int rala_b200_graph_transitive(rala_b200_graph* g);
 int rala_b200_graph_run(rala_b200_graph* g);
+/* rala_b200_graph_run() replays a captured CUDA graph of the whole chain once it has run a session shape (buffers,
+ * sizes, first run after set_piles or not) eagerly: one launch instead of ~45 dependent stream operations.  The
+ * per-stage timers of rala_b200_graph_stage_ms() are not recorded inside a graph: pass enabled = 0 before the
+ * runs you want stage times for.  Default: enabled. */
+int rala_b200_graph_use_cuda_graph(rala_b200_graph* g, int enabled);
 
 /* synchronises the stream and reads the device-side counters */
 int rala_b200_graph_counts(rala_b200_graph* g, rala_b200_counts_t* out);

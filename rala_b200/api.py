@@ -49,6 +49,7 @@ EXPORTS = [
     "rala_b200_graph_get_hill_coverage", "rala_b200_graph_get_piles", "rala_b200_graph_get_connections",
     "rala_b200_graph_get_lists", "rala_b200_graph_get_seq_to_node", "rala_b200_graph_get_edges",
     "rala_b200_graph_get_marked", "rala_b200_graph_stage_ms", "rala_b200_graph_set_kept_overlaps",
+    "rala_b200_graph_use_cuda_graph",
     # multi-GPU phases
     "rala_b200_create_on_stream", "rala_b200_graph_set_shard", "rala_b200_graph_phase_events",
     "rala_b200_graph_events_count", "rala_b200_graph_export_events", "rala_b200_graph_import_events",
@@ -248,6 +249,11 @@ class Graph:
         return self
 
     # ---- outputs -----------------------------------------------------------------------------
+    def use_cuda_graph(self, enabled: bool):
+        """run() replays a captured CUDA graph by default; stage_ms() needs the eager chain (enabled=False)."""
+        self._call("rala_b200_graph_use_cuda_graph", C.c_int(1 if enabled else 0))
+        return self
+
     def counts(self) -> dict:
         c = Counts()
         self._call("rala_b200_graph_counts", C.byref(c))

@@ -189,6 +189,9 @@ struct rala_b200_graph {
     uint32_t retrim_passes = 0;
     cudaEvent_t ev_start[RALA_B200_N_STAGES]{}, ev_stop[RALA_B200_N_STAGES]{};
     bool ev_valid[RALA_B200_N_STAGES]{};
+    // rala_b200_graph_run as a replayed CUDA graph (see run_key / RunGraph below)
+    bool use_cuda_graph = true, capturing = false;
+    struct RunGraph* run_graphs = nullptr;   // two cached instances: first run after set_piles / repeated run
 
     uint32_t* cnt() const { return counters.as<uint32_t>(); }
     Events events_view() const {
@@ -244,16 +247,21 @@ static void scan_state(rala_b200_graph* g, uint64_t n_max, unsigned long long** 
     g->scan_used += words;
 }
 
+// stage timers: plain event records, left out of a stream capture (an event recorded inside a capture cannot be timed)
+static cudaError_t stage_event(rala_b200_graph* g, cudaEvent_t ev) {
+    return g->capturing ? cudaSuccess : cudaEventRecord(ev, g->ctx->L.stream);
+}
+
 static cudaError_t begin_stage(rala_b200_graph* g, int stage) {
     g->scan_used = 0;
     cudaError_t e = cudaMemsetAsync(g->scan_pool.p, 0, g->scan_pool_words * 8, g->ctx->L.stream);
     if (e != cudaSuccess) return e;
-    return cudaEventRecord(g->ev_start[stage], g->ctx->L.stream);
+    return stage_event(g, g->ev_start[stage]);
 }
 
 static cudaError_t end_stage(rala_b200_graph* g, int stage) {
-    g->ev_valid[stage] = true;
-    return cudaEventRecord(g->ev_stop[stage], g->ctx->L.stream);
+    g->ev_valid[stage] = !g->capturing;
+    return stage_event(g, g->ev_stop[stage]);
 }
 
 static cudaError_t zero_counter(rala_b200_graph* g, int slot, int n = 1) {
@@ -281,10 +289,13 @@ extern "C" int rala_b200_graph_create(rala_b200_ctx* ctx, rala_b200_graph** out)
     return RALA_B200_OK;
 }
 
+static void drop_run_graphs(rala_b200_graph* g);
+
 extern "C" void rala_b200_graph_destroy(rala_b200_graph* g) {
     if (!g) return;
     cudaSetDevice(g->ctx->device);
     cudaStreamSynchronize(g->ctx->L.stream);
+    drop_run_graphs(g);
     DevBuf* bufs[] = {&g->rec, &g->recs.buf, &g->alive_bits, &g->piles, &g->piles_raw, &g->pile_flags_raw, &g->piles_initial, &g->hills, &g->ovl[0].buf,
                       &g->ovl[1].buf, &g->inl[0].buf, &g->inl[1].buf, &g->events, &g->hill_rec, &g->dbuf, &g->flags, &g->segs, &g->tiles,
                       &g->counters, &g->scan_pool, &g->seq_to_node, &g->edges, &g->row_ptr, &g->cursor, &g->col,
@@ -463,7 +474,7 @@ static int phase_events(rala_b200_graph* g) {
     CU(ctx, cudaMemsetAsync(g->counters.p, 0, C_COUNT * 4, ctx->L.stream));
     if (g->n_hills) CU(ctx, cudaMemsetAsync(g->hills.as<uint32_t>() + 3 * (size_t) g->n_hills, 0, (size_t) g->n_hills * 4, ctx->L.stream));
     CU(ctx, clear_victim_histogram(g));
-    CU(ctx, cudaEventRecord(g->ev_start[ST_K1_KERNEL], ctx->L.stream));
+    CU(ctx, stage_event(g, g->ev_start[ST_K1_KERNEL]));
     launch_classify_events(ctx->L, g->recs.view, g->n_rec, g->t0, g->piles.as<uint2>(), g->n_piles, g->events_view(),
                            g->ev_cap, resolve_bufs(g).vcursor, g->hill_rec.as<uint32_t>(), g->cap, g->cnt());
     CU(ctx, end_stage(g, ST_K1_KERNEL));
@@ -473,7 +484,7 @@ static int phase_events(rala_b200_graph* g) {
 
 static int phase_resolve(rala_b200_graph* g, bool first_pass) {
     rala_b200_ctx* ctx = g->ctx;
-    CU(ctx, cudaEventRecord(g->ev_start[ST_K1B_KERNEL], ctx->L.stream));
+    CU(ctx, stage_event(g, g->ev_start[ST_K1B_KERNEL]));
     int rc = resolve_containment(g);
     if (rc) return rc;
     CU(ctx, end_stage(g, ST_K1B_KERNEL));
@@ -496,7 +507,7 @@ static int phase_survivors(rala_b200_graph* g) {
     g->slot_inl = C_LIST0 + 1;
     g->next_slot = C_LIST0 + 2;
     CU(ctx, zero_counter(g, C_LIST0, 2));
-    CU(ctx, cudaEventRecord(g->ev_start[ST_K1S_KERNEL], ctx->L.stream));
+    CU(ctx, stage_event(g, g->ev_start[ST_K1S_KERNEL]));
     {
         const size_t nr = align_up((size_t) classify_num_runs(g->n_rec) + 8, 64);
         uint32_t* t = g->tiles.as<uint32_t>();
@@ -700,7 +711,7 @@ static int run_transitive(rala_b200_graph* g) {
     CU(ctx, zero_counter(g, C_HOP_LO, 2));
     CU(ctx, cudaMemsetAsync(g->work_counter.p, 0, 64, ctx->L.stream));
     CU(ctx, cudaMemsetAsync(g->T.p, 0, align_up(g->edge_cap, 256), ctx->L.stream));
-    CU(ctx, cudaEventRecord(g->ev_start[ST_K3_KERNELS], ctx->L.stream));
+    CU(ctx, stage_event(g, g->ev_start[ST_K3_KERNELS]));
     launch_transitive(ctx->L, g->graph_view(), g->n_nodes_max, g->edge_cap, g->heavy_view(), g->work_counter.as<uint32_t>(),
                       g->cnt(), 0u, 0xFFFFFFFFu, g->world > 1 ? g->work_counter.as<uint32_t>() + 4 : nullptr);
     CU(ctx, end_stage(g, ST_K3_KERNELS));
@@ -723,7 +734,7 @@ extern "C" int rala_b200_graph_transitive(rala_b200_graph* g) {
     return RALA_B200_OK;
 }
 
-extern "C" int rala_b200_graph_run(rala_b200_graph* g) {
+static int run_eager(rala_b200_graph* g) {
     int rc = rala_b200_graph_classify(g);
     if (!rc) rc = rala_b200_graph_retrim(g);
     if (!rc) rc = rala_b200_graph_retrim_promote(g, nullptr);
@@ -731,6 +742,118 @@ extern "C" int rala_b200_graph_run(rala_b200_graph* g) {
     if (!rc) rc = rala_b200_graph_build(g);
     if (!rc) rc = rala_b200_graph_transitive(g);
     return rc;
+}
+
+// Everything the sequence of stream operations of one run depends on.  The chain itself has no host
+// synchronisation and every data-dependent size stays on the device, so for a fixed key the ~45 stream
+// operations (27 kernels, memsets, small copies) are identical from run to run: the second run with a key is
+// captured into a CUDA graph and later runs replay it with one launch.
+struct RunKey {
+    const void *rec, *recs, *piles, *piles_initial, *events, *segs, *dbuf, *edges, *col, *scan_pool, *tiles, *ovl0, *inl0, *hills;
+    uint32_t n_rec, n_piles, n_hills, cap, ev_cap, edge_cap, heavy_cap, t0;
+    int world, rank, coop_blocks;
+    bool piles_fresh, skip_clean_retrim;
+};
+
+// host-side bookkeeping a run leaves behind (restored after a replay)
+struct RunHostState {
+    int ovl_cur, inl_cur, slot_ovl, slot_inl, next_slot, final_time_base_slot, state;
+    bool final_lists_ready, piles_dirty, piles_fresh;
+    uint32_t retrim_passes;
+    size_t scan_used;
+};
+
+struct RunGraph {
+    RunKey key{};
+    bool seen = false;          // the key was run once (eagerly): capture on the next occurrence
+    cudaGraphExec_t exec = nullptr;
+    RunHostState after{};
+    uint64_t launches = 0;      // kernels inside the graph
+};
+
+static RunKey run_key(const rala_b200_graph* g) {
+    RunKey k;
+    memset(&k, 0, sizeof(k));   // padding included: keys are compared with memcmp
+    k.rec = g->rec.p; k.recs = g->recs.buf.p; k.piles = g->piles.p; k.piles_initial = g->piles_initial.p;
+    k.events = g->events.p; k.segs = g->segs.p; k.dbuf = g->dbuf.p; k.edges = g->edges.p; k.col = g->col.p;
+    k.scan_pool = g->scan_pool.p; k.tiles = g->tiles.p; k.ovl0 = g->ovl[0].buf.p; k.inl0 = g->inl[0].buf.p; k.hills = g->hills.p;
+    k.n_rec = g->n_rec; k.n_piles = g->n_piles; k.n_hills = g->n_hills; k.cap = g->cap; k.ev_cap = g->ev_cap;
+    k.edge_cap = g->edge_cap; k.heavy_cap = g->heavy_cap; k.t0 = g->t0;
+    k.world = g->world; k.rank = g->rank; k.coop_blocks = g->ctx->coop_blocks;
+    k.piles_fresh = g->piles_fresh; k.skip_clean_retrim = g->skip_clean_retrim;
+    return k;
+}
+
+static RunHostState host_state(const rala_b200_graph* g) {
+    return RunHostState{g->ovl_cur, g->inl_cur, g->slot_ovl, g->slot_inl, g->next_slot, g->final_time_base_slot, g->state,
+                        g->final_lists_ready, g->piles_dirty, g->piles_fresh, g->retrim_passes, g->scan_used};
+}
+
+static void drop_run_graphs(rala_b200_graph* g) {
+    if (!g->run_graphs) return;
+    for (int i = 0; i < 2; ++i)
+        if (g->run_graphs[i].exec) cudaGraphExecDestroy(g->run_graphs[i].exec);
+    delete[] g->run_graphs;
+    g->run_graphs = nullptr;
+}
+
+extern "C" int rala_b200_graph_use_cuda_graph(rala_b200_graph* g, int enabled) {
+    if (!g) return RALA_B200_ERR_ARG;
+    g->use_cuda_graph = enabled != 0;
+    return RALA_B200_OK;
+}
+
+extern "C" int rala_b200_graph_run(rala_b200_graph* g) {
+    if (!g) return RALA_B200_ERR_ARG;
+    rala_b200_ctx* ctx = g->ctx;
+    if (!g->use_cuda_graph) return run_eager(g);
+    if (g->state < 1) return fail(ctx, RALA_B200_ERR_STATE, "run: set_overlaps and set_piles first");
+    CU(ctx, cudaSetDevice(ctx->device));
+    if (!g->run_graphs) g->run_graphs = new RunGraph[2];
+    const RunKey key = run_key(g);
+    RunGraph& R = g->run_graphs[key.piles_fresh ? 1 : 0];
+    if (!R.seen || memcmp(&R.key, &key, sizeof(key)) != 0) {   // new shape: run it eagerly once (this also sizes every buffer)
+        if (R.exec) cudaGraphExecDestroy(R.exec);
+        R.exec = nullptr;
+        R.key = key;
+        R.seen = true;
+        return run_eager(g);
+    }
+    if (!R.exec) {
+        const uint64_t launches0 = ctx->L.count;
+        cudaGraph_t graph = nullptr;
+        CU(ctx, cudaStreamBeginCapture(ctx->L.stream, cudaStreamCaptureModeThreadLocal));
+        g->capturing = true;
+        const int rc = run_eager(g);
+        g->capturing = false;
+        const cudaError_t e = cudaStreamEndCapture(ctx->L.stream, &graph);
+        if (rc || e != cudaSuccess) {
+            if (graph) cudaGraphDestroy(graph);
+            cudaGetLastError();
+            R.seen = false;
+            ctx->L.count = launches0;
+            if (rc) return rc;
+            return fail(ctx, RALA_B200_ERR_CUDA, "run: stream capture failed: %s", cudaGetErrorString(e));
+        }
+        const cudaError_t ei = cudaGraphInstantiate(&R.exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (ei != cudaSuccess) {
+            R.exec = nullptr;
+            R.seen = false;
+            return fail(ctx, RALA_B200_ERR_CUDA, "run: cudaGraphInstantiate failed: %s", cudaGetErrorString(ei));
+        }
+        R.launches = ctx->L.count - launches0;
+        R.after = host_state(g);
+        ctx->L.count = launches0;   // counted per replay below
+    }
+    CU(ctx, cudaGraphLaunch(R.exec, ctx->L.stream));
+    ctx->L.count += R.launches;
+    const RunHostState& a = R.after;
+    g->ovl_cur = a.ovl_cur; g->inl_cur = a.inl_cur; g->slot_ovl = a.slot_ovl; g->slot_inl = a.slot_inl; g->next_slot = a.next_slot;
+    g->final_time_base_slot = a.final_time_base_slot; g->state = a.state; g->final_lists_ready = a.final_lists_ready;
+    g->piles_dirty = a.piles_dirty; g->piles_fresh = a.piles_fresh; g->retrim_passes = a.retrim_passes; g->scan_used = a.scan_used;
+    for (int i = 0; i < RALA_B200_N_STAGES; ++i) g->ev_valid[i] = false;   // no stage timers inside a graph
+    return RALA_B200_OK;
 }
 
 static int read_counters(rala_b200_graph* g, uint32_t* h) {
@@ -1248,7 +1371,7 @@ extern "C" int rala_b200_graph_phase_transitive(rala_b200_graph* g) {
     CU(ctx, cudaMemsetAsync(g->work_counter.p, 0, 64, ctx->L.stream));
     CU(ctx, cudaMemsetAsync(g->T.p, 0, align_up(g->edge_cap, 256), ctx->L.stream));
     launch_node_range(ctx->L, g->graph_view(), g->cnt(), (uint32_t) g->rank, (uint32_t) g->world, g->work_counter.as<uint32_t>() + 4);
-    CU(ctx, cudaEventRecord(g->ev_start[ST_K3_KERNELS], ctx->L.stream));
+    CU(ctx, stage_event(g, g->ev_start[ST_K3_KERNELS]));
     launch_transitive(ctx->L, g->graph_view(), g->n_nodes_max, g->edge_cap, g->heavy_view(), g->work_counter.as<uint32_t>(),
                       g->cnt(), 0u, 0xFFFFFFFFu, g->work_counter.as<uint32_t>() + 4);
     CU(ctx, end_stage(g, ST_K3_KERNELS));

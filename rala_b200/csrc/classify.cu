@@ -34,7 +34,8 @@ namespace rb {
 constexpr int kRecItems = 4;                              // consecutive records per thread (one uint4 per column)
 constexpr int kRecTile = kTileThreads * kRecItems;        // records per block iteration
 constexpr uint32_t kInvalidBit = 0x80000000u;             // in column a
-constexpr uint32_t kRunRecords = 128;                     // survivors pass: records per warp iteration = one run
+constexpr uint32_t kRunRecords = 512;                     // survivors pass: records per warp iteration = one run
+constexpr int kRunGroups = kRunRecords / 128;             // 128-record groups per run (one 16-byte load per column, lane and group)
 
 __global__ void k_records_to_soa(const uint32_t* __restrict__ aos, uint32_t n, List recs) {
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
@@ -146,69 +147,100 @@ __global__ void __launch_bounds__(kTileThreads, MINB) k_classify_events(
     if (staged) flush();
 }
 
-// Survivors pass.  Every warp owns RUNS of 128 consecutive records (4 per lane): it writes the survivors of a
+// Survivors pass.  Every warp owns RUNS of 512 consecutive records (4 x 4 per lane): it writes the survivors of a
 // run, in record order, to the run's own slot range of the scratch lists (slot = record index of the run's
 // first record: the scratch lists are as long as the record set) and stores the run's two counts.  No atomics,
 // no block barriers, no dependence between runs.  k_scan_runs turns the counts into file-order offsets
 // (single-pass look-back scan) and k_relocate moves each run to its final place.
+//
+// Only ~7 % of the records have two live piles, so the pass is split in two phases per run:
+//   1. liveness: 16 records per lane, both id columns as 16-byte loads, 32 bitmap gathers in flight per lane;
+//      the candidates' positions inside the run are COMPACTED into a per-warp queue in shared memory (one packed
+//      warp scan ranks all four 128-record groups at once: one byte per group, each <= 128);
+//   2. trim + type run over the queue with (almost) every lane busy, instead of sixteen times over mostly idle
+//      warps (the first version of this kernel executed 12 of 32 lanes per instruction, profiles/r01f).
 __global__ void __launch_bounds__(kTileThreads) k_classify_survivors(
     List recs, uint32_t n, const uint2* __restrict__ piles, const uint32_t* __restrict__ alive_bits, uint32_t n_piles,
     List tmp_ovl, List tmp_inl, uint32_t cap, uint32_t* __restrict__ run_cnt) {
+    __shared__ uint16_t s_queue[kTileWarps][kRunRecords];
     const uint32_t lane = lane_id();
+    uint16_t* queue = s_queue[warp_id()];
     const uint32_t num_runs = (n + kRunRecords - 1) / kRunRecords;
     const uint32_t warps = gridDim.x * kTileWarps;
     for (uint32_t run = blockIdx.x * kTileWarps + warp_id(); run < num_runs; run += warps) {
-        const uint32_t q = run * 32u + lane;     // this lane's group of 4 records
-        uint32_t a[4] = {kInvalidBit, kInvalidBit, kInvalidBit, kInvalidBit}, b[4] = {0u, 0u, 0u, 0u};
-        if (4u * q < n) {
-            unpack4(reinterpret_cast<const uint4*>(recs.a)[q], a);
-            unpack4(reinterpret_cast<const uint4*>(recs.b)[q], b);
-        }
-        bool cand[kRecItems];
+        uint32_t a[kRunGroups][4], b[kRunGroups][4];
 #pragma unroll
-        for (int r = 0; r < kRecItems; ++r) {   // both piles alive at the end (graph.cpp:493-515)?  one L1-resident bit each
-            const uint32_t i = 4u * q + r, idb = b[r] & 0x7FFFFFFFu;
-            cand[r] = i < n && !(a[r] & kInvalidBit) && a[r] < n_piles && idb < n_piles &&
-                      ((__ldg(alive_bits + (a[r] >> 5)) >> (a[r] & 31u)) & 1u) && ((__ldg(alive_bits + (idb >> 5)) >> (idb & 31u)) & 1u);
-        }
-        int dest[kRecItems];
-        Entry e[kRecItems];
-        uint8_t tag[kRecItems];
-        uint32_t packed = 0;   // survivors of this lane: `overlaps` in the low half, `internals` in the high half
+        for (int j = 0; j < kRunGroups; ++j) {
+            const uint32_t q = run * (kRunRecords / 4) + j * 32u + lane;     // this lane's j-th group of 4 records
 #pragma unroll
-        for (int r = 0; r < kRecItems; ++r) {
-            dest[r] = 0;
-            tag[r] = kRejected;
-            if (cand[r]) {   // only now fetch the coordinates and the two piles
-                const uint32_t i = 4u * q + r;
-                e[r].a = a[r];
-                e[r].b = b[r] & 0x7FFFFFFFu;
-                e[r].ori = b[r] >> 31;
-                e[r].c.ab = recs.ab[i]; e[r].c.ae = recs.ae[i]; e[r].c.bb = recs.bb[i]; e[r].c.be = recs.be[i];
-                const Pile pa = load_pile(piles, e[r].a), pb = load_pile(piles, e[r].b);
-                if (trim(e[r].c, e[r].ori, pa, pb)) {
-                    tag[r] = classify(e[r].c, relative(e[r].c, e[r].ori, pa, pb));
-                    dest[r] = tag[r] == kX ? 2 : 1;   // a surviving kA/kB has a chimeric container (:470, :476)
-                    packed += dest[r] == 1 ? 1u : 0x10000u;
-                }
+            for (int r = 0; r < 4; ++r) { a[j][r] = kInvalidBit; b[j][r] = 0u; }
+            if (4u * q < n) {
+                unpack4(reinterpret_cast<const uint4*>(recs.a)[q], a[j]);
+                unpack4(reinterpret_cast<const uint4*>(recs.b)[q], b[j]);
             }
         }
+        uint32_t cand = 0;   // bit j * 4 + r
+#pragma unroll
+        for (int j = 0; j < kRunGroups; ++j) {
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {   // both piles alive at the end (graph.cpp:493-515)?  one L1-resident bit each
+                const uint32_t i = run * kRunRecords + j * 128u + 4u * lane + r, ida = a[j][r], idb = b[j][r] & 0x7FFFFFFFu;
+                const bool ok = i < n && !(ida & kInvalidBit) && ida < n_piles && idb < n_piles &&
+                                ((__ldg(alive_bits + (ida >> 5)) >> (ida & 31u)) & 1u) && ((__ldg(alive_bits + (idb >> 5)) >> (idb & 31u)) & 1u);
+                cand |= ok ? 1u << (j * 4 + r) : 0u;
+            }
+        }
+        // rank of every candidate in record order (group-major, then lane, then r)
+        uint32_t packed = 0;
+#pragma unroll
+        for (int j = 0; j < kRunGroups; ++j) packed |= (uint32_t) __popc((cand >> (4 * j)) & 0xFu) << (8 * j);
         const uint32_t inc = warp_inclusive_scan(packed);
-        if (lane == 31) run_cnt[run] = inc;
-        if (packed) {
-            const uint32_t before = inc - packed;
-            uint32_t pa_ = run * kRunRecords + (before & 0xFFFFu), pb_ = run * kRunRecords + (before >> 16);
+        const uint32_t tot = __shfl_sync(0xFFFFFFFFu, inc, 31);
+        uint32_t group_base = 0, total = 0;
 #pragma unroll
-            for (int r = 0; r < kRecItems; ++r) {
-                if (dest[r] == 1) {
-                    if (pa_ < cap) store_entry(tmp_ovl, pa_, e[r], tag[r]);
-                    ++pa_;
-                } else if (dest[r] == 2) {
-                    if (pb_ < cap) store_entry(tmp_inl, pb_, e[r], tag[r]);
-                    ++pb_;
+        for (int j = 0; j < kRunGroups; ++j) {
+            uint32_t p = group_base + (((inc - packed) >> (8 * j)) & 0xFFu);
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                if ((cand >> (j * 4 + r)) & 1u) queue[p++] = (uint16_t) (j * 128u + 4u * lane + r);
+            }
+            group_base += (tot >> (8 * j)) & 0xFFu;
+        }
+        total = group_base;
+        __syncwarp();
+        uint32_t n_a = 0, n_b = 0;   // warp-uniform: survivors of the run so far (`overlaps`, `internals`)
+        for (uint32_t k0 = 0; k0 < total; k0 += 32) {
+            const uint32_t k = k0 + lane;
+            int dest = 0;
+            uint8_t tag = kRejected;
+            Entry e;
+            if (k < total) {   // only now fetch the coordinates and the two piles
+                const uint32_t i = run * kRunRecords + queue[k];
+                const uint32_t vb = recs.b[i];
+                e.a = recs.a[i];
+                e.b = vb & 0x7FFFFFFFu;
+                e.ori = vb >> 31;
+                e.c.ab = recs.ab[i]; e.c.ae = recs.ae[i]; e.c.bb = recs.bb[i]; e.c.be = recs.be[i];
+                const Pile pa = load_pile(piles, e.a), pb = load_pile(piles, e.b);
+                if (trim(e.c, e.ori, pa, pb)) {
+                    tag = classify(e.c, relative(e.c, e.ori, pa, pb));
+                    dest = tag == kX ? 2 : 1;   // a surviving kA/kB has a chimeric container (:470, :476)
                 }
             }
+            const uint32_t ma = __ballot_sync(0xFFFFFFFFu, dest == 1), mb = __ballot_sync(0xFFFFFFFFu, dest == 2);
+            const uint32_t below = (1u << lane) - 1u;
+            if (dest == 1) {
+                const uint32_t p = run * kRunRecords + n_a + __popc(ma & below);
+                if (p < cap) store_entry(tmp_ovl, p, e, tag);
+            } else if (dest == 2) {
+                const uint32_t p = run * kRunRecords + n_b + __popc(mb & below);
+                if (p < cap) store_entry(tmp_inl, p, e, tag);
+            }
+            n_a += __popc(ma);
+            n_b += __popc(mb);
         }
+        if (lane == 0) run_cnt[run] = n_a | (n_b << 16);
+        __syncwarp();   // the queue is reused by the next run
     }
 }
 

@@ -162,6 +162,46 @@ def test_run_frozen_piles_vs_oracle(ctx, kw):
     G.close()
 
 
+def test_run_as_cuda_graph_matches_the_eager_chain(ctx):
+    """rala_b200_graph_run replays a captured CUDA graph from the second run of a session shape on; the replays
+    (repeated runs, and runs after re-uploading the same inputs) must leave exactly what the eager chain leaves."""
+    ds = synth.generate(1_200_000, 35, 9000, len_sd=2500, seed=71, noise=60, dual=True)
+    piles = ds.flat_piles()
+    P = O.Pipeline(ds.records, piles).run()
+    G = api.Graph(ctx)
+    G.use_cuda_graph(False)
+    G.set_piles(piles).set_hills(None).set_overlaps(ds.records)
+    G.run()
+    assert G.stage_ms()["classify"] > 0.0
+    keys = ("n_nodes", "n_edges", "n_transitive_pairs", "n_overlaps", "n_internals", "n_candidates", "n_two_hop")
+    want = (G.edges().copy(), G.marked().copy(), {k: G.counts()[k] for k in keys})
+    assert_same(want[0], P.edges, "eager edges vs oracle")
+    assert_same(want[1], P.marked, "eager marks vs oracle")
+    G.use_cuda_graph(True)
+    for i in range(5):          # 1st: eager (shape seen), 2nd: capture + launch, then replays
+        G.run()
+        assert_same(G.edges(), want[0], f"edges, repeated run {i}")
+        assert_same(G.marked(), want[1], f"marks, repeated run {i}")
+        assert {k: G.counts()[k] for k in keys} == want[2]
+    for i in range(4):          # the other cached instance: first run after set_piles
+        G.set_piles(piles).set_overlaps(ds.records)
+        G.run()
+        assert_same(G.edges(), want[0], f"edges, re-upload {i}")
+        assert_same(G.marked(), want[1], f"marks, re-upload {i}")
+        ovl, inl = G.lists()
+        assert_same(ovl, P.ovl, "final overlaps")
+        assert_same(inl, P.int, "final internals")
+    # a different batch in the same session must not replay the old graph's sizes
+    sub = ds.records[: ds.records.shape[0] // 2]
+    P2 = O.Pipeline(sub, piles).run()
+    for i in range(3):
+        G.set_piles(piles).set_overlaps(sub)
+        G.run()
+        assert_same(G.edges(), P2.edges, f"edges, half batch {i}")
+        assert_same(G.marked(), P2.marked, f"marks, half batch {i}")
+    G.close()
+
+
 def test_host_filtered_overlaps_before_build(ctx):
     """The -s option (Graph::preprocess(overlaps, path), graph.cpp:523, 882-1054) stays host code that only DROPS
     entries of `overlaps`; the kept list goes back to the device (rala_b200_graph_set_kept_overlaps) and edge creation
