@@ -248,8 +248,20 @@ static void scan_state(rala_b200_graph* g, uint64_t n_max, unsigned long long** 
 }
 
 // stage timers: plain event records, left out of a stream capture (an event recorded inside a capture cannot be timed)
+// `capturing` covers the library's own capture (rala_b200_graph_run); a caller may also capture the phase calls
+// into a graph of its own (rala_b200/multi.py: kernels + NCCL collectives of one multi-GPU step), so ask the stream.
+static bool stream_capturing(const rala_b200_graph* g) {
+    if (g->capturing) return true;
+    cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(g->ctx->L.stream, &st) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return st != cudaStreamCaptureStatusNone;
+}
+
 static cudaError_t stage_event(rala_b200_graph* g, cudaEvent_t ev) {
-    return g->capturing ? cudaSuccess : cudaEventRecord(ev, g->ctx->L.stream);
+    return stream_capturing(g) ? cudaSuccess : cudaEventRecord(ev, g->ctx->L.stream);
 }
 
 static cudaError_t begin_stage(rala_b200_graph* g, int stage) {
@@ -260,7 +272,7 @@ static cudaError_t begin_stage(rala_b200_graph* g, int stage) {
 }
 
 static cudaError_t end_stage(rala_b200_graph* g, int stage) {
-    g->ev_valid[stage] = !g->capturing;
+    g->ev_valid[stage] = !stream_capturing(g);
     return stage_event(g, g->ev_stop[stage]);
 }
 

@@ -163,6 +163,9 @@ class DistributedGraph:
         self.caps = None      # exchange capacities learned by the last sized run
         self.last_info = None
         self._bufs = {}
+        self._graph = None    # one bounded pass (kernels + NCCL collectives) captured in a CUDA graph
+        self.graph_launches = 0
+        self.graph_error = None
 
     def _gather_counts(self, values):
         t = torch.tensor(values, dtype=torch.int64, device=self.device)
@@ -207,8 +210,39 @@ class DistributedGraph:
         if self.caps is not None and self.s.overflowed():
             self.caps = None
             self._bufs = {}
+            self._graph = None
             return False
         return True
+
+    def capture(self) -> bool:
+        """Capture one capacity-bounded pass, NCCL collectives included, in a CUDA graph: `replay()` then costs one
+        launch per step instead of ~50 kernel launches, ~20 library calls and 5 collectives issued from Python.
+        Requires a sized pass before (capacities, buffers) and a session created on a non-default stream that is
+        torch's current stream.  Returns False (and keeps the eager path) when the capture fails."""
+        if self.caps is None:
+            self.run()
+        self.run_bounded()          # every exchange buffer exists before the capture starts
+        torch.cuda.synchronize(self.device)
+        stream = torch.cuda.current_stream(self.device)
+        launches0 = self.s.ctx.launch_count
+        try:
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph, stream=stream, capture_error_mode="thread_local"):
+                self.run_bounded()
+            self._graph = graph
+            self.graph_launches = self.s.ctx.launch_count - launches0
+            self.graph_error = None
+        except Exception as exc:   # noqa: BLE001 — the eager bounded path stays available
+            self._graph = None
+            self.graph_error = f"{type(exc).__name__}: {exc}"
+        return self._graph is not None
+
+    def replay(self):
+        """One pass: the captured graph when there is one, else the eager bounded (or sized) pass."""
+        if self._graph is not None:
+            self._graph.replay()
+            return dict(self.last_info, bounded=True, graph=True)
+        return self.run()
 
     def _buffers(self, name: str, cap: int):
         key = (name, cap)
@@ -363,11 +397,22 @@ def bench_main(args):
     dist.init_process_group("nccl", device_id=device)
     records, piles, t0, n_total_records = _global_dataset(args, rank, world, device)
 
+    # a side stream: the library enqueues on the stream that is current when the session is created, NCCL orders
+    # itself against torch's current stream, and a CUDA graph cannot be captured on the legacy default stream
+    torch.cuda.set_stream(torch.cuda.Stream(device))
     sess = CudaShardSession(local_rank)
     sess.set_inputs(records, piles, None, t0, rank, world)
     dg = DistributedGraph(sess, rank, world)
     for _ in range(max(args.warmup, 3)):
         info = dg.run()
+    torch.cuda.synchronize()
+    use_graph = not os.environ.get("RALA_B200_NO_STEP_GRAPH")
+    ok = torch.tensor([1 if (use_graph and dg.capture()) else 0], dtype=torch.int32, device=device)
+    dist.all_reduce(ok, op=dist.ReduceOp.MIN)          # all ranks replay, or none does
+    if not int(ok.item()):
+        dg._graph = None
+    for _ in range(3):
+        info = dg.replay()
     torch.cuda.synchronize()
     sampler = bench.ClockSampler(local_rank) if rank == 0 else None
     if sampler:
@@ -379,20 +424,23 @@ def bench_main(args):
     t_wall = time.perf_counter()
     ev0.record()
     for _ in range(args.steps):
-        info = dg.run()
+        info = dg.replay()
     ev1.record()
     torch.cuda.synchronize()
     dist.barrier()
     wall_ms = 1e3 * (time.perf_counter() - t_wall)
     dev_ms = ev0.elapsed_time(ev1)
-    launches = sess.ctx.launch_count - launches0
+    launches = (sess.ctx.launch_count - launches0) + (dg.graph_launches * args.steps if dg._graph is not None else 0)
     t = torch.tensor([dev_ms, wall_ms], dtype=torch.float64, device=device)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)           # max over ranks
     ms_per_step = float(t[0].item()) / args.steps
     if not dg.check():   # synchronises: an exchange block overflowed in a bounded pass -> the timing is void
         raise api.RalaB200Error("a capacity-bounded exchange overflowed during the timed region")
-    stage = sess.G.stage_ms()
     clocks = sampler.stop() if sampler else None
+    for _ in range(3):      # stage timers are CUDA events between the kernels: they only exist in the eager chain
+        dg.run()
+    torch.cuda.synchronize()
+    stage = sess.G.stage_ms()
     c = sess.counts()
     E = c["n_edges"]
     assert E == info["n_edges"], (E, info["n_edges"])
@@ -437,6 +485,8 @@ def bench_main(args):
                                       "transitive by source-node range, marks all-reduce(max)",
                        "l2": "inputs larger than L2 (each rank streams its 400 MB record shard per step)",
                        "collective_bytes_received_per_rank_per_step": dg.comm_bytes,
+                       "step_graph": ("one CUDA graph per step (kernels + NCCL collectives captured together)" if dg._graph is not None
+                                      else f"eager ({dg.graph_error or 'disabled'})"),
                        "exchange": "capacity-bounded blocks (counts inside the blocks, time bases on the device): no host "
                                    "synchronisation inside a step; capacities from the sized warm-up pass x 1.25"},
             "wall_ms_per_step": float(t[1].item()) / args.steps,

@@ -28,7 +28,7 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, out_dir):
+def _worker(rank, world, port, out_dir, graph):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
@@ -37,11 +37,17 @@ def _worker(rank, world, port, out_dir):
         piles = ds.flat_piles()
         flags = (np.random.Generator(np.random.PCG64(1)).random(ds.n_reads) < 0.05).astype(np.uint8) * 2
         lo, hi = multi.shard_bounds(ds.n_overlaps, world)[rank]
+        torch.cuda.set_stream(torch.cuda.Stream(torch.device("cuda", rank)))   # a step graph cannot be captured on the default stream
         sess = multi.CudaShardSession(rank)
         sess.set_inputs(np.ascontiguousarray(ds.records[lo:hi]), piles, flags, lo, rank, world)
         dg = multi.DistributedGraph(sess, rank, world)
-        for _ in range(2):   # twice: the session must be re-runnable (bench loop)
+        for _ in range(2):   # twice: the session must be re-runnable (bench loop); the second pass is capacity-bounded
             info = dg.run()
+        if graph:            # the whole step (kernels + NCCL collectives) captured once, replayed twice
+            assert dg.capture(), dg.graph_error
+            for _ in range(2):
+                dg.replay()
+            assert dg.check()
         c = sess.counts()
         np.savez(os.path.join(out_dir, f"r{rank}.npz"), edges=sess.edges(), marked=sess.marked(), piles=sess.G.piles(),
                  n_pairs=c["n_transitive_pairs"], n_nodes=c["n_nodes"], n_events=info["n_events"])
@@ -50,15 +56,16 @@ def _worker(rank, world, port, out_dir):
         dist.destroy_process_group()
 
 
+@pytest.mark.parametrize("graph", [False, True], ids=["eager", "step_graph"])
 @pytest.mark.parametrize("world", [1, 2, 4])
-def test_multi_gpu_matches_oracle(world, tmp_path):
+def test_multi_gpu_matches_oracle(world, graph, tmp_path):
     if torch.cuda.device_count() < world:
         pytest.skip(f"needs {world} GPUs")
     ds = synth.generate(**KW)
     flags = (np.random.Generator(np.random.PCG64(1)).random(ds.n_reads) < 0.05).astype(np.uint8) * 2
     want = O.Pipeline(ds.records, ds.flat_piles(), flags).run()
     assert want.edges.shape[0] > 5000
-    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path), graph), nprocs=world, join=True)
     for r in range(world):
         z = np.load(tmp_path / f"r{r}.npz")
         assert np.array_equal(z["edges"], want.edges), f"rank {r}: edge list"
