@@ -282,26 +282,55 @@ def run_single(args):
                         "k_transitive": {"ms": k3_ms, "algorithmic_bytes": k3_bytes, "gbs": k3_gbs, "frac": k3_gbs / peak}},
             "stage_ms": {k: float(np.mean(v)) for k, v in stage_acc.items()}}
 
-    # ---- end to end through the C ABI with host buffers ------------------------------------------
-    edges_pin = torch.empty((max(E, 1), 3), dtype=torch.int32).pin_memory()
-    marked_pin = torch.empty(max(E, 1), dtype=torch.uint8).pin_memory()
-    e2e_steps = max(3, min(args.steps, 10))
+    # ---- end to end through the C ABI with HOST buffers ----------------------------------------
+    # What the host shim does per batch (host/graph_b200.cpp): records marshalled column-wise in pinned memory
+    # (24 B / record, rala_b200_graph_set_overlaps_columns), pile table, one run, results written by the GPU
+    # straight into pinned host buffers (rala_b200_graph_set_outputs: edge rows leave while the transitive pass
+    # runs), counts read back.  Every copy is inside the timed region.
+    e2e = None
+    if not args.skip_e2e:
+        cols_pin = torch.from_numpy(api.records_to_columns(ds.records)).pin_memory()
+        edges_pin = torch.empty((max(E, 1), 3), dtype=torch.int32).pin_memory()
+        marked_pin = torch.empty(max(E, 1), dtype=torch.uint8).pin_memory()
+        e2e_steps = max(3, min(args.steps, 10))
 
-    def e2e_step():
-        G.set_piles(piles_pin).set_overlaps(rec_pin)
-        G.run()
-        G.edges(out=edges_pin)
-        G.marked(out=marked_pin)
+        def e2e_step():
+            G.set_piles(piles_pin).set_overlaps_columns(cols_pin)
+            G.run()
+            return G.counts()          # synchronises: edges_pin / marked_pin are complete
 
-    e2e_step()
-    ctx.synchronize()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        e2e_step()
-    ctx.synchronize()
-    e2e_s = (time.perf_counter() - t0) / e2e_steps
-    h2d = ds.records.nbytes + piles.nbytes
-    d2h = 12 * E + E + 4 * 30
+        def e2e_step_rows():           # the row form of the same call sequence (28 B / record + explicit downloads)
+            G.set_piles(piles_pin).set_overlaps(rec_pin)
+            G.run()
+            G.edges(out=edges_pin)
+            G.marked(out=marked_pin)
+
+        def timed(fn, n):
+            for _ in range(3):         # shape change -> eager run -> graph capture -> replay
+                fn()
+            ctx.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(n):
+                fn()
+            ctx.synchronize()
+            return (time.perf_counter() - t0) / n
+
+        rows_s = timed(e2e_step_rows, 3)
+        edges_rows = edges_pin.numpy().copy()
+        marked_rows = marked_pin.numpy().copy()
+        edges_pin.zero_()
+        marked_pin.zero_()
+        G.set_outputs(edges_pin, marked_pin)
+        e2e_s = timed(e2e_step, e2e_steps)
+        c2 = e2e_step()
+        G.set_outputs(None, None)
+        assert c2["n_edges"] == E and c2["n_transitive_pairs"] == counts["n_transitive_pairs"], (c2, counts)
+        assert np.array_equal(edges_pin.numpy(), edges_rows) and np.array_equal(marked_pin.numpy(), marked_rows), \
+            "direct-to-host outputs differ from get_edges / get_marked"
+        e2e = {"value": E / e2e_s, "unit": "edges/s", "h2d_bytes_per_step": int(cols_pin.numel() * 4 + piles.nbytes),
+               "d2h_bytes_per_step": int(12 * E + E + 4 * 34), "ms_per_step": 1e3 * e2e_s,
+               "path": "set_piles + set_overlaps_columns (pinned, 24 B/record) + run + outputs written to pinned host memory by the GPU + counts",
+               "row_form_ms_per_step": 1e3 * rows_s}
 
     # ---- CPU baseline on the same batch (rank 0, N = 1) -----------------------------------------
     cpu = None
@@ -323,14 +352,56 @@ def run_single(args):
                    "l2": f"inputs larger than L2 ({ds.records.nbytes / 1e6:.0f} MB of records streamed per step)",
                    "parallelism": "1 GPU"},
         "wall_ms_per_step": wall_ms / args.steps,
-        "e2e": {"value": E / e2e_s, "unit": "edges/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                "ms_per_step": 1e3 * e2e_s},
-        "gpu_launches": int(launches),
+        "e2e": e2e,
+        "gpu_launches": int(launches), "lib": os.path.relpath(api.LIB_PATH, ROOT),
         "roofline": roof, "cpu_baseline": cpu, "clocks": clocks,
     }
     print(json.dumps(line))
     G.close()
     ctx.close()
+
+
+def run_ab(args):
+    """A/B of single optimisations: the product library and the builds with ONE switch turned off each
+    (rala_b200/build.py VARIANTS, common.cuh RB_OPT_*), same batch, same process, device-resident steps."""
+    from rala_b200 import api, build as B
+    ds = make_dataset(args.workload, 1)
+    piles = ds.flat_piles()
+    libs = [("product", api.LIB_PATH, None)] + [(k, B.variant_path(k), None) for k in B.VARIANTS if os.path.exists(B.variant_path(k))]
+    prev = B.variant_path("prev")   # the previous commit's library, when profiles/capture_ab.sh built it
+    if os.path.exists(prev):
+        libs.append(("prev", prev, None))
+    # launch-time knobs are read once per loaded library: a byte-identical copy under another name is a fresh instance
+    import shutil
+    for minb in (4, 5):
+        copy = B.variant_path(f"minb{minb}")
+        shutil.copyfile(api.LIB_PATH, copy)
+        libs.append((f"events_minb{minb}", copy, ("RALA_B200_EV_MINB", str(minb))))
+    out = {}
+    for rnd in range(2):            # two rounds, interleaved: drift shows up as a difference between them
+        for name, path, env in libs:
+            os.environ.pop("RALA_B200_EV_MINB", None)
+            if env:
+                os.environ[env[0]] = env[1]
+            ctx = api.Context(0, lib=api.load_path(path))
+            G = api.Graph(ctx)
+            G.set_piles(piles).set_hills(None).set_overlaps(ds.records)
+            for _ in range(max(args.warmup, 3)):
+                G.run()
+            ctx.synchronize()
+            ctx.event_record(0)
+            for _ in range(args.steps):
+                G.run()
+            ctx.event_record(1)
+            ms = ctx.event_elapsed_ms() / args.steps
+            c = G.counts()
+            out.setdefault(name, {"ms_per_step": [], "edges": c["n_edges"], "pairs": c["n_transitive_pairs"]})["ms_per_step"].append(ms)
+            G.close()
+            ctx.close()
+    base = min(out["product"]["ms_per_step"])
+    for name, v in out.items():
+        v["delta_us_vs_product"] = 1e3 * (min(v["ms_per_step"]) - base)
+    print(json.dumps({"ab": out, "steps": args.steps, "workload": WORKLOADS[args.workload][3]}))
 
 
 def main():
@@ -341,10 +412,15 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c3", choices=list(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--skip-e2e", action="store_true", help="device-resident timing only")
+    ap.add_argument("--ab", action="store_true", help="time the product library against the one-switch-off builds (rala_b200/variants/)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":
         run_reference_arm(args)
+        return
+    if args.ab:
+        run_ab(args)
         return
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.gpus > 1 or world > 1:

@@ -100,6 +100,16 @@ rala_ovl_t marshal(const Overlap& o, bool valid) {
     return r;
 }
 
+// the same members, column-wise in the device layout (rala_b200_graph_set_overlaps_columns): 24 bytes per record
+void marshal(const Overlap& o, bool valid, rala_b200::OverlapColumns& c) {
+    c.a_id.push_back(valid ? static_cast<uint32_t>(o.a_id_) : 0x80000000u);
+    c.b_id.push_back((valid ? static_cast<uint32_t>(o.b_id_) : 0u) | ((o.orientation_ & 1u) << 31));
+    c.a_begin.push_back(o.a_begin_);
+    c.a_end.push_back(o.a_end_);
+    c.b_begin.push_back(o.b_begin_);
+    c.b_end.push_back(o.b_end_);
+}
+
 }  // namespace
 
 // ------------------------------------------------------------------------------------------------
@@ -120,8 +130,8 @@ void construct(Graph& g, const std::string& sensitive_overlaps_path) {
         exit(1);
     }
 
-    // second pass over the overlap file (:446-448): parse, name -> id, marshal 28 bytes per record, free the objects
-    std::vector<rala_ovl_t> records;
+    // second pass over the overlap file (:446-448): parse, name -> id, marshal 24 bytes per record, free the objects
+    rala_b200::OverlapColumns records;
     records.reserve(g.is_valid_overlap_.size());
     {
         std::vector<std::unique_ptr<Overlap>> chunk;
@@ -133,7 +143,7 @@ void construct(Graph& g, const std::string& sensitive_overlaps_path) {
                 // :450-451; transmute() sees the piles as initialize() left them: its "pile is already dead" gate for
                 // piles killed LATER in the loop is what the device resolves
                 bool valid = g.is_valid_overlap_[num_overlaps + i] && chunk[i]->transmute(g.piles_, g.name_to_id_);
-                records.emplace_back(marshal(*chunk[i], valid));
+                marshal(*chunk[i], valid, records);
             }
             num_overlaps += chunk.size();
             chunk.clear();
@@ -153,7 +163,7 @@ void construct(Graph& g, const std::string& sensitive_overlaps_path) {
     upload_piles(g, s);
     s.set_hills(hills);
     s.set_overlaps(records);
-    std::vector<rala_ovl_t>().swap(records);
+    records = rala_b200::OverlapColumns();
 
     s.classify();   // :448-517 on the device: trim, type, hill counters, ordered containment, dead-pile filter
 

@@ -18,6 +18,15 @@
 
 namespace rala_b200 {
 
+// Overlap records column-wise, in the layout the kernels read (rala_b200_graph_set_overlaps_columns):
+// bit 31 of a_id = invalid record, bit 31 of b_id = orientation.
+struct OverlapColumns {
+    std::vector<uint32_t> a_id, b_id, a_begin, a_end, b_begin, b_end;
+    void reserve(size_t n) {
+        a_id.reserve(n); b_id.reserve(n); a_begin.reserve(n); a_end.reserve(n); b_begin.reserve(n); b_end.reserve(n);
+    }
+};
+
 class Session {
 public:
     // `where` names the reference function on whose behalf the calls are made (for error messages)
@@ -42,6 +51,11 @@ public:
     void where(const std::string& w) { where_ = w; }
 
     // ---- inputs ---------------------------------------------------------------------------
+    void set_overlaps(const OverlapColumns& c) {
+        check(rala_b200_graph_set_overlaps_columns(graph_, c.a_id.data(), c.b_id.data(), c.a_begin.data(), c.a_end.data(),
+                                                   c.b_begin.data(), c.b_end.data(), c.a_id.size()), "set_overlaps_columns");
+        check(rala_b200_synchronize(ctx_), "synchronize");   // the columns may be released by the caller
+    }
     void set_overlaps(const std::vector<rala_ovl_t>& records) {
         check(rala_b200_graph_set_overlaps(graph_, records.data(), records.size()), "set_overlaps");
         check(rala_b200_synchronize(ctx_), "synchronize");   // `records` may be released by the caller

@@ -136,8 +136,24 @@ int rala_b200_graph_create(rala_b200_ctx* ctx, rala_b200_graph** out);
 void rala_b200_graph_destroy(rala_b200_graph* g);
 
 int rala_b200_graph_set_overlaps(rala_b200_graph* g, const rala_ovl_t* ovl, uint64_t n);
+/* The same records as six HOST COLUMNS in the layout the kernels read (replaces the same members of rala::Overlap,
+ * overlap.hpp:104-116, marshalled column-wise by the host shim): 24 bytes per record cross PCIe instead of 28 and
+ * land in place, with no staging copy and no transpose kernel.  Bit 31 of a_id[i] marks an INVALID record
+ * (RALA_OVL_INVALID), bit 31 of b_id[i] is the orientation (RALA_OVL_RC); ids are < 2^31.  File order as above. */
+int rala_b200_graph_set_overlaps_columns(rala_b200_graph* g, const uint32_t* a_id, const uint32_t* b_id,
+                                         const uint32_t* a_begin, const uint32_t* a_end, const uint32_t* b_begin,
+                                         const uint32_t* b_end, uint64_t n);
 int rala_b200_graph_set_piles(rala_b200_graph* g, const rala_pile_t* piles, const uint8_t* flags /* nullable */,
                               uint32_t n_piles);
+/* Optional: have build / transitive / run write their results STRAIGHT into caller memory the GPU can address
+ * (cudaHostAlloc / cudaHostRegister'ed host memory, or device memory): the rala_edge_t rows (graph.cpp:576-632)
+ * leave as soon as the edge list exists, on a forked stream beside the CSR build and the transitive pass, and the
+ * removed-edge marks (graph.cpp:1305-1309) as they are finalised.  Nothing beyond the given capacities (in edges)
+ * is written; the counts come from rala_b200_graph_counts.  The buffers hold valid data once the stream has been
+ * synchronised (rala_b200_graph_counts / rala_b200_synchronize).  NULL switches an output off again; pageable
+ * memory is refused (RALA_B200_ERR_ARG): use get_edges / get_marked for it. */
+int rala_b200_graph_set_outputs(rala_b200_graph* g, rala_edge_t* edges_out, uint64_t edges_cap, uint8_t* marked_out,
+                                uint64_t marked_cap);
 int rala_b200_graph_set_hills(rala_b200_graph* g, const rala_hill_t* hills, uint32_t n_hills);
 
 int rala_b200_graph_classify(rala_b200_graph* g);

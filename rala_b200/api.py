@@ -15,7 +15,9 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "librala_b200.so")
+# RALA_B200_LIB: another build of the same library (rala_b200/variants/: one optimisation switched off each), for
+# bench.py's A/B lines.  Never a fallback: the file must exist.
+LIB_PATH = os.environ.get("RALA_B200_LIB") or os.path.join(_HERE, "librala_b200.so")
 N_STAGES = 9
 STAGE_NAMES = ("classify", "retrim", "finalize", "build", "transitive", "k1_classify_kernel", "k1b_fixpoint_kernel",
                "k3_transitive_kernels", "k1_survivors_kernel")
@@ -49,7 +51,7 @@ EXPORTS = [
     "rala_b200_graph_get_hill_coverage", "rala_b200_graph_get_piles", "rala_b200_graph_get_connections",
     "rala_b200_graph_get_lists", "rala_b200_graph_get_seq_to_node", "rala_b200_graph_get_edges",
     "rala_b200_graph_get_marked", "rala_b200_graph_stage_ms", "rala_b200_graph_set_kept_overlaps",
-    "rala_b200_graph_use_cuda_graph",
+    "rala_b200_graph_use_cuda_graph", "rala_b200_graph_set_overlaps_columns", "rala_b200_graph_set_outputs",
     # multi-GPU phases
     "rala_b200_create_on_stream", "rala_b200_graph_set_shard", "rala_b200_graph_phase_events",
     "rala_b200_graph_events_count", "rala_b200_graph_export_events", "rala_b200_graph_import_events",
@@ -64,18 +66,23 @@ EXPORTS = [
 _LIB = None
 
 
+def load_path(path: str):
+    """Load one build of the CUDA extension; raises (never falls back) when the file is missing."""
+    if not os.path.exists(path):
+        raise RalaB200Error(f"{path} is missing: run `python -m rala_b200.build` (there is no CPU fallback)")
+    lib = C.CDLL(path)
+    lib.rala_b200_last_error.restype = C.c_char_p
+    lib.rala_b200_launch_count.restype = C.c_uint64
+    lib.rala_b200_destroy.restype = None
+    lib.rala_b200_graph_destroy.restype = None
+    return lib
+
+
 def load():
-    """Load the CUDA extension; raises (never falls back) when it has not been built."""
+    """The product library (LIB_PATH), loaded once."""
     global _LIB
     if _LIB is None:
-        if not os.path.exists(LIB_PATH):
-            raise RalaB200Error(f"{LIB_PATH} is missing: run `python -m rala_b200.build` (there is no CPU fallback)")
-        lib = C.CDLL(LIB_PATH)
-        lib.rala_b200_last_error.restype = C.c_char_p
-        lib.rala_b200_launch_count.restype = C.c_uint64
-        lib.rala_b200_destroy.restype = None
-        lib.rala_b200_graph_destroy.restype = None
-        _LIB = lib
+        _LIB = load_path(LIB_PATH)
     return _LIB
 
 
@@ -99,17 +106,31 @@ def _np(a, dtype, cols=None):
     return a
 
 
+def records_to_columns(records) -> np.ndarray:
+    """rala_ovl_t rows (n, 7) -> the six columns of rala_b200_graph_set_overlaps_columns as one contiguous (6, n)
+    array: bit 31 of a_id = invalid record (or an id >= 2^31), bit 31 of b_id = orientation."""
+    r = np.ascontiguousarray(records, dtype=np.uint32).reshape(-1, 7)
+    cols = np.empty((6, r.shape[0]), dtype=np.uint32)
+    top = np.uint32(0x80000000)
+    bad = ((r[:, 6] & 2) != 0) | ((r[:, 0] & top) != 0) | ((r[:, 1] & top) != 0)
+    cols[0] = (r[:, 0] & ~top) | np.where(bad, top, np.uint32(0))
+    cols[1] = (r[:, 1] & ~top) | ((r[:, 6] & 1) << 31)
+    cols[2:6] = r[:, 2:6].T
+    return cols
+
+
 class Context:
     """One CUDA device + stream (rala_b200_ctx)."""
 
-    def __init__(self, device: int = 0):
-        self.lib = load()
+    def __init__(self, device: int = 0, lib=None):
+        self.lib = lib or load()   # lib: another build of the same library (bench.py --ab)
         self.handle = C.c_void_p()
         rc = self.lib.rala_b200_create(C.byref(self.handle), C.c_int(device))
         if rc != 0:
             raise RalaB200Error(f"rala_b200_create(device={device}) failed with status {rc}: "
                                 "an sm_100 (B200) device is required, there is no CPU fallback")
         self.device = device
+        self._graphs = []   # weak references: sessions are destroyed before their context (rala_b200_graph holds a ctx pointer)
 
     def check(self, rc: int, what: str):
         if rc != 0:
@@ -133,6 +154,11 @@ class Context:
 
     def close(self):
         if self.handle:
+            for ref in getattr(self, "_graphs", []):
+                g = ref()
+                if g is not None:
+                    g.close()
+            self._graphs = []
             self.lib.rala_b200_destroy(self.handle)
             self.handle = C.c_void_p()
 
@@ -176,6 +202,9 @@ class Graph:
         self.lib = self.ctx.lib
         self.handle = C.c_void_p()
         self.ctx.check(self.lib.rala_b200_graph_create(self.ctx.handle, C.byref(self.handle)), "graph_create")
+        if hasattr(self.ctx, "_graphs"):
+            import weakref
+            self.ctx._graphs.append(weakref.ref(self))
         self.n_piles = 0
         self.n_hills = 0
         self._keep = []   # host buffers referenced by in-flight async copies
@@ -201,6 +230,25 @@ class Graph:
         n = rec.shape[0]
         self._keep = [rec]
         self._call("rala_b200_graph_set_overlaps", _ptr(rec), C.c_uint64(n))
+        return self
+
+    def set_overlaps_columns(self, columns):
+        """Six host columns (a_id | invalid << 31, b_id | orientation << 31, a_begin, a_end, b_begin, b_end), e.g. the
+        rows of a contiguous (6, n) array: 24 B per record cross PCIe and land in the device layout."""
+        cols = [_np(c, np.uint32) for c in columns]
+        n = cols[0].shape[0]
+        if len(cols) != 6 or any(c.shape[0] != n for c in cols):
+            raise RalaB200Error("set_overlaps_columns needs six columns of equal length")
+        self._keep = list(cols)
+        self._call("rala_b200_graph_set_overlaps_columns", *[_ptr(c) for c in cols], C.c_uint64(n))
+        return self
+
+    def set_outputs(self, edges_out=None, marked_out=None):
+        """Pinned host (or device-visible) buffers the run writes its edge rows and marks into directly."""
+        e_cap = 0 if edges_out is None else int(edges_out.shape[0])
+        m_cap = 0 if marked_out is None else int(marked_out.shape[0])
+        self._outputs = (edges_out, marked_out)
+        self._call("rala_b200_graph_set_outputs", _ptr(edges_out), C.c_uint64(e_cap), _ptr(marked_out), C.c_uint64(m_cap))
         return self
 
     def set_piles(self, piles, flags=None):

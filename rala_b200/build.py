@@ -35,14 +35,12 @@ def needs_build() -> bool:
     return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
 
 
-def build(verbose: bool = False, force: bool = False) -> str:
-    if not force and not needs_build():
-        return LIB
+def _compile(lib: str, objdir: str, defines, verbose: bool) -> str:
     objs, procs = [], []
-    os.makedirs(os.path.join(HERE, "build"), exist_ok=True)
+    os.makedirs(objdir, exist_ok=True)
     for s in SOURCES:
-        obj = os.path.join(HERE, "build", s.replace(".cu", ".o"))
-        cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, s), "-o", obj]
+        obj = os.path.join(objdir, s.replace(".cu", ".o"))
+        cmd = [_nvcc()] + NVCC_FLAGS + list(defines) + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, s), "-o", obj]
         procs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
         objs.append(obj)
     for cmd, p in procs:
@@ -51,10 +49,37 @@ def build(verbose: bool = False, force: bool = False) -> str:
             sys.stderr.write(out)
         if p.returncode != 0:
             raise RuntimeError("nvcc failed: " + " ".join(cmd))
-    link = [_nvcc(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs
+    os.makedirs(os.path.dirname(lib), exist_ok=True)
+    link = [_nvcc(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", lib] + objs
     subprocess.run(link, check=True)
-    return LIB
+    return lib
+
+
+def build(verbose: bool = False, force: bool = False) -> str:
+    if not force and not needs_build():
+        return LIB
+    return _compile(LIB, os.path.join(HERE, "build"), [], verbose)
+
+
+# A/B libraries: the product with ONE optimisation switched off each (common.cuh RB_OPT_*), for bench.py --ab.
+VARIANTS = {"no_events": "RB_OPT_EVENTS", "no_reloc": "RB_OPT_RELOC", "no_fill": "RB_OPT_FILL",
+            "no_conc": "RB_OPT_CONC", "no_bsearch": "RB_OPT_BSEARCH"}
+VARIANT_DIR = os.path.join(HERE, "variants")
+
+
+def variant_path(name: str) -> str:
+    return os.path.join(VARIANT_DIR, f"librala_b200_{name}.so")
+
+
+def build_variants(verbose: bool = False):
+    out = {}
+    for name, macro in VARIANTS.items():
+        out[name] = _compile(variant_path(name), os.path.join(HERE, "build", name), [f"-D{macro}=0"], verbose)
+    return out
 
 
 if __name__ == "__main__":
     print(build(verbose="--verbose" in sys.argv, force=True))
+    if "--variants" in sys.argv:
+        for k, v in build_variants().items():
+            print(k, v)

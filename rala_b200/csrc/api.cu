@@ -60,6 +60,14 @@ extern "C" int rala_b200_create(rala_b200_ctx** out, int device) {
     ctx->coop_blocks = resolve_max_blocks();
     cudaEventCreate(&ctx->ev[0]);
     cudaEventCreate(&ctx->ev[1]);
+    for (int k = 0; k < 2; ++k) {   // forked work inside a step (kernels.h Launch); without them everything stays on the main stream
+        if (cudaStreamCreateWithFlags(&ctx->L.side[k], cudaStreamNonBlocking) != cudaSuccess ||
+            cudaEventCreateWithFlags(&ctx->L.ev_fork[k], cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&ctx->L.ev_join[k], cudaEventDisableTiming) != cudaSuccess) {
+            ctx->L.side[k] = nullptr;
+            cudaGetLastError();
+        }
+    }
     *out = ctx;
     return RALA_B200_OK;
 }
@@ -77,6 +85,11 @@ extern "C" void rala_b200_destroy(rala_b200_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     if (ctx->L.stream && ctx->owns_stream) cudaStreamDestroy(ctx->L.stream);
+    for (int k = 0; k < 2; ++k) {
+        if (ctx->L.side[k]) cudaStreamDestroy(ctx->L.side[k]);
+        if (ctx->L.ev_fork[k]) cudaEventDestroy(ctx->L.ev_fork[k]);
+        if (ctx->L.ev_join[k]) cudaEventDestroy(ctx->L.ev_join[k]);
+    }
     delete ctx;
 }
 
@@ -180,6 +193,12 @@ struct rala_b200_graph {
     DevBuf edges_aos;
     DevBuf seq_to_node, edges, row_ptr, cursor, col, col_eid, T, marked, heavy, work_counter;
     uint32_t edge_cap = 0, heavy_cap = 0, n_nodes_max = 0;
+    // results written straight into the caller's memory by the run (rala_b200_graph_set_outputs)
+    uint32_t* out_edges = nullptr;   // device-visible address of the caller's rala_edge_t rows
+    uint8_t* out_marked = nullptr;
+    uint32_t out_edges_cap = 0, out_marked_cap = 0;
+    bool in_run = false;             // build is part of a whole run: the edge download may overlap the transitive pass
+    bool download_pending = false;   // side stream 0 is still writing edges: joined at the end of the transitive stage
     // bookkeeping
     int final_time_base_slot = C_LIST0;   // counter slot holding the time base of `internals` in the final pass
     bool final_lists_ready = true;  // after finalize: have the filtered lists of graph.cpp:867-877 been written out?
@@ -353,19 +372,12 @@ static int reserve_scan_pool(rala_b200_graph* g) {
     return RALA_B200_OK;
 }
 
-extern "C" int rala_b200_graph_set_overlaps(rala_b200_graph* g, const rala_ovl_t* ovl, uint64_t n) {
-    if (!g || (n && !ovl)) return RALA_B200_ERR_ARG;
+// device lists sized for n records (worst case every record survives; the scratch lists of the survivors pass are
+// indexed by record position)
+static int reserve_for_records(rala_b200_graph* g, uint64_t n) {
     rala_b200_ctx* ctx = g->ctx;
-    if (n >= (1ull << 31)) return fail(ctx, RALA_B200_ERR_LIMIT, "too many overlap records (%llu >= 2^31)", (unsigned long long) n);
-    CU(ctx, cudaSetDevice(ctx->device));
-    CU(ctx, g->rec.reserve(align_up((size_t) n * sizeof(rala_ovl_t) + 16, 256)));
-    if (n) CU(ctx, cudaMemcpyAsync(g->rec.p, ovl, (size_t) n * sizeof(rala_ovl_t), cudaMemcpyHostToDevice, ctx->L.stream));
     g->n_rec = (uint32_t) n;
-    // layout in HBM: rows -> six columns, once per upload (the kernels read 16 bytes per column and thread)
     CU(ctx, g->recs.reserve((uint32_t) ((n + 3) / 4 * 4 + 4)));
-    launch_records_to_soa(ctx->L, g->rec.as<uint32_t>(), (uint32_t) n, g->recs.view);
-    CU(ctx, cudaGetLastError());
-    // worst case every record survives; the scratch lists of the survivors pass are indexed by record position
     uint32_t cap = (uint32_t) align_up((size_t) n, 128);
     if (cap < 1024) cap = 1024;
     if (cap > g->cap) {
@@ -378,14 +390,75 @@ extern "C" int rala_b200_graph_set_overlaps(rala_b200_graph* g, const rala_ovl_t
         int rc2 = reserve_events(g, cap);
         if (!rc2) rc2 = reserve_edges(g, 2 * cap);
         if (rc2) return rc2;
-    } else {
-        // views depend on cap: re-derive them for the (unchanged) capacity
     }
     CU(ctx, g->tiles.reserve(align_up((size_t) classify_num_runs((uint32_t) n) + 8, 64) * 4 * 3));
     int rc = reserve_scan_pool(g);
     if (rc) return rc;
     if (g->state < 1 && g->n_piles) g->state = 1;
     if (g->state > 1) g->state = 1;
+    return RALA_B200_OK;
+}
+
+extern "C" int rala_b200_graph_set_overlaps(rala_b200_graph* g, const rala_ovl_t* ovl, uint64_t n) {
+    if (!g || (n && !ovl)) return RALA_B200_ERR_ARG;
+    rala_b200_ctx* ctx = g->ctx;
+    if (n >= (1ull << 31)) return fail(ctx, RALA_B200_ERR_LIMIT, "too many overlap records (%llu >= 2^31)", (unsigned long long) n);
+    CU(ctx, cudaSetDevice(ctx->device));
+    CU(ctx, g->rec.reserve(align_up((size_t) n * sizeof(rala_ovl_t) + 16, 256)));
+    if (n) CU(ctx, cudaMemcpyAsync(g->rec.p, ovl, (size_t) n * sizeof(rala_ovl_t), cudaMemcpyHostToDevice, ctx->L.stream));
+    int rc = reserve_for_records(g, n);
+    if (rc) return rc;
+    // layout in HBM: rows -> six columns, once per upload (the kernels read 16 bytes per column and thread)
+    launch_records_to_soa(ctx->L, g->rec.as<uint32_t>(), (uint32_t) n, g->recs.view);
+    CU(ctx, cudaGetLastError());
+    return RALA_B200_OK;
+}
+
+// The same records as six host columns in the device layout: 24 bytes per record cross PCIe instead of 28 and
+// land where the kernels read them (no staging buffer, no transpose kernel).
+extern "C" int rala_b200_graph_set_overlaps_columns(rala_b200_graph* g, const uint32_t* a_id, const uint32_t* b_id,
+                                                    const uint32_t* a_begin, const uint32_t* a_end, const uint32_t* b_begin,
+                                                    const uint32_t* b_end, uint64_t n) {
+    if (!g || (n && (!a_id || !b_id || !a_begin || !a_end || !b_begin || !b_end))) return RALA_B200_ERR_ARG;
+    rala_b200_ctx* ctx = g->ctx;
+    if (n >= (1ull << 31)) return fail(ctx, RALA_B200_ERR_LIMIT, "too many overlap records (%llu >= 2^31)", (unsigned long long) n);
+    CU(ctx, cudaSetDevice(ctx->device));
+    int rc = reserve_for_records(g, n);
+    if (rc) return rc;
+    if (n) {
+        const List& r = g->recs.view;
+        const uint32_t* src[6] = {a_id, b_id, a_begin, a_end, b_begin, b_end};
+        uint32_t* dst[6] = {r.a, r.b, r.ab, r.ae, r.bb, r.be};
+        for (int k = 0; k < 6; ++k)
+            CU(ctx, cudaMemcpyAsync(dst[k], src[k], (size_t) n * 4, cudaMemcpyHostToDevice, ctx->L.stream));
+    }
+    return RALA_B200_OK;
+}
+
+// Results straight into the caller's memory (pinned host memory or device memory the GPU can address).
+extern "C" int rala_b200_graph_set_outputs(rala_b200_graph* g, rala_edge_t* edges_out, uint64_t edges_cap, uint8_t* marked_out,
+                                           uint64_t marked_cap) {
+    if (!g) return RALA_B200_ERR_ARG;
+    rala_b200_ctx* ctx = g->ctx;
+    CU(ctx, cudaSetDevice(ctx->device));
+    void* dev[2] = {nullptr, nullptr};
+    const void* host[2] = {edges_out, marked_out};
+    for (int k = 0; k < 2; ++k) {
+        if (!host[k]) continue;
+        cudaPointerAttributes attr;
+        if (cudaPointerGetAttributes(&attr, host[k]) != cudaSuccess || attr.type == cudaMemoryTypeUnregistered || !attr.devicePointer) {
+            cudaGetLastError();
+            return fail(ctx, RALA_B200_ERR_ARG, "set_outputs: the %s buffer is not addressable by the GPU (use cudaHostAlloc / cudaHostRegister "
+                        "memory, or get_edges / get_marked for pageable memory)", k ? "marks" : "edge");
+        }
+        dev[k] = attr.devicePointer;
+    }
+    if (edges_cap >= (1ull << 31)) edges_cap = (1ull << 31) - 1;
+    if (marked_cap >= (1ull << 31)) marked_cap = (1ull << 31) - 1;
+    g->out_edges = reinterpret_cast<uint32_t*>(dev[0]);
+    g->out_edges_cap = edges_out ? (uint32_t) edges_cap : 0u;
+    g->out_marked = reinterpret_cast<uint8_t*>(dev[1]);
+    g->out_marked_cap = marked_out ? (uint32_t) marked_cap : 0u;
     return RALA_B200_OK;
 }
 
@@ -709,8 +782,19 @@ extern "C" int rala_b200_graph_build(rala_b200_graph* g) {
     scan_state(g, g->cap, &status, &ticket);
     launch_emit_edges(ctx->L, g->ovl[g->ovl_cur].view, g->cnt() + g->slot_ovl, g->cap, g->piles.as<uint2>(), g->graph_view(),
                       g->edge_cap, g->cnt(), status, ticket);
+    // the edge list is final: rows into the caller's buffer on a forked stream, beside the CSR build and (inside a
+    // whole run) the transitive pass; edges beyond the caller's capacity are not written (n_edges tells)
+    if (g->out_edges && g->out_edges_cap && fork_side(ctx->L, 0)) {
+        launch_pack_edges(ctx->L, ctx->L.side[0], g->graph_view(), g->edge_cap < g->out_edges_cap ? g->edge_cap : g->out_edges_cap,
+                          g->cnt() + C_EDGES, g->out_edges);
+        g->download_pending = true;
+    }
     scan_state(g, (uint64_t) g->n_nodes_max + 1, &status, &ticket);
     launch_build_csr(ctx->L, g->graph_view(), g->n_nodes_max, g->edge_cap, g->cnt(), status, ticket);
+    if (g->download_pending && !g->in_run) {
+        join_side(ctx->L, 0);
+        g->download_pending = false;
+    }
     CU(ctx, cudaGetLastError());
     CU(ctx, end_stage(g, ST_BUILD));
     g->state = 4;
@@ -727,7 +811,11 @@ static int run_transitive(rala_b200_graph* g) {
     launch_transitive(ctx->L, g->graph_view(), g->n_nodes_max, g->edge_cap, g->heavy_view(), g->work_counter.as<uint32_t>(),
                       g->cnt(), 0u, 0xFFFFFFFFu, g->world > 1 ? g->work_counter.as<uint32_t>() + 4 : nullptr);
     CU(ctx, end_stage(g, ST_K3_KERNELS));
-    launch_finalize_marks(ctx->L, g->graph_view(), g->edge_cap, g->cnt());
+    launch_finalize_marks(ctx->L, g->graph_view(), g->edge_cap, g->cnt(), g->out_marked, g->out_marked_cap);
+    if (g->download_pending) {
+        join_side(ctx->L, 0);
+        g->download_pending = false;
+    }
     CU(ctx, cudaGetLastError());
     return RALA_B200_OK;
 }
@@ -751,8 +839,14 @@ static int run_eager(rala_b200_graph* g) {
     if (!rc) rc = rala_b200_graph_retrim(g);
     if (!rc) rc = rala_b200_graph_retrim_promote(g, nullptr);
     if (!rc) rc = rala_b200_graph_finalize(g);
+    g->in_run = true;    // the transitive stage follows: it joins the forked edge download
     if (!rc) rc = rala_b200_graph_build(g);
+    g->in_run = false;
     if (!rc) rc = rala_b200_graph_transitive(g);
+    if (g->download_pending) {   // build forked, transitive failed before joining
+        join_side(g->ctx->L, 0);
+        g->download_pending = false;
+    }
     return rc;
 }
 
@@ -762,7 +856,8 @@ static int run_eager(rala_b200_graph* g) {
 // captured into a CUDA graph and later runs replay it with one launch.
 struct RunKey {
     const void *rec, *recs, *piles, *piles_initial, *events, *segs, *dbuf, *edges, *col, *scan_pool, *tiles, *ovl0, *inl0, *hills;
-    uint32_t n_rec, n_piles, n_hills, cap, ev_cap, edge_cap, heavy_cap, t0;
+    const void *out_edges, *out_marked;
+    uint32_t n_rec, n_piles, n_hills, cap, ev_cap, edge_cap, heavy_cap, t0, out_edges_cap, out_marked_cap;
     int world, rank, coop_blocks;
     bool piles_fresh, skip_clean_retrim;
 };
@@ -791,6 +886,7 @@ static RunKey run_key(const rala_b200_graph* g) {
     k.scan_pool = g->scan_pool.p; k.tiles = g->tiles.p; k.ovl0 = g->ovl[0].buf.p; k.inl0 = g->inl[0].buf.p; k.hills = g->hills.p;
     k.n_rec = g->n_rec; k.n_piles = g->n_piles; k.n_hills = g->n_hills; k.cap = g->cap; k.ev_cap = g->ev_cap;
     k.edge_cap = g->edge_cap; k.heavy_cap = g->heavy_cap; k.t0 = g->t0;
+    k.out_edges = g->out_edges; k.out_marked = g->out_marked; k.out_edges_cap = g->out_edges_cap; k.out_marked_cap = g->out_marked_cap;
     k.world = g->world; k.rank = g->rank; k.coop_blocks = g->ctx->coop_blocks;
     k.piles_fresh = g->piles_fresh; k.skip_clean_retrim = g->skip_clean_retrim;
     return k;
@@ -1007,7 +1103,7 @@ extern "C" int rala_b200_graph_get_edges(rala_b200_graph* g, rala_edge_t* out) {
     if (!n) return RALA_B200_OK;
     // columns -> rows on the device, then one contiguous copy
     CU(ctx, g->edges_aos.reserve((size_t) g->edge_cap * 12));
-    launch_pack_edges(ctx->L, g->graph_view(), g->edge_cap, g->cnt() + C_EDGES, g->edges_aos.as<uint32_t>());
+    launch_pack_edges(ctx->L, ctx->L.stream, g->graph_view(), g->edge_cap, g->cnt() + C_EDGES, g->edges_aos.as<uint32_t>());
     CU(ctx, cudaMemcpyAsync(out, g->edges_aos.p, (size_t) n * 12, cudaMemcpyDeviceToHost, ctx->L.stream));
     CU(ctx, cudaStreamSynchronize(ctx->L.stream));
     return RALA_B200_OK;
@@ -1405,7 +1501,7 @@ extern "C" int rala_b200_graph_phase_marks(rala_b200_graph* g, const uint8_t* d_
     rala_b200_ctx* ctx = g->ctx;
     CU(ctx, cudaSetDevice(ctx->device));
     if (n) CU(ctx, cudaMemcpyAsync(g->T.p, d_T, n, cudaMemcpyDeviceToDevice, ctx->L.stream));
-    launch_finalize_marks(ctx->L, g->graph_view(), g->edge_cap, g->cnt());
+    launch_finalize_marks(ctx->L, g->graph_view(), g->edge_cap, g->cnt(), nullptr, 0u);
     CU(ctx, cudaGetLastError());
     CU(ctx, end_stage(g, ST_TRANSITIVE));
     g->state = 5;

@@ -101,6 +101,7 @@ __global__ void __launch_bounds__(kTileThreads, MINB) k_classify_events(
         for (int r = 0; r < kRecItems; ++r) {
             const uint32_t idb = b[r] & 0x7FFFFFFFu;
             live[r] = q < n4 && 4u * q + r < n && !(a[r] & kInvalidBit) && a[r] < n_piles && idb < n_piles;   // graph.cpp:450-451
+            pa[r] = pb[r] = make_uint2(0u, 0u);   // a dead pile: rejects itself
             if (live[r]) {
                 pa[r] = __ldg(piles + a[r]);
                 pb[r] = __ldg(piles + idb);
@@ -110,6 +111,24 @@ __global__ void __launch_bounds__(kTileThreads, MINB) k_classify_events(
         for (int r = 0; r < kRecItems; ++r) {
             bool is_ev = false;
             uint32_t evv = 0, evc = 0;
+#if RB_OPT_EVENTS
+            {
+                // straight-line trim + type (common.cuh event_code): a dead pile (end == 0) rejects itself
+                const uint32_t idb = b[r] & 0x7FFFFFFFu;
+                const uint32_t code = event_code(ab[r], ae[r], bb[r], be[r], b[r] >> 31, pa[r].x, pa[r].y & kEndMask,
+                                                 pb[r].x, pb[r].y & kEndMask);                              // :451-452
+                const uint32_t fa = pa[r].y >> 30, fb = pb[r].y >> 30;
+                if ((code & 1u) && ((fa | fb) & 1u)) {                                                      // :457-462, resolved by k_hill_coverage
+                    uint32_t slot = atomicAdd(&counters[C_HILL], 1u);
+                    if (slot < hill_cap) hill_rec[slot] = 4u * q + r;
+                }
+                const bool ev_b = (code & 2u) && !(fb & 2u);                                                // :469-474
+                const bool ev_a = (code & 4u) && !(fa & 2u);                                                // :475-480
+                is_ev = ev_a | ev_b;
+                evv = ev_b ? a[r] : idb;
+                evc = ev_b ? idb : a[r];
+            }
+#else
             if (live[r]) {
                 Pile A, B;
                 A.begin = pa[r].x; A.end = pa[r].y & kEndMask; A.flags = pa[r].y >> 30;
@@ -129,6 +148,7 @@ __global__ void __launch_bounds__(kTileThreads, MINB) k_classify_events(
                     }
                 }
             }
+#endif
             const uint32_t m = __ballot_sync(0xFFFFFFFFu, is_ev);
             if (m) {
                 if (is_ev) {
@@ -330,6 +350,39 @@ __global__ void k_relocate(List tmp, List out, uint32_t cap, const uint32_t* __r
                 out.ab[j] = tmp.ab[s]; out.ae[j] = tmp.ae[s];
                 out.bb[j] = tmp.bb[s]; out.be[j] = tmp.be[s];
                 out.tag[j] = tmp.tag[s];
+            }
+        }
+    }
+}
+
+// The same move with one WARP per run, both lists in one launch: the run's survivors (~7 % of 512 records) are
+// contiguous in the scratch list and in the final list, so every column is read and written in coalesced pieces and
+// nobody searches for its run (k_relocate: a binary search per warp and a walk per lane, 28 + 3 us in profiles/r01h).
+__global__ void __launch_bounds__(kTileThreads) k_relocate_runs(List tmp_a, List out_a, List tmp_b, List out_b, uint32_t cap,
+                                                               const uint32_t* __restrict__ run_cnt, const uint32_t* __restrict__ off_a,
+                                                               const uint32_t* __restrict__ off_b, uint32_t num_runs) {
+    const uint32_t lane = lane_id();
+    const uint32_t warps = gridDim.x * kTileWarps;
+    for (uint32_t run = blockIdx.x * kTileWarps + warp_id(); run < num_runs; run += warps) {
+        const uint32_t c = __ldg(run_cnt + run), base = run * kRunRecords;
+        const uint32_t na = c & 0xFFFFu, nb = c >> 16;
+        const uint32_t oa = __ldg(off_a + run), ob = __ldg(off_b + run);
+        for (uint32_t j = lane; j < na; j += 32) {
+            const uint32_t s = base + j, d = oa + j;
+            if (s < cap && d < cap) {
+                out_a.a[d] = tmp_a.a[s]; out_a.b[d] = tmp_a.b[s];
+                out_a.ab[d] = tmp_a.ab[s]; out_a.ae[d] = tmp_a.ae[s];
+                out_a.bb[d] = tmp_a.bb[s]; out_a.be[d] = tmp_a.be[s];
+                out_a.tag[d] = tmp_a.tag[s];
+            }
+        }
+        for (uint32_t j = lane; j < nb; j += 32) {
+            const uint32_t s = base + j, d = ob + j;
+            if (s < cap && d < cap) {
+                out_b.a[d] = tmp_b.a[s]; out_b.b[d] = tmp_b.b[s];
+                out_b.ab[d] = tmp_b.ab[s]; out_b.ae[d] = tmp_b.ae[s];
+                out_b.bb[d] = tmp_b.bb[s]; out_b.be[d] = tmp_b.be[s];
+                out_b.tag[d] = tmp_b.tag[s];
             }
         }
     }
@@ -613,9 +666,15 @@ void launch_classify_survivors(Launch& L, List recs, uint32_t n, const uint2* pi
     k_scan_runs<<<grid_for(num_runs, kTile, kNumSMs * 4), kTileThreads, 0, L.stream>>>(runs.cnt, num_runs, runs.off_a, runs.off_b, n_ovl,
                                                                                        n_inl, status, ticket);
     L.count++;
+#if RB_OPT_RELOC
+    k_relocate_runs<<<grid_for(num_runs, kTileWarps, kNumSMs * 8), kTileThreads, 0, L.stream>>>(tmp_ovl, ovl, tmp_inl, inl, cap, runs.cnt,
+                                                                                               runs.off_a, runs.off_b, num_runs);
+    L.count++;
+#else
     k_relocate<<<grid_for(cap, 256, kNumSMs * 8), 256, 0, L.stream>>>(tmp_ovl, ovl, cap, runs.off_a, n_ovl, num_runs);
     k_relocate<<<grid_for(cap, 256, kNumSMs * 8), 256, 0, L.stream>>>(tmp_inl, inl, cap, runs.off_b, n_inl, num_runs);
     L.count += 2;
+#endif
 }
 
 uint32_t classify_num_runs(uint32_t n) { return (n + kRunRecords - 1) / kRunRecords; }

@@ -4,6 +4,25 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+// Compile-time switches of single optimisations (all on by default).  rala_b200/build.py builds one extra
+// library per switch turned off (rala_b200/variants/), so that bench.py can measure each contribution on the
+// GPU (RALA_B200_LIB selects the library).
+#ifndef RB_OPT_EVENTS
+#define RB_OPT_EVENTS 1   // branch-free event detection in the first pass over the records
+#endif
+#ifndef RB_OPT_RELOC
+#define RB_OPT_RELOC 1    // warp-per-run relocation of the survivors
+#endif
+#ifndef RB_OPT_FILL
+#define RB_OPT_FILL 1     // four independent atomics in flight per thread in the CSR fill
+#endif
+#ifndef RB_OPT_BSEARCH
+#define RB_OPT_BSEARCH 1  // transitive pass, low-degree nodes: branch-free binary search instead of a hash table
+#endif
+#ifndef RB_OPT_CONC
+#define RB_OPT_CONC 1     // independent kernels of one step on forked streams
+#endif
+
 namespace rb {
 
 constexpr uint32_t kInf = 0xFFFFFFFFu;         // "never dies" death time
@@ -17,7 +36,7 @@ enum : uint8_t { kX = 0, kA = 1, kB = 2, kAB = 3, kBA = 4, kRejected = 255 };
 // ---------------------------------------------------------------------------------------------
 struct Pile {
     uint32_t begin, end, flags;
-    __device__ __forceinline__ bool alive() const { return end != 0; }
+    __host__ __device__ __forceinline__ bool alive() const { return end != 0; }
 };
 
 __device__ __forceinline__ Pile load_pile(const uint2* __restrict__ piles, uint32_t id) {
@@ -35,7 +54,7 @@ struct Coords {
 
 // Overlap::trim, /root/reference/src/overlap.cpp:117-192.  u32 wrap-around is part
 // of the contract.  Both piles are alive.
-__device__ __forceinline__ bool trim(Coords& c, uint32_t ori, const Pile& pa, const Pile& pb) {
+__host__ __device__ __forceinline__ bool trim(Coords& c, uint32_t ori, const Pile& pa, const Pile& pb) {
     if (c.ab >= pa.end || c.ae <= pa.begin || c.bb >= pb.end || c.be <= pb.begin) return false;   // :139-142
     uint32_t cut_lb = c.bb < pb.begin ? pb.begin - c.bb : 0u, cut_rb = c.be > pb.end ? c.be - pb.end : 0u;
     uint32_t cut_la = c.ab < pa.begin ? pa.begin - c.ab : 0u, cut_ra = c.ae > pa.end ? c.ae - pa.end : 0u;
@@ -56,7 +75,7 @@ struct Rel {
     uint32_t a0, a1, b0, b1, al, bl;
 };
 
-__device__ __forceinline__ Rel relative(const Coords& c, uint32_t ori, const Pile& pa, const Pile& pb) {
+__host__ __device__ __forceinline__ Rel relative(const Coords& c, uint32_t ori, const Pile& pa, const Pile& pb) {
     Rel r;
     r.al = pa.end - pa.begin;
     r.a0 = c.ab - pa.begin;
@@ -67,7 +86,7 @@ __device__ __forceinline__ Rel relative(const Coords& c, uint32_t ori, const Pil
     return r;
 }
 
-__device__ __forceinline__ uint32_t absdiff(uint32_t a, uint32_t b) { return a > b ? a - b : b - a; }
+__host__ __device__ __forceinline__ uint32_t absdiff(uint32_t a, uint32_t b) { return a > b ? a - b : b - a; }
 
 // ---------------------------------------------------------------------------------------------
 // The reference's floating point on this path is three IEEE double products compared with integers
@@ -81,12 +100,12 @@ __device__ __forceinline__ uint32_t absdiff(uint32_t a, uint32_t b) { return a >
 //   (u32)(0.05 * (double)M)                ==  M / 20               (RN(M * 0.05) == M / 20 when 20 | M)
 //   a >= b * (1 - 0.12), a <= b * (1 + 0.12)  <=>  25 a >= 22 b,  25 a <= 28 b
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ bool lt_7_8(uint32_t s, uint32_t t) {   // (double)s < (double)t * 0.875
+__host__ __device__ __forceinline__ bool lt_7_8(uint32_t s, uint32_t t) {   // (double)s < (double)t * 0.875
     return (unsigned long long) s * 8ull < (unsigned long long) t * 7ull;
 }
 
 // Overlap::type, overlap.cpp:194-259.
-__device__ __forceinline__ uint8_t classify(const Coords& c, const Rel& r) {
+__host__ __device__ __forceinline__ uint8_t classify(const Coords& c, const Rel& r) {
     uint32_t overhang = min(r.a0, r.b0) + min(r.al - r.a1, r.bl - r.b1);                          // :218-219
     uint32_t sa = r.a1 - r.a0, sb = r.b1 - r.b0;
     if (lt_7_8(sa, sa + overhang) || lt_7_8(sb, sb + overhang)) return kX;                        // :221-224
@@ -103,18 +122,60 @@ __device__ __forceinline__ uint8_t classify(const Coords& c, const Rel& r) {
     return r.a0 > r.b0 ? kAB : kBA;                                                               // :255-258
 }
 
+// Event detection of the first pass over the records (k_classify_events): trim() followed by classify(), reduced to
+// what the ORDER-DEPENDENT part needs, as straight-line predicate arithmetic (no early returns: the compiler's branchy
+// translation of the two functions above executed ~220 warp instructions per record with divergent lanes waiting at
+// every reconvergence point, profiles/r01h).  Returns
+//     bit 0   trim() accepts the record (both piles alive)
+//     bit 1   type is kB (a contained in b)        bit 2   type is kA (b contained in a)
+// p = a's pile [p0, p1), q = b's pile [q0, q1); a dead pile has end == 0 and fails the first test below by itself.
+// Exactness (tests/test_exact_arith.py compares with trim() + classify() on boundary and random inputs): pile
+// ends are < 2^30 (rala_b200.h limits), so once the two range tests have passed every trimmed coordinate lies in
+// [0, 2^30]: differences fit a signed compare, span + overhang cannot wrap, and  8 s < 7 (s + oh)  <=>  s < 7 oh.
+__host__ __device__ __forceinline__ uint32_t event_code(uint32_t ab, uint32_t ae, uint32_t bb, uint32_t be, uint32_t ori,
+                                                        uint32_t p0, uint32_t p1, uint32_t q0, uint32_t q1) {
+    const bool r1 = (ab >= p1) | (ae <= p0) | (bb >= q1) | (be <= q0);                            // overlap.cpp:139-142
+    const uint32_t cut_lb = max(q0, bb) - bb, cut_rb = be - min(be, q1);                          // :146-164
+    const uint32_t cut_la = max(p0, ab) - ab, cut_ra = ae - min(ae, p1);
+    uint32_t nab = ab + (ori ? cut_rb : cut_lb);
+    uint32_t nae = ae - (ori ? cut_lb : cut_rb);
+    uint32_t nbb = bb + (ori ? cut_ra : cut_la);
+    uint32_t nbe = be - (ori ? cut_la : cut_ra);
+    const bool r2 = (nab >= p1) | (nae <= p0) | (nbb >= q1) | (nbe <= q0);                        // :166-169
+    nab = max(nab, p0); nae = min(nae, p1); nbb = max(nbb, q0); nbe = min(nbe, q1);               // :171-174
+    const uint32_t sa = nae - nab, sb = nbe - nbb;
+    const bool r3 = ((int32_t) sa < 84) | ((int32_t) sb < 84);                                    // :176-179
+    // Overlap::type on the trimmed coordinates (overlap.cpp:206-258)
+    const uint32_t a0 = nab - p0, ta = p1 - nae, x = nbb - q0, y = q1 - nbe;
+    const uint32_t b0 = ori ? y : x, tb = ori ? x : y;                                            // b flipped if RC (:211-216)
+    const unsigned long long oh7 = (unsigned long long) (min(a0, b0) + min(ta, tb)) * 7ull;       // :218-219
+    const bool kx = ((unsigned long long) sa < oh7) | ((unsigned long long) sb < oh7);            // :221-224
+    const bool a_ge = a0 >= b0, t_ge = ta >= tb;
+    const bool cont_b = (a0 <= b0) & (ta <= tb), cont_a = a_ge & t_ge;                            // :225-230
+    const uint32_t len = max(sa, sb);
+    const bool nearly = (unsigned long long) (len - min(sa, sb)) * 100ull < (unsigned long long) len;   // :236
+    const uint32_t me = max(p1 - p0, q1 - q0) / 20u;                                              // :237
+    const bool n1 = absdiff(a0, b0) < me, n2 = absdiff(ta, tb) < me;
+    const bool near_a = nearly & ((n1 & t_ge) | (!n1 & n2 & a_ge));                               // :239-252
+    const bool near_b = nearly & ((n1 & !t_ge) | (!n1 & n2 & !a_ge));
+    const bool is_b = cont_b | (!cont_a & near_b);
+    const bool is_a = !cont_b & (cont_a | near_a);
+    const bool ok = !(r1 | r2 | r3);
+    return (ok ? 1u : 0u) | ((ok & !kx & is_b) ? 2u : 0u) | ((ok & !kx & is_a) ? 4u : 0u);
+}
+
 // comparable(a, b, 0.12), graph.cpp:26-29; a = (double)(u32)(len_ab + len_bc), b = (double)len_ac:
 //   (a >= 0.88 b && a <= 1.12 b) || (b >= 0.88 a && b <= 1.12 a)
 // In exact arithmetic the two clauses are the intervals [22b/25, 28b/25] and [25b/28, 25b/22] for a; they
 // overlap (25/28 < 28/25), so their union is the hull:  25 a >= 22 b  &&  22 a <= 25 b.
-__device__ __forceinline__ bool comparable(uint32_t a, uint32_t b) {
+__host__ __device__ __forceinline__ bool comparable(uint32_t a, uint32_t b) {
     return (unsigned long long) a * 25ull >= (unsigned long long) b * 22ull &&
            (unsigned long long) a * 22ull <= (unsigned long long) b * 25ull;
 }
 
 // The same test as an interval of a for a fixed b: comparable(a, b) <=> a - lo <= range (unsigned),
 // lo = ceil(22 b / 25), range = min(floor(25 b / 22), 2^32 - 1) - lo.
-__device__ __forceinline__ uint2 comparable_interval(uint32_t b) {
+__host__ __device__ __forceinline__ uint2 comparable_interval(uint32_t b) {
     const unsigned long long lo = ((unsigned long long) b * 22ull + 24ull) / 25ull;
     unsigned long long hi = (unsigned long long) b * 25ull / 22ull;
     if (hi > 0xFFFFFFFFull) hi = 0xFFFFFFFFull;

@@ -41,11 +41,33 @@ __device__ __forceinline__ uint32_t ld_state(const uint32_t* p) {
 __global__ void k_events_fill(Events ev, const uint32_t* __restrict__ n_events, uint32_t ev_cap,
                               uint32_t* __restrict__ vcursor, uint32_t* __restrict__ seg_c, uint32_t* __restrict__ seg_t) {
     const uint32_t n = min(*n_events, ev_cap);
+#if RB_OPT_FILL
+    const uint32_t stride = gridDim.x * blockDim.x;   // four independent load -> atomic -> store chains per thread
+    for (uint32_t i0 = blockIdx.x * blockDim.x + threadIdx.x; i0 < n; i0 += 4u * stride) {
+        uint32_t v[4], c[4], t[4], p[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const uint32_t i = i0 + k * stride;
+            if (i < n) { v[k] = ev.v[i]; c[k] = ev.c[i]; t[k] = ev.t[i]; }
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (i0 + k * stride < n) p[k] = atomicAdd(&vcursor[v[k]], 1u);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (i0 + k * stride < n) {
+                seg_c[p[k]] = c[k];
+                seg_t[p[k]] = t[k];
+            }
+        }
+    }
+#else
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const uint32_t p = atomicAdd(&vcursor[ev.v[i]], 1u);
         seg_c[p] = ev.c[i];
         seg_t[p] = ev.t[i];
     }
+#endif
 }
 
 __global__ void k_events_hist(Events ev, const uint32_t* __restrict__ n_events, uint32_t ev_cap, uint32_t* __restrict__ vcount) {

@@ -177,21 +177,63 @@ __global__ void k_fill_csr(const uint32_t* __restrict__ src, const uint32_t* __r
                            const uint32_t* __restrict__ len, const uint32_t* __restrict__ n_edges_ptr, uint32_t edge_cap,
                            uint32_t* __restrict__ cursor, uint2* __restrict__ col, uint32_t* __restrict__ col_eid) {
     const uint32_t n = min(*n_edges_ptr, edge_cap);
+#if RB_OPT_FILL
+    // load -> returning atomic -> store is a chain of three dependent round trips: keep four edges of it in flight
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t e0 = blockIdx.x * blockDim.x + threadIdx.x; e0 < n; e0 += 4u * stride) {
+        uint32_t s[4], d[4], l[4], p[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const uint32_t e = e0 + k * stride;
+            if (e < n) { s[k] = src[e]; d[k] = dst[e]; l[k] = len[e]; }
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (e0 + k * stride < n) p[k] = atomicAdd(&cursor[s[k]], 1u);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const uint32_t e = e0 + k * stride;
+            if (e < n) {
+                col[p[k]] = make_uint2(d[k], l[k]);
+                col_eid[p[k]] = e;
+            }
+        }
+    }
+#else
     for (uint32_t e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
         const uint32_t p = atomicAdd(&cursor[src[e]], 1u);
         col[p] = make_uint2(dst[e], len[e]);
         col_eid[p] = e;
     }
+#endif
 }
 
-// edge columns -> rala_edge_t rows (download path)
-__global__ void k_pack_edges(const uint32_t* __restrict__ src, const uint32_t* __restrict__ dst, const uint32_t* __restrict__ len,
-                             const uint32_t* __restrict__ n_edges_ptr, uint32_t edge_cap, uint32_t* __restrict__ out) {
-    const uint32_t n = min(*n_edges_ptr, edge_cap);
-    for (uint32_t e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
-        out[3 * (size_t) e] = src[e];
-        out[3 * (size_t) e + 1] = dst[e];
-        out[3 * (size_t) e + 2] = len[e];
+// edge columns -> rala_edge_t rows (download path).  Rows are staged in shared memory and leave as 16-byte stores
+// of consecutive threads: `out` may be pinned HOST memory the GPU writes over PCIe (rala_b200_graph_set_outputs),
+// where three strided 4-byte stores per row would triple the number of write transactions.
+__global__ void __launch_bounds__(256) k_pack_edges(const uint32_t* __restrict__ src, const uint32_t* __restrict__ dst,
+                                                   const uint32_t* __restrict__ len, const uint32_t* __restrict__ n_edges_ptr,
+                                                   uint32_t edge_cap, uint32_t* __restrict__ out, int vec16) {
+    __shared__ __align__(16) uint32_t rows[256 * 3];
+    const uint32_t n = min(*n_edges_ptr, edge_cap), tid = threadIdx.x;
+    for (uint32_t base = blockIdx.x * 256u; base < n; base += gridDim.x * 256u) {
+        const uint32_t e = base + tid;
+        if (e < n) {
+            rows[3 * tid] = src[e];
+            rows[3 * tid + 1] = dst[e];
+            rows[3 * tid + 2] = len[e];
+        }
+        __syncthreads();
+        const uint32_t words = 3u * min(256u, n - base);
+        uint32_t* o = out + 3 * (size_t) base;   // 3072 bytes per full block iteration: 16-byte aligned when `out` is
+        if (vec16) {
+            const uint32_t w = 4u * tid;
+            if (w + 3u < words) *reinterpret_cast<uint4*>(o + w) = *reinterpret_cast<const uint4*>(rows + w);
+            else for (uint32_t k = w; k < words; ++k) o[k] = rows[k];
+        } else {
+            for (uint32_t k = tid; k < words; k += 256u) o[k] = rows[k];
+        }
+        __syncthreads();
     }
 }
 
@@ -271,8 +313,9 @@ void launch_emit_edges(Launch& L, List ovl, const uint32_t* n_ptr, uint32_t cap,
     L.count++;
 }
 
-void launch_pack_edges(Launch& L, GraphArrays g, uint32_t edge_cap, const uint32_t* n_edges_ptr, uint32_t* out) {
-    k_pack_edges<<<grid_for(edge_cap, 256, kNumSMs * 8), 256, 0, L.stream>>>(g.src, g.dst, g.len, n_edges_ptr, edge_cap, out);
+void launch_pack_edges(Launch& L, cudaStream_t stream, GraphArrays g, uint32_t edge_cap, const uint32_t* n_edges_ptr, uint32_t* out) {
+    k_pack_edges<<<grid_for(edge_cap, 256, kNumSMs * 8), 256, 0, stream>>>(g.src, g.dst, g.len, n_edges_ptr, edge_cap, out,
+                                                                           (reinterpret_cast<uintptr_t>(out) & 15u) == 0 ? 1 : 0);
     L.count++;
 }
 

@@ -33,7 +33,24 @@ enum Counter {
 struct Launch {
     cudaStream_t stream;
     uint64_t count;   // kernels launched so far
+    // forked work inside one step (also inside a stream capture: the side streams join the capture through the
+    // fork event and are joined back before it ends): [0] results written to the caller's memory while the
+    // transitive pass runs, [1] kernels that do not depend on each other
+    cudaStream_t side[2] = {nullptr, nullptr};
+    cudaEvent_t ev_fork[2] = {nullptr, nullptr}, ev_join[2] = {nullptr, nullptr};
 };
+
+// side[k] continues from the current end of the main stream; false when the context has no side streams
+inline bool fork_side(Launch& L, int k) {
+    if (!L.side[k]) return false;
+    if (cudaEventRecord(L.ev_fork[k], L.stream) != cudaSuccess) return false;
+    return cudaStreamWaitEvent(L.side[k], L.ev_fork[k], 0) == cudaSuccess;
+}
+// the main stream waits for everything enqueued on side[k]
+inline void join_side(Launch& L, int k) {
+    cudaEventRecord(L.ev_join[k], L.side[k]);
+    cudaStreamWaitEvent(L.stream, L.ev_join[k], 0);
+}
 
 // classify.cu
 void launch_records_to_soa(Launch& L, const uint32_t* aos, uint32_t n, List recs);
@@ -99,7 +116,7 @@ void launch_node_ids(Launch& L, const uint2* piles, uint32_t n_piles, uint32_t* 
                      unsigned long long* status, uint32_t* ticket);
 void launch_emit_edges(Launch& L, List ovl, const uint32_t* n_ptr, uint32_t cap, const uint2* piles, GraphArrays g,
                        uint32_t edge_cap, uint32_t* counters, unsigned long long* status, uint32_t* ticket);
-void launch_pack_edges(Launch& L, GraphArrays g, uint32_t edge_cap, const uint32_t* n_edges_ptr, uint32_t* out);
+void launch_pack_edges(Launch& L, cudaStream_t stream, GraphArrays g, uint32_t edge_cap, const uint32_t* n_edges_ptr, uint32_t* out);
 // degree histogram for an edge list that did not come from emit_edges (stateless transitive stage)
 void launch_degree_hist(Launch& L, const uint32_t* src, const uint32_t* n_edges_ptr, uint32_t edge_cap, uint32_t* cursor);
 void launch_export_padded(Launch& L, const uint32_t* c0, const uint32_t* c1, const uint32_t* c2, const uint32_t* n_ptr,
@@ -119,6 +136,7 @@ void launch_transitive(Launch& L, GraphArrays g, uint32_t n_nodes_max, uint32_t 
                        uint32_t* work_counter, uint32_t* counters, uint32_t node_begin, uint32_t node_end,
                        const uint32_t* node_range /* device {begin, end}, nullable */);
 void launch_node_range(Launch& L, GraphArrays g, const uint32_t* counters, uint32_t rank, uint32_t world, uint32_t* out);
-void launch_finalize_marks(Launch& L, GraphArrays g, uint32_t edge_cap, uint32_t* counters);
+void launch_finalize_marks(Launch& L, GraphArrays g, uint32_t edge_cap, uint32_t* counters, uint8_t* marked_copy /* nullable */,
+                           uint32_t copy_cap);
 
 }  // namespace rb

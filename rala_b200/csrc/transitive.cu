@@ -96,6 +96,175 @@ __device__ __forceinline__ uint32_t table_find(const uint32_t* keys, uint32_t ma
 // ---------------------------------------------------------------------------------------------
 // group path: 8 lanes per node
 // ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t group_inclusive_scan(uint32_t v, uint32_t gl) {
+#pragma unroll
+    for (int d = 1; d < kGroupLanes; d <<= 1) {
+        uint32_t t = __shfl_up_sync(0xFFFFFFFFu, v, d, kGroupLanes);
+        if ((int) gl >= d) v += t;
+    }
+    return v;
+}
+
+#if RB_OPT_BSEARCH
+// Membership of a two-hop destination in N+(a) is a BRANCH-FREE binary search over the (at most 16) neighbours,
+// sorted by (destination, edge id) with a rank sort during set-up: four dependent shared-memory loads, the same
+// for every lane.  The open-addressing table this replaces cost 48 % of the kernel's instructions at 7 of 32
+// lanes active: every lane left its probe loop after a different number of steps (profiles/r01i, source view).
+// Parallel edges a->c sit next to each other in edge-id order and the search returns the LAST key <= x, i.e. the
+// highest id: the candidate of graph.cpp:1291-1293; earlier duplicates can never be hit.
+struct GroupSmem {
+    unsigned long long ukey[kGroupMaxDeg];   // as loaded: destination << 32 | edge id, padded with ~0
+    uint32_t keys[kGroupMaxDeg];             // destinations, sorted; kEmpty behind the last one
+    uint32_t eid[kGroupMaxDeg];              // edge id at that position
+    uint2 iv[kGroupMaxDeg];                  // comparable(sum, len of that edge)  <=>  sum - iv.x <= iv.y
+    uint32_t nrow[kGroupMaxDeg];
+    uint32_t nlen[kGroupMaxDeg];
+    uint32_t noff[kGroupMaxDeg + 1];
+    uint32_t hit;                            // bit j: the edge at sorted position j passed the test
+};
+
+__global__ void __launch_bounds__(kLightWarps * 32, 6) k_transitive_group(
+    const uint32_t* __restrict__ row_ptr, const uint2* __restrict__ col, const uint32_t* __restrict__ col_eid,
+    uint8_t* __restrict__ T, uint32_t node_begin, uint32_t node_end, const uint32_t* __restrict__ node_range,
+    const uint32_t* __restrict__ n_nodes_ptr, uint32_t* __restrict__ work_counter, HeavyItems heavy,
+    uint32_t* __restrict__ counters) {
+    static_assert(kGroupMaxDeg == 16 && kGroupLanes == 8, "the search below is written for 16 keys, two per lane");
+    __shared__ GroupSmem smem[kLightWarps][kGroupsPerWarp];
+    const uint32_t lane = lane_id(), gl = lane & (kGroupLanes - 1), grp = lane / kGroupLanes;
+    GroupSmem& S = smem[warp_id()][grp];
+    if (node_range) {
+        node_begin = node_range[0];
+        node_end = node_range[1];
+    }
+    const uint32_t n_end = min(node_end, *n_nodes_ptr);
+    unsigned long long visits = 0;
+
+    while (true) {
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(work_counter, 32u);
+        base = node_begin + __shfl_sync(0xFFFFFFFFu, base, 0);
+        if (base >= n_end) break;
+        uint32_t r0 = 0, deg = 0;
+        if (base + lane < n_end) {
+            r0 = row_ptr[base + lane];
+            deg = row_ptr[base + lane + 1] - r0;
+        }
+#pragma unroll 1
+        for (uint32_t round = 0; round < 32 / kGroupsPerWarp; ++round) {
+            const uint32_t from = round * kGroupsPerWarp + grp;
+            const uint32_t a = base + from;
+            const uint32_t ra0 = __shfl_sync(0xFFFFFFFFu, r0, from);
+            const uint32_t d = __shfl_sync(0xFFFFFFFFu, deg, from);
+            bool act = d >= 2u && d <= (uint32_t) kGroupMaxDeg;   // < 2 neighbours: no two-hop witness can exist
+            if (!__any_sync(0xFFFFFFFFu, act)) continue;
+            // ---- this lane's (at most two) neighbours ----
+            unsigned long long mine[2] = {~0ull, ~0ull};
+            uint32_t dg[2] = {0u, 0u}, my_len[2] = {0u, 0u};
+            if (act) {
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const uint32_t i = gl + h * kGroupLanes;
+                    if (i < d) {
+                        const uint2 e = col[ra0 + i];
+                        mine[h] = ((unsigned long long) e.x << 32) | col_eid[ra0 + i];
+                        my_len[h] = e.y;
+                        const uint32_t rs = row_ptr[e.x];
+                        dg[h] = row_ptr[e.x + 1] - rs;
+                        S.nrow[i] = rs;
+                        S.nlen[i] = e.y;
+                    }
+                    S.ukey[i] = mine[h];
+                }
+                if (gl == 0) S.hit = 0u;
+            }
+            const uint32_t inc0 = group_inclusive_scan(dg[0], gl), inc1 = group_inclusive_scan(dg[1], gl);
+            const uint32_t tot0 = __shfl_sync(0xFFFFFFFFu, inc0, kGroupLanes - 1, kGroupLanes);
+            const uint32_t W = tot0 + __shfl_sync(0xFFFFFFFFu, inc1, kGroupLanes - 1, kGroupLanes);
+            if (act) {
+                if (gl < d) S.noff[gl] = inc0 - dg[0];
+                if (gl + kGroupLanes < d) S.noff[gl + kGroupLanes] = tot0 + inc1 - dg[1];
+                if (gl == 0) S.noff[d] = W;
+            }
+            __syncwarp();
+            if (act && W > kGroupMaxVisits) {   // short row, very long rows behind it: give the node to a block
+                if (gl == 0) {
+                    const uint32_t hb = atomicAdd(&counters[C_HEAVY], 1u);
+                    if (hb < heavy.cap) {
+                        heavy.node[hb] = a;
+                        heavy.hash_chunk[hb] = 0;
+                        heavy.nbr_chunk[hb] = 0;
+                    } else {
+                        counters[C_OVERFLOW] = 1u;
+                    }
+                }
+                act = false;
+            }
+            // ---- rank sort by (destination, edge id): composites are distinct, pads (~0) sort behind every edge ----
+            if (act) {
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const uint32_t i = gl + h * kGroupLanes;
+                    if (i < d) {
+                        uint32_t rank = 0;
+#pragma unroll
+                        for (int j = 0; j < kGroupMaxDeg; ++j) rank += S.ukey[j] < mine[h] ? 1u : 0u;
+                        S.keys[rank] = (uint32_t) (mine[h] >> 32);
+                        S.eid[rank] = (uint32_t) mine[h];
+                        S.iv[rank] = comparable_interval(my_len[h]);
+                    } else {
+                        S.keys[i] = kEmpty;   // positions d .. 15
+                    }
+                }
+            }
+            __syncwarp();
+            if (act) {
+                if (gl == 0) visits += W;
+                uint32_t i = 0;
+                for (uint32_t f0 = 0; f0 < W; f0 += 4 * kGroupLanes) {
+                    uint2 e[4];
+                    uint32_t lab[4];
+                    bool ok[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const uint32_t f = f0 + u * kGroupLanes + gl;
+                        ok[u] = f < W;
+                        e[u] = make_uint2(kEmpty, 0u);
+                        lab[u] = 0u;
+                        if (ok[u]) {
+                            while (f >= S.noff[i + 1]) ++i;
+                            e[u] = col[S.nrow[i] + (f - S.noff[i])];
+                            lab[u] = S.nlen[i];
+                        }
+                    }
+                    uint32_t pass = 0;   // bit j: a witness for the edge at sorted position j
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const uint32_t x = e[u].x;   // kEmpty for idle lanes: matches no key below position d
+                        uint32_t j = S.keys[8] <= x ? 8u : 0u;
+                        j += S.keys[j + 4] <= x ? 4u : 0u;
+                        j += S.keys[j + 2] <= x ? 2u : 0u;
+                        j += S.keys[j + 1] <= x ? 1u : 0u;
+                        const uint2 iv = S.iv[j];
+                        if (ok[u] && S.keys[j] == x && lab[u] + e[u].y - iv.x <= iv.y) pass |= 1u << j;   // graph.cpp:1301-1306
+                    }
+                    if (pass & ~S.hit) atomicOr(&S.hit, pass);
+                }
+            }
+            __syncwarp();
+            if (act) {
+                const uint32_t h = S.hit;
+#pragma unroll
+                for (uint32_t j = gl; j < (uint32_t) kGroupMaxDeg; j += kGroupLanes) {
+                    if ((h >> j) & 1u) T[S.eid[j]] = 1;
+                }
+            }
+            __syncwarp();
+        }
+    }
+    visits = warp_sum64(visits);
+    if (lane == 0 && visits) atomicAdd(reinterpret_cast<unsigned long long*>(counters + C_HOP_LO), visits);
+}
+#else
 struct GroupSmem {
     uint32_t keys[kGroupCap];
     uint32_t eid[kGroupCap];    // highest edge id a->key (graph.cpp:1291-1293)
@@ -106,15 +275,6 @@ struct GroupSmem {
     uint32_t noff[kGroupMaxDeg + 1];
     uint32_t hit;               // bit s: the candidate in slot s passed the test
 };
-
-__device__ __forceinline__ uint32_t group_inclusive_scan(uint32_t v, uint32_t gl) {
-#pragma unroll
-    for (int d = 1; d < kGroupLanes; d <<= 1) {
-        uint32_t t = __shfl_up_sync(0xFFFFFFFFu, v, d, kGroupLanes);
-        if ((int) gl >= d) v += t;
-    }
-    return v;
-}
 
 __global__ void __launch_bounds__(kLightWarps * 32, 6) k_transitive_group(
     const uint32_t* __restrict__ row_ptr, const uint2* __restrict__ col, const uint32_t* __restrict__ col_eid,
@@ -261,6 +421,7 @@ __global__ void __launch_bounds__(kLightWarps * 32, 6) k_transitive_group(
     visits = warp_sum64(visits);
     if (lane == 0 && visits) atomicAdd(reinterpret_cast<unsigned long long*>(counters + C_HOP_LO), visits);
 }
+#endif   // RB_OPT_BSEARCH
 
 struct LightSmem {
     unsigned long long vals[kLightCap];
@@ -499,16 +660,37 @@ __global__ void __launch_bounds__(kHeavyThreads) k_transitive_heavy(
     if (tid == 0 && visits) atomicAdd(reinterpret_cast<unsigned long long*>(counters + C_HOP_LO), visits);
 }
 
-// marked(e) = T(e) | T(e^1); count of marked pairs = the reference's return value (graph.cpp:1305-1309, 1334)
+// marked(e) = T(e) | T(e^1); count of marked pairs = the reference's return value (graph.cpp:1305-1309, 1334).
+// 16 edges (one 16-byte load / store) per thread: T and marked are padded to a multiple of 256 bytes and T is zero
+// behind the last edge.  marked_copy, when given, is the caller's buffer (rala_b200_graph_set_outputs: pinned host
+// memory the GPU addresses directly, so the marks cross PCIe as 16-byte stores while they are produced).
 __global__ void k_finalize_marks(const uint8_t* __restrict__ T, uint8_t* __restrict__ marked,
-                                 const uint32_t* __restrict__ n_edges_ptr, uint32_t edge_cap, uint32_t* __restrict__ counters) {
-    const uint32_t n_pairs = min(*n_edges_ptr, edge_cap) / 2;
+                                 const uint32_t* __restrict__ n_edges_ptr, uint32_t edge_cap, uint32_t* __restrict__ counters,
+                                 uint8_t* __restrict__ marked_copy, uint32_t copy_cap) {
+    const uint32_t n = min(*n_edges_ptr, edge_cap);
+    const uint32_t n16 = (n + 15u) / 16u;
+    const bool copy_vec = marked_copy && (reinterpret_cast<uintptr_t>(marked_copy) & 15u) == 0;
     uint32_t local = 0;
-    for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n_pairs; j += gridDim.x * blockDim.x) {
-        const uchar2 t = reinterpret_cast<const uchar2*>(T)[j];
-        const uint8_t m = (t.x | t.y) ? 1 : 0;
-        reinterpret_cast<uchar2*>(marked)[j] = make_uchar2(m, m);
-        local += m;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += gridDim.x * blockDim.x) {
+        const uint4 t = reinterpret_cast<const uint4*>(T)[i];
+        uint32_t w[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {   // bytes are 0 / 1: each 16-bit half holds one pair (e, e ^ 1)
+            const uint32_t any = (w[k] | (w[k] >> 8)) & 0x00010001u;
+            local += __popc(any);
+            w[k] = any | (any << 8);
+        }
+        const uint4 m = make_uint4(w[0], w[1], w[2], w[3]);
+        reinterpret_cast<uint4*>(marked)[i] = m;
+        if (marked_copy) {   // exactly min(n, copy_cap) bytes of the caller's buffer are written
+            const uint32_t lim = min(n, copy_cap);
+            if (copy_vec && 16u * i + 15u < lim) {
+                reinterpret_cast<uint4*>(marked_copy)[i] = m;
+            } else {
+                for (uint32_t k = 0; k < 16u && 16u * i + k < lim; ++k)
+                    marked_copy[16u * i + k] = (uint8_t) (w[k >> 2] >> (8u * (k & 3u)));
+            }
+        }
     }
 #pragma unroll
     for (int dlt = 16; dlt > 0; dlt >>= 1) local += __shfl_xor_sync(0xFFFFFFFFu, local, dlt);
@@ -551,21 +733,29 @@ void launch_transitive(Launch& L, GraphArrays g, uint32_t n_nodes_max, uint32_t 
     uint64_t blocks = (span + 32 * kLightWarps - 1) / (32 * kLightWarps);
     if (blocks < 1) blocks = 1;
     if (blocks > (uint64_t) kNumSMs * 8) blocks = kNumSMs * 8;
+    // the group and the light kernel take disjoint sets of nodes (by out-degree) and only meet in atomics (heavy work
+    // list, visit counter): the light one (14 us, mostly idle SMs) runs beside the group one on a forked stream
+#if RB_OPT_CONC
+    const bool forked = fork_side(L, 1);
+#else
+    const bool forked = false;
+#endif
     k_transitive_group<<<(int) blocks, kLightWarps * 32, 0, L.stream>>>(g.row_ptr, g.col, g.col_eid, g.T, node_begin, node_end,
                                                                        node_range, counters + C_NODES, work_counter + 1, heavy, counters);
     L.count++;
-    k_transitive_light<<<(int) blocks, kLightWarps * 32, 0, L.stream>>>(g.row_ptr, g.col, g.col_eid, g.T, node_begin, node_end,
-                                                                       node_range, counters + C_NODES, work_counter, heavy, counters);
+    k_transitive_light<<<(int) blocks, kLightWarps * 32, 0, forked ? L.side[1] : L.stream>>>(
+        g.row_ptr, g.col, g.col_eid, g.T, node_begin, node_end, node_range, counters + C_NODES, work_counter, heavy, counters);
     L.count++;
+    if (forked) join_side(L, 1);
     k_transitive_heavy<<<kNumSMs * 4, kHeavyThreads, 0, L.stream>>>(g.row_ptr, g.col, g.col_eid, g.T, heavy, counters);
     L.count++;
 }
 
-void launch_finalize_marks(Launch& L, GraphArrays g, uint32_t edge_cap, uint32_t* counters) {
-    uint64_t blocks = (edge_cap / 2 + 1023) / 1024;
+void launch_finalize_marks(Launch& L, GraphArrays g, uint32_t edge_cap, uint32_t* counters, uint8_t* marked_copy, uint32_t copy_cap) {
+    uint64_t blocks = (edge_cap / 16 + 255) / 256;
     if (blocks < 1) blocks = 1;
     if (blocks > (uint64_t) kNumSMs * 8) blocks = kNumSMs * 8;
-    k_finalize_marks<<<(int) blocks, 256, 0, L.stream>>>(g.T, g.marked, counters + C_EDGES, edge_cap, counters);
+    k_finalize_marks<<<(int) blocks, 256, 0, L.stream>>>(g.T, g.marked, counters + C_EDGES, edge_cap, counters, marked_copy, copy_cap);
     L.count++;
 }
 

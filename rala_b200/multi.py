@@ -41,6 +41,7 @@ class CudaShardSession:
         self.ctx.lib = lib
         self.ctx.handle = C.c_void_p()
         self.ctx.device = device_index
+        self.ctx._graphs = []
         stream = torch.cuda.current_stream(self.device).cuda_stream
         rc = lib.rala_b200_create_on_stream(C.byref(self.ctx.handle), C.c_int(device_index), C.c_void_p(stream))
         if rc != 0:
@@ -446,14 +447,14 @@ def bench_main(args):
     assert E == info["n_edges"], (E, info["n_edges"])
 
     # end to end: host (pinned) shard -> device, full pipeline, edges + marks back to the host on every rank
-    rec_pin = torch.from_numpy(records).pin_memory()
+    cols_pin = torch.from_numpy(api.records_to_columns(records)).pin_memory()   # 24 B / record, the device layout
     piles_pin = torch.from_numpy(piles).pin_memory()
     e2e_steps = max(3, min(args.steps, 5))
     edges_pin = torch.empty((max(E, 1), 3), dtype=torch.int32).pin_memory()
     marked_pin = torch.empty(max(E, 1), dtype=torch.uint8).pin_memory()
 
     def e2e_step():
-        sess.G.set_piles(piles_pin).set_overlaps(rec_pin)
+        sess.G.set_piles(piles_pin).set_overlaps_columns(cols_pin)
         dg.run()
         sess.G.edges(out=edges_pin)
         sess.G.marked(out=marked_pin)
@@ -490,7 +491,7 @@ def bench_main(args):
                        "exchange": "capacity-bounded blocks (counts inside the blocks, time bases on the device): no host "
                                    "synchronisation inside a step; capacities from the sized warm-up pass x 1.25"},
             "wall_ms_per_step": float(t[1].item()) / args.steps,
-            "e2e": {"value": E / e2e_s, "unit": "edges/s", "h2d_bytes_per_step": int((records.nbytes + piles.nbytes) * world),
+            "e2e": {"value": E / e2e_s, "unit": "edges/s", "h2d_bytes_per_step": int((cols_pin.numel() * 4 + piles.nbytes) * world),
                     "d2h_bytes_per_step": int(13 * E * world), "ms_per_step": 1e3 * e2e_s},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": "k_classify_first", "achieved": k1_gbs, "peak": peak, "unit": "GB/s",

@@ -109,3 +109,30 @@ def test_small_lengths_exhaustive():
     assert np.array_equal(comparable_interval(a, b), comparable_f64(a, b))
     assert np.array_equal(a.astype(np.float64) < b.astype(np.float64) * 0.875, 8 * a < 7 * b)
     assert np.array_equal(a.astype(np.float64) < b.astype(np.float64) * 0.01, 100 * a < b)
+
+
+def test_event_code_straight_line_form_vs_oracle():
+    """common.cuh event_code() — trim + type of the first pass over the records as straight-line predicate
+    arithmetic — and the kernels' trim() / classify(), compiled for the CPU (tests/host_event_code.cu, host-only
+    nvcc build), against the oracle's fp64 trim + type on boundary-heavy random geometries: every type class,
+    dead piles, garbage coordinates (u32 wrap-around), pile ends up to the 2^30 limit."""
+    import json
+    import os
+    import shutil
+    import subprocess
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    nvcc = "/usr/local/cuda/bin/nvcc" if os.path.exists("/usr/local/cuda/bin/nvcc") else shutil.which("nvcc")
+    assert nvcc, "nvcc is needed to compile the host harness"
+    out_dir = os.path.join(root, "tests", "_build")
+    os.makedirs(out_dir, exist_ok=True)
+    exe = os.path.join(out_dir, "host_event_code")
+    subprocess.run([nvcc, "-O2", "-std=c++17", "--expt-relaxed-constexpr", "-Wno-deprecated-gpu-targets", "-o", exe,
+                    os.path.join(root, "tests", "host_event_code.cu"), os.path.join(root, "oracle", "rala_oracle.c")],
+                   check=True, capture_output=True)
+    for seed in (1, 2, 3):
+        r = subprocess.run([exe, "4000000", str(seed)], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        res = json.loads(r.stdout.strip().splitlines()[-1])
+        assert res["mismatches"] == 0
+        assert all(n > 100000 for n in res["by_type"]), res   # kX, kA, kB, kAB, kBA and rejections all occur

@@ -202,6 +202,74 @@ def test_run_as_cuda_graph_matches_the_eager_chain(ctx):
     G.close()
 
 
+def test_column_upload_and_direct_outputs_match_the_row_form(ctx):
+    """rala_b200_graph_set_overlaps_columns (24 B / record, device layout) and rala_b200_graph_set_outputs (the GPU
+    writes edge rows and marks straight into pinned host memory, forked beside the transitive pass) must leave
+    exactly what set_overlaps + get_edges / get_marked leave: eagerly, as a replayed CUDA graph, stage by stage,
+    with invalid records, and with output buffers that are too small."""
+    import torch
+    ds = synth.generate(1_500_000, 35, 9000, len_sd=2500, seed=81, noise=60, dual=True)
+    rng = np.random.Generator(np.random.PCG64(81))
+    rec = ds.records.copy()
+    rec[rng.random(rec.shape[0]) < 0.01, 6] |= 2      # invalid records
+    piles = ds.flat_piles()
+    P = O.Pipeline(rec, piles).run()
+    E = P.edges.shape[0]
+    cols = torch.from_numpy(api.records_to_columns(rec)).pin_memory()
+    edges_pin = torch.zeros((E + 64, 3), dtype=torch.int32).pin_memory()
+    marked_pin = torch.zeros(E + 64, dtype=torch.uint8).pin_memory()
+    G = api.Graph(ctx)
+    G.set_outputs(edges_pin, marked_pin)
+    for i in range(5):          # eager, capture, replays: every run rewrites the host buffers
+        edges_pin.fill_(-1)
+        marked_pin.fill_(7)
+        G.set_piles(piles).set_hills(None).set_overlaps_columns(cols)
+        G.run()
+        c = G.counts()          # synchronises
+        assert c["n_edges"] == E and c["n_transitive_pairs"] == P.n_pairs and c["n_nodes"] == P.n_nodes
+        assert_same(edges_pin.numpy()[:E].view(np.uint32), P.edges, f"edge rows written to host memory, run {i}")
+        assert_same(marked_pin.numpy()[:E], P.marked, f"marks written to host memory, run {i}")
+        assert (edges_pin.numpy()[E:] == -1).all() and (marked_pin.numpy()[E:] == 7).all(), "nothing behind the last edge"
+        assert_same(G.edges(), P.edges, "get_edges")
+        assert_same(G.marked(), P.marked, "get_marked")
+    # stage by stage: build alone joins its download before it returns
+    edges_pin.fill_(-1)
+    marked_pin.fill_(7)
+    G.set_piles(piles).set_overlaps_columns(cols)
+    G.classify().retrim()
+    G.retrim_promote()
+    G.finalize().build()
+    ctx.synchronize()
+    assert_same(edges_pin.numpy()[:E].view(np.uint32), P.edges, "edge rows after build()")
+    assert (marked_pin.numpy() == 7).all()
+    G.transitive()
+    ctx.synchronize()
+    assert_same(marked_pin.numpy()[:E], P.marked, "marks after transitive()")
+    # buffers smaller than the result: filled up to their capacity, never beyond
+    small_e = torch.full((E // 2 + 5, 3), -1, dtype=torch.int32).pin_memory()
+    small_m = torch.full((E // 3 + 3,), 7, dtype=torch.uint8).pin_memory()
+    guard_e, guard_m = small_e[-2:], small_m[-1:]
+    G.set_outputs(small_e[:-2], small_m[:-1])
+    G.set_piles(piles).set_overlaps_columns(cols)
+    G.run()
+    assert G.counts()["n_edges"] == E
+    assert_same(small_e.numpy()[:-2].view(np.uint32), P.edges[: small_e.shape[0] - 2], "truncated edge rows")
+    assert_same(small_m.numpy()[:-1], P.marked[: small_m.shape[0] - 1], "truncated marks")
+    assert (guard_e.numpy() == -1).all() and (guard_m.numpy() == 7).all(), "wrote beyond the caller's capacity"
+    # pageable memory is refused, loudly
+    with pytest.raises(api.RalaB200Error):
+        G.set_outputs(np.zeros((E, 3), np.uint32), None)
+    # outputs off again: the row form of the same batch gives the same lists
+    G.set_outputs(None, None)
+    G.set_piles(piles).set_overlaps(rec)
+    G.run()
+    assert_same(G.edges(), P.edges, "row form edges")
+    ovl, inl = G.lists()
+    assert_same(ovl, P.ovl, "final overlaps")
+    assert_same(inl, P.int, "final internals")
+    G.close()
+
+
 def test_host_filtered_overlaps_before_build(ctx):
     """The -s option (Graph::preprocess(overlaps, path), graph.cpp:523, 882-1054) stays host code that only DROPS
     entries of `overlaps`; the kept list goes back to the device (rala_b200_graph_set_kept_overlaps) and edge creation
