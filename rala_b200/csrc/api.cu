@@ -532,13 +532,13 @@ static cudaError_t clear_victim_histogram(rala_b200_graph* g) {
     return cudaMemsetAsync(resolve_bufs(g).vcursor, 0, ((size_t) g->n_piles + 64) * 4, g->ctx->L.stream);
 }
 
-static int resolve_containment(rala_b200_graph* g) {
+static int resolve_containment(rala_b200_graph* g, bool decode) {
     rala_b200_ctx* ctx = g->ctx;
     unsigned long long* status;
     uint32_t* ticket;
     scan_state(g, (uint64_t) g->n_piles + 1, &status, &ticket);
     launch_resolve(ctx->L, g->events_view(), g->cnt() + C_EV, g->ev_cap, resolve_bufs(g), g->n_piles, g->cnt(), status, ticket,
-                   ctx->coop_blocks);
+                   ctx->coop_blocks, decode);
     CU(ctx, cudaGetLastError());
     return RALA_B200_OK;
 }
@@ -569,8 +569,11 @@ static int phase_events(rala_b200_graph* g) {
 
 static int phase_resolve(rala_b200_graph* g, bool first_pass) {
     rala_b200_ctx* ctx = g->ctx;
+    // the hill counters read the death times BEFORE the deaths are applied to the pile table; without hills nothing
+    // sits between the resolution and k_apply_deaths, which then decodes the states itself
+    const bool fused_decode = RB_OPT_FUSE && !(first_pass && g->n_hills);
     CU(ctx, stage_event(g, g->ev_start[ST_K1B_KERNEL]));
-    int rc = resolve_containment(g);
+    int rc = resolve_containment(g, !fused_decode);
     if (rc) return rc;
     CU(ctx, end_stage(g, ST_K1B_KERNEL));
     if (first_pass && g->n_hills) {
@@ -579,7 +582,7 @@ static int phase_resolve(rala_b200_graph* g, bool first_pass) {
                              h + g->n_hills, h + 2 * (size_t) g->n_hills, g->n_hills,
                              g->hills.as<uint32_t>() + 3 * (size_t) g->n_hills, g->dbuf.as<uint32_t>(), g->n_piles, g->cnt());
     }
-    launch_apply_deaths(ctx->L, g->piles.as<uint2>(), g->dbuf.as<uint32_t>(), g->n_piles, g->cnt(), g->alive_bits.as<uint32_t>());
+    launch_apply_deaths(ctx->L, g->piles.as<uint2>(), g->dbuf.as<uint32_t>(), g->n_piles, g->cnt(), g->alive_bits.as<uint32_t>(), fused_decode);
     CU(ctx, cudaGetLastError());
     return RALA_B200_OK;
 }
@@ -737,10 +740,9 @@ static int phase_final_events(rala_b200_graph* g, const uint32_t* ovl_base /* de
     CU(ctx, cudaMemcpyAsync(g->cnt() + C_ROUNDS_FIRST, g->cnt() + C_ROUNDS, 4, cudaMemcpyDeviceToDevice, ctx->L.stream));
     CU(ctx, zero_counter(g, C_EV));
     CU(ctx, clear_victim_histogram(g));
-    launch_classify_final(ctx->L, g->ovl[g->ovl_cur].view, g->cnt() + g->slot_ovl, g->cap, ovl_base, g->piles.as<uint2>(),
-                          g->events_view(), g->ev_cap, resolve_bufs(g).vcursor, g->cnt());
-    launch_classify_final(ctx->L, g->inl[g->inl_cur].view, g->cnt() + g->slot_inl, g->cap, inl_base,
-                          g->piles.as<uint2>(), g->events_view(), g->ev_cap, resolve_bufs(g).vcursor, g->cnt());
+    launch_classify_final(ctx->L, g->ovl[g->ovl_cur].view, g->cnt() + g->slot_ovl, ovl_base, g->inl[g->inl_cur].view,
+                          g->cnt() + g->slot_inl, inl_base, g->cap, g->piles.as<uint2>(), g->events_view(), g->ev_cap,
+                          resolve_bufs(g).vcursor, g->cnt());
     CU(ctx, cudaGetLastError());
     return RALA_B200_OK;
 }
@@ -806,7 +808,6 @@ static int run_transitive(rala_b200_graph* g) {
     CU(ctx, zero_counter(g, C_PAIRS, 2));   // C_PAIRS, C_HEAVY
     CU(ctx, zero_counter(g, C_HOP_LO, 2));
     CU(ctx, cudaMemsetAsync(g->work_counter.p, 0, 64, ctx->L.stream));
-    CU(ctx, cudaMemsetAsync(g->T.p, 0, align_up(g->edge_cap, 256), ctx->L.stream));
     CU(ctx, stage_event(g, g->ev_start[ST_K3_KERNELS]));
     launch_transitive(ctx->L, g->graph_view(), g->n_nodes_max, g->edge_cap, g->heavy_view(), g->work_counter.as<uint32_t>(),
                       g->cnt(), 0u, 0xFFFFFFFFu, g->world > 1 ? g->work_counter.as<uint32_t>() + 4 : nullptr);
@@ -1477,7 +1478,6 @@ extern "C" int rala_b200_graph_phase_transitive(rala_b200_graph* g) {
     CU(ctx, zero_counter(g, C_PAIRS, 2));
     CU(ctx, zero_counter(g, C_HOP_LO, 2));
     CU(ctx, cudaMemsetAsync(g->work_counter.p, 0, 64, ctx->L.stream));
-    CU(ctx, cudaMemsetAsync(g->T.p, 0, align_up(g->edge_cap, 256), ctx->L.stream));
     launch_node_range(ctx->L, g->graph_view(), g->cnt(), (uint32_t) g->rank, (uint32_t) g->world, g->work_counter.as<uint32_t>() + 4);
     CU(ctx, stage_event(g, g->ev_start[ST_K3_KERNELS]));
     launch_transitive(ctx->L, g->graph_view(), g->n_nodes_max, g->edge_cap, g->heavy_view(), g->work_counter.as<uint32_t>(),

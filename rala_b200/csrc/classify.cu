@@ -425,14 +425,23 @@ __global__ void k_hill_coverage(List recs, uint32_t t0, const uint2* __restrict_
 
 // Piles with a finite death time die (piles_[x].reset(), graph.cpp:471,477,838,842).
 // Also refreshes the one-bit-per-pile liveness bitmap the survivors pass tests first.
-__global__ void k_apply_deaths(uint2* __restrict__ piles, const uint32_t* __restrict__ dbuf, uint32_t n_piles,
+// DECODE: dbuf still holds the resolution's state words (containment.cu: settled bit | death time, 0x7FFFFFFF = never);
+// they are turned into death times (kInf = never) on the way, which saves the separate k_decode_state launch.
+template <bool DECODE>
+__global__ void k_apply_deaths(uint2* __restrict__ piles, uint32_t* __restrict__ dbuf, uint32_t n_piles,
                                const uint32_t* __restrict__ counters, uint32_t* __restrict__ alive_bits) {
-    const uint32_t* D = dbuf + (size_t) counters[C_DSEL] * n_piles;
+    uint32_t* D = dbuf + (size_t) counters[C_DSEL] * n_piles;
     for (uint32_t base = blockIdx.x * blockDim.x; base < n_piles; base += gridDim.x * blockDim.x) {
         const uint32_t i = base + threadIdx.x;
         bool alive = false;
         if (i < n_piles) {
-            if (D[i] != kInf) piles[i] = make_uint2(0u, 0u);
+            uint32_t d = D[i];
+            if (DECODE) {
+                d &= 0x7FFFFFFFu;
+                d = d == 0x7FFFFFFFu ? kInf : d;
+                D[i] = d;
+            }
+            if (d != kInf) piles[i] = make_uint2(0u, 0u);
             else alive = (piles[i].y & kEndMask) != 0u;
         }
         const uint32_t m = __ballot_sync(0xFFFFFFFFu, alive);
@@ -524,9 +533,14 @@ __global__ void __launch_bounds__(kTileThreads) k_list_pass(
 // Final containment, classification half (graph.cpp:831-866): type of every entry of `overlaps`
 // then `internals` against the final pile table; kA/kB become events with time = position in the
 // concatenation.  No chimeric gating in this pass.
-__global__ void k_classify_final(List lst, const uint32_t* __restrict__ n_ptr, uint32_t cap,
-                                 const uint32_t* __restrict__ time_base_ptr, const uint2* __restrict__ piles, Events ev,
+// blockIdx.y selects the list: 0 = `overlaps`, 1 = `internals` (one launch for both: the second list is tiny on clean data).
+__global__ void k_classify_final(List lst0, const uint32_t* __restrict__ n_ptr0, const uint32_t* __restrict__ time_base_ptr0,
+                                 List lst1, const uint32_t* __restrict__ n_ptr1, const uint32_t* __restrict__ time_base_ptr1,
+                                 uint32_t cap, const uint2* __restrict__ piles, Events ev,
                                  uint32_t ev_cap, uint32_t* __restrict__ vcount, uint32_t* __restrict__ counters) {
+    const List lst = blockIdx.y ? lst1 : lst0;
+    const uint32_t* n_ptr = blockIdx.y ? n_ptr1 : n_ptr0;
+    const uint32_t* time_base_ptr = blockIdx.y ? time_base_ptr1 : time_base_ptr0;
     const uint32_t n = min(*n_ptr, cap);
     const uint32_t time_base = time_base_ptr ? *time_base_ptr : 0u;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
@@ -688,10 +702,11 @@ void launch_hill_coverage(Launch& L, List recs, uint32_t t0, const uint2* piles,
     L.count++;
 }
 
-void launch_apply_deaths(Launch& L, uint2* piles, const uint32_t* dbuf, uint32_t n_piles, const uint32_t* counters,
-                         uint32_t* alive_bits) {
+void launch_apply_deaths(Launch& L, uint2* piles, uint32_t* dbuf, uint32_t n_piles, const uint32_t* counters,
+                         uint32_t* alive_bits, bool decode) {
     if (n_piles == 0) return;
-    k_apply_deaths<<<grid_for(n_piles, 256, kNumSMs * 8), 256, 0, L.stream>>>(piles, dbuf, n_piles, counters, alive_bits);
+    if (decode) k_apply_deaths<true><<<grid_for(n_piles, 256, kNumSMs * 8), 256, 0, L.stream>>>(piles, dbuf, n_piles, counters, alive_bits);
+    else k_apply_deaths<false><<<grid_for(n_piles, 256, kNumSMs * 8), 256, 0, L.stream>>>(piles, dbuf, n_piles, counters, alive_bits);
     L.count++;
 }
 
@@ -713,10 +728,11 @@ void launch_list_pass(Launch& L, int mode, List in, const uint32_t* n_in, uint32
     L.count++;
 }
 
-void launch_classify_final(Launch& L, List lst, const uint32_t* n_ptr, uint32_t cap, const uint32_t* time_base,
-                           const uint2* piles, Events ev, uint32_t ev_cap, uint32_t* vcount, uint32_t* counters) {
-    k_classify_final<<<grid_for(cap, 256, kNumSMs * 8), 256, 0, L.stream>>>(lst, n_ptr, cap, time_base, piles, ev, ev_cap,
-                                                                            vcount, counters);
+void launch_classify_final(Launch& L, List ovl, const uint32_t* n_ovl, const uint32_t* ovl_time_base, List inl,
+                           const uint32_t* n_inl, const uint32_t* inl_time_base, uint32_t cap, const uint2* piles, Events ev,
+                           uint32_t ev_cap, uint32_t* vcount, uint32_t* counters) {
+    k_classify_final<<<dim3(grid_for(cap, 256, kNumSMs * 4), 2), 256, 0, L.stream>>>(ovl, n_ovl, ovl_time_base, inl, n_inl, inl_time_base,
+                                                                                     cap, piles, ev, ev_cap, vcount, counters);
     L.count++;
 }
 

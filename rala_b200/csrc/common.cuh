@@ -19,6 +19,9 @@
 #ifndef RB_OPT_BSEARCH
 #define RB_OPT_BSEARCH 1  // transitive pass, low-degree nodes: branch-free binary search instead of a hash table
 #endif
+#ifndef RB_OPT_FUSE
+#define RB_OPT_FUSE 1     // small dependent-free kernels of the containment resolution share a launch
+#endif
 #ifndef RB_OPT_CONC
 #define RB_OPT_CONC 1     // independent kernels of one step on forked streams
 #endif

@@ -94,6 +94,54 @@ __global__ void k_resolve_init(const uint32_t* __restrict__ vstart, uint32_t n_p
     }
 }
 
+// k_events_fill and k_resolve_init do not depend on each other (both follow the scan of the victim histogram): one
+// launch, the first `fill_blocks` blocks scatter the events, the others initialise the states and the worklist.
+__global__ void __launch_bounds__(256) k_resolve_prepare(Events ev, const uint32_t* __restrict__ n_events, uint32_t ev_cap,
+                                                        uint32_t* __restrict__ vcursor, uint32_t* __restrict__ seg_c,
+                                                        uint32_t* __restrict__ seg_t, const uint32_t* __restrict__ vstart,
+                                                        uint32_t n_piles, uint32_t* __restrict__ S, uint32_t* __restrict__ work,
+                                                        uint32_t* __restrict__ n_work, uint32_t fill_blocks) {
+    if (blockIdx.x < fill_blocks) {
+        const uint32_t n = min(*n_events, ev_cap);
+        const uint32_t stride = fill_blocks * blockDim.x;   // four independent load -> atomic -> store chains per thread
+        for (uint32_t i0 = blockIdx.x * blockDim.x + threadIdx.x; i0 < n; i0 += 4u * stride) {
+            uint32_t v[4], c[4], t[4], p[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const uint32_t i = i0 + k * stride;
+                if (i < n) { v[k] = ev.v[i]; c[k] = ev.c[i]; t[k] = ev.t[i]; }
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (i0 + k * stride < n) p[k] = atomicAdd(&vcursor[v[k]], 1u);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                if (i0 + k * stride < n) {
+                    seg_c[p[k]] = c[k];
+                    seg_t[p[k]] = t[k];
+                }
+            }
+        }
+        return;
+    }
+    const uint32_t init_blocks = gridDim.x - fill_blocks, b = blockIdx.x - fill_blocks;
+    for (uint32_t base = b * blockDim.x; base < n_piles; base += init_blocks * blockDim.x) {
+        const uint32_t x = base + threadIdx.x;
+        bool victim = false;
+        if (x < n_piles) {
+            victim = vstart[x + 1] != vstart[x];
+            S[x] = victim ? 0u : (kSettled | kNever);
+        }
+        const uint32_t m = __ballot_sync(0xFFFFFFFFu, victim);
+        if (m) {
+            uint32_t gb = 0;
+            if (lane_id() == 0) gb = atomicAdd(n_work, (uint32_t) __popc(m));
+            gb = __shfl_sync(0xFFFFFFFFu, gb, 0);
+            if (victim) work[gb + __popc(m & ((1u << lane_id()) - 1u))] = x;
+        }
+    }
+}
+
 // Settle victim v0 (returns false only when the chase budget ran out; v0 then stays on the worklist).
 __device__ __forceinline__ bool resolve_victim(uint32_t v0, const uint32_t* __restrict__ vstart,
                                                const uint32_t* __restrict__ seg_c, uint32_t* __restrict__ seg_t,
@@ -239,18 +287,29 @@ int resolve_max_blocks() {
 
 // vcursor holds the per-victim event histogram on entry (filled by the classify kernels)
 void launch_resolve(Launch& L, Events ev, const uint32_t* n_events, uint32_t ev_cap, ResolveBufs rb, uint32_t n_piles,
-                    uint32_t* counters, unsigned long long* status, uint32_t* ticket, int coop_blocks) {
+                    uint32_t* counters, unsigned long long* status, uint32_t* ticket, int coop_blocks, bool decode) {
     launch_scan_u32(L, rb.vcursor, rb.vstart, n_piles + 1, status, ticket);
+    cudaMemsetAsync(rb.n_work, 0, 16, L.stream);
+#if RB_OPT_FUSE
+    {
+        const int fill_blocks = grid_for(ev_cap, 1024, kNumSMs * 4), init_blocks = grid_for(n_piles, 256, kNumSMs * 4);
+        k_resolve_prepare<<<fill_blocks + init_blocks, 256, 0, L.stream>>>(ev, n_events, ev_cap, rb.vcursor, rb.seg_c, rb.seg_t, rb.vstart,
+                                                                         n_piles, rb.S, rb.work0, rb.n_work, (uint32_t) fill_blocks);
+        L.count++;
+    }
+#else
     k_events_fill<<<grid_for(ev_cap, 256, kNumSMs * 8), 256, 0, L.stream>>>(ev, n_events, ev_cap, rb.vcursor, rb.seg_c, rb.seg_t);
     L.count++;
-    cudaMemsetAsync(rb.n_work, 0, 16, L.stream);
     k_resolve_init<<<grid_for(n_piles, 256, kNumSMs * 8), 256, 0, L.stream>>>(rb.vstart, n_piles, rb.S, rb.work0, rb.n_work);
     L.count++;
+#endif
     void* args[] = {&rb.vstart, &rb.seg_c, &rb.seg_t, &rb.S, &rb.work0, &rb.work1, &rb.n_work, &counters};
     cudaLaunchCooperativeKernel((void*) k_resolve, dim3(coop_blocks), dim3(256), args, 0, L.stream);
     L.count++;
-    k_decode_state<<<grid_for(n_piles, 256, kNumSMs * 8), 256, 0, L.stream>>>(rb.S, n_piles);
-    L.count++;
+    if (decode) {   // otherwise k_apply_deaths decodes while it applies (no consumer in between)
+        k_decode_state<<<grid_for(n_piles, 256, kNumSMs * 8), 256, 0, L.stream>>>(rb.S, n_piles);
+        L.count++;
+    }
 }
 
 }  // namespace rb

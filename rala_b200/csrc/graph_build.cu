@@ -173,10 +173,19 @@ __global__ void __launch_bounds__(kTileThreads) k_scan_degrees(uint32_t* __restr
 
 // Scatter every edge into its source row.  Slot order inside a row is arbitrary (atomic cursor);
 // nothing downstream depends on it: the transitive pass resolves parallel edges by edge id.
+// Also clears the per-edge "transitive test passed" bytes T[0 .. n rounded up to 16) for the pass that follows
+// (k_finalize_marks reads whole 16-byte groups): a memset of the buffer's CAPACITY (2 x the record count) would
+// write ~15 x more bytes than there are edges.
 __global__ void k_fill_csr(const uint32_t* __restrict__ src, const uint32_t* __restrict__ dst,
                            const uint32_t* __restrict__ len, const uint32_t* __restrict__ n_edges_ptr, uint32_t edge_cap,
-                           uint32_t* __restrict__ cursor, uint2* __restrict__ col, uint32_t* __restrict__ col_eid) {
+                           uint32_t* __restrict__ cursor, uint2* __restrict__ col, uint32_t* __restrict__ col_eid,
+                           uint8_t* __restrict__ T) {
     const uint32_t n = min(*n_edges_ptr, edge_cap);
+    {
+        const uint32_t n16 = (n + 15u) / 16u;   // T is padded to a multiple of 256 bytes
+        for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += gridDim.x * blockDim.x)
+            reinterpret_cast<uint4*>(T)[i] = make_uint4(0u, 0u, 0u, 0u);
+    }
 #if RB_OPT_FILL
     // load -> returning atomic -> store is a chain of three dependent round trips: keep four edges of it in flight
     const uint32_t stride = gridDim.x * blockDim.x;
@@ -356,7 +365,7 @@ void launch_build_csr(Launch& L, GraphArrays g, uint32_t n_nodes_max, uint32_t e
         g.cursor, g.row_ptr, n_nodes_max + 1, status, ticket);
     L.count++;
     k_fill_csr<<<grid_for(edge_cap, 256, kNumSMs * 8), 256, 0, L.stream>>>(g.src, g.dst, g.len, counters + C_EDGES,
-                                                                            edge_cap, g.cursor, g.col, g.col_eid);
+                                                                            edge_cap, g.cursor, g.col, g.col_eid, g.T);
     L.count++;
 }
 

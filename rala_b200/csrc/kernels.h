@@ -68,14 +68,15 @@ void launch_hill_coverage(Launch& L, List recs, uint32_t t0, const uint2* piles,
                           uint32_t hill_cap, const uint32_t* hill_pile, const uint32_t* hill_begin,
                           const uint32_t* hill_end, uint32_t n_hills, uint32_t* hill_cov, const uint32_t* dbuf,
                           uint32_t n_piles, const uint32_t* counters);
-void launch_apply_deaths(Launch& L, uint2* piles, const uint32_t* dbuf, uint32_t n_piles, const uint32_t* counters,
-                         uint32_t* alive_bits);
+void launch_apply_deaths(Launch& L, uint2* piles, uint32_t* dbuf, uint32_t n_piles, const uint32_t* counters,
+                         uint32_t* alive_bits, bool decode);
 void launch_list_pass(Launch& L, int mode, List in, const uint32_t* n_in, uint32_t in_cap, const uint2* piles, List out_a,
                       uint32_t* n_out_a, List out_b, uint32_t* n_out_b, const uint32_t* b_base, uint32_t cap,
                       const uint32_t* dbuf, uint32_t n_piles, const uint32_t* time_base, const uint32_t* counters,
                       unsigned long long* status, uint32_t* ticket);
-void launch_classify_final(Launch& L, List lst, const uint32_t* n_ptr, uint32_t cap, const uint32_t* time_base,
-                           const uint2* piles, Events ev, uint32_t ev_cap, uint32_t* vcount, uint32_t* counters);
+void launch_classify_final(Launch& L, List ovl, const uint32_t* n_ovl, const uint32_t* ovl_time_base, List inl,
+                           const uint32_t* n_inl, const uint32_t* inl_time_base, uint32_t cap, const uint2* piles, Events ev,
+                           uint32_t ev_cap, uint32_t* vcount, uint32_t* counters);
 void launch_trim_classify_aos(Launch& L, uint32_t* rec, uint32_t n, const uint2* piles, uint32_t n_piles, uint8_t* type_out);
 void launch_fill_u32(Launch& L, uint32_t* p, uint32_t v, size_t n);
 void launch_pack_piles(Launch& L, const uint2* in, const uint8_t* flags, uint2* out, uint32_t n);
@@ -96,8 +97,10 @@ struct ResolveBufs {
 int resolve_max_blocks();
 // per-victim histogram of an imported event list (the classify kernels build it on the fly otherwise)
 void launch_events_hist(Launch& L, Events ev, const uint32_t* n_events, uint32_t ev_cap, uint32_t* vcount);
+// decode = false leaves the resolution's state encoding in rb.S: the following launch_apply_deaths(decode = true) turns
+// it into death times while it applies them (one launch less when nothing reads the death times in between)
 void launch_resolve(Launch& L, Events ev, const uint32_t* n_events, uint32_t ev_cap, ResolveBufs rb, uint32_t n_piles,
-                    uint32_t* counters, unsigned long long* status, uint32_t* ticket, int coop_blocks);
+                    uint32_t* counters, unsigned long long* status, uint32_t* ticket, int coop_blocks, bool decode);
 
 // graph_build.cu
 void launch_scan_u32(Launch& L, uint32_t* values_inout, uint32_t* exclusive_out, uint32_t n, unsigned long long* status,
