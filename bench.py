@@ -127,7 +127,8 @@ def ncu_traffic(kernels):
         t = json.load(f)
     if not all(k in t["kernels"] for k in kernels):
         return None, t.get("tag")
-    return sum(t["kernels"][k]["dram_bytes"] for k in kernels), t.get("tag")
+    tags = sorted({t["kernels"][k].get("tag", t.get("tag")) for k in kernels})   # the capture(s) the numbers come from
+    return sum(t["kernels"][k]["dram_bytes"] for k in kernels), "+".join(tags)
 
 
 def make_dataset(workload: str, n_gpus: int, seed: int = 3):
@@ -367,7 +368,8 @@ def run_ab(args):
     from rala_b200 import api, build as B
     ds = make_dataset(args.workload, 1)
     piles = ds.flat_piles()
-    libs = [("product", api.LIB_PATH, None)] + [(k, B.variant_path(k), None) for k in B.VARIANTS if os.path.exists(B.variant_path(k))]
+    libs = [("product", api.LIB_PATH, None)] + [(k, B.variant_path(k), None) for k in list(B.VARIANTS) + list(B.TUNINGS)
+                                                if os.path.exists(B.variant_path(k))]
     prev = B.variant_path("prev")   # the previous commit's library, when profiles/capture_ab.sh built it
     if os.path.exists(prev):
         libs.append(("prev", prev, None))

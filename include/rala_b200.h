@@ -233,10 +233,14 @@ int rala_b200_graph_import_edges(rala_b200_graph* g, const uint32_t* d_cols, uin
 int rala_b200_graph_phase_csr(rala_b200_graph* g);
 /* Capacity-bounded variants of the exchange steps: element counts travel inside the blocks and the time bases are
  * computed on the device, so no call below synchronises with the host (the sized variants above read counts back).
- *   block (3 * cap + 4 words) = [n clamped to cap | overflow flag | 0 | 0 | column 0 [cap] | column 1 [cap] | column 2 [cap]]
- *   kind: 0 = containment events, 1 = edges.  d_gathered = the `world` blocks of an all-gather, in rank order.
+ *   kind 0, containment events: block (3 * cap + 4 words) = [n clamped to cap | overflow flag | 0 | 0 | victim [cap] | container [cap] | time [cap]]
+ *   kind 1, edges: the same layout with src | dst | len; with RALA_B200_EDGE_PAIRS=1 in the environment (opt-in until it has run on
+ *           several GPUs) as reverse-complement PAIRS (edge 2j = (s, d, l), edge 2j+1 = (d ^ 1, s ^ 1, l'), graph.cpp:594-629): cap even,
+ *           block (2 * cap + 4 words) = [n | overflow flag | 0 | 0 | s [cap/2] | d [cap/2] | l [cap/2] | l' [cap/2]]: 8 bytes per edge on the wire
+ *   rala_b200_exchange_block_words(kind, cap) is the block size in 32-bit words.  d_gathered = the `world` blocks of an all-gather, in rank order.
  * A count beyond `cap` raises the session's overflow flag (reported by rala_b200_graph_counts): re-run sized.
  * rala_b200_graph_phase_emit_edges accepts n_local_edges == NULL (no read-back). */
+uint64_t rala_b200_exchange_block_words(int kind, uint32_t cap);
 int rala_b200_graph_export_padded(rala_b200_graph* g, int kind, uint32_t* d_block, uint32_t cap);
 int rala_b200_graph_import_gathered(rala_b200_graph* g, int kind, const uint32_t* d_gathered, uint32_t cap, int world);
 int rala_b200_graph_export_list_counts(rala_b200_graph* g, uint32_t* d_pair /* n_overlaps, n_internals */);

@@ -60,7 +60,7 @@ EXPORTS = [
     "rala_b200_graph_import_edges", "rala_b200_graph_phase_csr", "rala_b200_graph_phase_transitive",
     "rala_b200_graph_export_marks", "rala_b200_graph_phase_marks",
     "rala_b200_graph_export_padded", "rala_b200_graph_import_gathered", "rala_b200_graph_export_list_counts",
-    "rala_b200_graph_phase_final_events_gathered",
+    "rala_b200_graph_phase_final_events_gathered", "rala_b200_exchange_block_words",
 ]
 
 _LIB = None
@@ -73,6 +73,7 @@ def load_path(path: str):
     lib = C.CDLL(path)
     lib.rala_b200_last_error.restype = C.c_char_p
     lib.rala_b200_launch_count.restype = C.c_uint64
+    lib.rala_b200_exchange_block_words.restype = C.c_uint64
     lib.rala_b200_destroy.restype = None
     lib.rala_b200_graph_destroy.restype = None
     return lib

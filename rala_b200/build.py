@@ -71,10 +71,16 @@ def variant_path(name: str) -> str:
     return os.path.join(VARIANT_DIR, f"librala_b200_{name}.so")
 
 
+# other settings of a tunable, same product otherwise
+TUNINGS = {"reloc8": ["-DRB_RELOC_LANES=8"], "packrow": ["-DRB_GROUP_PACKROW=1"]}
+
+
 def build_variants(verbose: bool = False):
     out = {}
     for name, macro in VARIANTS.items():
         out[name] = _compile(variant_path(name), os.path.join(HERE, "build", name), [f"-D{macro}=0"], verbose)
+    for name, defines in TUNINGS.items():
+        out[name] = _compile(variant_path(name), os.path.join(HERE, "build", name), defines, verbose)
     return out
 
 

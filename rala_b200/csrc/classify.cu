@@ -355,19 +355,24 @@ __global__ void k_relocate(List tmp, List out, uint32_t cap, const uint32_t* __r
     }
 }
 
-// The same move with one WARP per run, both lists in one launch: the run's survivors (~7 % of 512 records) are
+// The same move with one WARP (or a smaller lane group, RB_RELOC_LANES) per run, both lists in one launch: the run's survivors (~7 % of 512 records) are
 // contiguous in the scratch list and in the final list, so every column is read and written in coalesced pieces and
 // nobody searches for its run (k_relocate: a binary search per warp and a walk per lane, 28 + 3 us in profiles/r01h).
+#ifndef RB_RELOC_LANES
+#define RB_RELOC_LANES 32   // lanes per run; 8 (four runs in flight per warp, a run holds ~36 survivors) is built as a tuning variant
+#endif
+constexpr uint32_t kRelocLanes = RB_RELOC_LANES;
+
 __global__ void __launch_bounds__(kTileThreads) k_relocate_runs(List tmp_a, List out_a, List tmp_b, List out_b, uint32_t cap,
                                                                const uint32_t* __restrict__ run_cnt, const uint32_t* __restrict__ off_a,
                                                                const uint32_t* __restrict__ off_b, uint32_t num_runs) {
-    const uint32_t lane = lane_id();
-    const uint32_t warps = gridDim.x * kTileWarps;
-    for (uint32_t run = blockIdx.x * kTileWarps + warp_id(); run < num_runs; run += warps) {
+    const uint32_t gl = threadIdx.x & (kRelocLanes - 1);
+    const uint32_t groups = gridDim.x * (kTileThreads / kRelocLanes);
+    for (uint32_t run = blockIdx.x * (kTileThreads / kRelocLanes) + threadIdx.x / kRelocLanes; run < num_runs; run += groups) {
         const uint32_t c = __ldg(run_cnt + run), base = run * kRunRecords;
         const uint32_t na = c & 0xFFFFu, nb = c >> 16;
         const uint32_t oa = __ldg(off_a + run), ob = __ldg(off_b + run);
-        for (uint32_t j = lane; j < na; j += 32) {
+        for (uint32_t j = gl; j < na; j += kRelocLanes) {
             const uint32_t s = base + j, d = oa + j;
             if (s < cap && d < cap) {
                 out_a.a[d] = tmp_a.a[s]; out_a.b[d] = tmp_a.b[s];
@@ -376,7 +381,7 @@ __global__ void __launch_bounds__(kTileThreads) k_relocate_runs(List tmp_a, List
                 out_a.tag[d] = tmp_a.tag[s];
             }
         }
-        for (uint32_t j = lane; j < nb; j += 32) {
+        for (uint32_t j = gl; j < nb; j += kRelocLanes) {
             const uint32_t s = base + j, d = ob + j;
             if (s < cap && d < cap) {
                 out_b.a[d] = tmp_b.a[s]; out_b.b[d] = tmp_b.b[s];
@@ -681,7 +686,7 @@ void launch_classify_survivors(Launch& L, List recs, uint32_t n, const uint2* pi
                                                                                        n_inl, status, ticket);
     L.count++;
 #if RB_OPT_RELOC
-    k_relocate_runs<<<grid_for(num_runs, kTileWarps, kNumSMs * 8), kTileThreads, 0, L.stream>>>(tmp_ovl, ovl, tmp_inl, inl, cap, runs.cnt,
+    k_relocate_runs<<<grid_for(num_runs, kTileThreads / RB_RELOC_LANES, kNumSMs * 8), kTileThreads, 0, L.stream>>>(tmp_ovl, ovl, tmp_inl, inl, cap, runs.cnt,
                                                                                                runs.off_a, runs.off_b, num_runs);
     L.count++;
 #else

@@ -22,6 +22,9 @@
 #ifndef RB_OPT_FUSE
 #define RB_OPT_FUSE 1     // small dependent-free kernels of the containment resolution share a launch
 #endif
+#ifndef RB_GROUP_PACKROW
+#define RB_GROUP_PACKROW 0  // (not yet measured on a GPU) K3 group kernel: row base and edge length of a neighbour in one 8-byte smem word
+#endif
 #ifndef RB_OPT_CONC
 #define RB_OPT_CONC 1     // independent kernels of one step on forked streams
 #endif

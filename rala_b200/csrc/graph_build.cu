@@ -285,6 +285,46 @@ __global__ void k_import_gathered(const uint32_t* __restrict__ gathered, uint32_
     }
 }
 
+// Edge blocks travel as PAIRS: edge 2j = (s, d, l) and its reverse-complement twin 2j+1 = (d ^ 1, s ^ 1, l') share
+// their node ids (graph.cpp:594-629), so a pair is four words instead of six: 8 bytes per edge over NVLink instead of 12.
+//   block (2 * cap + 4 words) = [n edges (clamped to cap) | overflow | 0 | 0 | s [cap/2] | d [cap/2] | l [cap/2] | l' [cap/2]]
+__global__ void k_export_edge_pairs(const uint32_t* __restrict__ src, const uint32_t* __restrict__ dst, const uint32_t* __restrict__ len,
+                                    const uint32_t* __restrict__ n_ptr, uint32_t src_cap, uint32_t cap, uint32_t* __restrict__ block) {
+    const uint32_t n = min(*n_ptr, src_cap), m = min(n, cap) & ~1u, half = cap / 2;
+    if (blockIdx.x == 0 && threadIdx.x < 4) block[threadIdx.x] = threadIdx.x == 0 ? m : (threadIdx.x == 1 ? (n > cap ? 1u : 0u) : 0u);
+    for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < m / 2; j += gridDim.x * blockDim.x) {
+        const uint2 l = reinterpret_cast<const uint2*>(len)[j];
+        block[4 + j] = src[2 * j];
+        block[4 + (size_t) half + j] = dst[2 * j];
+        block[4 + 2 * (size_t) half + j] = l.x;
+        block[4 + 3 * (size_t) half + j] = l.y;
+    }
+}
+
+__global__ void k_import_edge_pairs(const uint32_t* __restrict__ gathered, uint32_t cap, uint32_t world, uint32_t* __restrict__ src,
+                                    uint32_t* __restrict__ dst, uint32_t* __restrict__ len, uint32_t dst_cap, uint32_t* __restrict__ n_out,
+                                    uint32_t* __restrict__ overflow) {
+    const size_t stride = 2 * (size_t) cap + 4;
+    const uint32_t r = blockIdx.y, half = cap / 2;
+    uint32_t offset = 0;
+    for (uint32_t q = 0; q < r; ++q) offset += gathered[q * stride];
+    const uint32_t* blk = gathered + r * stride;
+    const uint32_t n = blk[0];
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        if (blk[1] || offset + n > dst_cap) *overflow = 1u;
+        if (r == world - 1) *n_out = min(offset + n, dst_cap);
+    }
+    for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n / 2; j += gridDim.x * blockDim.x) {
+        const uint32_t e = offset + 2 * j;   // offsets are even: every rank holds whole pairs
+        if (e + 1 < dst_cap) {
+            const uint32_t s = blk[4 + j], d = blk[4 + (size_t) half + j];
+            reinterpret_cast<uint2*>(src + e)[0] = make_uint2(s, d ^ 1u);
+            reinterpret_cast<uint2*>(dst + e)[0] = make_uint2(d, s ^ 1u);
+            reinterpret_cast<uint2*>(len + e)[0] = make_uint2(blk[4 + 2 * (size_t) half + j], blk[4 + 3 * (size_t) half + j]);
+        }
+    }
+}
+
 // time bases of the local lists in the final containment pass (graph.cpp:831-866): position in the GLOBAL
 // overlaps ++ internals order.  counts = (n_overlaps, n_internals) of every rank.
 __global__ void k_time_bases(const uint32_t* __restrict__ counts, uint32_t rank, uint32_t world, uint32_t* __restrict__ bases) {
@@ -343,6 +383,19 @@ void launch_import_gathered(Launch& L, const uint32_t* gathered, uint32_t cap, u
                             uint32_t* d2, uint32_t dst_cap, uint32_t* n_out, uint32_t* overflow) {
     dim3 grid(grid_for(cap, 256, kNumSMs * 2), world);
     k_import_gathered<<<grid, 256, 0, L.stream>>>(gathered, cap, world, d0, d1, d2, dst_cap, n_out, overflow);
+    L.count++;
+}
+
+void launch_export_edge_pairs(Launch& L, const uint32_t* src, const uint32_t* dst, const uint32_t* len, const uint32_t* n_ptr,
+                              uint32_t src_cap, uint32_t cap, uint32_t* block) {
+    k_export_edge_pairs<<<grid_for(cap / 2, 256, kNumSMs * 4), 256, 0, L.stream>>>(src, dst, len, n_ptr, src_cap, cap, block);
+    L.count++;
+}
+
+void launch_import_edge_pairs(Launch& L, const uint32_t* gathered, uint32_t cap, uint32_t world, uint32_t* src, uint32_t* dst,
+                              uint32_t* len, uint32_t dst_cap, uint32_t* n_out, uint32_t* overflow) {
+    dim3 grid(grid_for(cap / 2, 256, kNumSMs * 2), world);
+    k_import_edge_pairs<<<grid, 256, 0, L.stream>>>(gathered, cap, world, src, dst, len, dst_cap, n_out, overflow);
     L.count++;
 }
 

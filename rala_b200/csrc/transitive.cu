@@ -117,8 +117,12 @@ struct GroupSmem {
     uint32_t keys[kGroupMaxDeg];             // destinations, sorted; kEmpty behind the last one
     uint32_t eid[kGroupMaxDeg];              // edge id at that position
     uint2 iv[kGroupMaxDeg];                  // comparable(sum, len of that edge)  <=>  sum - iv.x <= iv.y
+#if RB_GROUP_PACKROW
+    uint2 prow[kGroupMaxDeg];                // per neighbour b: (start of row b in col - its offset in the flat stream, len of a->b)
+#else
     uint32_t nrow[kGroupMaxDeg];
     uint32_t nlen[kGroupMaxDeg];
+#endif
     uint32_t noff[kGroupMaxDeg + 1];
     uint32_t hit;                            // bit j: the edge at sorted position j passed the test
 };
@@ -160,6 +164,9 @@ __global__ void __launch_bounds__(kLightWarps * 32, 6) k_transitive_group(
             // ---- this lane's (at most two) neighbours ----
             unsigned long long mine[2] = {~0ull, ~0ull};
             uint32_t dg[2] = {0u, 0u}, my_len[2] = {0u, 0u};
+#if RB_GROUP_PACKROW
+            uint32_t rs2[2] = {0u, 0u};
+#endif
             if (act) {
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
@@ -170,8 +177,12 @@ __global__ void __launch_bounds__(kLightWarps * 32, 6) k_transitive_group(
                         my_len[h] = e.y;
                         const uint32_t rs = row_ptr[e.x];
                         dg[h] = row_ptr[e.x + 1] - rs;
+#if RB_GROUP_PACKROW
+                        rs2[h] = rs;
+#else
                         S.nrow[i] = rs;
                         S.nlen[i] = e.y;
+#endif
                     }
                     S.ukey[i] = mine[h];
                 }
@@ -184,6 +195,11 @@ __global__ void __launch_bounds__(kLightWarps * 32, 6) k_transitive_group(
                 if (gl < d) S.noff[gl] = inc0 - dg[0];
                 if (gl + kGroupLanes < d) S.noff[gl + kGroupLanes] = tot0 + inc1 - dg[1];
                 if (gl == 0) S.noff[d] = W;
+#if RB_GROUP_PACKROW
+                // element f of the flat stream that falls into row i is col[prow[i].x + f]
+                if (gl < d) S.prow[gl] = make_uint2(rs2[0] - (inc0 - dg[0]), my_len[0]);
+                if (gl + kGroupLanes < d) S.prow[gl + kGroupLanes] = make_uint2(rs2[1] - (tot0 + inc1 - dg[1]), my_len[1]);
+#endif
             }
             __syncwarp();
             if (act && W > kGroupMaxVisits) {   // short row, very long rows behind it: give the node to a block
@@ -232,8 +248,14 @@ __global__ void __launch_bounds__(kLightWarps * 32, 6) k_transitive_group(
                         lab[u] = 0u;
                         if (ok[u]) {
                             while (f >= S.noff[i + 1]) ++i;
+#if RB_GROUP_PACKROW
+                            const uint2 row = S.prow[i];
+                            e[u] = col[row.x + f];
+                            lab[u] = row.y;
+#else
                             e[u] = col[S.nrow[i] + (f - S.noff[i])];
                             lab[u] = S.nlen[i];
+#endif
                         }
                     }
                     uint32_t pass = 0;   // bit j: a witness for the edge at sorted position j

@@ -119,6 +119,10 @@ class CudaShardSession:
     def phase_emit_edges_async(self):
         self.G._call("rala_b200_graph_phase_emit_edges", None)
 
+    def block_words(self, kind: int, cap: int) -> int:
+        """32-bit words of one exchange block (edges travel as reverse-complement pairs: 8 B per edge)."""
+        return int(self.ctx.lib.rala_b200_exchange_block_words(C.c_int(kind), C.c_uint32(cap)))
+
     def export_padded(self, kind: int, block: torch.Tensor, cap: int):
         self.G._call("rala_b200_graph_export_padded", C.c_int(kind), self._dp(block), C.c_uint32(cap))
 
@@ -245,16 +249,16 @@ class DistributedGraph:
             return dict(self.last_info, bounded=True, graph=True)
         return self.run()
 
-    def _buffers(self, name: str, cap: int):
+    def _buffers(self, name: str, cap: int, kind: int = 0):
         key = (name, cap)
         if key not in self._bufs:
-            words = 3 * cap + 4
+            words = self.s.block_words(kind, cap) if hasattr(self.s, "block_words") else 3 * cap + 4
             self._bufs[key] = (torch.zeros(words, dtype=torch.int32, device=self.device),
                                torch.zeros((self.world, words), dtype=torch.int32, device=self.device))
         return self._bufs[key]
 
     def _exchange_bounded(self, name: str, kind: int, cap: int):
-        block, gathered = self._buffers(name, cap)
+        block, gathered = self._buffers(name, cap, kind)
         self.s.export_padded(kind, block, cap)
         dist.all_gather_into_tensor(gathered.view(-1), block, group=self.group)
         self.comm_bytes += block.numel() * 4 * (self.world - 1)
@@ -500,5 +504,22 @@ def bench_main(args):
                          "stage_ms": stage},
             "cpu_baseline": None, "clocks": clocks,
         }))
+    _finish(dg, sess, world)
+
+
+def _finish(dg, sess, world: int):
+    """End of a multi-rank process.  With world > 1 a captured step graph holds NCCL kernel nodes, and tearing the
+    communicator down next to it blocked on the 2-GPU box (r01k: the bench line was printed, the ranks never left
+    destroy_process_group).  So: meet the other ranks once more and leave the process without any teardown; everything
+    the caller needs has been printed / written by then."""
+    import sys
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)       # no destructors: neither the graph nor the communicator is torn down
+    dg._graph = None
     sess.close()
     dist.destroy_process_group()

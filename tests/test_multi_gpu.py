@@ -29,6 +29,8 @@ def _free_port():
 
 
 def _worker(rank, world, port, out_dir, graph):
+    import signal
+    signal.alarm(420)    # a rank stuck in a collective must not hold the GPU suite (and the box) for its whole time limit
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
@@ -51,6 +53,8 @@ def _worker(rank, world, port, out_dir, graph):
         c = sess.counts()
         np.savez(os.path.join(out_dir, f"r{rank}.npz"), edges=sess.edges(), marked=sess.marked(), piles=sess.G.piles(),
                  n_pairs=c["n_transitive_pairs"], n_nodes=c["n_nodes"], n_events=info["n_events"])
+        if graph and world > 1:
+            multi._finish(dg, sess, world)   # results are on disk; leaves the process without the NCCL teardown (see there)
         sess.close()
     finally:
         dist.destroy_process_group()
