@@ -23,7 +23,7 @@
 #define RB_OPT_FUSE 1     // small dependent-free kernels of the containment resolution share a launch
 #endif
 #ifndef RB_GROUP_PACKROW
-#define RB_GROUP_PACKROW 0  // (not yet measured on a GPU) K3 group kernel: row base and edge length of a neighbour in one 8-byte smem word
+#define RB_GROUP_PACKROW 1  // K3 group kernel: row base and edge length of a neighbour in one 8-byte smem word (-4 % per step, r01l)
 #endif
 #ifndef RB_OPT_CONC
 #define RB_OPT_CONC 1     // independent kernels of one step on forked streams
