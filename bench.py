@@ -281,6 +281,10 @@ def run_single(args):
                            "frac": step_bytes / (ms_per_step * 1e-3) / 1e9 / peak},
             "kernels": {"k_classify_first": {"ms": k1_ms, "algorithmic_bytes": k1_bytes, "gbs": k1_gbs, "frac": k1_gbs / peak},
                         "k_transitive": {"ms": k3_ms, "algorithmic_bytes": k3_bytes, "gbs": k3_gbs, "frac": k3_gbs / peak}},
+            # the per-stage rates reported next to the metric (eager-chain stage timers)
+            "rates": {"k1_overlaps_per_s": n_ovl / (k1_ms * 1e-3) if k1_ms > 0 else None,
+                      "k3_edges_per_s": E / (k3_ms * 1e-3) if k3_ms > 0 else None,
+                      "k3_two_hop_visits_per_s": counts["n_two_hop"] / (k3_ms * 1e-3) if k3_ms > 0 else None},
             "stage_ms": {k: float(np.mean(v)) for k, v in stage_acc.items()}}
 
     # ---- end to end through the C ABI with HOST buffers ----------------------------------------
@@ -375,16 +379,20 @@ def run_ab(args):
         libs.append(("prev", prev, None))
     # launch-time knobs are read once per loaded library: a byte-identical copy under another name is a fresh instance
     import shutil
-    for minb in (4, 5):
-        copy = B.variant_path(f"minb{minb}")
+    knobs = ("RALA_B200_EV_MINB", "RALA_B200_EV_V2", "RALA_B200_SURV_V2")
+    for tag, env in (("events_minb4", {"RALA_B200_EV_MINB": "4"}), ("events_minb5", {"RALA_B200_EV_MINB": "5"}),
+                     # experiments written at the end of round 1 without GPU time (classify.cu *_v2 kernels)
+                     ("events_v2", {"RALA_B200_EV_V2": "1"}), ("events_v2_2blk", {"RALA_B200_EV_V2": "2"}),
+                     ("survivors_v2", {"RALA_B200_SURV_V2": "1"})):
+        copy = B.variant_path(f"copy_{tag}")
         shutil.copyfile(api.LIB_PATH, copy)
-        libs.append((f"events_minb{minb}", copy, ("RALA_B200_EV_MINB", str(minb))))
+        libs.append((tag, copy, env))
     out = {}
     for rnd in range(2):            # two rounds, interleaved: drift shows up as a difference between them
         for name, path, env in libs:
-            os.environ.pop("RALA_B200_EV_MINB", None)
-            if env:
-                os.environ[env[0]] = env[1]
+            for k in knobs:
+                os.environ.pop(k, None)
+            os.environ.update(env or {})
             ctx = api.Context(0, lib=api.load_path(path))
             G = api.Graph(ctx)
             G.set_piles(piles).set_hills(None).set_overlaps(ds.records)
@@ -397,12 +405,18 @@ def run_ab(args):
             ctx.event_record(1)
             ms = ctx.event_elapsed_ms() / args.steps
             c = G.counts()
-            out.setdefault(name, {"ms_per_step": [], "edges": c["n_edges"], "pairs": c["n_transitive_pairs"]})["ms_per_step"].append(ms)
+            import zlib
+            crc = zlib.crc32(G.marked().tobytes(), zlib.crc32(G.edges().tobytes()))   # an experiment must not change a single bit
+            out.setdefault(name, {"ms_per_step": [], "edges": c["n_edges"], "pairs": c["n_transitive_pairs"],
+                                  "edges_marks_crc32": crc})["ms_per_step"].append(ms)
             G.close()
             ctx.close()
+    for k in knobs:
+        os.environ.pop(k, None)
     base = min(out["product"]["ms_per_step"])
     for name, v in out.items():
         v["delta_us_vs_product"] = 1e3 * (min(v["ms_per_step"]) - base)
+        v["same_result_as_product"] = v["edges_marks_crc32"] == out["product"]["edges_marks_crc32"]
     print(json.dumps({"ab": out, "steps": args.steps, "workload": WORKLOADS[args.workload][3]}))
 
 

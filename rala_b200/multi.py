@@ -482,7 +482,7 @@ def bench_main(args):
         print(json.dumps({
             "metric": "graph_edges_per_sec", "value": E / (ms_per_step * 1e-3), "unit": "edges/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "u32+f64", "data": "synthetic",
+            "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
             "config": {"workload": f"{world} x ({bench.WORKLOADS[args.workload][3]}), read ids shuffled globally",
                        "n_overlaps": n_total_records, "n_overlaps_per_gpu": int(records.shape[0]), "n_reads": int(piles.shape[0]),
                        "edges": E, "nodes": c["n_nodes"], "containment_events": info["n_events"],

@@ -50,3 +50,25 @@ def test_product_package_never_imports_the_oracle():
         for f in files:
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 assert not pat.search(open(os.path.join(dirpath, f)).read()), f
+
+
+def test_records_to_columns_layout():
+    """api.records_to_columns: the host-side marshalling of rala_b200_graph_set_overlaps_columns (bit 31 of a_id =
+    invalid record or an id the 32-bit device ids cannot name, bit 31 of b_id = orientation; coordinates verbatim)."""
+    import numpy as np
+    from rala_b200 import api
+    rec = np.array([[5, 9, 10, 900, 20, 910, 0],
+                    [6, 7, 0, 5000, 100, 5100, 1],           # reverse complement
+                    [8, 3, 1, 2, 3, 4, 2],                   # invalid
+                    [2, 4, 11, 12, 13, 14, 3],               # invalid + reverse complement
+                    [0x80000001, 4, 1, 2, 3, 4, 0],          # id beyond 2^31: cannot name a pile
+                    [1, 0x80000002, 1, 2, 3, 4, 1]], dtype=np.uint32)
+    c = api.records_to_columns(rec)
+    assert c.shape == (6, 6) and c.dtype == np.uint32 and c.flags["C_CONTIGUOUS"]
+    top = 0x80000000
+    assert [int(x) & top != 0 for x in c[0]] == [False, False, True, True, True, True]
+    assert [int(x) & ~top & 0xFFFFFFFF for x in c[0]] == [5, 6, 8, 2, 1, 1]
+    assert [int(x) >> 31 for x in c[1]] == [0, 1, 0, 1, 0, 1]
+    assert [int(x) & 0x7FFFFFFF for x in c[1]] == [9, 7, 3, 4, 4, 2]
+    assert np.array_equal(c[2:6].T, rec[:, 2:6])
+    assert api.records_to_columns(np.zeros((0, 7), np.uint32)).shape == (6, 0)
