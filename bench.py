@@ -439,6 +439,11 @@ def main():
         run_ab(args)
         return
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.gpus > 1 and "WORLD_SIZE" not in os.environ:
+        # started as plain `python bench.py --gpus N`: one rank per GPU needs the launcher the driver uses
+        os.execv(sys.executable, [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+                                  "--master-addr", "127.0.0.1", "--master-port", os.environ.get("MASTER_PORT", "29533"),
+                                  os.path.abspath(__file__)] + sys.argv[1:])
     if args.gpus > 1 or world > 1:
         from rala_b200 import multi
         multi.bench_main(args)

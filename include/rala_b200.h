@@ -151,7 +151,8 @@ int rala_b200_graph_set_piles(rala_b200_graph* g, const rala_pile_t* piles, cons
  * removed-edge marks (graph.cpp:1305-1309) as they are finalised.  Nothing beyond the given capacities (in edges)
  * is written; the counts come from rala_b200_graph_counts.  The buffers hold valid data once the stream has been
  * synchronised (rala_b200_graph_counts / rala_b200_synchronize).  NULL switches an output off again; pageable
- * memory is refused (RALA_B200_ERR_ARG): use get_edges / get_marked for it. */
+ * memory is refused (RALA_B200_ERR_ARG): use get_edges / get_marked for it.  The caller keeps the buffers alive
+ * (and pinned) until it has switched them off or destroyed the session: every later build / run writes into them. */
 int rala_b200_graph_set_outputs(rala_b200_graph* g, rala_edge_t* edges_out, uint64_t edges_cap, uint8_t* marked_out,
                                 uint64_t marked_cap);
 int rala_b200_graph_set_hills(rala_b200_graph* g, const rala_hill_t* hills, uint32_t n_hills);
