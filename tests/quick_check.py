@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""profiles/quick_check.py — a GPU check that fits in seconds (no torch import): parity of the product library and
+"""tests/quick_check.py — TEST INFRASTRUCTURE (uses the oracle as the checker): a GPU check that fits in seconds (no torch import): parity of the product library and
 of the tuning variants against the oracle on a small noisy batch, then device-resident step times on a 20 Mbp batch.
 Prints one JSON line."""
 import json
@@ -21,7 +21,9 @@ P = O.Pipeline(small.records, sp).run()
 big = synth.generate(int(sys.argv[1]) if len(sys.argv) > 1 else 20_000_000, 40, 10000, seed=3)
 bp = big.flat_piles()
 out["t_setup_s"] = round(time.time() - T0, 2)
-names = [("product", api.LIB_PATH)] + [(k, B.variant_path(k)) for k in ("reloc8", "packrow") if os.path.exists(B.variant_path(k))]
+names = [("product", api.LIB_PATH)]
+if not os.environ.get("QUICK_ONLY_PRODUCT"):
+    names += [(k, B.variant_path(k)) for k in ("reloc8", "no_packrow") if os.path.exists(B.variant_path(k))]
 for name, path in names:
     r = {}
     try:
@@ -30,8 +32,10 @@ for name, path in names:
         for _ in range(3):   # eager, capture, replay
             G.set_piles(sp).set_hills(None).set_overlaps(small.records)
             G.run()
+        ovl, inl = G.lists()
         r["parity"] = bool(np.array_equal(G.edges(), P.edges) and np.array_equal(G.marked(), P.marked)
-                           and G.counts()["n_transitive_pairs"] == P.n_pairs)
+                           and G.counts()["n_transitive_pairs"] == P.n_pairs and np.array_equal(ovl, P.ovl)
+                           and np.array_equal(inl, P.int) and np.array_equal(G.piles(), P.piles))
         G.set_piles(bp).set_hills(None).set_overlaps(big.records)
         for _ in range(4):
             G.run()
