@@ -379,11 +379,12 @@ def run_ab(args):
         libs.append(("prev", prev, None))
     # launch-time knobs are read once per loaded library: a byte-identical copy under another name is a fresh instance
     import shutil
-    knobs = ("RALA_B200_EV_MINB", "RALA_B200_EV_V2", "RALA_B200_SURV_V2")
+    knobs = ("RALA_B200_EV_MINB", "RALA_B200_EV_V2", "RALA_B200_SURV_V2", "RALA_B200_AGG_ATOMICS")
     for tag, env in (("events_minb4", {"RALA_B200_EV_MINB": "4"}), ("events_minb5", {"RALA_B200_EV_MINB": "5"}),
                      # experiments written at the end of round 1 without GPU time (classify.cu *_v2 kernels)
                      ("events_v2", {"RALA_B200_EV_V2": "1"}), ("events_v2_2blk", {"RALA_B200_EV_V2": "2"}),
-                     ("survivors_v2", {"RALA_B200_SURV_V2": "1"})):
+                     ("survivors_v2", {"RALA_B200_SURV_V2": "1"}), ("agg_atomics", {"RALA_B200_AGG_ATOMICS": "1"}),
+                     ("all_experiments", {"RALA_B200_EV_V2": "1", "RALA_B200_SURV_V2": "1", "RALA_B200_AGG_ATOMICS": "1"})):
         copy = B.variant_path(f"copy_{tag}")
         shutil.copyfile(api.LIB_PATH, copy)
         libs.append((tag, copy, env))

@@ -2,6 +2,8 @@
 //
 // Replaces graph.cpp:552-632 (reference): sequence_id_to_node_id (:553-574), the two Edge objects per
 // dovetail overlap with their lengths (:576-632) and the implicit adjacency (suffix_edges_ vectors).
+#include <cstdlib>
+
 #include "kernels.h"
 #include "lists.cuh"
 
@@ -217,6 +219,38 @@ __global__ void k_fill_csr(const uint32_t* __restrict__ src, const uint32_t* __r
 #endif
 }
 
+// EXPERIMENT (RALA_B200_AGG_ATOMICS=1, off by default, not yet run on a GPU): the same scatter with ONE cursor atomic
+// per distinct source node per warp.  Consecutive edges 2j, 2j+2, ... of consecutive list entries share their source
+// (the entries are grouped by query read), so a warp of 32 consecutive edges holds only ~20 distinct sources.
+__global__ void k_fill_csr_agg(const uint32_t* __restrict__ src, const uint32_t* __restrict__ dst,
+                               const uint32_t* __restrict__ len, const uint32_t* __restrict__ n_edges_ptr, uint32_t edge_cap,
+                               uint32_t* __restrict__ cursor, uint2* __restrict__ col, uint32_t* __restrict__ col_eid,
+                               uint8_t* __restrict__ T) {
+    const uint32_t n = min(*n_edges_ptr, edge_cap);
+    {
+        const uint32_t n16 = (n + 15u) / 16u;
+        for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += gridDim.x * blockDim.x)
+            reinterpret_cast<uint4*>(T)[i] = make_uint4(0u, 0u, 0u, 0u);
+    }
+    const uint32_t lane = lane_id();
+    for (uint32_t base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {   // block-uniform bound: full warps vote
+        const uint32_t e = base + threadIdx.x;
+        const bool ok = e < n;
+        uint32_t s = 0, d = 0, l = 0;
+        if (ok) { s = src[e]; d = dst[e]; l = len[e]; }
+        const uint32_t active = __ballot_sync(0xFFFFFFFFu, ok);
+        if (ok) {
+            const uint32_t peers = __match_any_sync(active, s);
+            const uint32_t leader = __ffs(peers) - 1u, rank = __popc(peers & ((1u << lane) - 1u));
+            uint32_t p = 0;
+            if (lane == leader) p = atomicAdd(&cursor[s], (uint32_t) __popc(peers));
+            p = __shfl_sync(peers, p, leader) + rank;
+            col[p] = make_uint2(d, l);
+            col_eid[p] = e;
+        }
+    }
+}
+
 // edge columns -> rala_edge_t rows (download path).  Rows are staged in shared memory and leave as 16-byte stores
 // of consecutive threads: `out` may be pinned HOST memory the GPU writes over PCIe (rala_b200_graph_set_outputs),
 // where three strided 4-byte stores per row would triple the number of write transactions.
@@ -417,8 +451,13 @@ void launch_build_csr(Launch& L, GraphArrays g, uint32_t n_nodes_max, uint32_t e
     k_scan_degrees<<<grid_for(n_nodes_max + 1, kTile, kNumSMs * 8), kTileThreads, 0, L.stream>>>(
         g.cursor, g.row_ptr, n_nodes_max + 1, status, ticket);
     L.count++;
-    k_fill_csr<<<grid_for(edge_cap, 256, kNumSMs * 8), 256, 0, L.stream>>>(g.src, g.dst, g.len, counters + C_EDGES,
-                                                                            edge_cap, g.cursor, g.col, g.col_eid, g.T);
+    static const int agg = getenv("RALA_B200_AGG_ATOMICS") ? atoi(getenv("RALA_B200_AGG_ATOMICS")) : 0;   // experiment, see k_fill_csr_agg
+    if (agg)
+        k_fill_csr_agg<<<grid_for(edge_cap, 256, kNumSMs * 8), 256, 0, L.stream>>>(g.src, g.dst, g.len, counters + C_EDGES,
+                                                                                    edge_cap, g.cursor, g.col, g.col_eid, g.T);
+    else
+        k_fill_csr<<<grid_for(edge_cap, 256, kNumSMs * 8), 256, 0, L.stream>>>(g.src, g.dst, g.len, counters + C_EDGES,
+                                                                                edge_cap, g.cursor, g.col, g.col_eid, g.T);
     L.count++;
 }
 

@@ -16,8 +16,9 @@ REASON = "experimental kernel, off by default, never run on a GPU before: this r
 
 @pytest.mark.xfail(strict=False, reason=REASON)
 @pytest.mark.parametrize("env", [{"RALA_B200_EV_V2": "1"}, {"RALA_B200_EV_V2": "2"}, {"RALA_B200_SURV_V2": "1"},
-                                 {"RALA_B200_EV_V2": "1", "RALA_B200_SURV_V2": "1"}],
-                         ids=["events_v2", "events_v2_2blk", "survivors_v2", "events_v2+survivors_v2"])
+                                 {"RALA_B200_AGG_ATOMICS": "1"},
+                                 {"RALA_B200_EV_V2": "1", "RALA_B200_SURV_V2": "1", "RALA_B200_AGG_ATOMICS": "1"}],
+                         ids=["events_v2", "events_v2_2blk", "survivors_v2", "agg_atomics", "all_three"])
 def test_experimental_kernel_is_bit_exact(env):
     """tests/quick_check.py: whole pipeline on a noisy dual-record batch against the oracle (lists, piles, edges,
     marks), then 50 timed steps of a 20 Mbp batch; the timing is printed for the log."""
