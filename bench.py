@@ -275,7 +275,7 @@ def run_single(args):
             "unit": "GB/s", "frac": (k1_gbs if k1_ms >= k3_ms else k3_gbs) / peak, "traffic": traffic,
             "traffic_source": f"profiles/{traffic_tag}_kernels.csv (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch)" if traffic else None,
             "peak_source": peak_src,
-            "kernel_members": ["k_classify_events", "k_classify_survivors (+ k_scan_runs, k_relocate)"] if k1_ms >= k3_ms
+            "kernel_members": ["k_classify_events", "k_classify_survivors (+ k_scan_runs, k_relocate_runs)"] if k1_ms >= k3_ms
                               else ["k_transitive_group", "k_transitive_light", "k_transitive_heavy"],
             "whole_step": {"algorithmic_bytes": int(step_bytes), "gbs": step_bytes / (ms_per_step * 1e-3) / 1e9,
                            "frac": step_bytes / (ms_per_step * 1e-3) / 1e9 / peak},

@@ -291,7 +291,7 @@ __global__ void __launch_bounds__(kTileThreads, MINB) k_classify_events_v2(
 // run, in record order, to the run's own slot range of the scratch lists (slot = record index of the run's
 // first record: the scratch lists are as long as the record set) and stores the run's two counts.  No atomics,
 // no block barriers, no dependence between runs.  k_scan_runs turns the counts into file-order offsets
-// (single-pass look-back scan) and k_relocate moves each run to its final place.
+// (single-pass look-back scan) and k_relocate_runs moves each run to its final place.
 //
 // Only ~7 % of the records have two live piles, so the pass is split in two phases per run:
 //   1. liveness: 16 records per lane, both id columns as 16-byte loads, 32 bitmap gathers in flight per lane;
