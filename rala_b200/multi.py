@@ -397,6 +397,12 @@ def bench_main(args):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", str(rank)))
+    # a rank stuck in a collective (a peer died, a teardown that waits for ever) must not hold N GPUs until somebody
+    # else's time limit: after 15 minutes the process leaves with a non-zero status
+    import threading
+    watchdog = threading.Timer(900.0, lambda: os._exit(3))
+    watchdog.daemon = True
+    watchdog.start()
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
     dist.init_process_group("nccl", device_id=device)
