@@ -377,23 +377,9 @@ def run_ab(args):
     prev = B.variant_path("prev")   # the previous commit's library, when profiles/capture_ab.sh built it
     if os.path.exists(prev):
         libs.append(("prev", prev, None))
-    # launch-time knobs are read once per loaded library: a byte-identical copy under another name is a fresh instance
-    import shutil
-    knobs = ("RALA_B200_EV_MINB", "RALA_B200_EV_V2", "RALA_B200_SURV_V2", "RALA_B200_AGG_ATOMICS")
-    for tag, env in (("events_minb4", {"RALA_B200_EV_MINB": "4"}), ("events_minb5", {"RALA_B200_EV_MINB": "5"}),
-                     # experiments written at the end of round 1 without GPU time (classify.cu *_v2 kernels)
-                     ("events_v2", {"RALA_B200_EV_V2": "1"}), ("events_v2_2blk", {"RALA_B200_EV_V2": "2"}),
-                     ("survivors_v2", {"RALA_B200_SURV_V2": "1"}), ("agg_atomics", {"RALA_B200_AGG_ATOMICS": "1"}),
-                     ("all_experiments", {"RALA_B200_EV_V2": "1", "RALA_B200_SURV_V2": "1", "RALA_B200_AGG_ATOMICS": "1"})):
-        copy = B.variant_path(f"copy_{tag}")
-        shutil.copyfile(api.LIB_PATH, copy)
-        libs.append((tag, copy, env))
     out = {}
     for rnd in range(2):            # two rounds, interleaved: drift shows up as a difference between them
-        for name, path, env in libs:
-            for k in knobs:
-                os.environ.pop(k, None)
-            os.environ.update(env or {})
+        for name, path, _env in libs:
             ctx = api.Context(0, lib=api.load_path(path))
             G = api.Graph(ctx)
             G.set_piles(piles).set_hills(None).set_overlaps(ds.records)
@@ -412,8 +398,6 @@ def run_ab(args):
                                   "edges_marks_crc32": crc})["ms_per_step"].append(ms)
             G.close()
             ctx.close()
-    for k in knobs:
-        os.environ.pop(k, None)
     base = min(out["product"]["ms_per_step"])
     for name, v in out.items():
         v["delta_us_vs_product"] = 1e3 * (min(v["ms_per_step"]) - base)

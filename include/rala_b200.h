@@ -235,9 +235,7 @@ int rala_b200_graph_phase_csr(rala_b200_graph* g);
 /* Capacity-bounded variants of the exchange steps: element counts travel inside the blocks and the time bases are
  * computed on the device, so no call below synchronises with the host (the sized variants above read counts back).
  *   kind 0, containment events: block (3 * cap + 4 words) = [n clamped to cap | overflow flag | 0 | 0 | victim [cap] | container [cap] | time [cap]]
- *   kind 1, edges: the same layout with src | dst | len; with RALA_B200_EDGE_PAIRS=1 in the environment (opt-in until it has run on
- *           several GPUs) as reverse-complement PAIRS (edge 2j = (s, d, l), edge 2j+1 = (d ^ 1, s ^ 1, l'), graph.cpp:594-629): cap even,
- *           block (2 * cap + 4 words) = [n | overflow flag | 0 | 0 | s [cap/2] | d [cap/2] | l [cap/2] | l' [cap/2]]: 8 bytes per edge on the wire
+ *   kind 1, edges: the same layout with src | dst | len
  *   rala_b200_exchange_block_words(kind, cap) is the block size in 32-bit words.  d_gathered = the `world` blocks of an all-gather, in rank order.
  * A count beyond `cap` raises the session's overflow flag (reported by rala_b200_graph_counts): re-run sized.
  * rala_b200_graph_phase_emit_edges accepts n_local_edges == NULL (no read-back). */

@@ -1394,8 +1394,6 @@ extern "C" int rala_b200_graph_import_edges(rala_b200_graph* g, const uint32_t* 
 }
 
 // ---- capacity-bounded exchange: counts travel inside the blocks, nothing is read back by the host ------------------------
-static bool edge_pairs_enabled();
-
 extern "C" int rala_b200_graph_export_padded(rala_b200_graph* g, int kind, uint32_t* d_block, uint32_t cap) {
     if (!g || !d_block || cap == 0 || (kind != 0 && kind != 1)) return RALA_B200_ERR_ARG;
     rala_b200_ctx* ctx = g->ctx;
@@ -1405,12 +1403,7 @@ extern "C" int rala_b200_graph_export_padded(rala_b200_graph* g, int kind, uint3
         launch_export_padded(ctx->L, ev.v, ev.c, ev.t, g->cnt() + C_EV, g->ev_cap, cap, d_block);
     } else {
         GraphArrays ga = g->graph_view();
-        if (edge_pairs_enabled()) {
-            if (cap & 1u) return fail(ctx, RALA_B200_ERR_ARG, "export_padded: the edge capacity must be even (edges travel as pairs)");
-            launch_export_edge_pairs(ctx->L, ga.src, ga.dst, ga.len, g->cnt() + C_EDGES, g->edge_cap, cap, d_block);
-        } else {
-            launch_export_padded(ctx->L, ga.src, ga.dst, ga.len, g->cnt() + C_EDGES, g->edge_cap, cap, d_block);
-        }
+        launch_export_padded(ctx->L, ga.src, ga.dst, ga.len, g->cnt() + C_EDGES, g->edge_cap, cap, d_block);
     }
     CU(ctx, cudaGetLastError());
     return RALA_B200_OK;
@@ -1433,26 +1426,15 @@ extern "C" int rala_b200_graph_import_gathered(rala_b200_graph* g, int kind, con
         int rc = reserve_edges(g, (uint32_t) total_cap);     // the local edges were exported before
         if (rc) return rc;
         GraphArrays ga = g->graph_view();
-        if (edge_pairs_enabled()) {
-            if (cap & 1u) return fail(ctx, RALA_B200_ERR_ARG, "import_gathered: the edge capacity must be even (edges travel as pairs)");
-            launch_import_edge_pairs(ctx->L, d_gathered, cap, (uint32_t) world, ga.src, ga.dst, ga.len, g->edge_cap, g->cnt() + C_EDGES, g->cnt() + C_OVERFLOW);
-        } else {
-            launch_import_gathered(ctx->L, d_gathered, cap, (uint32_t) world, ga.src, ga.dst, ga.len, g->edge_cap, g->cnt() + C_EDGES, g->cnt() + C_OVERFLOW);
-        }
+        launch_import_gathered(ctx->L, d_gathered, cap, (uint32_t) world, ga.src, ga.dst, ga.len, g->edge_cap, g->cnt() + C_EDGES, g->cnt() + C_OVERFLOW);
     }
     CU(ctx, cudaGetLastError());
     return RALA_B200_OK;
 }
 
-// Edge blocks as reverse-complement pairs (8 bytes per edge on the wire instead of 12): written and covered by the
-// gloo / world = 1 layout, but NOT yet run on two or more GPUs, so it is opt-in (RALA_B200_EDGE_PAIRS=1) for now.
-static bool edge_pairs_enabled() {
-    static const bool on = getenv("RALA_B200_EDGE_PAIRS") && atoi(getenv("RALA_B200_EDGE_PAIRS")) != 0;
-    return on;
-}
-
 extern "C" uint64_t rala_b200_exchange_block_words(int kind, uint32_t cap) {
-    return kind == 1 && edge_pairs_enabled() ? 2ull * cap + 4ull : 3ull * cap + 4ull;
+    (void) kind;
+    return 3ull * cap + 4ull;
 }
 
 extern "C" int rala_b200_graph_export_list_counts(rala_b200_graph* g, uint32_t* d_pair) {

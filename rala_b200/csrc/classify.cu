@@ -167,126 +167,6 @@ __global__ void __launch_bounds__(kTileThreads, MINB) k_classify_events(
     if (staged) flush();
 }
 
-// ---------------------------------------------------------------------------------------------------------------
-// EXPERIMENT (RALA_B200_EV_V2=1, not the default: written without GPU time left in round 1, to be measured with
-// bench.py --ab in round 2).  Same contract as k_classify_events, three changes aimed at its issue rate (57 % with
-// 2.9 of 6 warps per scheduler waiting on loads, profiles/r01i):
-//   1. software pipelining: the six column loads of the thread's NEXT quad are issued before the current quad is
-//      processed (a second set of 24 registers), so their DRAM latency overlaps ~600 instructions of work;
-//   2. one warp scan per quad (events per thread: 0 .. 4) instead of one ballot + staging sequence per record;
-//   3. the validity test folded: bit 31 of column a makes the id >= n_piles by itself.
-// ---------------------------------------------------------------------------------------------------------------
-constexpr int kEvStage2 = 256;
-
-template <int MINB>
-__global__ void __launch_bounds__(kTileThreads, MINB) k_classify_events_v2(
-    List recs, uint32_t n, uint32_t t0, const uint2* __restrict__ piles, uint32_t n_piles,
-    Events ev, uint32_t ev_cap, uint32_t* __restrict__ vcount, uint32_t* __restrict__ hill_rec, uint32_t hill_cap,
-    uint32_t* __restrict__ counters) {
-    __shared__ uint32_t s_ev[kTileWarps][3][kEvStage2];
-    const uint32_t lane = lane_id(), warp = warp_id();
-    const uint32_t n4 = (n + 3u) / 4u;
-    const uint32_t stride = gridDim.x * kTileThreads;
-    uint32_t staged = 0;   // warp-uniform
-
-    auto flush = [&]() {
-        uint32_t gbase = 0;
-        if (lane == 0) gbase = atomicAdd(&counters[C_EV], staged);
-        gbase = __shfl_sync(0xFFFFFFFFu, gbase, 0);
-        for (uint32_t i = lane; i < staged; i += 32) {
-            if (gbase + i < ev_cap) {
-                ev.v[gbase + i] = s_ev[warp][0][i];
-                ev.c[gbase + i] = s_ev[warp][1][i];
-                ev.t[gbase + i] = s_ev[warp][2][i];
-            }
-        }
-        __syncwarp();
-        staged = 0;
-    };
-
-    const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
-    uint4 na = make_uint4(kInvalidBit, kInvalidBit, kInvalidBit, kInvalidBit), nb = zero4, nab = zero4, nae = zero4, nbb = zero4, nbe = zero4;
-    {
-        const uint32_t q0 = blockIdx.x * kTileThreads + threadIdx.x;
-        if (q0 < n4) {
-            na = reinterpret_cast<const uint4*>(recs.a)[q0];
-            nb = reinterpret_cast<const uint4*>(recs.b)[q0];
-            nab = reinterpret_cast<const uint4*>(recs.ab)[q0];
-            nae = reinterpret_cast<const uint4*>(recs.ae)[q0];
-            nbb = reinterpret_cast<const uint4*>(recs.bb)[q0];
-            nbe = reinterpret_cast<const uint4*>(recs.be)[q0];
-        }
-    }
-    for (uint32_t qbase = blockIdx.x * kTileThreads; qbase < n4; qbase += stride) {
-        const uint32_t q = qbase + threadIdx.x;
-        uint32_t a[4], b[4], ab[4], ae[4], bb[4], be[4];
-        unpack4(na, a); unpack4(nb, b); unpack4(nab, ab); unpack4(nae, ae); unpack4(nbb, bb); unpack4(nbe, be);
-        // pile gathers of the current quad first, then the column loads of the next one
-        const uint32_t nrec = q < n4 ? min(4u, n - 4u * q) : 0u;   // records of this quad that exist
-        uint2 pa[4], pb[4];
-#pragma unroll
-        for (int r = 0; r < kRecItems; ++r) {
-            const uint32_t idb = b[r] & 0x7FFFFFFFu;
-            const bool live = (uint32_t) r < nrec && a[r] < n_piles && idb < n_piles;   // graph.cpp:450-451 (bit 31 of a = invalid)
-            pa[r] = pb[r] = make_uint2(0u, 0u);   // a dead pile: rejects itself
-            if (live) {
-                pa[r] = __ldg(piles + a[r]);
-                pb[r] = __ldg(piles + idb);
-            }
-        }
-        {
-            const uint32_t qn = q + stride;
-            na = make_uint4(kInvalidBit, kInvalidBit, kInvalidBit, kInvalidBit);
-            if (qn < n4) {
-                na = reinterpret_cast<const uint4*>(recs.a)[qn];
-                nb = reinterpret_cast<const uint4*>(recs.b)[qn];
-                nab = reinterpret_cast<const uint4*>(recs.ab)[qn];
-                nae = reinterpret_cast<const uint4*>(recs.ae)[qn];
-                nbb = reinterpret_cast<const uint4*>(recs.bb)[qn];
-                nbe = reinterpret_cast<const uint4*>(recs.be)[qn];
-            }
-        }
-        uint32_t evmask = 0, evv[4], evc[4];
-#pragma unroll
-        for (int r = 0; r < kRecItems; ++r) {
-            const uint32_t idb = b[r] & 0x7FFFFFFFu;
-            const uint32_t code = event_code(ab[r], ae[r], bb[r], be[r], b[r] >> 31, pa[r].x, pa[r].y & kEndMask,
-                                             pb[r].x, pb[r].y & kEndMask);                              // :451-452
-            const uint32_t fa = pa[r].y >> 30, fb = pb[r].y >> 30;
-            if ((code & 1u) && ((fa | fb) & 1u)) {                                                      // :457-462, resolved by k_hill_coverage
-                uint32_t slot = atomicAdd(&counters[C_HILL], 1u);
-                if (slot < hill_cap) hill_rec[slot] = 4u * q + r;
-            }
-            const bool ev_b = (code & 2u) && !(fb & 2u);                                                // :469-474
-            const bool ev_a = (code & 4u) && !(fa & 2u);                                                // :475-480
-            evmask |= (ev_a | ev_b) ? 1u << r : 0u;
-            evv[r] = ev_b ? a[r] : idb;
-            evc[r] = ev_b ? idb : a[r];
-        }
-        // one scan per quad: this lane's events go behind those of the lanes below
-        const uint32_t cnt = __popc(evmask);
-        const uint32_t inc = warp_inclusive_scan(cnt);
-        const uint32_t total = __shfl_sync(0xFFFFFFFFu, inc, 31);
-        if (total) {
-            uint32_t p = staged + inc - cnt;
-#pragma unroll
-            for (int r = 0; r < kRecItems; ++r) {
-                if ((evmask >> r) & 1u) {
-                    atomicAdd(&vcount[evv[r]], 1u);   // per-victim histogram for the resolution's counting sort
-                    s_ev[warp][0][p] = evv[r];
-                    s_ev[warp][1][p] = evc[r];
-                    s_ev[warp][2][p] = t0 + 4u * q + r;
-                    ++p;
-                }
-            }
-            staged += total;
-            __syncwarp();
-            if (staged > (uint32_t) kEvStage2 - 128u) flush();   // room for the 128 events one quad can add
-        }
-    }
-    if (staged) flush();
-}
-
 // Survivors pass.  Every warp owns RUNS of 512 consecutive records (4 x 4 per lane): it writes the survivors of a
 // run, in record order, to the run's own slot range of the scratch lists (slot = record index of the run's
 // first record: the scratch lists are as long as the record set) and stores the run's two counts.  No atomics,
@@ -328,113 +208,6 @@ __global__ void __launch_bounds__(kTileThreads) k_classify_survivors(
                 const bool ok = i < n && !(ida & kInvalidBit) && ida < n_piles && idb < n_piles &&
                                 ((__ldg(alive_bits + (ida >> 5)) >> (ida & 31u)) & 1u) && ((__ldg(alive_bits + (idb >> 5)) >> (idb & 31u)) & 1u);
                 cand |= ok ? 1u << (j * 4 + r) : 0u;
-            }
-        }
-        // rank of every candidate in record order (group-major, then lane, then r)
-        uint32_t packed = 0;
-#pragma unroll
-        for (int j = 0; j < kRunGroups; ++j) packed |= (uint32_t) __popc((cand >> (4 * j)) & 0xFu) << (8 * j);
-        const uint32_t inc = warp_inclusive_scan(packed);
-        const uint32_t tot = __shfl_sync(0xFFFFFFFFu, inc, 31);
-        uint32_t group_base = 0, total = 0;
-#pragma unroll
-        for (int j = 0; j < kRunGroups; ++j) {
-            uint32_t p = group_base + (((inc - packed) >> (8 * j)) & 0xFFu);
-#pragma unroll
-            for (int r = 0; r < 4; ++r) {
-                if ((cand >> (j * 4 + r)) & 1u) queue[p++] = (uint16_t) (j * 128u + 4u * lane + r);
-            }
-            group_base += (tot >> (8 * j)) & 0xFFu;
-        }
-        total = group_base;
-        __syncwarp();
-        uint32_t n_a = 0, n_b = 0;   // warp-uniform: survivors of the run so far (`overlaps`, `internals`)
-        for (uint32_t k0 = 0; k0 < total; k0 += 32) {
-            const uint32_t k = k0 + lane;
-            int dest = 0;
-            uint8_t tag = kRejected;
-            Entry e;
-            if (k < total) {   // only now fetch the coordinates and the two piles
-                const uint32_t i = run * kRunRecords + queue[k];
-                const uint32_t vb = recs.b[i];
-                e.a = recs.a[i];
-                e.b = vb & 0x7FFFFFFFu;
-                e.ori = vb >> 31;
-                e.c.ab = recs.ab[i]; e.c.ae = recs.ae[i]; e.c.bb = recs.bb[i]; e.c.be = recs.be[i];
-                const Pile pa = load_pile(piles, e.a), pb = load_pile(piles, e.b);
-                if (trim(e.c, e.ori, pa, pb)) {
-                    tag = classify(e.c, relative(e.c, e.ori, pa, pb));
-                    dest = tag == kX ? 2 : 1;   // a surviving kA/kB has a chimeric container (:470, :476)
-                }
-            }
-            const uint32_t ma = __ballot_sync(0xFFFFFFFFu, dest == 1), mb = __ballot_sync(0xFFFFFFFFu, dest == 2);
-            const uint32_t below = (1u << lane) - 1u;
-            if (dest == 1) {
-                const uint32_t p = run * kRunRecords + n_a + __popc(ma & below);
-                if (p < cap) store_entry(tmp_ovl, p, e, tag);
-            } else if (dest == 2) {
-                const uint32_t p = run * kRunRecords + n_b + __popc(mb & below);
-                if (p < cap) store_entry(tmp_inl, p, e, tag);
-            }
-            n_a += __popc(ma);
-            n_b += __popc(mb);
-        }
-        if (lane == 0) run_cnt[run] = n_a | (n_b << 16);
-        __syncwarp();   // the queue is reused by the next run
-    }
-}
-
-// EXPERIMENT (RALA_B200_SURV_V2=1, not the default: written without GPU time left in round 1, to be measured in round 2).
-// Same contract as k_classify_survivors; phase 1 tests the query's liveness first (see inside).
-__global__ void __launch_bounds__(kTileThreads) k_classify_survivors_v2(
-    List recs, uint32_t n, const uint2* __restrict__ piles, const uint32_t* __restrict__ alive_bits, uint32_t n_piles,
-    List tmp_ovl, List tmp_inl, uint32_t cap, uint32_t* __restrict__ run_cnt) {
-    __shared__ uint16_t s_queue[kTileWarps][kRunRecords];
-    const uint32_t lane = lane_id();
-    uint16_t* queue = s_queue[warp_id()];
-    const uint32_t num_runs = (n + kRunRecords - 1) / kRunRecords;
-    const uint32_t warps = gridDim.x * kTileWarps;
-    for (uint32_t run = blockIdx.x * kTileWarps + warp_id(); run < num_runs; run += warps) {
-        // liveness of the QUERY first: records are grouped by query (a PAF lists a read's overlaps together) and only
-        // ~27 % of the piles survive the containment pass, so three out of four 4-record groups are decided by one
-        // bit of one pile; the b column is only loaded (and its piles only tested) where some query is alive
-        uint32_t a[kRunGroups][4];
-#pragma unroll
-        for (int j = 0; j < kRunGroups; ++j) {
-            const uint32_t q = run * (kRunRecords / 4) + j * 32u + lane;     // this lane's j-th group of 4 records
-#pragma unroll
-            for (int r = 0; r < 4; ++r) a[j][r] = kInvalidBit;
-            if (4u * q < n) unpack4(reinterpret_cast<const uint4*>(recs.a)[q], a[j]);
-        }
-        uint32_t alive_a = 0;   // bit j * 4 + r
-#pragma unroll
-        for (int j = 0; j < kRunGroups; ++j) {
-            uint32_t prev_id = 0xFFFFFFFFu;
-            bool prev_ok = false;
-#pragma unroll
-            for (int r = 0; r < 4; ++r) {
-                const uint32_t i = run * kRunRecords + j * 128u + 4u * lane + r, ida = a[j][r];
-                bool ok = prev_ok;
-                if (ida != prev_id) ok = ida < n_piles && ((__ldg(alive_bits + (ida >> 5)) >> (ida & 31u)) & 1u);   // bit 31 (invalid) fails ida < n_piles
-                prev_id = ida;
-                prev_ok = ok;
-                alive_a |= (ok && i < n) ? 1u << (j * 4 + r) : 0u;
-            }
-        }
-        uint32_t cand = 0;   // bit j * 4 + r
-#pragma unroll
-        for (int j = 0; j < kRunGroups; ++j) {
-            if ((alive_a >> (4 * j)) & 0xFu) {
-                const uint32_t q = run * (kRunRecords / 4) + j * 32u + lane;
-                uint32_t b[4];
-                unpack4(reinterpret_cast<const uint4*>(recs.b)[q], b);
-#pragma unroll
-                for (int r = 0; r < 4; ++r) {   // both piles alive at the end (graph.cpp:493-515)?
-                    const uint32_t idb = b[r] & 0x7FFFFFFFu;
-                    const bool ok = ((alive_a >> (j * 4 + r)) & 1u) && idb < n_piles &&
-                                    ((__ldg(alive_bits + (idb >> 5)) >> (idb & 31u)) & 1u);
-                    cand |= ok ? 1u << (j * 4 + r) : 0u;
-                }
             }
         }
         // rank of every candidate in record order (group-major, then lane, then r)
@@ -888,27 +661,9 @@ void launch_records_to_soa(Launch& L, const uint32_t* aos, uint32_t n, List recs
 void launch_classify_events(Launch& L, List recs, uint32_t n, uint32_t t0, const uint2* piles, uint32_t n_piles,
                             Events ev, uint32_t ev_cap, uint32_t* vcount, uint32_t* hill_rec, uint32_t hill_cap, uint32_t* counters) {
     if (n == 0) return;
-    static const int minb = getenv("RALA_B200_EV_MINB") ? atoi(getenv("RALA_B200_EV_MINB")) : 3;   // tuning knob (blocks / SM)
-    static const int v2 = getenv("RALA_B200_EV_V2") ? atoi(getenv("RALA_B200_EV_V2")) : 0;          // experiment, see k_classify_events_v2
-    if (v2) {
-        const int blocks = v2 == 2 ? 2 : 3;   // RALA_B200_EV_V2=2: two blocks per SM, up to 128 registers
-        int grid2 = grid_for(n, kRecTile, kNumSMs * blocks);
-        if (blocks == 2)
-            k_classify_events_v2<2><<<grid2, kTileThreads, 0, L.stream>>>(recs, n, t0, piles, n_piles, ev, ev_cap, vcount, hill_rec, hill_cap, counters);
-        else
-            k_classify_events_v2<3><<<grid2, kTileThreads, 0, L.stream>>>(recs, n, t0, piles, n_piles, ev, ev_cap, vcount, hill_rec, hill_cap, counters);
-        L.count++;
-        return;
-    }
-    int grid = grid_for(n, kRecTile, kNumSMs * minb);
-    if (minb == 4)
-        k_classify_events<4><<<grid, kTileThreads, 0, L.stream>>>(recs, n, t0, piles, n_piles, ev, ev_cap, vcount, hill_rec, hill_cap, counters);
-    else if (minb == 5)
-        k_classify_events<5><<<grid, kTileThreads, 0, L.stream>>>(recs, n, t0, piles, n_piles, ev, ev_cap, vcount, hill_rec, hill_cap, counters);
-    else if (minb == 6)
-        k_classify_events<6><<<grid, kTileThreads, 0, L.stream>>>(recs, n, t0, piles, n_piles, ev, ev_cap, vcount, hill_rec, hill_cap, counters);
-    else
-        k_classify_events<3><<<grid, kTileThreads, 0, L.stream>>>(recs, n, t0, piles, n_piles, ev, ev_cap, vcount, hill_rec, hill_cap, counters);
+    // 3 blocks / SM at 80 registers: 4 and 5 blocks (64 / 48 registers) lost 15 and 25 us per step (profiles/r02a_ab.json)
+    k_classify_events<3><<<grid_for(n, kRecTile, kNumSMs * 3), kTileThreads, 0, L.stream>>>(recs, n, t0, piles, n_piles, ev, ev_cap, vcount,
+                                                                                          hill_rec, hill_cap, counters);
     L.count++;
 }
 
@@ -917,13 +672,8 @@ void launch_classify_survivors(Launch& L, List recs, uint32_t n, const uint2* pi
                                RunBufs runs, unsigned long long* status, uint32_t* ticket) {
     if (n == 0) return;   // n_ovl / n_inl were zeroed by the caller
     const uint32_t num_runs = (n + kRunRecords - 1) / kRunRecords;
-    static const int v2 = getenv("RALA_B200_SURV_V2") ? atoi(getenv("RALA_B200_SURV_V2")) : 0;   // experiment, see k_classify_survivors_v2
-    if (v2)
-        k_classify_survivors_v2<<<grid_for(num_runs, kTileWarps, kNumSMs * 8), kTileThreads, 0, L.stream>>>(
-            recs, n, piles, alive_bits, n_piles, tmp_ovl, tmp_inl, cap, runs.cnt);
-    else
-        k_classify_survivors<<<grid_for(num_runs, kTileWarps, kNumSMs * 8), kTileThreads, 0, L.stream>>>(
-            recs, n, piles, alive_bits, n_piles, tmp_ovl, tmp_inl, cap, runs.cnt);
+    k_classify_survivors<<<grid_for(num_runs, kTileWarps, kNumSMs * 8), kTileThreads, 0, L.stream>>>(
+        recs, n, piles, alive_bits, n_piles, tmp_ovl, tmp_inl, cap, runs.cnt);
     L.count++;
     k_scan_runs<<<grid_for(num_runs, kTile, kNumSMs * 4), kTileThreads, 0, L.stream>>>(runs.cnt, num_runs, runs.off_a, runs.off_b, n_ovl,
                                                                                        n_inl, status, ticket);

@@ -219,38 +219,6 @@ __global__ void k_fill_csr(const uint32_t* __restrict__ src, const uint32_t* __r
 #endif
 }
 
-// EXPERIMENT (RALA_B200_AGG_ATOMICS=1, off by default, not yet run on a GPU): the same scatter with ONE cursor atomic
-// per distinct source node per warp.  Consecutive edges 2j, 2j+2, ... of consecutive list entries share their source
-// (the entries are grouped by query read), so a warp of 32 consecutive edges holds only ~20 distinct sources.
-__global__ void k_fill_csr_agg(const uint32_t* __restrict__ src, const uint32_t* __restrict__ dst,
-                               const uint32_t* __restrict__ len, const uint32_t* __restrict__ n_edges_ptr, uint32_t edge_cap,
-                               uint32_t* __restrict__ cursor, uint2* __restrict__ col, uint32_t* __restrict__ col_eid,
-                               uint8_t* __restrict__ T) {
-    const uint32_t n = min(*n_edges_ptr, edge_cap);
-    {
-        const uint32_t n16 = (n + 15u) / 16u;
-        for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += gridDim.x * blockDim.x)
-            reinterpret_cast<uint4*>(T)[i] = make_uint4(0u, 0u, 0u, 0u);
-    }
-    const uint32_t lane = lane_id();
-    for (uint32_t base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {   // block-uniform bound: full warps vote
-        const uint32_t e = base + threadIdx.x;
-        const bool ok = e < n;
-        uint32_t s = 0, d = 0, l = 0;
-        if (ok) { s = src[e]; d = dst[e]; l = len[e]; }
-        const uint32_t active = __ballot_sync(0xFFFFFFFFu, ok);
-        if (ok) {
-            const uint32_t peers = __match_any_sync(active, s);
-            const uint32_t leader = __ffs(peers) - 1u, rank = __popc(peers & ((1u << lane) - 1u));
-            uint32_t p = 0;
-            if (lane == leader) p = atomicAdd(&cursor[s], (uint32_t) __popc(peers));
-            p = __shfl_sync(peers, p, leader) + rank;
-            col[p] = make_uint2(d, l);
-            col_eid[p] = e;
-        }
-    }
-}
-
 // edge columns -> rala_edge_t rows (download path).  Rows are staged in shared memory and leave as 16-byte stores
 // of consecutive threads: `out` may be pinned HOST memory the GPU writes over PCIe (rala_b200_graph_set_outputs),
 // where three strided 4-byte stores per row would triple the number of write transactions.
@@ -319,46 +287,6 @@ __global__ void k_import_gathered(const uint32_t* __restrict__ gathered, uint32_
     }
 }
 
-// Edge blocks travel as PAIRS: edge 2j = (s, d, l) and its reverse-complement twin 2j+1 = (d ^ 1, s ^ 1, l') share
-// their node ids (graph.cpp:594-629), so a pair is four words instead of six: 8 bytes per edge over NVLink instead of 12.
-//   block (2 * cap + 4 words) = [n edges (clamped to cap) | overflow | 0 | 0 | s [cap/2] | d [cap/2] | l [cap/2] | l' [cap/2]]
-__global__ void k_export_edge_pairs(const uint32_t* __restrict__ src, const uint32_t* __restrict__ dst, const uint32_t* __restrict__ len,
-                                    const uint32_t* __restrict__ n_ptr, uint32_t src_cap, uint32_t cap, uint32_t* __restrict__ block) {
-    const uint32_t n = min(*n_ptr, src_cap), m = min(n, cap) & ~1u, half = cap / 2;
-    if (blockIdx.x == 0 && threadIdx.x < 4) block[threadIdx.x] = threadIdx.x == 0 ? m : (threadIdx.x == 1 ? (n > cap ? 1u : 0u) : 0u);
-    for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < m / 2; j += gridDim.x * blockDim.x) {
-        const uint2 l = reinterpret_cast<const uint2*>(len)[j];
-        block[4 + j] = src[2 * j];
-        block[4 + (size_t) half + j] = dst[2 * j];
-        block[4 + 2 * (size_t) half + j] = l.x;
-        block[4 + 3 * (size_t) half + j] = l.y;
-    }
-}
-
-__global__ void k_import_edge_pairs(const uint32_t* __restrict__ gathered, uint32_t cap, uint32_t world, uint32_t* __restrict__ src,
-                                    uint32_t* __restrict__ dst, uint32_t* __restrict__ len, uint32_t dst_cap, uint32_t* __restrict__ n_out,
-                                    uint32_t* __restrict__ overflow) {
-    const size_t stride = 2 * (size_t) cap + 4;
-    const uint32_t r = blockIdx.y, half = cap / 2;
-    uint32_t offset = 0;
-    for (uint32_t q = 0; q < r; ++q) offset += gathered[q * stride];
-    const uint32_t* blk = gathered + r * stride;
-    const uint32_t n = blk[0];
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
-        if (blk[1] || offset + n > dst_cap) *overflow = 1u;
-        if (r == world - 1) *n_out = min(offset + n, dst_cap);
-    }
-    for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n / 2; j += gridDim.x * blockDim.x) {
-        const uint32_t e = offset + 2 * j;   // offsets are even: every rank holds whole pairs
-        if (e + 1 < dst_cap) {
-            const uint32_t s = blk[4 + j], d = blk[4 + (size_t) half + j];
-            reinterpret_cast<uint2*>(src + e)[0] = make_uint2(s, d ^ 1u);
-            reinterpret_cast<uint2*>(dst + e)[0] = make_uint2(d, s ^ 1u);
-            reinterpret_cast<uint2*>(len + e)[0] = make_uint2(blk[4 + 2 * (size_t) half + j], blk[4 + 3 * (size_t) half + j]);
-        }
-    }
-}
-
 // time bases of the local lists in the final containment pass (graph.cpp:831-866): position in the GLOBAL
 // overlaps ++ internals order.  counts = (n_overlaps, n_internals) of every rank.
 __global__ void k_time_bases(const uint32_t* __restrict__ counts, uint32_t rank, uint32_t world, uint32_t* __restrict__ bases) {
@@ -420,19 +348,6 @@ void launch_import_gathered(Launch& L, const uint32_t* gathered, uint32_t cap, u
     L.count++;
 }
 
-void launch_export_edge_pairs(Launch& L, const uint32_t* src, const uint32_t* dst, const uint32_t* len, const uint32_t* n_ptr,
-                              uint32_t src_cap, uint32_t cap, uint32_t* block) {
-    k_export_edge_pairs<<<grid_for(cap / 2, 256, kNumSMs * 4), 256, 0, L.stream>>>(src, dst, len, n_ptr, src_cap, cap, block);
-    L.count++;
-}
-
-void launch_import_edge_pairs(Launch& L, const uint32_t* gathered, uint32_t cap, uint32_t world, uint32_t* src, uint32_t* dst,
-                              uint32_t* len, uint32_t dst_cap, uint32_t* n_out, uint32_t* overflow) {
-    dim3 grid(grid_for(cap / 2, 256, kNumSMs * 2), world);
-    k_import_edge_pairs<<<grid, 256, 0, L.stream>>>(gathered, cap, world, src, dst, len, dst_cap, n_out, overflow);
-    L.count++;
-}
-
 void launch_time_bases(Launch& L, const uint32_t* counts, uint32_t rank, uint32_t world, uint32_t* bases) {
     k_time_bases<<<1, 32, 0, L.stream>>>(counts, rank, world, bases);
     L.count++;
@@ -451,13 +366,8 @@ void launch_build_csr(Launch& L, GraphArrays g, uint32_t n_nodes_max, uint32_t e
     k_scan_degrees<<<grid_for(n_nodes_max + 1, kTile, kNumSMs * 8), kTileThreads, 0, L.stream>>>(
         g.cursor, g.row_ptr, n_nodes_max + 1, status, ticket);
     L.count++;
-    static const int agg = getenv("RALA_B200_AGG_ATOMICS") ? atoi(getenv("RALA_B200_AGG_ATOMICS")) : 0;   // experiment, see k_fill_csr_agg
-    if (agg)
-        k_fill_csr_agg<<<grid_for(edge_cap, 256, kNumSMs * 8), 256, 0, L.stream>>>(g.src, g.dst, g.len, counters + C_EDGES,
-                                                                                    edge_cap, g.cursor, g.col, g.col_eid, g.T);
-    else
-        k_fill_csr<<<grid_for(edge_cap, 256, kNumSMs * 8), 256, 0, L.stream>>>(g.src, g.dst, g.len, counters + C_EDGES,
-                                                                                edge_cap, g.cursor, g.col, g.col_eid, g.T);
+    k_fill_csr<<<grid_for(edge_cap, 256, kNumSMs * 8), 256, 0, L.stream>>>(g.src, g.dst, g.len, counters + C_EDGES,
+                                                                            edge_cap, g.cursor, g.col, g.col_eid, g.T);
     L.count++;
 }
 

@@ -126,11 +126,6 @@ void launch_export_padded(Launch& L, const uint32_t* c0, const uint32_t* c1, con
                           uint32_t src_cap, uint32_t cap, uint32_t* block);
 void launch_import_gathered(Launch& L, const uint32_t* gathered, uint32_t cap, uint32_t world, uint32_t* d0, uint32_t* d1,
                             uint32_t* d2, uint32_t dst_cap, uint32_t* n_out, uint32_t* overflow);
-// edges as reverse-complement pairs: 2 * cap + 4 words per block (cap even)
-void launch_export_edge_pairs(Launch& L, const uint32_t* src, const uint32_t* dst, const uint32_t* len, const uint32_t* n_ptr,
-                              uint32_t src_cap, uint32_t cap, uint32_t* block);
-void launch_import_edge_pairs(Launch& L, const uint32_t* gathered, uint32_t cap, uint32_t world, uint32_t* src, uint32_t* dst,
-                              uint32_t* len, uint32_t dst_cap, uint32_t* n_out, uint32_t* overflow);
 void launch_time_bases(Launch& L, const uint32_t* counts, uint32_t rank, uint32_t world, uint32_t* bases);
 void launch_build_csr(Launch& L, GraphArrays g, uint32_t n_nodes_max, uint32_t edge_cap, uint32_t* counters,
                       unsigned long long* status, uint32_t* ticket);
