@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define RALA_B200_ABI_VERSION 1
+#define RALA_B200_ABI_VERSION 2
 
 /* One PAF/MHAP overlap after name->id translation; replaces the numeric members of rala::Overlap
  * (overlap.hpp:104-116).  Records are passed in FILE ORDER: the position of a record is its
@@ -247,6 +247,100 @@ int rala_b200_graph_phase_final_events_gathered(rala_b200_graph* g, const uint32
 int rala_b200_graph_phase_transitive(rala_b200_graph* g);
 int rala_b200_graph_export_marks(rala_b200_graph* g, uint8_t* d_T, uint32_t n);
 int rala_b200_graph_phase_marks(rala_b200_graph* g, const uint8_t* d_T, uint32_t n);
+
+/* ------------------------------------------------------------------------------------------------
+ * Multi-GPU session (ABI version 2): Graph::construct's hot loops + Graph::remove_transitive_edges on `world` ranks,
+ * one rank per GPU, with the whole orchestration INSIDE the library.  The reference has no distributed code
+ * (rvaser/rala is one process); this is the partition BASELINE.json's north_star names: overlap records by
+ * contiguous FILE RANGE (classification), piles / nodes by id range (ordered containment of graph.cpp:469-480 and
+ * 831-866, adjacency rows of :576-632, the two-hop test of :1281-1318), CSR of the whole graph replicated.
+ *
+ * Exchange steps are kernels that write straight into the peer GPUs' memory over NVLink (peer access inside one
+ * process, CUDA IPC between processes) separated by device-side flag barriers: one step enqueues kernels only, has
+ * no host synchronisation and no library collective, and is replayed as one CUDA graph per rank.
+ *
+ *   single process, n GPUs (the drop-in CLI, host/graph_b200.cpp):
+ *       rala_b200_multi_create(&m, devices, n, 0, n); set_piles; set_overlaps(k, shard k) for every k;
+ *       rala_b200_multi_plan(m);  rala_b200_multi_run(m);  get_* ...
+ *   one process per GPU (torch.distributed / MPI launchers; rala_b200/multi.py):
+ *       rala_b200_multi_create(&m, &device, 1, rank, world); set_piles; set_overlaps(0, own shard);
+ *       default_caps -> [max over ranks] -> reserve -> export_handle -> [all-gather handles] -> import_handles;
+ *       run; synchronize; demand -> [max over ranks]: re-reserve with larger capacities if something did not fit.
+ *
+ * A device id may be listed more than once (several ranks share a GPU): that is how the parity tests cover
+ * world > 1 on a one-GPU box.  Restrictions: frozen pile table (no hills, no host pile breaking between the
+ * passes: the clean-data chain rala_b200_graph_run executes); read ids, coordinates and counts 32-bit as above.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct rala_b200_multi rala_b200_multi;
+
+#define RALA_B200_MAX_RANKS 16
+/* capacities of the exchange buffers (identical on every rank) */
+enum { RALA_B200_CAP_EVENTS = 0,   /* containment events one rank sends to one owner */
+       RALA_B200_CAP_EDGES,        /* edges one rank sends to one owner */
+       RALA_B200_CAP_SLICE,        /* edges of one rank's CSR slice */
+       RALA_B200_CAP_ROUNDS,       /* resolution rounds of the first containment pass */
+       RALA_B200_CAP_FINAL_ROUNDS, /* resolution rounds of the final containment pass */
+       RALA_B200_CAP_LOCAL_EDGES,  /* edges one rank emits */
+       RALA_B200_N_CAPS };
+
+typedef struct {
+    int world, n_local;
+    uint64_t n_records;            /* records of the local ranks */
+    uint32_t n_piles, n_alive_piles, n_nodes;
+    uint64_t n_edges;              /* edges_.size(): all ranks (every rank knows the total) */
+    uint64_t n_local_edges;        /* edges emitted by the local ranks */
+    uint64_t n_candidates, n_final_candidates;   /* containment events emitted by the local ranks */
+    uint32_t n_rounds, n_final_rounds;           /* resolution rounds needed (same on every rank) */
+    uint64_t n_two_hop, n_transitive_pairs;      /* local ranks' share (sum over all ranks = the reference's values) */
+    uint32_t n_heavy_items;
+    uint32_t fabric_error;         /* 0, or bits: 1 barrier timeout, 2 rounds exhausted, 4 exchange buffer too small */
+} rala_b200_multi_counts_t;
+
+/* ranks [first_rank, first_rank + n_local) of `world` live in this process, local rank k on devices[k] */
+int rala_b200_multi_create(rala_b200_multi** out, const int* devices, int n_local, int first_rank, int world);
+void rala_b200_multi_destroy(rala_b200_multi* m);
+const char* rala_b200_multi_last_error(const rala_b200_multi* m);
+/* replicated pile table (every local rank gets a copy); as rala_b200_graph_set_piles */
+int rala_b200_multi_set_piles(rala_b200_multi* m, const rala_pile_t* piles, const uint8_t* flags, uint32_t n_piles);
+/* shard of local rank k: records [t0, t0 + n) of the file, in file order */
+int rala_b200_multi_set_overlaps(rala_b200_multi* m, int k, const rala_ovl_t* ovl, uint64_t n, uint64_t t0);
+int rala_b200_multi_set_overlaps_columns(rala_b200_multi* m, int k, const uint32_t* a_id, const uint32_t* b_id, const uint32_t* a_begin,
+                                         const uint32_t* a_end, const uint32_t* b_begin, const uint32_t* b_end, uint64_t n, uint64_t t0);
+/* as rala_b200_graph_set_outputs, for the edges local rank k emits (edge ids rala_b200_multi_edge_range) and their marks */
+int rala_b200_multi_set_outputs(rala_b200_multi* m, int k, rala_edge_t* edges_out, uint64_t edges_cap, uint8_t* marked_out,
+                                uint64_t marked_cap);
+/* capacities this process would choose for its own shards (take the maximum over all processes) */
+int rala_b200_multi_default_caps(rala_b200_multi* m, uint64_t* caps /* RALA_B200_N_CAPS */);
+/* (re)allocate the exchange arenas; with all ranks in one process this also connects them */
+int rala_b200_multi_reserve(rala_b200_multi* m, const uint64_t* caps /* RALA_B200_N_CAPS */);
+/* one process per GPU: 64-byte CUDA IPC handle of local rank k's arena / the handles of all `world` ranks in rank order */
+int rala_b200_multi_export_handle(rala_b200_multi* m, int k, void* handle64);
+int rala_b200_multi_import_handles(rala_b200_multi* m, const void* handles /* world x 64 bytes */);
+/* one step on every local rank: classify .. transitive.  Enqueues only (replays one CUDA graph per rank from the
+ * third call with the same inputs on). */
+int rala_b200_multi_run(rala_b200_multi* m);
+int rala_b200_multi_use_cuda_graph(rala_b200_multi* m, int enabled);
+/* How long a rank waits for its peers at a device-side barrier before it gives up (default 10 000 ms).  After a timeout
+ * the step's results are void, no later barrier waits, and demand / counts report RALA_B200_ERR_CUDA. */
+int rala_b200_multi_set_barrier_timeout_ms(rala_b200_multi* m, uint32_t ms);
+int rala_b200_multi_synchronize(rala_b200_multi* m);
+/* after synchronize: what the last step needed (per capacity; rounds: rounds needed) and whether everything fit */
+int rala_b200_multi_demand(rala_b200_multi* m, uint64_t* need /* RALA_B200_N_CAPS */, int* fits);
+/* all ranks in one process: reserve with the default capacities, run, grow what did not fit, until a step fits */
+int rala_b200_multi_plan(rala_b200_multi* m);
+int rala_b200_multi_counts(rala_b200_multi* m, rala_b200_multi_counts_t* out);
+/* results of local rank k: the edges it emitted are edge ids [*first_edge, *first_edge + *n) (rows in id order) */
+int rala_b200_multi_edge_range(rala_b200_multi* m, int k, uint64_t* first_edge, uint64_t* n);
+int rala_b200_multi_get_edges(rala_b200_multi* m, int k, rala_edge_t* out);
+int rala_b200_multi_get_marked(rala_b200_multi* m, int k, uint8_t* out);
+int rala_b200_multi_get_seq_to_node(rala_b200_multi* m, uint32_t* out /* n_piles */);
+int rala_b200_multi_get_piles(rala_b200_multi* m, rala_pile_t* out /* n_piles */);
+/* CUDA events on every local rank's stream; elapsed = max over the local ranks */
+int rala_b200_multi_event_record(rala_b200_multi* m, int which);
+int rala_b200_multi_event_elapsed_ms(rala_b200_multi* m, float* ms);
+uint64_t rala_b200_multi_launch_count(const rala_b200_multi* m);
+/* device time of the stages of the last EAGER step of local rank k (as rala_b200_graph_stage_ms) */
+int rala_b200_multi_stage_ms(rala_b200_multi* m, int k, float* ms_out /* RALA_B200_N_STAGES */);
 
 #ifdef __cplusplus
 }

@@ -61,6 +61,15 @@ EXPORTS = [
     "rala_b200_graph_export_marks", "rala_b200_graph_phase_marks",
     "rala_b200_graph_export_padded", "rala_b200_graph_import_gathered", "rala_b200_graph_export_list_counts",
     "rala_b200_graph_phase_final_events_gathered", "rala_b200_exchange_block_words",
+    # multi-GPU session (orchestration inside the library, exchanges over peer memory)
+    "rala_b200_multi_create", "rala_b200_multi_destroy", "rala_b200_multi_last_error", "rala_b200_multi_set_piles",
+    "rala_b200_multi_set_overlaps", "rala_b200_multi_set_overlaps_columns", "rala_b200_multi_default_caps",
+    "rala_b200_multi_reserve", "rala_b200_multi_export_handle", "rala_b200_multi_import_handles", "rala_b200_multi_run",
+    "rala_b200_multi_use_cuda_graph", "rala_b200_multi_synchronize", "rala_b200_multi_demand", "rala_b200_multi_plan",
+    "rala_b200_multi_counts", "rala_b200_multi_edge_range", "rala_b200_multi_get_edges", "rala_b200_multi_get_marked",
+    "rala_b200_multi_get_seq_to_node", "rala_b200_multi_get_piles", "rala_b200_multi_event_record",
+    "rala_b200_multi_event_elapsed_ms", "rala_b200_multi_launch_count", "rala_b200_multi_stage_ms",
+    "rala_b200_multi_set_outputs", "rala_b200_multi_set_barrier_timeout_ms",
 ]
 
 _LIB = None
@@ -76,6 +85,9 @@ def load_path(path: str):
     lib.rala_b200_exchange_block_words.restype = C.c_uint64
     lib.rala_b200_destroy.restype = None
     lib.rala_b200_graph_destroy.restype = None
+    lib.rala_b200_multi_destroy.restype = None
+    lib.rala_b200_multi_last_error.restype = C.c_char_p
+    lib.rala_b200_multi_launch_count.restype = C.c_uint64
     return lib
 
 
@@ -400,3 +412,219 @@ class Graph:
         self.transitive_edges = pairs[order]
         self.removed = marked
         return c["n_transitive_pairs"]
+
+
+N_CAPS = 6
+CAP_NAMES = ("events_per_pair", "edges_per_pair", "slice_edges", "rounds", "final_rounds", "local_edges")
+
+
+class MultiCounts(C.Structure):
+    _fields_ = [("world", C.c_int), ("n_local", C.c_int), ("n_records", C.c_uint64), ("n_piles", C.c_uint32),
+                ("n_alive_piles", C.c_uint32), ("n_nodes", C.c_uint32), ("n_edges", C.c_uint64), ("n_local_edges", C.c_uint64),
+                ("n_candidates", C.c_uint64), ("n_final_candidates", C.c_uint64), ("n_rounds", C.c_uint32),
+                ("n_final_rounds", C.c_uint32), ("n_two_hop", C.c_uint64), ("n_transitive_pairs", C.c_uint64),
+                ("n_heavy_items", C.c_uint32), ("fabric_error", C.c_uint32)]
+
+    def as_dict(self):
+        return {k: int(getattr(self, k)) for k, _ in self._fields_}
+
+
+class Multi:
+    """The multi-GPU session (rala_b200_multi): ranks [first_rank, first_rank + len(devices)) of `world` live in this
+    process, one per entry of `devices` (an id may repeat: several ranks on one GPU, which is how the parity tests
+    cover world > 1 on a one-GPU box).  Graph::construct's hot half + remove_transitive_edges with the pile table
+    frozen, bit-identical to the single-GPU session on the concatenation of the shards."""
+
+    def __init__(self, devices, first_rank: int = 0, world: int | None = None, lib=None):
+        self.lib = lib or load()
+        self.devices = list(devices)
+        self.n_local = len(self.devices)
+        self.world = self.n_local if world is None else world
+        self.first_rank = first_rank
+        self.handle = C.c_void_p()
+        dev = (C.c_int * self.n_local)(*self.devices)
+        rc = self.lib.rala_b200_multi_create(C.byref(self.handle), dev, C.c_int(self.n_local), C.c_int(first_rank), C.c_int(self.world))
+        if rc != 0:
+            raise RalaB200Error(f"rala_b200_multi_create(devices={self.devices}) failed with status {rc}: "
+                                "sm_100 (B200) devices are required, there is no CPU fallback")
+        self.n_piles = 0
+        self._keep = {}
+        if len(set(self.devices)) < self.n_local:
+            # ranks sharing a GPU wait for each other INSIDE kernels: every stream needs a hardware queue of its own
+            # (3 streams per rank), or work of one rank queues up behind another rank's waiting barrier
+            if int(os.environ.get("CUDA_DEVICE_MAX_CONNECTIONS", "8")) < 3 * self.n_local + 3:
+                raise RalaB200Error("several ranks on one device need CUDA_DEVICE_MAX_CONNECTIONS=32 in the environment "
+                                    "before CUDA is initialised (tests/conftest.py sets it)")
+
+    def _call(self, name, *args):
+        rc = getattr(self.lib, name)(self.handle, *args)
+        if rc != 0:
+            msg = self.lib.rala_b200_multi_last_error(self.handle)
+            raise RalaB200Error(f"{name}: status {rc}: {msg.decode() if msg else ''}")
+
+    def close(self):
+        if self.handle:
+            self.lib.rala_b200_multi_destroy(self.handle)
+            self.handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- inputs ------------------------------------------------------------------------------
+    def set_piles(self, piles, flags=None):
+        p = _np(piles, np.uint32, 2)
+        f = None if flags is None else _np(flags, np.uint8)
+        self.n_piles = p.shape[0]
+        self._keep["piles"] = (p, f)
+        self._call("rala_b200_multi_set_piles", _ptr(p), _ptr(f), C.c_uint32(self.n_piles))
+        return self
+
+    def set_overlaps(self, k: int, records, t0: int):
+        """Shard of local rank k: records [t0, t0 + n) of the file, in file order."""
+        rec = _np(records, np.uint32, 7)
+        self._keep[("rec", k)] = rec
+        self._call("rala_b200_multi_set_overlaps", C.c_int(k), _ptr(rec), C.c_uint64(rec.shape[0]), C.c_uint64(t0))
+        return self
+
+    def set_overlaps_columns(self, k: int, columns, t0: int):
+        cols = [_np(c, np.uint32) for c in columns]
+        n = cols[0].shape[0]
+        if len(cols) != 6 or any(c.shape[0] != n for c in cols):
+            raise RalaB200Error("set_overlaps_columns needs six columns of equal length")
+        self._keep[("rec", k)] = cols
+        self._call("rala_b200_multi_set_overlaps_columns", C.c_int(k), *[_ptr(c) for c in cols], C.c_uint64(n), C.c_uint64(t0))
+        return self
+
+    def set_outputs(self, k: int, edges_out=None, marked_out=None):
+        """Pinned host buffers local rank k writes the rows of the edges it emitted, and their marks, into directly."""
+        e_cap = 0 if edges_out is None else int(edges_out.shape[0])
+        m_cap = 0 if marked_out is None else int(marked_out.shape[0])
+        self._keep[("out", k)] = (edges_out, marked_out)
+        self._call("rala_b200_multi_set_outputs", C.c_int(k), _ptr(edges_out), C.c_uint64(e_cap), _ptr(marked_out), C.c_uint64(m_cap))
+        return self
+
+    def set_shards(self, records, bounds=None):
+        """All ranks local: cut the record list into `world` contiguous file ranges (equal record counts, 4-record aligned)."""
+        rec = _np(records, np.uint32, 7)
+        n = rec.shape[0]
+        if bounds is None:
+            per = ((n + self.world - 1) // self.world + 3) // 4 * 4
+            bounds = [(min(n, r * per), min(n, (r + 1) * per)) for r in range(self.world)]
+        for k, (b, e) in enumerate(bounds):
+            self.set_overlaps(k, rec[b:e], b)
+        return self
+
+    # ---- exchange buffers ----------------------------------------------------------------------
+    def default_caps(self):
+        caps = np.zeros(N_CAPS, dtype=np.uint64)
+        self._call("rala_b200_multi_default_caps", _ptr(caps))
+        return caps
+
+    def reserve(self, caps):
+        caps = np.ascontiguousarray(caps, dtype=np.uint64)
+        self._call("rala_b200_multi_reserve", _ptr(caps))
+        self.caps = caps.copy()
+        return self
+
+    def export_handle(self, k: int = 0) -> bytes:
+        buf = C.create_string_buffer(64)
+        self._call("rala_b200_multi_export_handle", C.c_int(k), buf)
+        return buf.raw
+
+    def import_handles(self, handles: bytes):
+        if len(handles) != 64 * self.world:
+            raise RalaB200Error("import_handles needs one 64-byte handle per rank")
+        self._call("rala_b200_multi_import_handles", C.c_char_p(handles))
+        return self
+
+    def plan(self):
+        """All ranks local: size the exchange buffers from a first step (grows what did not fit)."""
+        self._call("rala_b200_multi_plan")
+        return self
+
+    # ---- step ------------------------------------------------------------------------------------
+    def run(self):
+        self._call("rala_b200_multi_run")
+        return self
+
+    def use_cuda_graph(self, enabled: bool):
+        self._call("rala_b200_multi_use_cuda_graph", C.c_int(1 if enabled else 0))
+        return self
+
+    def synchronize(self):
+        self._call("rala_b200_multi_synchronize")
+        return self
+
+    def set_barrier_timeout_ms(self, ms: int):
+        self._call("rala_b200_multi_set_barrier_timeout_ms", C.c_uint32(ms))
+        return self
+
+    def demand(self):
+        need = np.zeros(N_CAPS, dtype=np.uint64)
+        fits = C.c_int(0)
+        self._call("rala_b200_multi_demand", _ptr(need), C.byref(fits))
+        return need, bool(fits.value)
+
+    def counts(self) -> dict:
+        c = MultiCounts()
+        self._call("rala_b200_multi_counts", C.byref(c))
+        return c.as_dict()
+
+    # ---- results -----------------------------------------------------------------------------------
+    def edge_range(self, k: int):
+        first, n = C.c_uint64(0), C.c_uint64(0)
+        self._call("rala_b200_multi_edge_range", C.c_int(k), C.byref(first), C.byref(n))
+        return int(first.value), int(n.value)
+
+    def edges(self, k: int, out=None):
+        _, n = self.edge_range(k)
+        if out is None:
+            out = np.zeros((n, 3), dtype=np.uint32)
+        if n:
+            self._call("rala_b200_multi_get_edges", C.c_int(k), _ptr(out))
+        return out
+
+    def marked(self, k: int, out=None):
+        _, n = self.edge_range(k)
+        if out is None:
+            out = np.zeros(n, dtype=np.uint8)
+        if n:
+            self._call("rala_b200_multi_get_marked", C.c_int(k), _ptr(out))
+        return out
+
+    def all_edges(self):
+        """Edge rows and marks of the local ranks in edge-id order (the whole graph when every rank is local)."""
+        e = [self.edges(k) for k in range(self.n_local)]
+        m = [self.marked(k) for k in range(self.n_local)]
+        return np.concatenate(e), np.concatenate(m)
+
+    def seq_to_node(self):
+        out = np.zeros(self.n_piles, dtype=np.uint32)
+        self._call("rala_b200_multi_get_seq_to_node", _ptr(out))
+        return out
+
+    def piles(self):
+        out = np.zeros((self.n_piles, 2), dtype=np.uint32)
+        self._call("rala_b200_multi_get_piles", _ptr(out))
+        return out
+
+    # ---- timing ------------------------------------------------------------------------------------
+    def event_record(self, which: int):
+        self._call("rala_b200_multi_event_record", C.c_int(which))
+
+    def event_elapsed_ms(self) -> float:
+        ms = C.c_float(0)
+        self._call("rala_b200_multi_event_elapsed_ms", C.byref(ms))
+        return float(ms.value)
+
+    @property
+    def launch_count(self) -> int:
+        return int(self.lib.rala_b200_multi_launch_count(self.handle))
+
+    def stage_ms(self, k: int = 0) -> dict:
+        ms = (C.c_float * N_STAGES)()
+        self._call("rala_b200_multi_stage_ms", C.c_int(k), ms)
+        return dict(zip(STAGE_NAMES, [float(x) for x in ms]))

@@ -9,37 +9,9 @@
 #include <vector>
 
 #include "../../include/rala_b200.h"
-#include "kernels.h"
-#include "lists.cuh"
+#include "session.h"
 
 using namespace rb;
-
-struct rala_b200_ctx {
-    bool owns_stream = true;
-    cudaEvent_t ev[2]{};
-    int device = 0;
-    Launch L{nullptr, 0};
-    std::string error;
-    int coop_blocks = 0;
-};
-
-static int fail(rala_b200_ctx* ctx, int code, const char* fmt, ...) {
-    char buf[512];
-    va_list ap;
-    va_start(ap, fmt);
-    vsnprintf(buf, sizeof(buf), fmt, ap);
-    va_end(ap);
-    if (ctx) ctx->error = buf;
-    return code;
-}
-
-#define CU(ctx, call)                                                                                   \
-    do {                                                                                                \
-        cudaError_t err__ = (call);                                                                     \
-        if (err__ != cudaSuccess)                                                                       \
-            return fail((ctx), RALA_B200_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(err__), \
-                        __FILE__, __LINE__);                                                            \
-    } while (0)
 
 extern "C" int rala_b200_abi_version(void) { return RALA_B200_ABI_VERSION; }
 
@@ -59,6 +31,12 @@ extern "C" int rala_b200_create(rala_b200_ctx** out, int device) {
         return RALA_B200_ERR_CUDA;
     }
     ctx->coop_blocks = resolve_max_blocks();
+    preload_classify();
+    preload_containment();
+    preload_graph_build();
+    preload_transitive();
+    preload_fabric();
+    cudaGetLastError();
     cudaEventCreate(&ctx->ev[0]);
     cudaEventCreate(&ctx->ev[1]);
     for (int k = 0; k < 2; ++k) {   // forked work inside a step (kernels.h Launch); without them everything stays on the main stream
@@ -119,158 +97,29 @@ extern "C" int rala_b200_synchronize(rala_b200_ctx* ctx) {
 extern "C" const char* rala_b200_last_error(const rala_b200_ctx* ctx) { return ctx ? ctx->error.c_str() : "no context"; }
 extern "C" uint64_t rala_b200_launch_count(const rala_b200_ctx* ctx) { return ctx ? ctx->L.count : 0; }
 
-// ---------------------------------------------------------------------------------------------
-// device buffer helper
-// ---------------------------------------------------------------------------------------------
-struct DevBuf {
-    void* p = nullptr;
-    size_t bytes = 0;
-    cudaError_t reserve(size_t want) {
-        if (want <= bytes) return cudaSuccess;
-        if (p) cudaFree(p);
-        p = nullptr;
-        bytes = 0;
-        cudaError_t e = cudaMalloc(&p, want);
-        if (e == cudaSuccess) bytes = want;
-        return e;
-    }
-    void release() {
-        if (p) cudaFree(p);
-        p = nullptr;
-        bytes = 0;
-    }
-    template <class T> T* as() const { return reinterpret_cast<T*>(p); }
-};
-
-static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
-
-struct ListBuf {
-    DevBuf buf;
-    List view{};
-    cudaError_t reserve(uint32_t cap) {
-        size_t col = align_up((size_t) cap * 4, 256);
-        cudaError_t e = buf.reserve(col * 6 + align_up(cap, 256));
-        if (e != cudaSuccess) return e;
-        char* b = buf.as<char>();
-        view.a = (uint32_t*) b;
-        view.b = (uint32_t*) (b + col);
-        view.ab = (uint32_t*) (b + 2 * col);
-        view.ae = (uint32_t*) (b + 3 * col);
-        view.bb = (uint32_t*) (b + 4 * col);
-        view.be = (uint32_t*) (b + 5 * col);
-        view.tag = (uint8_t*) (b + 6 * col);
-        return cudaSuccess;
-    }
-};
-
-enum Stage { ST_CLASSIFY = 0, ST_RETRIM, ST_FINALIZE, ST_BUILD, ST_TRANSITIVE, ST_K1_KERNEL, ST_K1B_KERNEL, ST_K3_KERNELS, ST_K1S_KERNEL };
-
-struct rala_b200_graph {
-    rala_b200_ctx* ctx = nullptr;
-    // inputs
-    DevBuf rec;        // the host's rala_ovl_t rows as uploaded (staging of the transpose)
-    ListBuf recs;      // device-resident records: six columns, 24 B / record (classify.cu)
-    DevBuf alive_bits; // one bit per pile: alive after the last containment resolution
-    uint32_t n_rec = 0;
-    DevBuf piles, piles_raw, pile_flags_raw, piles_initial;
-    bool piles_fresh = false;       // set_piles since the last classify
-    uint32_t n_piles = 0;
-    DevBuf hills;   // 4 columns of n_hills: pile begin end cov
-    uint32_t n_hills = 0;
-    // lists
-    uint32_t cap = 0;      // capacity of every overlap list
-    uint32_t ev_cap = 0;   // capacity of the event arrays and victim segments (multi-GPU: events of ALL ranks)
-    int rank = 0, world = 1;   // multi-GPU: which share of the source nodes the transitive phase takes
-    uint32_t t0 = 0;       // global time (file position) of the first local record (multi-GPU shards)
-    ListBuf ovl[2], inl[2];
-    int ovl_cur = 0, inl_cur = 0;
-    int slot_ovl = C_LIST0, slot_inl = C_LIST0 + 1, next_slot = C_LIST0 + 2;
-    DevBuf events, hill_rec;
-    DevBuf dbuf, flags, segs, tiles;   // dbuf: S | vcursor | vstart | work0 | work1 ; segs: seg_c | seg_t ; tiles: info | off
-    DevBuf counters;
-    DevBuf scan_pool;
-    size_t scan_pool_words = 0, scan_used = 0;
-    // graph
-    DevBuf edges_aos;
-    DevBuf seq_to_node, edges, row_ptr, cursor, col, col_eid, T, marked, heavy, work_counter;
-    uint32_t edge_cap = 0, heavy_cap = 0, n_nodes_max = 0;
-    // results written straight into the caller's memory by the run (rala_b200_graph_set_outputs)
-    uint32_t* out_edges = nullptr;   // device-visible address of the caller's rala_edge_t rows
-    uint8_t* out_marked = nullptr;
-    uint32_t out_edges_cap = 0, out_marked_cap = 0;
-    bool in_run = false;             // build is part of a whole run: the edge download may overlap the transitive pass
-    bool download_pending = false;   // side stream 0 is still writing edges: joined at the end of the transitive stage
-    // bookkeeping
-    int final_time_base_slot = C_LIST0;   // counter slot holding the time base of `internals` in the final pass
-    bool final_lists_ready = true;  // after finalize: have the filtered lists of graph.cpp:867-877 been written out?
-    bool piles_dirty = true;        // pile table changed since the lists were last trimmed against it
-    bool skip_clean_retrim = true;  // re-trimming against an unchanged table is the identity: skip the pass
-    int state = 0;                  // 0 empty, 1 inputs set, 2 classified, 3 finalized, 4 built, 5 reduced
-    uint32_t retrim_passes = 0;
-    cudaEvent_t ev_start[RALA_B200_N_STAGES]{}, ev_stop[RALA_B200_N_STAGES]{};
-    bool ev_valid[RALA_B200_N_STAGES]{};
-    // rala_b200_graph_run as a replayed CUDA graph (see run_key / RunGraph below)
-    bool use_cuda_graph = true, capturing = false;
-    struct RunGraph* run_graphs = nullptr;   // two cached instances: first run after set_piles / repeated run
-
-    uint32_t* cnt() const { return counters.as<uint32_t>(); }
-    Events events_view() const {
-        Events e;
-        size_t col = align_up((size_t) ev_cap * 4, 256);
-        char* b = events.as<char>();
-        e.v = (uint32_t*) b;
-        e.c = (uint32_t*) (b + col);
-        e.t = (uint32_t*) (b + 2 * col);
-        return e;
-    }
-    GraphArrays graph_view() const {
-        GraphArrays g;
-        size_t col_b = align_up((size_t) edge_cap * 4, 256);
-        g.seq_to_node = seq_to_node.as<uint32_t>();
-        g.src = (uint32_t*) edges.as<char>();
-        g.dst = (uint32_t*) (edges.as<char>() + col_b);
-        g.len = (uint32_t*) (edges.as<char>() + 2 * col_b);
-        g.row_ptr = row_ptr.as<uint32_t>();
-        g.cursor = cursor.as<uint32_t>();
-        g.col = col.as<uint2>();
-        g.col_eid = col_eid.as<uint32_t>();
-        g.T = T.as<uint8_t>();
-        g.marked = marked.as<uint8_t>();
-        return g;
-    }
-    HeavyItems heavy_view() const {
-        HeavyItems h;
-        size_t colb = align_up((size_t) heavy_cap * 4, 256);
-        h.node = (uint32_t*) heavy.as<char>();
-        h.hash_chunk = (uint32_t*) (heavy.as<char>() + colb);
-        h.nbr_chunk = (uint32_t*) (heavy.as<char>() + 2 * colb);
-        h.cap = heavy_cap;
-        return h;
-    }
-    int new_slot() {
-        int s = next_slot;
-        next_slot = next_slot + 1 >= C_COUNT ? C_LIST0 : next_slot + 1;
-        if (s == slot_ovl || s == slot_inl) return new_slot();
-        return s;
-    }
-};
-
-static size_t tiles_of(uint64_t n) { return (size_t) ((n + kTile - 1) / kTile) + 1; }
+size_t tiles_of(uint64_t n) { return (size_t) ((n + kTile - 1) / kTile) + 1; }
 
 // a fresh, zeroed (status words, ticket) pair from the pool for one look-back kernel
-static void scan_state(rala_b200_graph* g, uint64_t n_max, unsigned long long** status, uint32_t** ticket) {
+bool scan_state(rala_b200_graph* g, uint64_t n_max, unsigned long long** status, uint32_t** ticket) {
     size_t words = tiles_of(n_max) + 1;
-    if (g->scan_used + words > g->scan_pool_words) g->scan_used = 0;   // never happens within one stage (pool is sized for it)
+    if (g->scan_used + words > g->scan_pool_words) {
+        // Handing out words an earlier look-back kernel of the same stage already wrote would give wrong prefixes (or spin).
+        // The pool is sized for every stage (reserve_scan_pool); should a new caller break that, the run is declared
+        // void (read_counters reports it) and the words are recycled only so that the kernel arguments stay valid.
+        g->scan_pool_exhausted = true;
+        g->scan_used = 0;
+    }
     unsigned long long* base = g->scan_pool.as<unsigned long long>() + g->scan_used;
     *ticket = reinterpret_cast<uint32_t*>(base);
     *status = base + 1;
     g->scan_used += words;
+    return !g->scan_pool_exhausted;
 }
 
 // stage timers: plain event records, left out of a stream capture (an event recorded inside a capture cannot be timed)
 // `capturing` covers the library's own capture (rala_b200_graph_run); a caller may also capture the phase calls
 // into a graph of its own (rala_b200/multi.py: kernels + NCCL collectives of one multi-GPU step), so ask the stream.
-static bool stream_capturing(const rala_b200_graph* g) {
+bool stream_capturing(const rala_b200_graph* g) {
     if (g->capturing) return true;
     cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
     if (cudaStreamIsCapturing(g->ctx->L.stream, &st) != cudaSuccess) {
@@ -280,23 +129,23 @@ static bool stream_capturing(const rala_b200_graph* g) {
     return st != cudaStreamCaptureStatusNone;
 }
 
-static cudaError_t stage_event(rala_b200_graph* g, cudaEvent_t ev) {
+cudaError_t stage_event(rala_b200_graph* g, cudaEvent_t ev) {
     return stream_capturing(g) ? cudaSuccess : cudaEventRecord(ev, g->ctx->L.stream);
 }
 
-static cudaError_t begin_stage(rala_b200_graph* g, int stage) {
+cudaError_t begin_stage(rala_b200_graph* g, int stage) {
     g->scan_used = 0;
     cudaError_t e = cudaMemsetAsync(g->scan_pool.p, 0, g->scan_pool_words * 8, g->ctx->L.stream);
     if (e != cudaSuccess) return e;
     return stage_event(g, g->ev_start[stage]);
 }
 
-static cudaError_t end_stage(rala_b200_graph* g, int stage) {
+cudaError_t end_stage(rala_b200_graph* g, int stage) {
     g->ev_valid[stage] = !stream_capturing(g);
     return stage_event(g, g->ev_stop[stage]);
 }
 
-static cudaError_t zero_counter(rala_b200_graph* g, int slot, int n = 1) {
+cudaError_t zero_counter(rala_b200_graph* g, int slot, int n) {
     return cudaMemsetAsync(g->cnt() + slot, 0, 4 * (size_t) n, g->ctx->L.stream);
 }
 
@@ -340,7 +189,7 @@ extern "C" void rala_b200_graph_destroy(rala_b200_graph* g) {
     delete g;
 }
 
-static int reserve_events(rala_b200_graph* g, uint32_t ev_cap) {
+int reserve_events(rala_b200_graph* g, uint32_t ev_cap) {
     if (ev_cap <= g->ev_cap) return RALA_B200_OK;
     rala_b200_ctx* ctx = g->ctx;
     // growing re-allocates: contents are not preserved (callers grow before they fill)
@@ -350,7 +199,7 @@ static int reserve_events(rala_b200_graph* g, uint32_t ev_cap) {
     return RALA_B200_OK;
 }
 
-static int reserve_edges(rala_b200_graph* g, uint32_t edge_cap) {
+int reserve_edges(rala_b200_graph* g, uint32_t edge_cap) {
     if (edge_cap <= g->edge_cap) return RALA_B200_OK;
     rala_b200_ctx* ctx = g->ctx;
     g->edge_cap = edge_cap;
@@ -365,7 +214,9 @@ static int reserve_edges(rala_b200_graph* g, uint32_t edge_cap) {
 }
 
 static int reserve_scan_pool(rala_b200_graph* g) {
-    size_t words = 8 * (tiles_of(g->n_rec) + tiles_of(2ull * g->n_piles + 8) + 8);
+    // worst stage: classify = runs scan + two containment scans over the piles; build = piles + list + node degrees;
+    // the multi-GPU session adds scans over its exchange capacities (<= 2 x the record count): 16 x leaves room
+    size_t words = 16 * (tiles_of(g->n_rec) + tiles_of(2ull * g->n_piles + 8) + 8);
     if (words > g->scan_pool_words) {
         CU(g->ctx, g->scan_pool.reserve(words * 8));
         g->scan_pool_words = words;
@@ -469,6 +320,11 @@ extern "C" int rala_b200_graph_set_piles(rala_b200_graph* g, const rala_pile_t* 
     rala_b200_ctx* ctx = g->ctx;
     CU(ctx, cudaSetDevice(ctx->device));
     if (n_piles >= (1u << 31)) return fail(ctx, RALA_B200_ERR_LIMIT, "too many piles");
+    // event_code (common.cuh) and the packed table (end | flags << 30) rely on the documented limit: valid regions end below 2^30
+    for (uint32_t i = 0; i < n_piles; ++i) {
+        if (piles[i].end >= (1u << 30)) return fail(ctx, RALA_B200_ERR_LIMIT, "pile %u ends at %u: read lengths must be < 2^30", i, piles[i].end);
+        if (piles[i].end && piles[i].begin > piles[i].end) return fail(ctx, RALA_B200_ERR_ARG, "pile %u: begin %u > end %u", i, piles[i].begin, piles[i].end);
+    }
     CU(ctx, g->piles.reserve((size_t) n_piles * 8 + 16));
     CU(ctx, g->piles_raw.reserve((size_t) n_piles * 8 + 16));
     CU(ctx, g->piles_initial.reserve((size_t) n_piles * 8 + 16));
@@ -489,6 +345,7 @@ extern "C" int rala_b200_graph_set_piles(rala_b200_graph* g, const rala_pile_t* 
         if (rc) return rc;
     }
     g->piles_dirty = true;
+    g->promote_pending = true;
     g->piles_fresh = true;
     if (g->state < 1 && g->n_rec) g->state = 1;
     return RALA_B200_OK;
@@ -513,7 +370,7 @@ extern "C" int rala_b200_graph_set_hills(rala_b200_graph* g, const rala_hill_t* 
     return RALA_B200_OK;
 }
 
-static ResolveBufs resolve_bufs(const rala_b200_graph* g) {
+ResolveBufs resolve_bufs(const rala_b200_graph* g) {
     ResolveBufs r;
     const size_t stride = align_up((size_t) g->n_piles + 64, 64);   // 256-byte aligned sub-arrays (16-byte vector loads)
     uint32_t* b = g->dbuf.as<uint32_t>();
@@ -529,7 +386,7 @@ static ResolveBufs resolve_bufs(const rala_b200_graph* g) {
 }
 
 // the classify kernels bump the per-victim histogram while they emit events: clear it first
-static cudaError_t clear_victim_histogram(rala_b200_graph* g) {
+cudaError_t clear_victim_histogram(rala_b200_graph* g) {
     return cudaMemsetAsync(resolve_bufs(g).vcursor, 0, ((size_t) g->n_piles + 64) * 4, g->ctx->L.stream);
 }
 
@@ -545,7 +402,7 @@ static int resolve_containment(rala_b200_graph* g, bool decode) {
 }
 
 // ---- graph.cpp:443-518 in three phases (the multi-GPU path exchanges events between them) ----------------
-static int phase_events(rala_b200_graph* g) {
+int phase_events(rala_b200_graph* g) {
     rala_b200_ctx* ctx = g->ctx;
     if (g->state < 1) return fail(ctx, RALA_B200_ERR_STATE, "classify: set_overlaps and set_piles first");
     CU(ctx, cudaSetDevice(ctx->device));
@@ -588,7 +445,7 @@ static int phase_resolve(rala_b200_graph* g, bool first_pass) {
     return RALA_B200_OK;
 }
 
-static int phase_survivors(rala_b200_graph* g) {
+int phase_survivors(rala_b200_graph* g) {
     rala_b200_ctx* ctx = g->ctx;
     g->ovl_cur = 0;
     g->inl_cur = 0;
@@ -612,6 +469,7 @@ static int phase_survivors(rala_b200_graph* g) {
     CU(ctx, cudaGetLastError());
     CU(ctx, end_stage(g, ST_CLASSIFY));
     g->piles_dirty = false;   // lists are trimmed against the table as it stands (only liveness changed, and the split filtered on it)
+    g->promote_pending = false;   // and every internal was typed against it
     g->state = 2;
     g->final_lists_ready = true;
     g->retrim_passes = 0;
@@ -665,8 +523,10 @@ extern "C" int rala_b200_graph_retrim_promote(rala_b200_graph* g, int* is_change
     rala_b200_ctx* ctx = g->ctx;
     if (g->state != 2) return fail(ctx, RALA_B200_ERR_STATE, "retrim_promote: classify first");
     if (is_changed) *is_changed = 0;
-    // Against an unchanged pile table trim() is the identity and the internals keep their (non-dovetail) type.
-    if (!g->piles_dirty && g->skip_clean_retrim) return RALA_B200_OK;
+    // Against a pile table the internals were already trimmed AND typed with, trim() is the identity and they keep their
+    // (non-dovetail) type.  retrim() trims them but does not re-type them: after set_piles -> retrim the promotion of
+    // graph.cpp:809-823 still has to run (promote_pending), although piles_dirty is clear.
+    if (!g->piles_dirty && !g->promote_pending && g->skip_clean_retrim) return RALA_B200_OK;
     CU(ctx, cudaSetDevice(ctx->device));
     CU(ctx, begin_stage(g, ST_RETRIM));
     int before_slot = g->slot_ovl;
@@ -689,6 +549,7 @@ extern "C" int rala_b200_graph_retrim_promote(rala_b200_graph* g, int* is_change
     CU(ctx, cudaGetLastError());
     CU(ctx, end_stage(g, ST_RETRIM));
     g->piles_dirty = false;
+    g->promote_pending = false;
     g->retrim_passes += 1;
     if (is_changed) {
         uint32_t h[C_COUNT];
@@ -701,7 +562,7 @@ extern "C" int rala_b200_graph_retrim_promote(rala_b200_graph* g, int* is_change
 
 // graph.cpp:849-877 on demand: the final `internals` (alive at their own time, not kA/kB) and `overlaps`
 // (both piles alive at the end, not kA/kB)
-static int materialize_final_lists(rala_b200_graph* g) {
+int materialize_final_lists(rala_b200_graph* g) {
     if (g->final_lists_ready || g->state < 3) return RALA_B200_OK;
     rala_b200_ctx* ctx = g->ctx;
     unsigned long long* status;
@@ -731,7 +592,7 @@ static int materialize_final_lists(rala_b200_graph* g) {
 }
 
 // ---- graph.cpp:831-877 in two phases ---------------------------------------------------------------------
-static int phase_final_events(rala_b200_graph* g, const uint32_t* ovl_base /* device, nullable */,
+int phase_final_events(rala_b200_graph* g, const uint32_t* ovl_base /* device, nullable */,
                               const uint32_t* inl_base /* device */) {
     rala_b200_ctx* ctx = g->ctx;
     if (g->state != 2) return fail(ctx, RALA_B200_ERR_STATE, "finalize: classify first");
@@ -867,7 +728,7 @@ struct RunKey {
 // host-side bookkeeping a run leaves behind (restored after a replay)
 struct RunHostState {
     int ovl_cur, inl_cur, slot_ovl, slot_inl, next_slot, final_time_base_slot, state;
-    bool final_lists_ready, piles_dirty, piles_fresh;
+    bool final_lists_ready, piles_dirty, piles_fresh, promote_pending;
     uint32_t retrim_passes;
     size_t scan_used;
 };
@@ -896,7 +757,7 @@ static RunKey run_key(const rala_b200_graph* g) {
 
 static RunHostState host_state(const rala_b200_graph* g) {
     return RunHostState{g->ovl_cur, g->inl_cur, g->slot_ovl, g->slot_inl, g->next_slot, g->final_time_base_slot, g->state,
-                        g->final_lists_ready, g->piles_dirty, g->piles_fresh, g->retrim_passes, g->scan_used};
+                        g->final_lists_ready, g->piles_dirty, g->piles_fresh, g->promote_pending, g->retrim_passes, g->scan_used};
 }
 
 static void drop_run_graphs(rala_b200_graph* g) {
@@ -961,16 +822,18 @@ extern "C" int rala_b200_graph_run(rala_b200_graph* g) {
     const RunHostState& a = R.after;
     g->ovl_cur = a.ovl_cur; g->inl_cur = a.inl_cur; g->slot_ovl = a.slot_ovl; g->slot_inl = a.slot_inl; g->next_slot = a.next_slot;
     g->final_time_base_slot = a.final_time_base_slot; g->state = a.state; g->final_lists_ready = a.final_lists_ready;
-    g->piles_dirty = a.piles_dirty; g->piles_fresh = a.piles_fresh; g->retrim_passes = a.retrim_passes; g->scan_used = a.scan_used;
+    g->piles_dirty = a.piles_dirty; g->piles_fresh = a.piles_fresh; g->promote_pending = a.promote_pending; g->retrim_passes = a.retrim_passes; g->scan_used = a.scan_used;
     for (int i = 0; i < RALA_B200_N_STAGES; ++i) g->ev_valid[i] = false;   // no stage timers inside a graph
     return RALA_B200_OK;
 }
 
-static int read_counters(rala_b200_graph* g, uint32_t* h) {
+int read_counters(rala_b200_graph* g, uint32_t* h) {
     rala_b200_ctx* ctx = g->ctx;
     CU(ctx, cudaSetDevice(ctx->device));
     CU(ctx, cudaMemcpyAsync(h, g->counters.p, C_COUNT * 4, cudaMemcpyDeviceToHost, ctx->L.stream));
     CU(ctx, cudaStreamSynchronize(ctx->L.stream));
+    if (g->scan_pool_exhausted)
+        return fail(ctx, RALA_B200_ERR_LIMIT, "the look-back status pool was exhausted inside a stage (%zu words): the results are void", g->scan_pool_words);
     if (h[C_OVERFLOW] || (g->state >= 2 && (h[g->slot_ovl] > g->cap || h[g->slot_inl] > g->cap)) || h[C_EV] > g->ev_cap || h[C_HILL] > g->cap || h[C_HEAVY] > g->heavy_cap)
         return fail(ctx, RALA_B200_ERR_LIMIT, "a device list overflowed its capacity (cap=%u events=%u hills=%u heavy=%u/%u)",
                     g->cap, h[C_EV], h[C_HILL], h[C_HEAVY], g->heavy_cap);

@@ -774,4 +774,32 @@ void launch_list_connections(Launch& L, List l, const uint32_t* n_ptr, uint32_t 
     L.count++;
 }
 
+// CUDA loads kernels lazily, at their first launch, and that load waits for the device to drain: fatal when the
+// first launch of a kernel happens while another rank's barrier kernel is spinning on the same device (ranks sharing
+// a GPU) — the barrier waits for this rank, this rank's kernel waits for the barrier.  rala_b200_create loads them all.
+void preload_classify() {
+    cudaFuncAttributes a;
+    cudaFuncGetAttributes(&a, k_records_to_soa);
+    cudaFuncGetAttributes(&a, k_classify_events<3>);
+    cudaFuncGetAttributes(&a, k_classify_survivors);
+    cudaFuncGetAttributes(&a, k_scan_runs);
+    cudaFuncGetAttributes(&a, k_relocate_runs);
+    cudaFuncGetAttributes(&a, k_hill_coverage);
+    cudaFuncGetAttributes(&a, k_apply_deaths<true>);
+    cudaFuncGetAttributes(&a, k_apply_deaths<false>);
+    cudaFuncGetAttributes(&a, k_list_pass<kSplitAlive>);
+    cudaFuncGetAttributes(&a, k_list_pass<kRetrim>);
+    cudaFuncGetAttributes(&a, k_list_pass<kPromote>);
+    cudaFuncGetAttributes(&a, k_list_pass<kFinalOvl>);
+    cudaFuncGetAttributes(&a, k_list_pass<kFinalInt>);
+    cudaFuncGetAttributes(&a, k_classify_final);
+    cudaFuncGetAttributes(&a, k_trim_classify_aos);
+    cudaFuncGetAttributes(&a, k_fill_u32);
+    cudaFuncGetAttributes(&a, k_pack_piles);
+    cudaFuncGetAttributes(&a, k_unpack_piles);
+    cudaFuncGetAttributes(&a, k_list_to_aos);
+    cudaFuncGetAttributes(&a, k_aos_to_list);
+    cudaFuncGetAttributes(&a, k_list_connections);
+}
+
 }  // namespace rb

@@ -167,7 +167,9 @@ __device__ __forceinline__ bool resolve_victim(uint32_t v0, const uint32_t* __re
         atomicMax(&S[v], best_t);                 // v cannot die before its earliest open event
         if (best_t > stack_need[sp]) { --sp; continue; }   // whoever asked only cares about earlier times
         const uint32_t c = seg_c[best_p];
-        const uint32_t q = ld_state(&S[c]);
+        // a record with a_id == b_id makes the pile its own container: both "are alive" at that time and the pile dies
+        // (graph.cpp:469-480 reset piles_[a] either way); without this the pile would wait for its own fate for ever
+        const uint32_t q = c == v ? (kSettled | kNever) : ld_state(&S[c]);
         if (q & kSettled) {
             if ((q & kNever) > best_t) {          // container still alive at best_t: the event fires
                 atomicMax(&S[v], kSettled | best_t);
@@ -241,9 +243,18 @@ __global__ void __launch_bounds__(256) k_resolve(const uint32_t* __restrict__ vs
     int k = 0;
     if (threadIdx.x == 0) { s_n[0] = n; s_n[1] = 0u; }
     __syncthreads();
+    uint32_t stalled = 0, prev_n = 0xFFFFFFFFu;
     while (true) {
         const uint32_t m_n = s_n[k];
         if (m_n == 0) break;
+        // every sweep settles at least the victim with the globally earliest open event, so the list shrinks; a list
+        // that stops shrinking means the events are not well-founded (corrupt input): give up instead of spinning
+        stalled = m_n >= prev_n ? stalled + 1u : 0u;
+        prev_n = m_n;
+        if (stalled > 64u) {
+            if (threadIdx.x == 0) counters[C_OVERFLOW] = 1u;
+            break;
+        }
         for (uint32_t i = threadIdx.x; i < m_n; i += blockDim.x) {
             const uint32_t v = in[i];
             if (!resolve_victim(v, vstart, seg_c, seg_t, S)) out[atomicAdd(&s_n[k ^ 1], 1u)] = v;
@@ -310,6 +321,17 @@ void launch_resolve(Launch& L, Events ev, const uint32_t* n_events, uint32_t ev_
         k_decode_state<<<grid_for(n_piles, 256, kNumSMs * 8), 256, 0, L.stream>>>(rb.S, n_piles);
         L.count++;
     }
+}
+
+// CUDA loads kernels lazily, at their first launch, and that load waits for the device to drain: fatal when the
+// first launch of a kernel happens while another rank's barrier kernel is spinning on the same device (ranks sharing
+// a GPU) — the barrier waits for this rank, this rank's kernel waits for the barrier.  rala_b200_create loads them all.
+void preload_containment() {
+    cudaFuncAttributes a;
+    cudaFuncGetAttributes(&a, k_events_hist);
+    cudaFuncGetAttributes(&a, k_resolve_prepare);
+    cudaFuncGetAttributes(&a, k_decode_state);
+    cudaFuncGetAttributes(&a, k_resolve);
 }
 
 }  // namespace rb

@@ -1,0 +1,640 @@
+// fabric.cu — kernels of the multi-rank exchange layer (fabric.cuh): flag barrier over peer memory, routing of
+// containment events / edges / transitive marks to their owners, the distributed containment resolution, and the
+// replication of the owner-built CSR slices.  Every remote access is a store or a reduction INTO the consumer's
+// arena; consumers only ever read their own memory.
+#include "fabric.cuh"
+#include "kernels.h"
+
+namespace rb {
+
+// ---------------------------------------------------------------------------------------------
+// system-scope accesses (peer memory over NVLink)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void st_sys(uint32_t* p, uint32_t v) {
+    asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint32_t ld_relaxed_sys(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void red_max_sys(uint32_t* p, uint32_t v) {
+    asm volatile("red.relaxed.sys.global.max.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+__device__ __forceinline__ FabricHdr* hdr_of(const Peers& P, int q) { return reinterpret_cast<FabricHdr*>(P.base[q]); }
+template <class T>
+__device__ __forceinline__ T* section(const Peers& P, int q, size_t off) { return reinterpret_cast<T*>(P.base[q] + off); }
+
+static inline int grid_for(uint64_t n, int per_block, int max_blocks) {
+    uint64_t b = (n + per_block - 1) / per_block;
+    if (b < 1) b = 1;
+    return (int) (b < (uint64_t) max_blocks ? b : (uint64_t) max_blocks);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Barrier.  Lane q publishes this rank's mail to peer q, makes everything this rank pushed before visible
+// (the pushes were issued by EARLIER kernels of the same stream, so they are complete; the fence orders the mail),
+// raises its flag in q's header and waits for q's flag in its own header.  Epochs count up for ever, so flags never
+// have to be reset; mail is double-buffered by epoch parity because a peer may enter the next barrier (and publish
+// again) while this rank still reads the mail of the current one.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(32) k_fabric_barrier(Peers P, Publish pub) {
+    const int q = threadIdx.x, me = P.rank, W = P.world;
+    FabricHdr* mine = hdr_of(P, me);
+    const uint32_t e = mine->epoch + 1u, par = e & 1u;
+    if (q < W) {
+        FabricHdr* peer = hdr_of(P, q);
+#pragma unroll
+        for (int k = 0; k < kMailSlots; ++k)
+            if (pub.scalar[k]) st_sys(&peer->mail[par][me][k], *pub.scalar[k]);
+        if (pub.per_dst) st_sys(&peer->mail[par][me][M_SENT_TO_YOU], pub.per_dst[q]);
+        if (pub.bcast)
+            for (int d = 0; d < W; ++d) st_sys(&peer->sent[par][me][d], pub.bcast[d]);
+        __threadfence_system();
+        st_release_sys(&peer->flag[me], e);
+        // a peer that never arrives must not hang the GPU: after the timeout the fabric is dead, and no later barrier waits
+        const unsigned long long t0 = global_timer_ns();
+        while ((int32_t) (ld_acquire_sys(&mine->flag[q]) - e) < 0) {
+            if (ld_relaxed_sys(&mine->dead) || global_timer_ns() - t0 > pub.timeout_ns) {
+                atomicOr(&mine->error, (uint32_t) FE_TIMEOUT);
+                if (atomicExch(&mine->dead, 1u) == 0u) {
+                    mine->dead_epoch = e;
+                    mine->dead_peer = (uint32_t) q;
+                }
+                break;
+            }
+            __nanosleep(64);
+        }
+    }
+    __syncwarp();
+    if (q == 0) {
+        if (pub.bookkeeping) {   // after a resolution round: is any victim still open anywhere?
+            uint32_t open = 0;
+            for (int p = 0; p < W; ++p) open += mine->mail[par][p][M_UNSETTLED];
+            if (open == 0u && mine->rounds_needed[pub.pass] == 0u) mine->rounds_needed[pub.pass] = (uint32_t) pub.round + 1u;
+            if (open != 0u && pub.round == pub.last_round) atomicOr(&mine->error, (uint32_t) FE_ROUNDS);
+        }
+        __threadfence();
+        mine->epoch = e;
+    }
+}
+
+void launch_fabric_barrier(Launch& L, Peers P, Publish pub) {
+    k_fabric_barrier<<<1, 32, 0, L.stream>>>(P, pub);
+    L.count++;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Containment events -> the rank that owns the victim pile (fused all-to-all: every event is stored straight
+// into the owner's inbox, block = this rank).  Slots come from a local counter per destination, one atomic per
+// destination and warp.  The counter keeps counting beyond the capacity, so it is also the observed demand.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_route_events(Peers P, ArenaLayout A, Events ev, const uint32_t* __restrict__ n_events,
+                                                     uint32_t ev_cap, uint32_t* __restrict__ out_cnt) {
+    const uint32_t n = min(*n_events, ev_cap), lane = lane_id();
+    const uint32_t me = (uint32_t) P.rank;
+    for (uint32_t base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {   // block-uniform bound: full warps vote
+        const uint32_t i = base + threadIdx.x;
+        const bool ok = i < n;
+        uint32_t v = 0, c = 0, t = 0, q = 0;
+        if (ok) {
+            v = ev.v[i]; c = ev.c[i]; t = ev.t[i];
+            q = min(v / A.ppr, (uint32_t) P.world - 1u);
+        }
+        const uint32_t active = __ballot_sync(0xFFFFFFFFu, ok);
+        if (ok) {
+            const uint32_t peers = __match_any_sync(active, q);
+            const uint32_t leader = __ffs(peers) - 1u, rank = __popc(peers & ((1u << lane) - 1u));
+            uint32_t slot = 0;
+            if (lane == leader) slot = atomicAdd(&out_cnt[q], (uint32_t) __popc(peers));
+            slot = __shfl_sync(peers, slot, leader) + rank;
+            if (slot < A.cap_ev) {
+                uint32_t* blk = section<uint32_t>(P, (int) q, A.ev_inbox) + (size_t) me * 3u * A.cap_ev;
+                blk[slot] = v;
+                blk[(size_t) A.cap_ev + slot] = c;
+                blk[2 * (size_t) A.cap_ev + slot] = t;
+            }
+        }
+    }
+}
+
+void launch_route_events(Launch& L, Peers P, ArenaLayout A, Events ev, const uint32_t* n_events, uint32_t ev_cap, uint32_t* out_cnt) {
+    k_route_events<<<grid_for(ev_cap, 256, kNumSMs * 4), 256, 0, L.stream>>>(P, A, ev, n_events, ev_cap, out_cnt);
+    L.count++;
+}
+
+// inbox blocks (counts in the mail of the barrier just passed) -> one local event list, per-victim histogram for the
+// counting sort, earliest event time per victim (initial lower bound of its death time).  blockIdx.y = source rank.
+__global__ void __launch_bounds__(256) k_gather_events(Peers P, ArenaLayout A, Events ev, uint32_t ev_cap, uint32_t* __restrict__ n_events_out,
+                                                      uint32_t* __restrict__ vcount, uint32_t* __restrict__ tmin) {
+    FabricHdr* mine = hdr_of(P, P.rank);
+    const uint32_t par = mine->epoch & 1u, src = blockIdx.y;
+    uint32_t offset = 0;
+    for (uint32_t p = 0; p < src; ++p) offset += min(mine->mail[par][p][M_SENT_TO_YOU], A.cap_ev);
+    const uint32_t sent = mine->mail[par][src][M_SENT_TO_YOU], n = min(sent, A.cap_ev);
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        if (sent > A.cap_ev || offset + n > ev_cap) atomicOr(&mine->error, (uint32_t) FE_INBOX);
+        if (src == (uint32_t) P.world - 1u) *n_events_out = min(offset + n, ev_cap);
+    }
+    const uint32_t* blk = section<uint32_t>(P, P.rank, A.ev_inbox) + (size_t) src * 3u * A.cap_ev;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        if (offset + i >= ev_cap) break;
+        const uint32_t v = blk[i], c = blk[(size_t) A.cap_ev + i], t = blk[2 * (size_t) A.cap_ev + i];
+        ev.v[offset + i] = v;
+        ev.c[offset + i] = c;
+        ev.t[offset + i] = t;
+        if (v < A.n_piles) {
+            atomicAdd(&vcount[v], 1u);
+            atomicMin(&tmin[v], t);
+        }
+    }
+}
+
+void launch_gather_events(Launch& L, Peers P, ArenaLayout A, Events ev, uint32_t ev_cap, uint32_t* n_events_out, uint32_t* vcount,
+                          uint32_t* tmin) {
+    dim3 grid(grid_for(A.cap_ev, 256, kNumSMs), P.world);
+    k_gather_events<<<grid, 256, 0, L.stream>>>(P, A, ev, ev_cap, n_events_out, vcount, tmin);
+    L.count++;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Distributed ordered containment.  Same monotone state word per pile as containment.cu
+//     S[x] = h (bit 31 clear)   open: x cannot die before time h        S[x] = 0x80000000 | t   settled (t = 0x7FFFFFFF: never)
+// replicated on every rank.  A rank resolves the piles it OWNS (it holds all their events) and pushes every change
+// of their state to all replicas with a remote max-reduction; states of foreign piles are only read.  A victim whose
+// earliest open event hangs on a foreign container that is still open stays on the worklist for the next round.
+// ---------------------------------------------------------------------------------------------
+constexpr uint32_t kSettled = 0x80000000u;
+constexpr uint32_t kNever = 0x7FFFFFFFu;
+constexpr uint32_t kDeadEvent = 0xFFFFFFFFu;
+constexpr int kChaseDepth = 24;
+constexpr int kChaseBudget = 96;
+
+// scatter the gathered events into their victim's segment; initialise the states of the OWNED piles and the worklist
+__global__ void __launch_bounds__(256) k_fabric_prepare(Peers P, ArenaLayout A, Events ev, const uint32_t* __restrict__ n_events, uint32_t ev_cap,
+                                                       uint32_t* __restrict__ vcursor, uint32_t* __restrict__ seg_c, uint32_t* __restrict__ seg_t,
+                                                       const uint32_t* __restrict__ vstart, const uint32_t* __restrict__ tmin,
+                                                       uint32_t* __restrict__ work, uint32_t* __restrict__ n_work, uint32_t fill_blocks) {
+    if (blockIdx.x < fill_blocks) {
+        const uint32_t n = min(*n_events, ev_cap);
+        const uint32_t stride = fill_blocks * blockDim.x;
+        for (uint32_t i0 = blockIdx.x * blockDim.x + threadIdx.x; i0 < n; i0 += 4u * stride) {
+            uint32_t v[4], c[4], t[4], p[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const uint32_t i = i0 + k * stride;
+                if (i < n) { v[k] = ev.v[i]; c[k] = ev.c[i]; t[k] = ev.t[i]; }
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (i0 + k * stride < n) p[k] = atomicAdd(&vcursor[v[k]], 1u);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                if (i0 + k * stride < n) {
+                    seg_c[p[k]] = c[k];
+                    seg_t[p[k]] = t[k];
+                }
+            }
+        }
+        return;
+    }
+    uint32_t* S = section<uint32_t>(P, P.rank, A.S);
+    const uint32_t lo = min((uint32_t) P.rank * A.ppr, A.n_piles), hi = min(lo + A.ppr, A.n_piles);
+    const uint32_t init_blocks = gridDim.x - fill_blocks, b = blockIdx.x - fill_blocks;
+    for (uint32_t base = lo + b * blockDim.x; base < hi; base += init_blocks * blockDim.x) {
+        const uint32_t x = base + threadIdx.x;
+        bool victim = false;
+        if (x < hi) {
+            victim = vstart[x + 1] != vstart[x];
+            S[x] = victim ? min(tmin[x], kNever - 1u) : (kSettled | kNever);
+        }
+        const uint32_t m = __ballot_sync(0xFFFFFFFFu, victim);
+        if (m) {
+            uint32_t gb = 0;
+            if (lane_id() == 0) gb = atomicAdd(n_work, (uint32_t) __popc(m));
+            gb = __shfl_sync(0xFFFFFFFFu, gb, 0);
+            if (victim) work[gb + __popc(m & ((1u << lane_id()) - 1u))] = x;
+        }
+    }
+}
+
+void launch_fabric_prepare(Launch& L, Peers P, ArenaLayout A, Events ev, const uint32_t* n_events, uint32_t ev_cap, ResolveBufs rb,
+                           const uint32_t* tmin) {
+    const int fill_blocks = grid_for(ev_cap, 1024, kNumSMs * 2), init_blocks = grid_for(A.ppr, 256, kNumSMs * 2);
+    k_fabric_prepare<<<fill_blocks + init_blocks, 256, 0, L.stream>>>(P, A, ev, n_events, ev_cap, rb.vcursor, rb.seg_c, rb.seg_t, rb.vstart,
+                                                                    tmin, rb.work0, rb.n_work, (uint32_t) fill_blocks);
+    L.count++;
+}
+
+// the initial states of the owned piles -> every replica (coalesced 16-byte stores; ppr is a multiple of 32)
+__global__ void __launch_bounds__(256) k_push_slice(Peers P, ArenaLayout A) {
+    const uint32_t lo = min((uint32_t) P.rank * A.ppr, A.n_piles), hi = min(lo + A.ppr, A.n_piles);
+    const uint32_t* S = section<uint32_t>(P, P.rank, A.S);
+    const uint32_t n4 = (hi - lo) / 4u;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += gridDim.x * blockDim.x) {
+        const uint4 v = reinterpret_cast<const uint4*>(S + lo)[i];
+        for (int q = 0; q < P.world; ++q)
+            if (q != P.rank) reinterpret_cast<uint4*>(section<uint32_t>(P, q, A.S) + lo)[i] = v;
+    }
+    if (blockIdx.x == 0) {
+        for (uint32_t x = lo + 4u * n4 + threadIdx.x; x < hi; x += blockDim.x)
+            for (int q = 0; q < P.world; ++q)
+                if (q != P.rank) section<uint32_t>(P, q, A.S)[x] = S[x];
+    }
+}
+
+void launch_push_slice(Launch& L, Peers P, ArenaLayout A) {
+    if (P.world == 1) return;
+    k_push_slice<<<grid_for(A.ppr / 4, 256, kNumSMs * 2), 256, 0, L.stream>>>(P, A);
+    L.count++;
+}
+
+// raise the state of an OWNED pile; a change is pushed to every replica
+__device__ __forceinline__ void raise_state(const Peers& P, const ArenaLayout& A, uint32_t* S, uint32_t x, uint32_t val) {
+    const uint32_t old = atomicMax(&S[x], val);
+    if (old < val)
+        for (int q = 0; q < P.world; ++q)
+            if (q != P.rank) red_max_sys(section<uint32_t>(P, q, A.S) + x, val);
+}
+
+// Settle victim v0 (owned).  Returns false when it has to wait: for a foreign container whose fate is open, or
+// because the chase budget ran out.
+__device__ __forceinline__ bool resolve_owned(const Peers& P, const ArenaLayout& A, uint32_t v0, uint32_t lo, uint32_t hi,
+                                              const uint32_t* __restrict__ vstart, const uint32_t* __restrict__ seg_c,
+                                              uint32_t* __restrict__ seg_t, uint32_t* __restrict__ S) {
+    uint32_t stack_v[kChaseDepth], stack_need[kChaseDepth];
+    int sp = 0, budget = kChaseBudget;
+    stack_v[0] = v0;
+    stack_need[0] = kNever;
+    while (sp >= 0) {
+        const uint32_t v = stack_v[sp];
+        if (ld_relaxed_sys(&S[v]) & kSettled) { --sp; continue; }
+        const uint32_t s0 = vstart[v], s1 = vstart[v + 1];
+        uint32_t best_t = kDeadEvent, best_p = 0;
+        for (uint32_t p = s0; p < s1; ++p) {
+            const uint32_t t = seg_t[p];
+            if (t < best_t) { best_t = t; best_p = p; }
+        }
+        if (best_t == kDeadEvent) {               // every event found its container dead: v is never killed
+            raise_state(P, A, S, v, kSettled | kNever);
+            --sp;
+            continue;
+        }
+        raise_state(P, A, S, v, best_t);          // v cannot die before its earliest open event
+        if (best_t > stack_need[sp]) { --sp; continue; }
+        const uint32_t c = seg_c[best_p];
+        const uint32_t q = c == v ? kSettled | kNever : ld_relaxed_sys(&S[c]);   // a == b record: the pile is its own (alive) container
+        if (q & kSettled) {
+            if ((q & kNever) > best_t) {          // container alive at best_t: the event fires
+                raise_state(P, A, S, v, kSettled | best_t);
+                --sp;
+            } else {
+                seg_t[best_p] = kDeadEvent;       // container died first: the event never fires; look again
+            }
+            continue;
+        }
+        if (q > best_t) {                         // open, but certainly alive at best_t
+            raise_state(P, A, S, v, kSettled | best_t);
+            --sp;
+            continue;
+        }
+        if (c < lo || c >= hi) return false;      // foreign and open: its owner will tell
+        if (sp + 1 >= kChaseDepth || --budget <= 0) return false;
+        ++sp;
+        stack_v[sp] = c;
+        stack_need[sp] = best_t;
+    }
+    return true;
+}
+
+// one round over the worklist of open owned victims: in = work[round & 1], out = the other one; three rotating counters
+__global__ void __launch_bounds__(256) k_fabric_round(Peers P, ArenaLayout A, const uint32_t* __restrict__ vstart,
+                                                     const uint32_t* __restrict__ seg_c, uint32_t* __restrict__ seg_t,
+                                                     uint32_t* __restrict__ work0, uint32_t* __restrict__ work1,
+                                                     uint32_t* __restrict__ n_work, uint32_t round) {
+    uint32_t* S = section<uint32_t>(P, P.rank, A.S);
+    const uint32_t lo = min((uint32_t) P.rank * A.ppr, A.n_piles), hi = min(lo + A.ppr, A.n_piles);
+    const uint32_t n = n_work[round % 3u];
+    const uint32_t* in = (round & 1u) ? work1 : work0;
+    uint32_t* out = (round & 1u) ? work0 : work1;
+    uint32_t* n_out = &n_work[(round + 1u) % 3u];
+    if (blockIdx.x == 0 && threadIdx.x == 0) n_work[(round + 2u) % 3u] = 0u;   // read last in round - 1, written next in round + 1
+    const uint32_t lane = lane_id();
+    for (uint32_t base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
+        const uint32_t i = base + threadIdx.x;
+        uint32_t v = 0;
+        bool keep = false;
+        if (i < n) {
+            v = in[i];
+            keep = !resolve_owned(P, A, v, lo, hi, vstart, seg_c, seg_t, S);
+        }
+        const uint32_t m = __ballot_sync(0xFFFFFFFFu, keep);
+        if (m) {
+            uint32_t gb = 0;
+            if (lane == 0) gb = atomicAdd(n_out, (uint32_t) __popc(m));
+            gb = __shfl_sync(0xFFFFFFFFu, gb, 0);
+            if (keep) out[gb + __popc(m & ((1u << lane) - 1u))] = v;
+        }
+    }
+}
+
+void launch_fabric_round(Launch& L, Peers P, ArenaLayout A, ResolveBufs rb, uint32_t round) {
+    k_fabric_round<<<grid_for(A.ppr, 256, kNumSMs * 2), 256, 0, L.stream>>>(P, A, rb.vstart, rb.seg_c, rb.seg_t, rb.work0, rb.work1,
+                                                                          rb.n_work, round);
+    L.count++;
+}
+
+// time bases of the local lists in the final containment pass (graph.cpp:831-866): position in the GLOBAL
+// overlaps ++ internals order, from the list counts every rank published in the barrier just passed
+__global__ void k_time_bases_mail(Peers P, uint32_t* __restrict__ bases) {
+    if (blockIdx.x || threadIdx.x) return;
+    const FabricHdr* mine = hdr_of(P, P.rank);
+    const uint32_t par = mine->epoch & 1u;
+    uint32_t total_ovl = 0, ovl_before = 0, int_before = 0;
+    for (int q = 0; q < P.world; ++q) {
+        if (q < P.rank) {
+            ovl_before += mine->mail[par][q][M_NOVL];
+            int_before += mine->mail[par][q][M_NINL];
+        }
+        total_ovl += mine->mail[par][q][M_NOVL];
+    }
+    bases[0] = ovl_before;
+    bases[1] = total_ovl + int_before;
+}
+
+void launch_time_bases_mail(Launch& L, Peers P, uint32_t* bases) {
+    k_time_bases_mail<<<1, 32, 0, L.stream>>>(P, bases);
+    L.count++;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Build stage.  Nodes are owned by the rank that owns their pile: node_begin[q] = 2 * (alive piles below q * ppr),
+// a popcount over the liveness bitmap (one word per 32 piles, ppr is a multiple of 32).  Block q computes entry q.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_node_bounds(Peers P, ArenaLayout A, const uint32_t* __restrict__ alive_bits, BuildMeta* __restrict__ meta) {
+    __shared__ uint32_t s_sum[8];
+    const uint32_t q = blockIdx.x;
+    const uint32_t piles_below = min(q * A.ppr, A.n_piles);
+    const uint32_t words = piles_below / 32u, tail = piles_below & 31u;
+    uint32_t local = 0;
+    for (uint32_t w = threadIdx.x; w < words; w += blockDim.x) local += __popc(alive_bits[w]);
+    if (threadIdx.x == 0 && tail) local += __popc(alive_bits[words] & ((1u << tail) - 1u));
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) local += __shfl_xor_sync(0xFFFFFFFFu, local, d);
+    if (lane_id() == 0) s_sum[warp_id()] = local;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t total = 0;
+        for (int w = 0; w < 8; ++w) total += s_sum[w];
+        meta->node_begin[q] = 2u * total;
+    }
+}
+
+void launch_node_bounds(Launch& L, Peers P, ArenaLayout A, const uint32_t* alive_bits, BuildMeta* meta) {
+    k_node_bounds<<<P.world + 1, 256, 0, L.stream>>>(P, A, alive_bits, meta);
+    L.count++;
+}
+
+// zero bytes [0, *n_ptr rounded up to 16) of a 256-byte padded buffer
+__global__ void k_clear_bytes16(uint8_t* __restrict__ p, const uint32_t* __restrict__ n_ptr, uint32_t cap) {
+    const uint32_t n16 = (min(*n_ptr, cap) + 15u) / 16u;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += gridDim.x * blockDim.x)
+        reinterpret_cast<uint4*>(p)[i] = make_uint4(0u, 0u, 0u, 0u);
+}
+
+void launch_clear_bytes16(Launch& L, uint8_t* p, const uint32_t* n_ptr, uint32_t cap) {
+    k_clear_bytes16<<<grid_for(cap / 16 + 1, 256, kNumSMs * 2), 256, 0, L.stream>>>(p, n_ptr, cap);
+    L.count++;
+}
+
+__device__ __forceinline__ uint32_t owner_of(const uint32_t* bounds, uint32_t world, uint32_t x) {   // bounds[q] <= x < bounds[q + 1]
+    uint32_t q = 0;
+    while (q + 1u < world && x >= bounds[q + 1u]) ++q;
+    return q;
+}
+
+// Edges -> the rank that owns their source node (src | dst | len | LOCAL edge id; the receiver adds the emitting
+// rank's id base, which it learns from the edge counts published in the same barrier).
+__global__ void __launch_bounds__(256) k_route_edges(Peers P, ArenaLayout A, const uint32_t* __restrict__ src, const uint32_t* __restrict__ dst,
+                                                    const uint32_t* __restrict__ len, const uint32_t* __restrict__ n_edges, uint32_t edge_cap,
+                                                    const BuildMeta* __restrict__ meta, uint32_t* __restrict__ out_cnt) {
+    __shared__ uint32_t s_bounds[kMaxRanks + 1];
+    if (threadIdx.x <= (uint32_t) P.world) s_bounds[threadIdx.x] = meta->node_begin[threadIdx.x];
+    __syncthreads();
+    const uint32_t n = min(*n_edges, edge_cap), lane = lane_id(), me = (uint32_t) P.rank;
+    for (uint32_t base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
+        const uint32_t e = base + threadIdx.x;
+        const bool ok = e < n;
+        uint32_t s = 0, d = 0, l = 0, q = 0;
+        if (ok) {
+            s = src[e]; d = dst[e]; l = len[e];
+            q = owner_of(s_bounds, (uint32_t) P.world, s);
+        }
+        const uint32_t active = __ballot_sync(0xFFFFFFFFu, ok);
+        if (ok) {
+            const uint32_t peers = __match_any_sync(active, q);
+            const uint32_t leader = __ffs(peers) - 1u, rank = __popc(peers & ((1u << lane) - 1u));
+            uint32_t slot = 0;
+            if (lane == leader) slot = atomicAdd(&out_cnt[q], (uint32_t) __popc(peers));
+            slot = __shfl_sync(peers, slot, leader) + rank;
+            if (slot < A.cap_edge) {
+                uint32_t* blk = section<uint32_t>(P, (int) q, A.edge_inbox) + (size_t) me * 4u * A.cap_edge;
+                blk[slot] = s;
+                blk[(size_t) A.cap_edge + slot] = d;
+                blk[2 * (size_t) A.cap_edge + slot] = l;
+                blk[3 * (size_t) A.cap_edge + slot] = e;
+            }
+        }
+    }
+}
+
+void launch_route_edges(Launch& L, Peers P, ArenaLayout A, const uint32_t* src, const uint32_t* dst, const uint32_t* len,
+                        const uint32_t* n_edges, uint32_t edge_cap, const BuildMeta* meta, uint32_t* out_cnt) {
+    k_route_edges<<<grid_for(edge_cap, 256, kNumSMs * 4), 256, 0, L.stream>>>(P, A, src, dst, len, n_edges, edge_cap, meta, out_cnt);
+    L.count++;
+}
+
+// after the edge barrier: global edge-id bases (edge counts of the emitting ranks), slice sizes (column sums of the
+// send-count matrix) and slice offsets of the replicated CSR
+__global__ void k_edge_meta(Peers P, ArenaLayout A, BuildMeta* __restrict__ meta, uint32_t* __restrict__ counters) {
+    if (blockIdx.x || threadIdx.x) return;
+    FabricHdr* mine = hdr_of(P, P.rank);
+    const uint32_t par = mine->epoch & 1u;
+    uint32_t base = 0, off = 0, widest = 0;
+    bool overflow = false;
+    for (int q = 0; q < P.world; ++q) {
+        meta->eid_base[q] = base;
+        base += mine->mail[par][q][M_NEDGES];
+        uint32_t slice = 0, wanted = 0;
+        for (int p = 0; p < P.world; ++p) {
+            const uint32_t s = mine->sent[par][p][q];
+            if (s > A.cap_edge) overflow = true;
+            slice += min(s, A.cap_edge);
+            wanted += s;
+        }
+        widest = max(widest, wanted);
+        if (slice > A.cap_slice) { overflow = true; slice = A.cap_slice; }
+        meta->off[q] = off;
+        off += slice;
+    }
+    mine->demand[2] = widest;
+    meta->eid_base[P.world] = base;
+    meta->off[P.world] = off;
+    if (overflow) atomicOr(&mine->error, (uint32_t) FE_INBOX);
+    (void) counters;
+}
+
+void launch_edge_meta(Launch& L, Peers P, ArenaLayout A, BuildMeta* meta, uint32_t* counters) {
+    k_edge_meta<<<1, 32, 0, L.stream>>>(P, A, meta, counters);
+    L.count++;
+}
+
+// out-degree histogram of the owned rows over the received edges (blockIdx.y = emitting rank)
+__global__ void __launch_bounds__(256) k_inbox_degree(Peers P, ArenaLayout A, const BuildMeta* __restrict__ meta, uint32_t* __restrict__ degree) {
+    const FabricHdr* mine = hdr_of(P, P.rank);
+    const uint32_t par = mine->epoch & 1u, from = blockIdx.y;
+    const uint32_t n = min(mine->sent[par][from][P.rank], A.cap_edge);
+    const uint32_t nb = meta->node_begin[P.rank], owned = meta->node_begin[P.rank + 1] - nb;
+    const uint32_t* blk = section<uint32_t>(P, P.rank, A.edge_inbox) + (size_t) from * 4u * A.cap_edge;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint32_t row = blk[i] - nb;
+        if (row < owned) atomicAdd(&degree[row], 1u);
+    }
+}
+
+void launch_inbox_degree(Launch& L, Peers P, ArenaLayout A, const BuildMeta* meta, uint32_t* degree) {
+    dim3 grid(grid_for(A.cap_edge, 256, kNumSMs), P.world);
+    k_inbox_degree<<<grid, 256, 0, L.stream>>>(P, A, meta, degree);
+    L.count++;
+}
+
+// scatter the received edges into the rows of this rank's slice of the replicated CSR (slot order inside a row is
+// arbitrary, as in k_fill_csr).  col_eid[pos] = GLOBAL edge id (the transitive kernels break ties between parallel
+// edges by it, graph.cpp:1291-1293, and address their result bytes with it); T[that id] is cleared on the way.
+__global__ void __launch_bounds__(256) k_inbox_fill(Peers P, ArenaLayout A, const BuildMeta* __restrict__ meta, uint32_t* __restrict__ cursor,
+                                                   uint32_t* __restrict__ col_eid, uint8_t* __restrict__ T) {
+    const FabricHdr* mine = hdr_of(P, P.rank);
+    const uint32_t par = mine->epoch & 1u, from = blockIdx.y;
+    const uint32_t n = min(mine->sent[par][from][P.rank], A.cap_edge);
+    const uint32_t nb = meta->node_begin[P.rank], owned = meta->node_begin[P.rank + 1] - nb;
+    const uint32_t off = meta->off[P.rank], slice = meta->off[P.rank + 1] - off, id_base = meta->eid_base[from];
+    const uint32_t* blk = section<uint32_t>(P, P.rank, A.edge_inbox) + (size_t) from * 4u * A.cap_edge;
+    uint2* col = section<uint2>(P, P.rank, A.col);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint32_t row = blk[i] - nb;
+        if (row >= owned) continue;
+        const uint32_t p = atomicAdd(&cursor[row], 1u);
+        if (p >= slice) continue;
+        const uint32_t e = id_base + blk[3 * (size_t) A.cap_edge + i];
+        col[off + p] = make_uint2(blk[(size_t) A.cap_edge + i], blk[2 * (size_t) A.cap_edge + i]);
+        col_eid[off + p] = e;
+        T[e] = 0;
+    }
+}
+
+void launch_inbox_fill(Launch& L, Peers P, ArenaLayout A, const BuildMeta* meta, uint32_t* cursor, uint32_t* col_eid, uint8_t* T) {
+    dim3 grid(grid_for(A.cap_edge, 256, kNumSMs), P.world);
+    k_inbox_fill<<<grid, 256, 0, L.stream>>>(P, A, meta, cursor, col_eid, T);
+    L.count++;
+}
+
+// this rank's slice -> every replica: row offsets (rebased to the slice's position) and (dst, len) entries, as
+// coalesced stores; blockIdx.y = destination rank (the own replica only needs the row offsets)
+__global__ void __launch_bounds__(256) k_push_csr(Peers P, ArenaLayout A, const BuildMeta* __restrict__ meta, const uint32_t* __restrict__ row_ptr_local) {
+    const int q = blockIdx.y;
+    const uint32_t nb = meta->node_begin[P.rank], owned = meta->node_begin[P.rank + 1] - nb;
+    const uint32_t off = meta->off[P.rank], slice = meta->off[P.rank + 1] - off;
+    uint32_t* rp = section<uint32_t>(P, q, A.row_ptr);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i <= owned; i += gridDim.x * blockDim.x)
+        if (nb + i <= A.n_nodes_max) rp[nb + i] = off + min(row_ptr_local[i], slice);
+    if (q == P.rank) return;
+    const uint2* mine = section<uint2>(P, P.rank, A.col) + off;
+    uint2* theirs = section<uint2>(P, q, A.col) + off;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < slice; i += gridDim.x * blockDim.x) theirs[i] = mine[i];
+}
+
+void launch_push_csr(Launch& L, Peers P, ArenaLayout A, const BuildMeta* meta, const uint32_t* row_ptr_local) {
+    dim3 grid(grid_for(A.cap_slice, 1024, kNumSMs), P.world);
+    k_push_csr<<<grid, 256, 0, L.stream>>>(P, A, meta, row_ptr_local);
+    L.count++;
+}
+
+// T(e) = 1 results of the owned candidate edges -> the rank that emitted e (its T_in byte array, indexed by local edge id)
+__global__ void __launch_bounds__(256) k_route_marks(Peers P, ArenaLayout A, const BuildMeta* __restrict__ meta, const uint8_t* __restrict__ T,
+                                                    const uint32_t* __restrict__ col_eid) {
+    __shared__ uint32_t s_base[kMaxRanks + 1];
+    if (threadIdx.x <= (uint32_t) P.world) s_base[threadIdx.x] = meta->eid_base[threadIdx.x];
+    __syncthreads();
+    const uint32_t off = meta->off[P.rank], slice = meta->off[P.rank + 1] - off;
+    for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < slice; p += gridDim.x * blockDim.x) {
+        const uint32_t e = col_eid[off + p];
+        if (!T[e]) continue;
+        const uint32_t r = owner_of(s_base, (uint32_t) P.world, e);
+        const uint32_t local = e - s_base[r];
+        if (local < A.t_cap) section<uint8_t>(P, (int) r, A.T_in)[local] = 1;
+    }
+}
+
+void launch_route_marks(Launch& L, Peers P, ArenaLayout A, const BuildMeta* meta, const uint8_t* T, const uint32_t* col_eid) {
+    k_route_marks<<<grid_for(A.cap_slice, 256, kNumSMs * 4), 256, 0, L.stream>>>(P, A, meta, T, col_eid);
+    L.count++;
+}
+
+// observed demands of this step, for the capacity planning of the host (max over the destinations)
+__global__ void k_fabric_demand(Peers P, const uint32_t* __restrict__ ev_cnt0, const uint32_t* __restrict__ ev_cnt1,
+                                const uint32_t* __restrict__ edge_cnt, const BuildMeta* __restrict__ meta) {
+    if (blockIdx.x || threadIdx.x) return;
+    FabricHdr* mine = hdr_of(P, P.rank);
+    uint32_t ev = 0, ed = 0;
+    for (int q = 0; q < P.world; ++q) {
+        ev = max(ev, max(ev_cnt0[q], ev_cnt1[q]));
+        ed = max(ed, edge_cnt[q]);
+    }
+    mine->demand[0] = ev;
+    mine->demand[1] = ed;
+    (void) meta;
+}
+
+void launch_demand(Launch& L, Peers P, const uint32_t* ev_cnt0, const uint32_t* ev_cnt1, const uint32_t* edge_cnt, const BuildMeta* meta) {
+    k_fabric_demand<<<1, 32, 0, L.stream>>>(P, ev_cnt0, ev_cnt1, edge_cnt, meta);
+    L.count++;
+}
+
+// CUDA loads kernels lazily, at their first launch, and that load waits for the device to drain: fatal when the
+// first launch of a kernel happens while another rank's barrier kernel is spinning on the same device (ranks sharing
+// a GPU) — the barrier waits for this rank, this rank's kernel waits for the barrier.  rala_b200_create loads them all.
+void preload_fabric() {
+    cudaFuncAttributes a;
+    cudaFuncGetAttributes(&a, k_fabric_barrier);
+    cudaFuncGetAttributes(&a, k_route_events);
+    cudaFuncGetAttributes(&a, k_gather_events);
+    cudaFuncGetAttributes(&a, k_fabric_prepare);
+    cudaFuncGetAttributes(&a, k_push_slice);
+    cudaFuncGetAttributes(&a, k_fabric_round);
+    cudaFuncGetAttributes(&a, k_time_bases_mail);
+    cudaFuncGetAttributes(&a, k_node_bounds);
+    cudaFuncGetAttributes(&a, k_clear_bytes16);
+    cudaFuncGetAttributes(&a, k_route_edges);
+    cudaFuncGetAttributes(&a, k_edge_meta);
+    cudaFuncGetAttributes(&a, k_inbox_degree);
+    cudaFuncGetAttributes(&a, k_inbox_fill);
+    cudaFuncGetAttributes(&a, k_push_csr);
+    cudaFuncGetAttributes(&a, k_route_marks);
+    cudaFuncGetAttributes(&a, k_fabric_demand);
+}
+
+}  // namespace rb

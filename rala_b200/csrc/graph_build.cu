@@ -107,8 +107,10 @@ __global__ void __launch_bounds__(kTileThreads) k_emit_edges(List ovl, const uin
                 reinterpret_cast<uint2*>(src)[j] = make_uint2(e_src[r], e_dst[r] ^ 1u);
                 reinterpret_cast<uint2*>(dst)[j] = make_uint2(e_dst[r], e_src[r] ^ 1u);
                 reinterpret_cast<uint2*>(len)[j] = make_uint2(e_len[r], c_len[r]);
-                atomicAdd(&degree[e_src[r]], 1u);
-                atomicAdd(&degree[e_dst[r] ^ 1u], 1u);
+                if (degree) {   // nullptr: the edges are routed to the owners of their source nodes, who count them
+                    atomicAdd(&degree[e_src[r]], 1u);
+                    atomicAdd(&degree[e_dst[r] ^ 1u], 1u);
+                }
             }
         }
         __syncthreads();
@@ -369,6 +371,22 @@ void launch_build_csr(Launch& L, GraphArrays g, uint32_t n_nodes_max, uint32_t e
     k_fill_csr<<<grid_for(edge_cap, 256, kNumSMs * 8), 256, 0, L.stream>>>(g.src, g.dst, g.len, counters + C_EDGES,
                                                                             edge_cap, g.cursor, g.col, g.col_eid, g.T);
     L.count++;
+}
+
+// CUDA loads kernels lazily, at their first launch, and that load waits for the device to drain: fatal when the
+// first launch of a kernel happens while another rank's barrier kernel is spinning on the same device (ranks sharing
+// a GPU) — the barrier waits for this rank, this rank's kernel waits for the barrier.  rala_b200_create loads them all.
+void preload_graph_build() {
+    cudaFuncAttributes a;
+    cudaFuncGetAttributes(&a, k_node_ids);
+    cudaFuncGetAttributes(&a, k_emit_edges);
+    cudaFuncGetAttributes(&a, k_degree_hist);
+    cudaFuncGetAttributes(&a, k_scan_degrees);
+    cudaFuncGetAttributes(&a, k_fill_csr);
+    cudaFuncGetAttributes(&a, k_pack_edges);
+    cudaFuncGetAttributes(&a, k_export_padded);
+    cudaFuncGetAttributes(&a, k_import_gathered);
+    cudaFuncGetAttributes(&a, k_time_bases);
 }
 
 }  // namespace rb

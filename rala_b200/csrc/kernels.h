@@ -142,4 +142,12 @@ void launch_node_range(Launch& L, GraphArrays g, const uint32_t* counters, uint3
 void launch_finalize_marks(Launch& L, GraphArrays g, uint32_t edge_cap, uint32_t* counters, uint8_t* marked_copy /* nullable */,
                            uint32_t copy_cap);
 
+// force-load every kernel of a translation unit (CUDA's lazy loading otherwise loads at the first launch, which waits
+// for the device to drain: a deadlock next to a spinning barrier kernel, see fabric.cu)
+void preload_classify();
+void preload_containment();
+void preload_graph_build();
+void preload_transitive();
+void preload_fabric();
+
 }  // namespace rb

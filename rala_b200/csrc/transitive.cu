@@ -781,4 +781,16 @@ void launch_finalize_marks(Launch& L, GraphArrays g, uint32_t edge_cap, uint32_t
     L.count++;
 }
 
+// CUDA loads kernels lazily, at their first launch, and that load waits for the device to drain: fatal when the
+// first launch of a kernel happens while another rank's barrier kernel is spinning on the same device (ranks sharing
+// a GPU) — the barrier waits for this rank, this rank's kernel waits for the barrier.  rala_b200_create loads them all.
+void preload_transitive() {
+    cudaFuncAttributes a;
+    cudaFuncGetAttributes(&a, k_transitive_group);
+    cudaFuncGetAttributes(&a, k_transitive_light);
+    cudaFuncGetAttributes(&a, k_transitive_heavy);
+    cudaFuncGetAttributes(&a, k_finalize_marks);
+    cudaFuncGetAttributes(&a, k_node_range);
+}
+
 }  // namespace rb

@@ -3,6 +3,10 @@ import sys
 
 import pytest
 
+# several ranks of the multi-GPU session share device 0 in the GPU suite and wait for each other inside kernels:
+# every stream needs its own hardware queue (must be set before CUDA is initialised)
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)

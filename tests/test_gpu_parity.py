@@ -352,3 +352,70 @@ def test_full_size_config3_properties_and_oracle(ctx):
     assert_same(m, P.marked, "marks vs oracle")
     assert c["n_transitive_pairs"] == P.n_pairs
     G.close()
+
+
+def test_promotion_runs_after_a_retrim_without_a_new_pile_table(ctx):
+    """set_piles(changed) -> retrim -> retrim_promote with NO set_piles in between (what Graph.construct does when a
+    hill break changed the table and the first pit round changes nothing): retrim() trims the internals but does not
+    re-type them, so the promotion of graph.cpp:809-823 still has to happen."""
+    ds = synth.generate(genome_len=800_000, coverage=50, read_len=10000, len_sd=3000, seed=43, noise=30, chimera_frac=0.05,
+                        repeats=(2, 10, 3000))
+    piles = ds.flat_piles()
+    P = O.Pipeline(ds.records, piles).classify()
+    G = api.Graph(ctx)
+    G.set_piles(piles).set_hills(None).set_overlaps(ds.records)
+    G.classify()
+    assert P.int.shape[0] > 100, "the dataset needs internal (kX) overlaps"
+    # shrink the piles that internals touch: some internals now type as dovetails
+    shrunk = P.piles.copy()
+    ids = np.unique(P.int[:, :2])
+    alive = shrunk[ids, 1] > 0
+    shrunk[ids[alive], 0] += 600
+    shrunk[ids[alive], 1] -= 600
+    P.set_piles(shrunk).retrim()
+    n_before = P.ovl.shape[0]
+    changed = P.retrim_promote()
+    assert P.ovl.shape[0] > n_before, "the dataset must promote at least one internal"
+    G.set_piles(shrunk).retrim()
+    got_changed = G.retrim_promote()        # no set_piles since retrim()
+    ovl, inl = G.lists()
+    assert_same(ovl, P.ovl, "overlaps after the promotion")
+    assert_same(inl, P.int, "internals after the promotion")
+    assert got_changed == changed
+    G.close()
+
+
+def test_self_overlap_record_kills_its_pile_and_terminates(ctx):
+    """A record with a_id == b_id that types as a containment makes the pile its own container.  The reference resets
+    the pile (graph.cpp:469-480); the resolution must not wait for the pile's own fate."""
+    ds = synth.generate(300_000, 30, 10000, seed=52)
+    piles = ds.flat_piles()
+    survivors = np.nonzero(O.Pipeline(ds.records, piles).run().piles[:, 1])[0]
+    x, y = int(survivors[3]), int(survivors[11])          # two reads that survive without the self overlaps
+    extra = np.array([[x, x, 0, 9000, 100, 9100, 0], [y, y, 200, 9500, 200, 9500, 0]], np.uint32)   # type kA / kB
+    rec = np.concatenate([ds.records[:500], extra, ds.records[500:]])
+    P = O.Pipeline(rec, piles).run()
+    assert P.piles[x, 1] == 0 and P.piles[y, 1] == 0, "the reference kills a pile through its self overlap"
+    G = api.Graph(ctx)
+    G.set_piles(piles).set_hills(None).set_overlaps(rec)
+    G.run()
+    assert_same(G.piles(), P.piles, "pile liveness")
+    assert_same(G.edges(), P.edges, "edges")
+    assert_same(G.marked(), P.marked, "marks")
+    M = api.Multi([0, 0])
+    M.set_piles(piles).set_shards(rec).plan().run()
+    e, m = M.all_edges()
+    assert_same(M.piles(), P.piles, "pile liveness (2 ranks)")
+    assert_same(e, P.edges, "edges (2 ranks)")
+    assert_same(m, P.marked, "marks (2 ranks)")
+    M.close()
+    G.close()
+
+
+def test_pile_table_limits_are_enforced(ctx):
+    G = api.Graph(ctx)
+    with pytest.raises(api.RalaB200Error, match="2\\^30"):
+        G.set_piles(np.array([[15, 9985], [15, 1 << 30]], np.uint32))
+    with pytest.raises(api.RalaB200Error, match="begin"):
+        G.set_piles(np.array([[15, 9985], [9000, 100]], np.uint32))
+    G.close()
