@@ -35,7 +35,7 @@ WORKLOADS = {
     # name: (genome bp per GPU, coverage, read length, description)
     "c3": (100_000_000, 40, 10000, "configs[2]: synthetic 100 Mbp genome, 40x 10 kbp reads (~400k reads), shuffled read ids"),
     "c1": (5_000_000, 30, 10000, "configs[0]: synthetic 5 Mbp genome, 30x 10 kbp reads (~15k reads)"),
-    "c4s": (387_500_000, 30, 10000, "configs[3] shard: 3.1 Gbp / 8 per GPU, 30x 10 kbp reads"),
+    "c4s": (387_500_000, 30, 10000, "configs[3] shard: 3.1 Gbp / 8 per GPU, 30x 10 kbp reads (31.4 M overlap records per GPU, pairs listed once)"),
 }
 K1_BYTES_PER_OVERLAP = 41      # 24 read + 16 trimmed coords + 1 type (+ pile table amortised)
 K3_BYTES_PER_VISIT = 8         # each two-hop visit streams one (dst, len)
@@ -414,6 +414,10 @@ def main():
     ap.add_argument("--workload", default="c3", choices=list(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true", help="device-resident timing only")
+    ap.add_argument("--skip-parity", action="store_true", help="N > 1: do not verify the assembled result on rank 0")
+    ap.add_argument("--parity-oracle-max", type=int, default=130_000_000,
+                    help="N > 1: run the plain-C oracle on the whole batch when it has at most this many records")
+    ap.add_argument("--force-multi", action="store_true", help="run the multi-GPU path even with one rank (under torchrun)")
     ap.add_argument("--ab", action="store_true", help="time the product library against the one-switch-off builds (rala_b200/variants/)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
@@ -429,7 +433,7 @@ def main():
         os.execv(sys.executable, [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
                                   "--master-addr", "127.0.0.1", "--master-port", os.environ.get("MASTER_PORT", "29533"),
                                   os.path.abspath(__file__)] + sys.argv[1:])
-    if args.gpus > 1 or world > 1:
+    if args.gpus > 1 or world > 1 or args.force_multi:
         from rala_b200 import multi
         multi.bench_main(args)
         return

@@ -313,6 +313,8 @@ int rala_b200_multi_set_outputs(rala_b200_multi* m, int k, rala_edge_t* edges_ou
 int rala_b200_multi_default_caps(rala_b200_multi* m, uint64_t* caps /* RALA_B200_N_CAPS */);
 /* (re)allocate the exchange arenas; with all ranks in one process this also connects them */
 int rala_b200_multi_reserve(rala_b200_multi* m, const uint64_t* caps /* RALA_B200_N_CAPS */);
+/* change the number of resolution rounds a step enqueues (same value on every rank) without touching the arenas */
+int rala_b200_multi_set_rounds(rala_b200_multi* m, uint32_t rounds, uint32_t final_rounds);
 /* one process per GPU: 64-byte CUDA IPC handle of local rank k's arena / the handles of all `world` ranks in rank order */
 int rala_b200_multi_export_handle(rala_b200_multi* m, int k, void* handle64);
 int rala_b200_multi_import_handles(rala_b200_multi* m, const void* handles /* world x 64 bytes */);

@@ -69,7 +69,7 @@ EXPORTS = [
     "rala_b200_multi_counts", "rala_b200_multi_edge_range", "rala_b200_multi_get_edges", "rala_b200_multi_get_marked",
     "rala_b200_multi_get_seq_to_node", "rala_b200_multi_get_piles", "rala_b200_multi_event_record",
     "rala_b200_multi_event_elapsed_ms", "rala_b200_multi_launch_count", "rala_b200_multi_stage_ms",
-    "rala_b200_multi_set_outputs", "rala_b200_multi_set_barrier_timeout_ms",
+    "rala_b200_multi_set_outputs", "rala_b200_multi_set_barrier_timeout_ms", "rala_b200_multi_set_rounds",
 ]
 
 _LIB = None
@@ -527,6 +527,11 @@ class Multi:
         caps = np.ascontiguousarray(caps, dtype=np.uint64)
         self._call("rala_b200_multi_reserve", _ptr(caps))
         self.caps = caps.copy()
+        return self
+
+    def set_rounds(self, rounds: int, final_rounds: int):
+        self._call("rala_b200_multi_set_rounds", C.c_uint32(rounds), C.c_uint32(final_rounds))
+        self.caps[3], self.caps[4] = rounds, final_rounds
         return self
 
     def export_handle(self, k: int = 0) -> bytes:

@@ -325,6 +325,15 @@ extern "C" int rala_b200_multi_reserve(rala_b200_multi* m, const uint64_t* caps)
     return RALA_B200_OK;
 }
 
+extern "C" int rala_b200_multi_set_rounds(rala_b200_multi* m, uint32_t rounds, uint32_t final_rounds) {
+    if (!m || rounds < 1 || final_rounds < 1 || rounds > 4096 || final_rounds > 4096) return RALA_B200_ERR_ARG;
+    if (!m->reserved) return mfail(m, RALA_B200_ERR_STATE, "set_rounds: reserve first");
+    m->caps[RALA_B200_CAP_ROUNDS] = rounds;
+    m->caps[RALA_B200_CAP_FINAL_ROUNDS] = final_rounds;
+    drop_graphs(m);   // the rounds are part of the captured step
+    return RALA_B200_OK;
+}
+
 extern "C" int rala_b200_multi_export_handle(rala_b200_multi* m, int k, void* handle64) {
     if (!m || k < 0 || k >= m->n_local || !handle64) return RALA_B200_ERR_ARG;
     if (!m->reserved) return mfail(m, RALA_B200_ERR_STATE, "export_handle: reserve first");
@@ -730,8 +739,8 @@ extern "C" int rala_b200_multi_plan(rala_b200_multi* m) {
             if (r0 < caps[RALA_B200_CAP_ROUNDS] || r1 < caps[RALA_B200_CAP_FINAL_ROUNDS]) {
                 caps[RALA_B200_CAP_ROUNDS] = r0 < caps[RALA_B200_CAP_ROUNDS] ? r0 : caps[RALA_B200_CAP_ROUNDS];
                 caps[RALA_B200_CAP_FINAL_ROUNDS] = r1 < caps[RALA_B200_CAP_FINAL_ROUNDS] ? r1 : caps[RALA_B200_CAP_FINAL_ROUNDS];
-                memcpy(m->caps, caps, sizeof(caps));   // same arenas: only the number of rounds enqueued changes
-                drop_graphs(m);
+                rc = rala_b200_multi_set_rounds(m, (uint32_t) caps[RALA_B200_CAP_ROUNDS], (uint32_t) caps[RALA_B200_CAP_FINAL_ROUNDS]);
+                if (rc) return rc;
             }
             return RALA_B200_OK;
         }

@@ -1,7 +1,16 @@
-"""Multi-GPU hot path: one process per GPU, torch.distributed (NCCL over NVLink / NVSwitch) for the
-exchange steps, the CUDA phases of librala_b200.so for everything else.
+"""Multi-GPU hot path, one process per GPU.
 
-Partition (BASELINE.json north_star):
+PRODUCT PATH — `FabricGraph`: the multi-GPU session of the C ABI (rala_b200_multi_*, include/rala_b200.h).  The
+whole orchestration and every exchange live inside the library as CUDA kernels that write straight into the peer
+GPUs' memory over NVLink (CUDA IPC between the processes) with device-side barriers in between; torch.distributed is
+only the plumbing around it: it carries the 64-byte IPC handles and the capacity agreement at set-up time, and the
+timing reductions of the bench.  A step enqueues kernels only and is replayed as one CUDA graph per rank.
+
+FALLBACK TRANSPORT — `DistributedGraph` over `CudaShardSession`: the round-1 path, NCCL collectives issued through
+torch.distributed between the library's phases, with the CSR built on every rank.  Used only when the GPUs cannot map
+each other's memory (no peer access / no CUDA IPC); both are checked against the oracle by the same tests.
+
+Partition of the fallback transport (BASELINE.json north_star):
   * overlap records are sharded by contiguous FILE RANGE (rank r holds records [t0_r, t0_r + n_r)); the
     pile table is replicated;
   * the containment events of all shards are all-gathered and the ordered-containment resolution runs
@@ -334,6 +343,114 @@ def shard_bounds(n_records: int, world: int):
 
 
 # -------------------------------------------------------------------------------------------------------------
+# product path: the library's own multi-GPU session, one rank per process
+# -------------------------------------------------------------------------------------------------------------
+class FabricGraph:
+    """One rank of rala_b200_multi.  Collective calls (every rank must make them): connect(), plan()."""
+
+    def __init__(self, local_rank: int, rank: int, world: int, group=None):
+        self.rank, self.world, self.group = rank, world, group
+        self.device = torch.device("cuda", local_rank)
+        self.M = api.Multi([local_rank], first_rank=rank, world=world)
+        self.caps = None
+
+    # ---- inputs (local) ---------------------------------------------------------------------------------------
+    def set_inputs(self, records, piles, flags, t0: int):
+        self.M.set_piles(piles, flags)
+        self.M.set_overlaps(0, records, t0)
+        return self
+
+    # ---- set-up (collective) ----------------------------------------------------------------------------------
+    def _plumbing_device(self):
+        """NCCL moves CUDA tensors, gloo (tests with several ranks on one GPU: NCCL refuses those) CPU tensors."""
+        return self.device if dist.get_backend(self.group) == "nccl" else torch.device("cpu")
+
+    def _max_over_ranks(self, values):
+        t = torch.tensor([int(v) for v in values], dtype=torch.int64, device=self._plumbing_device())
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
+        return [int(v) for v in t.cpu().tolist()]
+
+    def connect(self, caps=None):
+        """Agree on the exchange capacities, allocate the arenas and map every peer's arena (CUDA IPC)."""
+        if caps is None:
+            caps = self.M.default_caps()
+        self.caps = np.array(self._max_over_ranks(caps), dtype=np.uint64)
+        self.M.reserve(self.caps)
+        mine = torch.frombuffer(bytearray(self.M.export_handle(0)), dtype=torch.uint8).to(self._plumbing_device())
+        parts = [torch.empty_like(mine) for _ in range(self.world)]
+        dist.all_gather(parts, mine, group=self.group)
+        self.M.import_handles(b"".join(bytes(p.cpu().numpy().tobytes()) for p in parts))
+        dist.barrier(group=self.group)   # nobody starts a step before every rank has mapped every arena
+        return self
+
+    def plan(self, max_attempts: int = 6):
+        """Size the exchange buffers from real steps: run, read what the step needed, grow what did not fit (all ranks
+        together), until a step fits; then trim the resolution rounds to what the data needs (+ 2)."""
+        if self.caps is None:
+            self.connect()
+        for _ in range(max_attempts):
+            self.M.use_cuda_graph(False)
+            self.M.run().synchronize()
+            need, fits = self.M.demand()
+            agreed = self._max_over_ranks(list(need) + [0 if fits else 1])
+            need, misfit = np.array(agreed[:-1], dtype=np.uint64), agreed[-1]
+            r0, r1 = int(need[3]) + 2, int(need[4]) + 2
+            if not misfit:
+                if r0 < self.caps[3] or r1 < self.caps[4]:
+                    self.caps[3], self.caps[4] = min(r0, int(self.caps[3])), min(r1, int(self.caps[4]))
+                    self.M.set_rounds(int(self.caps[3]), int(self.caps[4]))
+                self.M.use_cuda_graph(True)
+                return self
+            caps = self.caps.copy()
+            for i in range(3):
+                if need[i] > caps[i]:
+                    caps[i] = (int(need[i]) * 5 // 4 + 1024 + 255) // 256 * 256
+            caps[3], caps[4], caps[5] = max(int(caps[3]), r0), max(int(caps[4]), r1), max(int(caps[5]), int(need[5]))
+            self.connect(caps)
+        raise api.RalaB200Error("plan: the exchange buffers still did not fit")
+
+    # ---- step / results ----------------------------------------------------------------------------------------
+    def run(self):
+        self.M.run()
+        return self
+
+    def check(self) -> dict:
+        """Synchronises; raises when the last step did not fit its buffers or rounds, or a peer went missing."""
+        return self.M.counts()
+
+    def edges(self):
+        return self.M.edge_range(0), self.M.edges(0), self.M.marked(0)
+
+    def close(self):
+        self.M.close()
+
+
+def make_graph(local_rank: int, rank: int, world: int, records, piles, flags, t0: int):
+    """The product path when the GPUs can map each other's memory, else the NCCL fallback transport.
+    Returns (kind, object); collective."""
+    ok, fg, err = 1, None, ""
+    try:
+        fg = FabricGraph(local_rank, rank, world)
+        fg.set_inputs(records, piles, flags, t0)
+        fg.connect()
+    except api.RalaB200Error as exc:   # e.g. cudaIpcOpenMemHandle refused: the other ranks must take the same branch
+        ok, err = 0, str(exc)
+    t = torch.tensor([ok], dtype=torch.int32, device=torch.device("cuda", local_rank))
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    if int(t.item()):
+        return "fabric", fg
+    if fg is not None:
+        fg.close()
+    if rank == 0:
+        print(f"[rala_b200.multi] peer memory unavailable ({err or 'on another rank'}): falling back to NCCL collectives",
+              file=__import__("sys").stderr)
+    torch.cuda.set_stream(torch.cuda.Stream(torch.device("cuda", local_rank)))
+    sess = CudaShardSession(local_rank)
+    sess.set_inputs(records, piles, flags, t0, rank, world)
+    return "nccl", DistributedGraph(sess, rank, world)
+
+
+# -------------------------------------------------------------------------------------------------------------
 # bench entry (python -m torch.distributed.run ... bench.py --gpus N)
 # -------------------------------------------------------------------------------------------------------------
 def _global_dataset(args, rank, world, device):
@@ -390,6 +507,54 @@ def _global_dataset(args, rank, world, device):
     return np.ascontiguousarray(local), piles, t0, sum(allc)
 
 
+def verify_against_single_gpu_and_oracle(records, piles, flags, edges, marked, device_index: int, oracle_max_records: int):
+    """Rank 0, outside every timed region: the edge list + removed-edge set assembled from all ranks must be
+    bit-identical to (a) the single-GPU session of this library on the whole batch, which the GPU suite pins against
+    the oracle at this size, and (b) the plain-C oracle itself when the batch is small enough to finish in about a
+    minute.  Returns the `parity` object of the bench line; raises on a mismatch."""
+    import zlib
+    out = {"edges": int(edges.shape[0]), "marks_crc32": zlib.crc32(marked.tobytes(), zlib.crc32(edges.tobytes()))}
+    ctx = api.Context(device_index)
+    G = api.Graph(ctx)
+    G.set_piles(piles, flags).set_hills(None).set_overlaps(records)
+    G.run()
+    e1, m1 = G.edges(), G.marked()
+    G.close()
+    ctx.close()
+    if not (np.array_equal(e1, edges) and np.array_equal(m1, marked)):
+        raise api.RalaB200Error(f"multi-GPU result differs from the single-GPU session on the same batch "
+                                f"({edges.shape[0]} vs {e1.shape[0]} edges)")
+    out["vs_single_gpu_same_batch"] = True
+    if records.shape[0] <= oracle_max_records:
+        from oracle import oracle as O   # bench.py's checker leg: the oracle is never on the measured path
+        t0 = time.perf_counter()
+        P = O.Pipeline(records, piles, flags).run()
+        if not (np.array_equal(P.edges, edges) and np.array_equal(P.marked, marked)):
+            raise api.RalaB200Error("multi-GPU result differs from the oracle")
+        out["vs_oracle"] = True
+        out["oracle_seconds"] = round(time.perf_counter() - t0, 2)
+    else:
+        out["vs_oracle"] = f"skipped: {records.shape[0]} records > {oracle_max_records} (the single-GPU session is pinned against the oracle)"
+    return out
+
+
+def _share_through_files(rank, world, arrays: dict):
+    """Single node: every rank leaves its arrays in a directory rank 0 names; rank 0 reads them all back."""
+    import shutil
+    import tempfile
+    box = [tempfile.mkdtemp(prefix="rala_b200_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None) if rank == 0 else None]
+    dist.broadcast_object_list(box, src=0)
+    for k, v in arrays.items():
+        np.save(os.path.join(box[0], f"{k}_{rank}.npy"), v)
+    dist.barrier()
+    got = None
+    if rank == 0:
+        got = {k: [np.load(os.path.join(box[0], f"{k}_{r}.npy")) for r in range(world)] for k in arrays}
+        shutil.rmtree(box[0], ignore_errors=True)
+    dist.barrier()
+    return got
+
+
 def bench_main(args):
     import json
     import bench
@@ -397,79 +562,128 @@ def bench_main(args):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", str(rank)))
-    # a rank stuck in a collective (a peer died, a teardown that waits for ever) must not hold N GPUs until somebody
-    # else's time limit: after 15 minutes the process leaves with a non-zero status
+    # a rank stuck in a collective (a peer died) must not hold N GPUs until somebody else's time limit
     import threading
-    watchdog = threading.Timer(900.0, lambda: os._exit(3))
+    watchdog = threading.Timer(1500.0, lambda: os._exit(3))
     watchdog.daemon = True
     watchdog.start()
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
     dist.init_process_group("nccl", device_id=device)
     records, piles, t0, n_total_records = _global_dataset(args, rank, world, device)
+    steps, warmup = args.steps, max(args.warmup, 3)
 
-    # a side stream: the library enqueues on the stream that is current when the session is created, NCCL orders
-    # itself against torch's current stream, and a CUDA graph cannot be captured on the legacy default stream
-    torch.cuda.set_stream(torch.cuda.Stream(device))
-    sess = CudaShardSession(local_rank)
-    sess.set_inputs(records, piles, None, t0, rank, world)
-    dg = DistributedGraph(sess, rank, world)
-    for _ in range(max(args.warmup, 3)):
-        info = dg.run()
-    torch.cuda.synchronize()
-    use_graph = not os.environ.get("RALA_B200_NO_STEP_GRAPH")
-    ok = torch.tensor([1 if (use_graph and dg.capture()) else 0], dtype=torch.int32, device=device)
-    dist.all_reduce(ok, op=dist.ReduceOp.MIN)          # all ranks replay, or none does
-    if not int(ok.item()):
-        dg._graph = None
-    for _ in range(3):
-        info = dg.replay()
-    torch.cuda.synchronize()
+    kind, dg = make_graph(local_rank, rank, world, records, piles, None, t0)
+    if kind == "fabric":
+        dg.plan()
+        run, sync, launches_now = dg.run, dg.M.synchronize, (lambda: dg.M.launch_count)
+    else:
+        sess = dg.s
+        run, sync, launches_now = dg.run, (lambda: torch.cuda.synchronize()), (lambda: sess.ctx.launch_count)
+    for _ in range(warmup + 2):   # eager, capture, replays
+        run()
+    sync()
     sampler = bench.ClockSampler(local_rank) if rank == 0 else None
     if sampler:
         sampler.start()
-    launches0 = sess.ctx.launch_count
+    launches0 = launches_now()
     dist.barrier()
     torch.cuda.synchronize()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_wall = time.perf_counter()
-    ev0.record()
-    for _ in range(args.steps):
-        info = dg.replay()
-    ev1.record()
-    torch.cuda.synchronize()
+    if kind == "fabric":
+        dg.M.event_record(0)
+        for _ in range(steps):
+            run()
+        dg.M.event_record(1)
+        dev_ms = dg.M.event_elapsed_ms()
+    else:
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        for _ in range(steps):
+            run()
+        ev1.record()
+        torch.cuda.synchronize()
+        dev_ms = ev0.elapsed_time(ev1)
+    sync()
     dist.barrier()
     wall_ms = 1e3 * (time.perf_counter() - t_wall)
-    dev_ms = ev0.elapsed_time(ev1)
-    launches = (sess.ctx.launch_count - launches0) + (dg.graph_launches * args.steps if dg._graph is not None else 0)
+    launches = launches_now() - launches0
     t = torch.tensor([dev_ms, wall_ms], dtype=torch.float64, device=device)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)           # max over ranks
-    ms_per_step = float(t[0].item()) / args.steps
-    if not dg.check():   # synchronises: an exchange block overflowed in a bounded pass -> the timing is void
-        raise api.RalaB200Error("a capacity-bounded exchange overflowed during the timed region")
+    ms_per_step = float(t[0].item()) / steps
     clocks = sampler.stop() if sampler else None
-    for _ in range(3):      # stage timers are CUDA events between the kernels: they only exist in the eager chain
-        dg.run()
-    torch.cuda.synchronize()
-    stage = sess.G.stage_ms()
-    c = sess.counts()
-    E = c["n_edges"]
-    assert E == info["n_edges"], (E, info["n_edges"])
 
-    # end to end: host (pinned) shard -> device, full pipeline, edges + marks back to the host on every rank
+    # ---- results of the timed steps: validity, then parity (outside the timed region) -----------------------------
+    if kind == "fabric":
+        c = dg.check()                                  # raises if a step did not fit its buffers / rounds
+        (first, n_mine), e_mine, m_mine = dg.edges()
+        E = c["n_edges"]
+        sums = torch.tensor([c["n_two_hop"], c["n_transitive_pairs"], c["n_candidates"], c["n_final_candidates"]],
+                            dtype=torch.int64, device=device)
+        dist.all_reduce(sums)
+        n_two_hop, n_pairs, n_events, n_final_events = [int(x) for x in sums.tolist()]
+        n_nodes, rounds = c["n_nodes"], [c["n_rounds"], c["n_final_rounds"]]
+    else:
+        if not dg.check():
+            raise api.RalaB200Error("a capacity-bounded exchange overflowed during the timed region")
+        c = sess.counts()
+        E, n_nodes, n_pairs, n_two_hop = c["n_edges"], c["n_nodes"], c["n_transitive_pairs"], c["n_two_hop"]
+        n_events, n_final_events, rounds = dg.last_info["n_events"], dg.last_info["n_final_events"], [c["n_rounds"], c["n_final_rounds"]]
+        first = 0
+        e_mine, m_mine = (sess.edges(), sess.marked()) if rank == 0 else (np.zeros((0, 3), np.uint32), np.zeros(0, np.uint8))
+    parity = None
+    if not args.skip_parity:
+        got = _share_through_files(rank, world, {"rec": records, "edges": e_mine, "marked": m_mine,
+                                                 "first": np.array([first], np.int64)})
+        if rank == 0:
+            order = np.argsort([int(f[0]) for f in got["first"]], kind="stable") if kind == "fabric" else [0]
+            edges = np.concatenate([got["edges"][r] for r in order])
+            marked = np.concatenate([got["marked"][r] for r in order])
+            assert edges.shape[0] == E, (edges.shape, E)
+            parity = verify_against_single_gpu_and_oracle(np.concatenate(got["rec"]), piles, None, edges, marked, local_rank,
+                                                          args.parity_oracle_max)
+            del got
+        dist.barrier()
+
+    # ---- stage times of one eager step (CUDA events between the kernels do not exist inside a graph) ---------------
+    if kind == "fabric":
+        dg.M.use_cuda_graph(False)
+        for _ in range(2):
+            run()
+        sync()
+        stage = dg.M.stage_ms(0)
+        dg.M.use_cuda_graph(True)
+    else:
+        for _ in range(2):
+            run()
+        torch.cuda.synchronize()
+        stage = sess.G.stage_ms()
+
+    # ---- end to end: pinned host shard -> device, one step, the edges this rank emitted + their marks back ---------
     cols_pin = torch.from_numpy(api.records_to_columns(records)).pin_memory()   # 24 B / record, the device layout
     piles_pin = torch.from_numpy(piles).pin_memory()
-    e2e_steps = max(3, min(args.steps, 5))
-    edges_pin = torch.empty((max(E, 1), 3), dtype=torch.int32).pin_memory()
-    marked_pin = torch.empty(max(E, 1), dtype=torch.uint8).pin_memory()
+    e2e_steps = max(3, min(steps, 10))
+    n_out = max(int(e_mine.shape[0]), 1) if kind == "fabric" else max(E, 1)
+    edges_pin = torch.empty((n_out, 3), dtype=torch.int32).pin_memory()
+    marked_pin = torch.empty(n_out, dtype=torch.uint8).pin_memory()
+    if kind == "fabric":
+        dg.M.set_outputs(0, edges_pin, marked_pin)
 
-    def e2e_step():
-        sess.G.set_piles(piles_pin).set_overlaps_columns(cols_pin)
-        dg.run()
-        sess.G.edges(out=edges_pin)
-        sess.G.marked(out=marked_pin)
-
-    e2e_step()
+        def e2e_step():
+            dg.M.set_piles(piles_pin)
+            dg.M.set_overlaps_columns(0, cols_pin, t0)
+            dg.M.run()
+            dg.M.synchronize()           # edges_pin / marked_pin are complete
+    else:
+        def e2e_step():
+            sess.G.set_piles(piles_pin).set_overlaps_columns(cols_pin)
+            dg.run()
+            if rank == 0:                # the result is replicated: one download
+                sess.G.edges(out=edges_pin)
+                sess.G.marked(out=marked_pin)
+            torch.cuda.synchronize()
+    for _ in range(4):                   # new shape: eager, capture, replay
+        e2e_step()
     dist.barrier()
     torch.cuda.synchronize()
     t1 = time.perf_counter()
@@ -480,52 +694,51 @@ def bench_main(args):
     e2e_s = torch.tensor([(time.perf_counter() - t1) / e2e_steps], dtype=torch.float64, device=device)
     dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
     e2e_s = float(e2e_s.item())
+    if kind == "fabric":
+        dg.check()
+        assert np.array_equal(edges_pin.numpy().view(np.uint32)[:e_mine.shape[0]], e_mine) and \
+            np.array_equal(marked_pin.numpy()[:m_mine.shape[0]], m_mine), "e2e outputs differ from the resident run"
+        dg.M.set_outputs(0, None, None)
 
     if rank == 0:
         peak, peak_src = bench.measured_peaks()
         k1_ms = stage["k1_classify_kernel"] + stage["k1_survivors_kernel"]   # both passes over the shard, as at N = 1
         k1_gbs = bench.K1_BYTES_PER_OVERLAP * records.shape[0] / (k1_ms * 1e-3) / 1e9 if k1_ms > 0 else 0.0
+        step_bytes = (bench.K1_BYTES_PER_OVERLAP * n_total_records + bench.K3_BYTES_PER_VISIT * n_two_hop + 9 * E + 8 * n_nodes
+                      + 20 * (n_events + n_final_events) + 4 * int(piles.shape[0]) * world + 73 * E)
+        agg_gbs = step_bytes / (ms_per_step * 1e-3) / 1e9
+        parallelism = (f"{world} GPUs: records by file range; containment events to the victim's owner, edges to the source node's "
+                       "owner, CSR slices pushed to every replica, marks back to the emitting rank: all as kernels storing into "
+                       "peer memory (NVLink, CUDA IPC) between device-side barriers" if kind == "fabric" else
+                       f"{world} GPUs, NCCL fallback: records by file range, CSR replicated (all-gather), marks all-reduce(max)")
         print(json.dumps({
             "metric": "graph_edges_per_sec", "value": E / (ms_per_step * 1e-3), "unit": "edges/s", "n_gpus": world,
-            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
+            "steps": steps, "warmup": warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
             "config": {"workload": f"{world} x ({bench.WORKLOADS[args.workload][3]}), read ids shuffled globally",
                        "n_overlaps": n_total_records, "n_overlaps_per_gpu": int(records.shape[0]), "n_reads": int(piles.shape[0]),
-                       "edges": E, "nodes": c["n_nodes"], "containment_events": info["n_events"],
-                       "parallelism": f"{world} GPUs: records by file range, CSR replicated (all-gather), "
-                                      "transitive by source-node range, marks all-reduce(max)",
-                       "l2": "inputs larger than L2 (each rank streams its 400 MB record shard per step)",
-                       "collective_bytes_received_per_rank_per_step": dg.comm_bytes,
-                       "step_graph": ("one CUDA graph per step (kernels + NCCL collectives captured together)" if dg._graph is not None
-                                      else f"eager ({dg.graph_error or 'disabled'})"),
-                       "exchange": "capacity-bounded blocks (counts inside the blocks, time bases on the device): no host "
-                                   "synchronisation inside a step; capacities from the sized warm-up pass x 1.25"},
-            "wall_ms_per_step": float(t[1].item()) / args.steps,
+                       "edges": E, "nodes": n_nodes, "two_hop_visits": n_two_hop, "transitive_pairs": n_pairs,
+                       "containment_events": n_events, "final_containment_events": n_final_events, "resolution_rounds": rounds,
+                       "parallelism": parallelism, "transport": kind,
+                       "l2": f"inputs larger than L2 (each rank streams its {records.nbytes * 6 // 7 / 1e6:.0f} MB record shard per step)",
+                       "step_graph": "one CUDA graph per rank and step (kernels only: the exchanges are kernels)" if kind == "fabric"
+                                     else "eager (NCCL collectives between the phases)",
+                       "exchange_capacities": dict(zip(api.CAP_NAMES, [int(x) for x in dg.caps])) if kind == "fabric" else dg.caps},
+            "parity": parity,
+            "wall_ms_per_step": float(t[1].item()) / steps,
             "e2e": {"value": E / e2e_s, "unit": "edges/s", "h2d_bytes_per_step": int((cols_pin.numel() * 4 + piles.nbytes) * world),
-                    "d2h_bytes_per_step": int(13 * E * world), "ms_per_step": 1e3 * e2e_s},
-            "gpu_launches": int(launches),
+                    "d2h_bytes_per_step": int(13 * E) if kind == "fabric" else int(13 * E), "ms_per_step": 1e3 * e2e_s,
+                    "path": "per rank: set_piles + set_overlaps_columns (pinned) + run + the rows / marks of the edges the rank emitted "
+                            "written to pinned host memory by the GPU + synchronize"},
+            "gpu_launches": int(launches) * (world if kind == "fabric" else 1),
             "roofline": {"bound": "hbm", "kernel": "k_classify_first", "achieved": k1_gbs, "peak": peak, "unit": "GB/s",
                          "frac": k1_gbs / peak, "traffic": None, "peak_source": peak_src,
-                         "note": "rank 0's two passes over its record shard (events + survivors kernels); stage_ms are rank 0's last step",
+                         "note": "rank 0's two passes over its record shard (events + survivors kernels); stage_ms are rank 0's eager step",
+                         "aggregate_whole_step": {"algorithmic_bytes": int(step_bytes), "gbs": agg_gbs, "peak_gbs": peak * world,
+                                                  "frac": agg_gbs / (peak * world)},
                          "stage_ms": stage},
             "cpu_baseline": None, "clocks": clocks,
         }))
-    _finish(dg, sess, world)
-
-
-def _finish(dg, sess, world: int):
-    """End of a multi-rank process.  With world > 1 a captured step graph holds NCCL kernel nodes, and tearing the
-    communicator down next to it blocked on the 2-GPU box (r01k: the bench line was printed, the ranks never left
-    destroy_process_group).  So: meet the other ranks once more and leave the process without any teardown; everything
-    the caller needs has been printed / written by then."""
-    import sys
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-        torch.cuda.synchronize()
-        sys.stdout.flush()
-        sys.stderr.flush()
-        os._exit(0)       # no destructors: neither the graph nor the communicator is torn down
-    dg._graph = None
-    sess.close()
+    dist.barrier()
+    dg.close() if kind == "fabric" else sess.close()
     dist.destroy_process_group()

@@ -1,5 +1,12 @@
-"""GPU suite: the multi-GPU phases of the C ABI (CudaShardSession) under the real orchestrator over NCCL,
-against the single-process oracle.  world = 1 runs on any GPU box; world = 2 / 4 need that many GPUs."""
+"""GPU suite: one PROCESS per rank, against the single-process oracle.
+
+  fabric  the product path (rala_b200.multi.FabricGraph): the library's multi-GPU session, arenas mapped between the
+          processes with CUDA IPC, exchanges as kernels over peer memory.  world = 1, 2, 4, 8 with one GPU per rank
+          (skipped when the box has fewer), plus world = 2 with BOTH processes on device 0 (CUDA IPC works between
+          processes on one device too; the kernels of the two processes are time-sliced, so this is slow but it
+          exercises the IPC mapping on a one-GPU box).
+  nccl    the fallback transport (DistributedGraph over CudaShardSession, NCCL collectives between the phases).
+tests/test_multi_fabric.py covers world 1 .. 8 of the product path inside one process on any GPU box."""
 import os
 import socket
 import sys
@@ -28,51 +35,83 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, out_dir, graph):
+def _flags(ds):
+    return (np.random.Generator(np.random.PCG64(1)).random(ds.n_reads) < 0.05).astype(np.uint8) * 2
+
+
+def _worker(rank, world, port, out_dir, transport, same_device):
     import signal
-    signal.alarm(420)    # a rank stuck in a collective must not hold the GPU suite (and the box) for its whole time limit
+    signal.alarm(300)    # a rank stuck waiting for a peer must not hold the GPU suite (and the box) for its whole time limit
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
-    torch.cuda.set_device(rank)
-    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    dev = 0 if same_device else rank
+    torch.cuda.set_device(dev)
+    if same_device:
+        dist.init_process_group("gloo", rank=rank, world_size=world)      # NCCL refuses two ranks on one GPU
+    else:
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", dev))
     try:
         ds = synth.generate(**KW)
-        piles = ds.flat_piles()
-        flags = (np.random.Generator(np.random.PCG64(1)).random(ds.n_reads) < 0.05).astype(np.uint8) * 2
+        piles, flags = ds.flat_piles(), _flags(ds)
         lo, hi = multi.shard_bounds(ds.n_overlaps, world)[rank]
-        torch.cuda.set_stream(torch.cuda.Stream(torch.device("cuda", rank)))   # a step graph cannot be captured on the default stream
-        sess = multi.CudaShardSession(rank)
-        sess.set_inputs(np.ascontiguousarray(ds.records[lo:hi]), piles, flags, lo, rank, world)
-        dg = multi.DistributedGraph(sess, rank, world)
-        for _ in range(2):   # twice: the session must be re-runnable (bench loop); the second pass is capacity-bounded
-            info = dg.run()
-        if graph:            # the whole step (kernels + NCCL collectives) captured once, replayed twice
-            assert dg.capture(), dg.graph_error
-            for _ in range(2):
-                dg.replay()
+        shard = np.ascontiguousarray(ds.records[lo:hi])
+        if transport == "fabric":
+            fg = multi.FabricGraph(dev, rank, world)
+            fg.M.set_barrier_timeout_ms(20000 if same_device else 5000)
+            fg.set_inputs(shard, piles, flags, lo)
+            fg.plan()
+            for _ in range(2 if same_device else 4):     # eager, captured, replayed
+                fg.run()
+            c = fg.check()
+            (first, n), edges, marked = fg.edges()
+            np.savez(os.path.join(out_dir, f"r{rank}.npz"), edges=edges, marked=marked, first=first, piles=fg.M.piles(),
+                     n_edges=c["n_edges"], n_pairs=c["n_transitive_pairs"], n_nodes=c["n_nodes"])
+            dist.barrier()
+            fg.close()
+        else:
+            torch.cuda.set_stream(torch.cuda.Stream(torch.device("cuda", dev)))
+            sess = multi.CudaShardSession(dev)
+            sess.set_inputs(shard, piles, flags, lo, rank, world)
+            dg = multi.DistributedGraph(sess, rank, world)
+            for _ in range(3):   # sized, then capacity-bounded passes
+                dg.run()
             assert dg.check()
-        c = sess.counts()
-        np.savez(os.path.join(out_dir, f"r{rank}.npz"), edges=sess.edges(), marked=sess.marked(), piles=sess.G.piles(),
-                 n_pairs=c["n_transitive_pairs"], n_nodes=c["n_nodes"], n_events=info["n_events"])
-        if graph and world > 1:
-            multi._finish(dg, sess, world)   # results are on disk; leaves the process without the NCCL teardown (see there)
-        sess.close()
+            c = sess.counts()
+            np.savez(os.path.join(out_dir, f"r{rank}.npz"), edges=sess.edges() if rank == 0 else np.zeros((0, 3), np.uint32),
+                     marked=sess.marked() if rank == 0 else np.zeros(0, np.uint8), first=0 if rank == 0 else c["n_edges"],
+                     piles=sess.G.piles(), n_edges=c["n_edges"], n_pairs=c["n_transitive_pairs"] if rank == 0 else 0, n_nodes=c["n_nodes"])
+            dist.barrier()
+            sess.close()
     finally:
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("graph", [False, True], ids=["eager", "step_graph"])
-@pytest.mark.parametrize("world", [1, 2, 4])
-def test_multi_gpu_matches_oracle(world, graph, tmp_path):
+def _run_and_compare(world, transport, same_device, tmp_path):
+    ds = synth.generate(**KW)
+    want = O.Pipeline(ds.records, ds.flat_piles(), _flags(ds)).run()
+    assert want.edges.shape[0] > 5000
+    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path), transport, same_device), nprocs=world, join=True)
+    parts = sorted((np.load(tmp_path / f"r{r}.npz") for r in range(world)), key=lambda z: int(z["first"]))
+    assert np.array_equal(np.concatenate([z["edges"] for z in parts]), want.edges), "edge list"
+    assert np.array_equal(np.concatenate([z["marked"] for z in parts]), want.marked), "removed-edge set"
+    assert sum(int(z["n_pairs"]) for z in parts) == want.n_pairs
+    for z in parts:
+        assert np.array_equal(z["piles"], want.piles), "pile liveness"
+        assert int(z["n_nodes"]) == want.n_nodes and int(z["n_edges"]) == want.edges.shape[0]
+
+
+@pytest.mark.parametrize("world", [1, 2, 4, 8])
+def test_fabric_one_process_per_gpu(world, tmp_path):
     if torch.cuda.device_count() < world:
         pytest.skip(f"needs {world} GPUs")
-    ds = synth.generate(**KW)
-    flags = (np.random.Generator(np.random.PCG64(1)).random(ds.n_reads) < 0.05).astype(np.uint8) * 2
-    want = O.Pipeline(ds.records, ds.flat_piles(), flags).run()
-    assert want.edges.shape[0] > 5000
-    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path), graph), nprocs=world, join=True)
-    for r in range(world):
-        z = np.load(tmp_path / f"r{r}.npz")
-        assert np.array_equal(z["edges"], want.edges), f"rank {r}: edge list"
-        assert np.array_equal(z["marked"], want.marked), f"rank {r}: removed-edge set"
-        assert np.array_equal(z["piles"], want.piles), f"rank {r}: pile liveness"
-        assert int(z["n_pairs"]) == want.n_pairs and int(z["n_nodes"]) == want.n_nodes
+    _run_and_compare(world, "fabric", False, tmp_path)
+
+
+def test_fabric_two_processes_on_one_device(tmp_path):
+    _run_and_compare(2, "fabric", True, tmp_path)
+
+
+@pytest.mark.parametrize("world", [1, 2])
+def test_nccl_fallback_transport(world, tmp_path):
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    _run_and_compare(world, "nccl", False, tmp_path)
