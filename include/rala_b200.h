@@ -341,6 +341,9 @@ int rala_b200_multi_get_piles(rala_b200_multi* m, rala_pile_t* out /* n_piles */
 int rala_b200_multi_event_record(rala_b200_multi* m, int which);
 int rala_b200_multi_event_elapsed_ms(rala_b200_multi* m, float* ms);
 uint64_t rala_b200_multi_launch_count(const rala_b200_multi* m);
+/* Diagnostics: device timestamps (ns) of the last barriers of local rank k, oldest first, as pairs (barrier kernel started,
+ * every peer had arrived); out holds 2 x 128 values, *n_out = number of valid pairs.  Synchronises. */
+int rala_b200_multi_barrier_log(rala_b200_multi* m, int k, uint64_t* out, uint32_t* n_out);
 /* device time of the stages of the last EAGER step of local rank k (as rala_b200_graph_stage_ms) */
 int rala_b200_multi_stage_ms(rala_b200_multi* m, int k, float* ms_out /* RALA_B200_N_STAGES */);
 

@@ -69,7 +69,7 @@ EXPORTS = [
     "rala_b200_multi_counts", "rala_b200_multi_edge_range", "rala_b200_multi_get_edges", "rala_b200_multi_get_marked",
     "rala_b200_multi_get_seq_to_node", "rala_b200_multi_get_piles", "rala_b200_multi_event_record",
     "rala_b200_multi_event_elapsed_ms", "rala_b200_multi_launch_count", "rala_b200_multi_stage_ms",
-    "rala_b200_multi_set_outputs", "rala_b200_multi_set_barrier_timeout_ms", "rala_b200_multi_set_rounds",
+    "rala_b200_multi_set_outputs", "rala_b200_multi_set_barrier_timeout_ms", "rala_b200_multi_set_rounds", "rala_b200_multi_barrier_log",
 ]
 
 _LIB = None
@@ -628,6 +628,16 @@ class Multi:
     @property
     def launch_count(self) -> int:
         return int(self.lib.rala_b200_multi_launch_count(self.handle))
+
+    def barrier_log(self, k: int = 0):
+        """(n, 2) device timestamps in ns of the last barriers of local rank k: kernel started, all peers arrived."""
+        out = np.zeros((128, 2), dtype=np.uint64)
+        n = C.c_uint32(0)
+        self._call("rala_b200_multi_barrier_log", C.c_int(k), _ptr(out), C.byref(n))
+        return out[:int(n.value)]
+
+    def barriers_per_step(self) -> int:
+        return 8 + int(self.caps[3]) + int(self.caps[4])
 
     def stage_ms(self, k: int = 0) -> dict:
         ms = (C.c_float * N_STAGES)()

@@ -434,7 +434,8 @@ __global__ void k_hill_coverage(List recs, uint32_t t0, const uint2* __restrict_
 // they are turned into death times (kInf = never) on the way, which saves the separate k_decode_state launch.
 template <bool DECODE>
 __global__ void k_apply_deaths(uint2* __restrict__ piles, uint32_t* __restrict__ dbuf, uint32_t n_piles,
-                               const uint32_t* __restrict__ counters, uint32_t* __restrict__ alive_bits) {
+                               const uint32_t* __restrict__ counters, uint32_t* __restrict__ alive_bits, const uint32_t* __restrict__ skip) {
+    if (skip && *skip) return;
     uint32_t* D = dbuf + (size_t) counters[C_DSEL] * n_piles;
     for (uint32_t base = blockIdx.x * blockDim.x; base < n_piles; base += gridDim.x * blockDim.x) {
         const uint32_t i = base + threadIdx.x;
@@ -701,10 +702,10 @@ void launch_hill_coverage(Launch& L, List recs, uint32_t t0, const uint2* piles,
 }
 
 void launch_apply_deaths(Launch& L, uint2* piles, uint32_t* dbuf, uint32_t n_piles, const uint32_t* counters,
-                         uint32_t* alive_bits, bool decode) {
+                         uint32_t* alive_bits, bool decode, const uint32_t* skip) {
     if (n_piles == 0) return;
-    if (decode) k_apply_deaths<true><<<grid_for(n_piles, 256, kNumSMs * 8), 256, 0, L.stream>>>(piles, dbuf, n_piles, counters, alive_bits);
-    else k_apply_deaths<false><<<grid_for(n_piles, 256, kNumSMs * 8), 256, 0, L.stream>>>(piles, dbuf, n_piles, counters, alive_bits);
+    if (decode) k_apply_deaths<true><<<grid_for(n_piles, 256, kNumSMs * 8), 256, 0, L.stream>>>(piles, dbuf, n_piles, counters, alive_bits, skip);
+    else k_apply_deaths<false><<<grid_for(n_piles, 256, kNumSMs * 8), 256, 0, L.stream>>>(piles, dbuf, n_piles, counters, alive_bits, skip);
     L.count++;
 }
 

@@ -56,6 +56,16 @@ __global__ void __launch_bounds__(32) k_fabric_barrier(Peers P, Publish pub) {
     const int q = threadIdx.x, me = P.rank, W = P.world;
     FabricHdr* mine = hdr_of(P, me);
     const uint32_t e = mine->epoch + 1u, par = e & 1u;
+    if (pub.skippable && mine->skip_pass) {   // every rank took the same decision from the same mail: nobody signals, nobody waits
+        __syncwarp();
+        if (q == 0) {
+            if (pub.bookkeeping == 1 && pub.round == 0) mine->rounds_needed[pub.pass] = 1u;
+            mine->tlog[e % kBarrierLog][0] = mine->tlog[e % kBarrierLog][1] = global_timer_ns();
+            mine->epoch = e;
+        }
+        return;
+    }
+    if (q == 0) mine->tlog[e % kBarrierLog][0] = global_timer_ns();
     if (q < W) {
         FabricHdr* peer = hdr_of(P, q);
 #pragma unroll
@@ -82,16 +92,24 @@ __global__ void __launch_bounds__(32) k_fabric_barrier(Peers P, Publish pub) {
     }
     __syncwarp();
     if (q == 0) {
-        if (pub.bookkeeping) {   // after a resolution round: is any victim still open anywhere?
+        if (pub.bookkeeping == 2) {   // events of a pass routed: a pass without a single event anywhere is skipped by every rank
+            uint32_t emitted = 0;
+            for (int p = 0; p < W; ++p) emitted += mine->mail[par][p][M_EMITTED];
+            mine->skip_pass = (pub.pass == 1 && emitted == 0u) ? 1u : 0u;
+        }
+        if (pub.bookkeeping == 1) {   // after a resolution round: is any victim still open anywhere?
             uint32_t open = 0;
             for (int p = 0; p < W; ++p) open += mine->mail[par][p][M_UNSETTLED];
             if (open == 0u && mine->rounds_needed[pub.pass] == 0u) mine->rounds_needed[pub.pass] = (uint32_t) pub.round + 1u;
             if (open != 0u && pub.round == pub.last_round) atomicOr(&mine->error, (uint32_t) FE_ROUNDS);
         }
+        mine->tlog[e % kBarrierLog][1] = global_timer_ns();
         __threadfence();
         mine->epoch = e;
     }
 }
+
+const uint32_t* skip_flag(const Peers& P) { return &reinterpret_cast<const FabricHdr*>(P.base[P.rank])->skip_pass; }
 
 void launch_fabric_barrier(Launch& L, Peers P, Publish pub) {
     k_fabric_barrier<<<1, 32, 0, L.stream>>>(P, pub);
@@ -113,7 +131,7 @@ __global__ void __launch_bounds__(256) k_route_events(Peers P, ArenaLayout A, Ev
         uint32_t v = 0, c = 0, t = 0, q = 0;
         if (ok) {
             v = ev.v[i]; c = ev.c[i]; t = ev.t[i];
-            q = min(v / A.ppr, (uint32_t) P.world - 1u);
+            q = pile_owner(v, (uint32_t) P.world);
         }
         const uint32_t active = __ballot_sync(0xFFFFFFFFu, ok);
         if (ok) {
@@ -142,6 +160,10 @@ void launch_route_events(Launch& L, Peers P, ArenaLayout A, Events ev, const uin
 __global__ void __launch_bounds__(256) k_gather_events(Peers P, ArenaLayout A, Events ev, uint32_t ev_cap, uint32_t* __restrict__ n_events_out,
                                                       uint32_t* __restrict__ vcount, uint32_t* __restrict__ tmin) {
     FabricHdr* mine = hdr_of(P, P.rank);
+    if (mine->skip_pass) {
+        if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) *n_events_out = 0u;
+        return;
+    }
     const uint32_t par = mine->epoch & 1u, src = blockIdx.y;
     uint32_t offset = 0;
     for (uint32_t p = 0; p < src; ++p) offset += min(mine->mail[par][p][M_SENT_TO_YOU], A.cap_ev);
@@ -189,6 +211,7 @@ __global__ void __launch_bounds__(256) k_fabric_prepare(Peers P, ArenaLayout A, 
                                                        uint32_t* __restrict__ vcursor, uint32_t* __restrict__ seg_c, uint32_t* __restrict__ seg_t,
                                                        const uint32_t* __restrict__ vstart, const uint32_t* __restrict__ tmin,
                                                        uint32_t* __restrict__ work, uint32_t* __restrict__ n_work, uint32_t fill_blocks) {
+    if (hdr_of(P, P.rank)->skip_pass) return;
     if (blockIdx.x < fill_blocks) {
         const uint32_t n = min(*n_events, ev_cap);
         const uint32_t stride = fill_blocks * blockDim.x;
@@ -213,12 +236,11 @@ __global__ void __launch_bounds__(256) k_fabric_prepare(Peers P, ArenaLayout A, 
         return;
     }
     uint32_t* S = section<uint32_t>(P, P.rank, A.S);
-    const uint32_t lo = min((uint32_t) P.rank * A.ppr, A.n_piles), hi = min(lo + A.ppr, A.n_piles);
     const uint32_t init_blocks = gridDim.x - fill_blocks, b = blockIdx.x - fill_blocks;
-    for (uint32_t base = lo + b * blockDim.x; base < hi; base += init_blocks * blockDim.x) {
-        const uint32_t x = base + threadIdx.x;
+    for (uint32_t base = b * blockDim.x; base < A.ppr; base += init_blocks * blockDim.x) {
+        const uint32_t x = owned_pile(base + threadIdx.x, (uint32_t) P.rank, (uint32_t) P.world);
         bool victim = false;
-        if (x < hi) {
+        if (base + threadIdx.x < A.ppr && x < A.n_piles) {
             victim = vstart[x + 1] != vstart[x];
             S[x] = victim ? min(tmin[x], kNever - 1u) : (kSettled | kNever);
         }
@@ -240,26 +262,22 @@ void launch_fabric_prepare(Launch& L, Peers P, ArenaLayout A, Events ev, const u
     L.count++;
 }
 
-// the initial states of the owned piles -> every replica (coalesced 16-byte stores; ppr is a multiple of 32)
+// the initial states of the owned piles -> every replica: one warp per owned block of 32 piles (128 contiguous bytes)
 __global__ void __launch_bounds__(256) k_push_slice(Peers P, ArenaLayout A) {
-    const uint32_t lo = min((uint32_t) P.rank * A.ppr, A.n_piles), hi = min(lo + A.ppr, A.n_piles);
+    if (hdr_of(P, P.rank)->skip_pass) return;
     const uint32_t* S = section<uint32_t>(P, P.rank, A.S);
-    const uint32_t n4 = (hi - lo) / 4u;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += gridDim.x * blockDim.x) {
-        const uint4 v = reinterpret_cast<const uint4*>(S + lo)[i];
+    for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < A.ppr; j += gridDim.x * blockDim.x) {
+        const uint32_t x = owned_pile(j, (uint32_t) P.rank, (uint32_t) P.world);
+        if (x >= A.n_piles) continue;
+        const uint32_t v = S[x];
         for (int q = 0; q < P.world; ++q)
-            if (q != P.rank) reinterpret_cast<uint4*>(section<uint32_t>(P, q, A.S) + lo)[i] = v;
-    }
-    if (blockIdx.x == 0) {
-        for (uint32_t x = lo + 4u * n4 + threadIdx.x; x < hi; x += blockDim.x)
-            for (int q = 0; q < P.world; ++q)
-                if (q != P.rank) section<uint32_t>(P, q, A.S)[x] = S[x];
+            if (q != P.rank) section<uint32_t>(P, q, A.S)[x] = v;
     }
 }
 
 void launch_push_slice(Launch& L, Peers P, ArenaLayout A) {
     if (P.world == 1) return;
-    k_push_slice<<<grid_for(A.ppr / 4, 256, kNumSMs * 2), 256, 0, L.stream>>>(P, A);
+    k_push_slice<<<grid_for(A.ppr, 256, kNumSMs * 2), 256, 0, L.stream>>>(P, A);
     L.count++;
 }
 
@@ -273,7 +291,7 @@ __device__ __forceinline__ void raise_state(const Peers& P, const ArenaLayout& A
 
 // Settle victim v0 (owned).  Returns false when it has to wait: for a foreign container whose fate is open, or
 // because the chase budget ran out.
-__device__ __forceinline__ bool resolve_owned(const Peers& P, const ArenaLayout& A, uint32_t v0, uint32_t lo, uint32_t hi,
+__device__ __forceinline__ bool resolve_owned(const Peers& P, const ArenaLayout& A, uint32_t v0,
                                               const uint32_t* __restrict__ vstart, const uint32_t* __restrict__ seg_c,
                                               uint32_t* __restrict__ seg_t, uint32_t* __restrict__ S) {
     uint32_t stack_v[kChaseDepth], stack_need[kChaseDepth];
@@ -312,7 +330,7 @@ __device__ __forceinline__ bool resolve_owned(const Peers& P, const ArenaLayout&
             --sp;
             continue;
         }
-        if (c < lo || c >= hi) return false;      // foreign and open: its owner will tell
+        if (pile_owner(c, (uint32_t) P.world) != (uint32_t) P.rank) return false;   // foreign and open: its owner will tell
         if (sp + 1 >= kChaseDepth || --budget <= 0) return false;
         ++sp;
         stack_v[sp] = c;
@@ -326,8 +344,8 @@ __global__ void __launch_bounds__(256) k_fabric_round(Peers P, ArenaLayout A, co
                                                      const uint32_t* __restrict__ seg_c, uint32_t* __restrict__ seg_t,
                                                      uint32_t* __restrict__ work0, uint32_t* __restrict__ work1,
                                                      uint32_t* __restrict__ n_work, uint32_t round) {
+    if (hdr_of(P, P.rank)->skip_pass) return;
     uint32_t* S = section<uint32_t>(P, P.rank, A.S);
-    const uint32_t lo = min((uint32_t) P.rank * A.ppr, A.n_piles), hi = min(lo + A.ppr, A.n_piles);
     const uint32_t n = n_work[round % 3u];
     const uint32_t* in = (round & 1u) ? work1 : work0;
     uint32_t* out = (round & 1u) ? work0 : work1;
@@ -340,7 +358,7 @@ __global__ void __launch_bounds__(256) k_fabric_round(Peers P, ArenaLayout A, co
         bool keep = false;
         if (i < n) {
             v = in[i];
-            keep = !resolve_owned(P, A, v, lo, hi, vstart, seg_c, seg_t, S);
+            keep = !resolve_owned(P, A, v, vstart, seg_c, seg_t, S);
         }
         const uint32_t m = __ballot_sync(0xFFFFFFFFu, keep);
         if (m) {
@@ -353,7 +371,7 @@ __global__ void __launch_bounds__(256) k_fabric_round(Peers P, ArenaLayout A, co
 }
 
 void launch_fabric_round(Launch& L, Peers P, ArenaLayout A, ResolveBufs rb, uint32_t round) {
-    k_fabric_round<<<grid_for(A.ppr, 256, kNumSMs * 2), 256, 0, L.stream>>>(P, A, rb.vstart, rb.seg_c, rb.seg_t, rb.work0, rb.work1,
+    k_fabric_round<<<grid_for(A.ppr, 256, kNumSMs * 8), 256, 0, L.stream>>>(P, A, rb.vstart, rb.seg_c, rb.seg_t, rb.work0, rb.work1,
                                                                           rb.n_work, round);
     L.count++;
 }
@@ -382,30 +400,21 @@ void launch_time_bases_mail(Launch& L, Peers P, uint32_t* bases) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// Build stage.  Nodes are owned by the rank that owns their pile: node_begin[q] = 2 * (alive piles below q * ppr),
-// a popcount over the liveness bitmap (one word per 32 piles, ppr is a multiple of 32).  Block q computes entry q.
+// Build stage.  Node ids are split EVENLY over the ranks (whole reverse-complement pairs): node_begin[q] =
+// min(n_nodes, q * 2 * ceil(n_nodes / 2 / world)).  The surviving piles are not spread evenly over the pile ids
+// (the ordered containment favours late ids), so following the pile ownership would give the last rank several
+// times the rows of the first.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_node_bounds(Peers P, ArenaLayout A, const uint32_t* __restrict__ alive_bits, BuildMeta* __restrict__ meta) {
-    __shared__ uint32_t s_sum[8];
-    const uint32_t q = blockIdx.x;
-    const uint32_t piles_below = min(q * A.ppr, A.n_piles);
-    const uint32_t words = piles_below / 32u, tail = piles_below & 31u;
-    uint32_t local = 0;
-    for (uint32_t w = threadIdx.x; w < words; w += blockDim.x) local += __popc(alive_bits[w]);
-    if (threadIdx.x == 0 && tail) local += __popc(alive_bits[words] & ((1u << tail) - 1u));
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) local += __shfl_xor_sync(0xFFFFFFFFu, local, d);
-    if (lane_id() == 0) s_sum[warp_id()] = local;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        uint32_t total = 0;
-        for (int w = 0; w < 8; ++w) total += s_sum[w];
-        meta->node_begin[q] = 2u * total;
-    }
+__global__ void k_node_bounds(Peers P, ArenaLayout A, const uint32_t* __restrict__ n_nodes_ptr, BuildMeta* __restrict__ meta) {
+    const uint32_t q = threadIdx.x;
+    if (q > (uint32_t) P.world) return;
+    const uint32_t n_nodes = min(*n_nodes_ptr, A.n_nodes_max);
+    const uint32_t per = 2u * ((n_nodes / 2u + (uint32_t) P.world - 1u) / (uint32_t) P.world);
+    meta->node_begin[q] = (unsigned long long) q * per < n_nodes ? q * per : n_nodes;
 }
 
-void launch_node_bounds(Launch& L, Peers P, ArenaLayout A, const uint32_t* alive_bits, BuildMeta* meta) {
-    k_node_bounds<<<P.world + 1, 256, 0, L.stream>>>(P, A, alive_bits, meta);
+void launch_node_bounds(Launch& L, Peers P, ArenaLayout A, const uint32_t* n_nodes_ptr, BuildMeta* meta) {
+    k_node_bounds<<<1, 32, 0, L.stream>>>(P, A, n_nodes_ptr, meta);
     L.count++;
 }
 

@@ -23,9 +23,10 @@ namespace rb {
 
 constexpr int kMaxRanks = 16;
 constexpr int kMailSlots = 8;
+constexpr int kBarrierLog = 128;
 
 // mail slots: small scalars a rank publishes to every peer inside a barrier
-enum Mail { M_UNSETTLED = 0, M_NOVL, M_NINL, M_NEDGES, M_SENT_TO_YOU, M_SPARE0, M_SPARE1, M_SPARE2 };
+enum Mail { M_UNSETTLED = 0, M_NOVL, M_NINL, M_NEDGES, M_SENT_TO_YOU, M_EMITTED, M_SPARE1, M_SPARE2 };
 
 enum FabricError : uint32_t {
     FE_TIMEOUT = 1u,     // a peer did not reach a barrier in time
@@ -42,9 +43,11 @@ struct FabricHdr {
     uint32_t demand[4];                             // observed: events sent to one peer, edges sent to one peer, slice size, (spare)
     uint32_t dead;                                  // sticky: a barrier timed out; later barriers do not wait any more (cleared by a new reservation)
     uint32_t dead_epoch, dead_peer;                 // which barrier / which peer timed out first (diagnostics)
-    uint32_t pad[5];
+    uint32_t skip_pass;                             // no rank has a containment event in the current pass: its kernels and barriers return at once
+    uint32_t pad[4];
     uint32_t mail[2][kMaxRanks][kMailSlots];        // [epoch parity][source rank][slot]
     uint32_t sent[2][kMaxRanks][kMaxRanks];         // [epoch parity][source rank][destination]: edges routed src -> dst
+    unsigned long long tlog[kBarrierLog][2];        // ring by epoch: %globaltimer when the barrier kernel started / when every peer had arrived
 };
 
 struct Peers {
@@ -63,16 +66,29 @@ struct ArenaLayout {
     size_t total;
     uint32_t cap_ev, cap_edge, cap_slice, t_cap;
     uint32_t n_piles, n_nodes_max;
-    uint32_t ppr;         // piles per rank (multiple of 32): owner(pile x) = x / ppr
+    uint32_t ppr;         // piles per rank, rounded up to whole blocks of 32 (sizes the per-rank loops)
+    uint32_t npr_max;     // upper bound of the nodes one rank owns (sizes the row scan)
 };
+
+// Piles are owned BLOCK-CYCLICALLY, 32 piles per block: owner(x) = (x / 32) % world.  Ranges of ids would be simpler,
+// but ids correlate with file order (a pair is listed under its lower id), so the low range would resolve almost
+// everything locally while the high range waits for it, and the surviving piles pile up in the high range
+// (profiles/r02g: 2.5 x the work on the last rank).  One block = 128 contiguous bytes of every per-pile array.
+__host__ __device__ __forceinline__ uint32_t pile_owner(uint32_t x, uint32_t world) { return (x >> 5) % world; }
+// j-th pile slot owned by `rank` (j = 0 .. ppr): may be >= n_piles in the last block
+__host__ __device__ __forceinline__ uint32_t owned_pile(uint32_t j, uint32_t rank, uint32_t world) {
+    return ((j >> 5) * world + rank) * 32u + (j & 31u);
+}
 
 // values published by a rank when it enters a barrier
 struct Publish {
     const uint32_t* scalar[kMailSlots];   // device scalars -> mail[parity][me][k] on every peer (nullptr: skip)
     const uint32_t* per_dst;              // world entries: element q -> mail[parity][me][M_SENT_TO_YOU] on peer q
     const uint32_t* bcast;                // world entries: the whole vector -> sent[parity][me][*] on every peer
-    int bookkeeping;                      // 0 none; 1 after a resolution round: record rounds_needed[pass], flag FE_ROUNDS on the last round
+    int bookkeeping;                      // 0 none; 1 after a resolution round: record rounds_needed[pass], flag FE_ROUNDS on the last round;
+                                          // 2 after the events of a pass were routed: set skip_pass when no rank emitted any
     int pass, round, last_round;
+    int skippable;                        // belongs to a pass that is skipped when it has no events (skip_pass)
     unsigned long long timeout_ns;        // how long to wait for a peer before the fabric is declared dead
 };
 
@@ -89,12 +105,13 @@ void launch_fabric_barrier(Launch& L, Peers P, Publish pub);
 void launch_route_events(Launch& L, Peers P, ArenaLayout A, Events ev, const uint32_t* n_events, uint32_t ev_cap, uint32_t* out_cnt);
 void launch_gather_events(Launch& L, Peers P, ArenaLayout A, Events ev, uint32_t ev_cap, uint32_t* n_events_out, uint32_t* vcount,
                           uint32_t* tmin);
+const uint32_t* skip_flag(const Peers& P);   // device address of this rank's skip_pass word
 void launch_fabric_prepare(Launch& L, Peers P, ArenaLayout A, Events ev, const uint32_t* n_events, uint32_t ev_cap, ResolveBufs rb,
                            const uint32_t* tmin);
 void launch_push_slice(Launch& L, Peers P, ArenaLayout A);
 void launch_fabric_round(Launch& L, Peers P, ArenaLayout A, ResolveBufs rb, uint32_t round);
 void launch_time_bases_mail(Launch& L, Peers P, uint32_t* bases);
-void launch_node_bounds(Launch& L, Peers P, ArenaLayout A, const uint32_t* alive_bits, BuildMeta* meta);
+void launch_node_bounds(Launch& L, Peers P, ArenaLayout A, const uint32_t* n_nodes_ptr, BuildMeta* meta);
 void launch_clear_bytes16(Launch& L, uint8_t* p, const uint32_t* n_ptr, uint32_t cap);
 void launch_route_edges(Launch& L, Peers P, ArenaLayout A, const uint32_t* src, const uint32_t* dst, const uint32_t* len,
                         const uint32_t* n_edges, uint32_t edge_cap, const BuildMeta* meta, uint32_t* out_cnt);

@@ -68,8 +68,9 @@ void launch_hill_coverage(Launch& L, List recs, uint32_t t0, const uint2* piles,
                           uint32_t hill_cap, const uint32_t* hill_pile, const uint32_t* hill_begin,
                           const uint32_t* hill_end, uint32_t n_hills, uint32_t* hill_cov, const uint32_t* dbuf,
                           uint32_t n_piles, const uint32_t* counters);
+// skip: optional device flag; non-zero = do nothing (multi-GPU: a containment pass without events)
 void launch_apply_deaths(Launch& L, uint2* piles, uint32_t* dbuf, uint32_t n_piles, const uint32_t* counters,
-                         uint32_t* alive_bits, bool decode);
+                         uint32_t* alive_bits, bool decode, const uint32_t* skip = nullptr);
 void launch_list_pass(Launch& L, int mode, List in, const uint32_t* n_in, uint32_t in_cap, const uint2* piles, List out_a,
                       uint32_t* n_out_a, List out_b, uint32_t* n_out_b, const uint32_t* b_base, uint32_t cap,
                       const uint32_t* dbuf, uint32_t n_piles, const uint32_t* time_base, const uint32_t* counters,
@@ -104,7 +105,7 @@ void launch_resolve(Launch& L, Events ev, const uint32_t* n_events, uint32_t ev_
 
 // graph_build.cu
 void launch_scan_u32(Launch& L, uint32_t* values_inout, uint32_t* exclusive_out, uint32_t n, unsigned long long* status,
-                     uint32_t* ticket);
+                     uint32_t* ticket, const uint32_t* skip = nullptr);
 struct GraphArrays {
     uint32_t* seq_to_node;   // n_piles
     uint32_t *src, *dst, *len;   // edge id order

@@ -253,8 +253,10 @@ static ArenaLayout make_layout(const rala_b200_multi* m, const uint64_t* caps) {
     A.t_cap = (uint32_t) align_up(caps[RALA_B200_CAP_LOCAL_EDGES] + 16, 256);
     A.n_piles = m->n_piles;
     A.n_nodes_max = 2 * m->n_piles;
-    A.ppr = (uint32_t) align_up((m->n_piles + W - 1) / W, 32);
+    const size_t blocks = ((size_t) m->n_piles + 31) / 32;
+    A.ppr = (uint32_t) (((blocks + W - 1) / W) * 32);   // block-cyclic ownership: whole blocks of 32 piles
     if (A.ppr == 0) A.ppr = 32;
+    A.npr_max = (uint32_t) (2 * (((size_t) m->n_piles + W - 1) / W) + 2);   // nodes <= 2 * piles, split evenly in pairs
     size_t off = align_up(sizeof(FabricHdr), 4096);
     A.ev_inbox = off;   off += align_up(W * 3 * (size_t) A.cap_ev * 4, 256);
     A.edge_inbox = off; off += align_up(W * 4 * (size_t) A.cap_edge * 4, 256);
@@ -294,10 +296,12 @@ extern "C" int rala_b200_multi_reserve(rala_b200_multi* m, const uint64_t* caps)
         MCU(m, fr.out_cnt.reserve(3 * kMaxRanks * 4));
         MCU(m, fr.tmin.reserve(((size_t) m->n_piles + 64) * 4));
         MCU(m, fr.col_eid.reserve(W * (size_t) A.cap_slice * 4 + 256));
-        MCU(m, fr.T.reserve(align_up(W * (size_t) A.cap_slice + 16, 256)));
+        // result bytes of the transitive pass, indexed by GLOBAL edge id: an id is < world x the edges one rank can emit,
+        // whatever happened to the exchange buffers (nothing clears the array: the row fill clears the bytes it needs)
+        MCU(m, fr.T.reserve(align_up(W * (size_t) A.t_cap + 16, 256)));
         MRC(m, fr, reserve_events(fr.g, (uint32_t) (W * A.cap_ev)));
-        // the owned rows are scanned over 2 * ppr + 1 entries (ppr is rounded up to a multiple of 32)
-        const size_t rows = 2 * (size_t) A.ppr + 16;
+        // the owned rows are scanned over npr_max + 1 entries
+        const size_t rows = (size_t) A.npr_max + 16;
         if (rows > (size_t) fr.g->n_nodes_max + 8) {
             MCU(m, fr.g->row_ptr.reserve(rows * 4));
             MCU(m, fr.g->cursor.reserve(rows * 4));
@@ -393,6 +397,9 @@ static int route_and_meet(rala_b200_multi* m, FabricRank& fr, int pass) {
     launch_route_events(L, fr.P, fr.A, g->events_view(), g->cnt() + C_EV, g->ev_cap, fr.cnt_ev(pass));
     Publish pub = no_mail(m);
     pub.per_dst = fr.cnt_ev(pass);
+    pub.scalar[M_EMITTED] = g->cnt() + C_EV;   // still the number of events this rank emitted (the gather overwrites it)
+    pub.bookkeeping = 2;                       // a pass in which no rank has an event is skipped by all of them
+    pub.pass = pass;
     launch_fabric_barrier(L, fr.P, pub);
     MCU(m, cudaGetLastError());
     return RALA_B200_OK;
@@ -412,10 +419,12 @@ static int resolve_owned_piles(rala_b200_multi* m, FabricRank& fr, int pass) {
     unsigned long long* status;
     uint32_t* ticket;
     scan_state(g, (uint64_t) g->n_piles + 1, &status, &ticket);
-    launch_scan_u32(L, rb.vcursor, rb.vstart, g->n_piles + 1, status, ticket);
+    launch_scan_u32(L, rb.vcursor, rb.vstart, g->n_piles + 1, status, ticket, skip_flag(fr.P));
     launch_fabric_prepare(L, fr.P, fr.A, g->events_view(), g->cnt() + C_EV, g->ev_cap, rb, fr.tmin.as<uint32_t>());
     launch_push_slice(L, fr.P, fr.A);
-    launch_fabric_barrier(L, fr.P, no_mail(m));
+    Publish meet = no_mail(m);
+    meet.skippable = 1;
+    launch_fabric_barrier(L, fr.P, meet);
     for (uint32_t r = 0; r < rounds; ++r) {
         launch_fabric_round(L, fr.P, fr.A, rb, r);
         Publish pub = no_mail(m);
@@ -424,11 +433,14 @@ static int resolve_owned_piles(rala_b200_multi* m, FabricRank& fr, int pass) {
         pub.pass = pass;
         pub.round = (int) r;
         pub.last_round = (int) rounds - 1;
+        pub.skippable = 1;
         launch_fabric_barrier(L, fr.P, pub);
     }
     MCU(m, end_stage(g, ST_K1B_KERNEL));
     // every replica now holds every pile's final state: piles with a finite death time die (graph.cpp:471,477,838,842)
-    launch_apply_deaths(L, g->piles.as<uint2>(), fr.sec<uint32_t>(fr.A.S), g->n_piles, g->cnt(), g->alive_bits.as<uint32_t>(), true);
+    // (a skipped pass killed nobody: the table and the liveness bitmap stay as they are)
+    launch_apply_deaths(L, g->piles.as<uint2>(), fr.sec<uint32_t>(fr.A.S), g->n_piles, g->cnt(), g->alive_bits.as<uint32_t>(), true,
+                        skip_flag(fr.P));
     MCU(m, cudaGetLastError());
     return RALA_B200_OK;
 }
@@ -489,7 +501,7 @@ static int phase_f_edges(rala_b200_multi* m, FabricRank& fr) {
     uint32_t* ticket;
     scan_state(g, g->n_piles, &status, &ticket);
     launch_node_ids(L, g->piles.as<uint2>(), g->n_piles, g->seq_to_node.as<uint32_t>(), g->cnt(), status, ticket);
-    launch_node_bounds(L, fr.P, fr.A, g->alive_bits.as<uint32_t>(), fr.meta_dev());
+    launch_node_bounds(L, fr.P, fr.A, g->cnt() + C_NODES, fr.meta_dev());
     scan_state(g, g->cap, &status, &ticket);
     GraphArrays ga = g->graph_view();
     ga.cursor = nullptr;   // no local degree histogram: the owners count what they receive
@@ -516,7 +528,7 @@ static int phase_g_csr(rala_b200_multi* m, FabricRank& fr) {
     rala_b200_graph* g = fr.g;
     Launch& L = fr.ctx->L;
     launch_edge_meta(L, fr.P, fr.A, fr.meta_dev(), g->cnt());
-    const uint32_t rows = 2u * fr.A.ppr + 1u;   // owned nodes <= 2 * ppr
+    const uint32_t rows = fr.A.npr_max + 1u;
     MCU(m, cudaMemsetAsync(g->cursor.p, 0, ((size_t) rows + 7) * 4, L.stream));
     launch_inbox_degree(L, fr.P, fr.A, fr.meta_dev(), g->cursor.as<uint32_t>());
     unsigned long long* status;
@@ -830,6 +842,27 @@ extern "C" int rala_b200_multi_get_piles(rala_b200_multi* m, rala_pile_t* out) {
     if (!m || !out) return RALA_B200_ERR_ARG;
     FabricRank& fr = m->ranks[0];
     MRC(m, fr, rala_b200_graph_get_piles(fr.g, out));
+    return RALA_B200_OK;
+}
+
+// diagnostics: the last kBarrierLog barriers of local rank k as (start, all peers arrived) device timestamps in ns,
+// oldest first; *n_out = how many are valid
+extern "C" int rala_b200_multi_barrier_log(rala_b200_multi* m, int k, uint64_t* out, uint32_t* n_out) {
+    if (!m || k < 0 || k >= m->n_local || !out || !n_out) return RALA_B200_ERR_ARG;
+    if (!m->reserved) return mfail(m, RALA_B200_ERR_STATE, "barrier_log: nothing has run");
+    FabricRank& fr = m->ranks[k];
+    MCU(m, cudaSetDevice(fr.device));
+    MCU(m, cudaStreamSynchronize(fr.ctx->L.stream));
+    std::vector<unsigned char> raw(sizeof(FabricHdr));
+    MCU(m, cudaMemcpy(raw.data(), fr.arena.p, sizeof(FabricHdr), cudaMemcpyDeviceToHost));
+    const FabricHdr* h = reinterpret_cast<const FabricHdr*>(raw.data());
+    const uint32_t n = h->epoch < (uint32_t) kBarrierLog ? h->epoch : (uint32_t) kBarrierLog;
+    for (uint32_t i = 0; i < n; ++i) {
+        const uint32_t e = h->epoch - n + 1u + i;
+        out[2 * i] = h->tlog[e % kBarrierLog][0];
+        out[2 * i + 1] = h->tlog[e % kBarrierLog][1];
+    }
+    *n_out = n;
     return RALA_B200_OK;
 }
 
