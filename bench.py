@@ -415,7 +415,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true", help="device-resident timing only")
     ap.add_argument("--skip-parity", action="store_true", help="N > 1: do not verify the assembled result on rank 0")
-    ap.add_argument("--parity-oracle-max", type=int, default=130_000_000,
+    ap.add_argument("--parity-oracle-max", type=int, default=60_000_000,
                     help="N > 1: run the plain-C oracle on the whole batch when it has at most this many records")
     ap.add_argument("--force-multi", action="store_true", help="run the multi-GPU path even with one rank (under torchrun)")
     ap.add_argument("--ab", action="store_true", help="time the product library against the one-switch-off builds (rala_b200/variants/)")

@@ -278,8 +278,8 @@ typedef struct rala_b200_multi rala_b200_multi;
 enum { RALA_B200_CAP_EVENTS = 0,   /* containment events one rank sends to one owner */
        RALA_B200_CAP_EDGES,        /* edges one rank sends to one owner */
        RALA_B200_CAP_SLICE,        /* edges of one rank's CSR slice */
-       RALA_B200_CAP_ROUNDS,       /* resolution rounds of the first containment pass */
-       RALA_B200_CAP_FINAL_ROUNDS, /* resolution rounds of the final containment pass */
+       RALA_B200_CAP_ROUNDS,       /* sweeps after which the resolution of the first containment pass gives up (it ends by itself) */
+       RALA_B200_CAP_FINAL_ROUNDS, /* the same for the final containment pass */
        RALA_B200_CAP_LOCAL_EDGES,  /* edges one rank emits */
        RALA_B200_N_CAPS };
 
@@ -313,7 +313,7 @@ int rala_b200_multi_set_outputs(rala_b200_multi* m, int k, rala_edge_t* edges_ou
 int rala_b200_multi_default_caps(rala_b200_multi* m, uint64_t* caps /* RALA_B200_N_CAPS */);
 /* (re)allocate the exchange arenas; with all ranks in one process this also connects them */
 int rala_b200_multi_reserve(rala_b200_multi* m, const uint64_t* caps /* RALA_B200_N_CAPS */);
-/* change the number of resolution rounds a step enqueues (same value on every rank) without touching the arenas */
+/* change the sweep limits of the two containment resolutions without touching the arenas */
 int rala_b200_multi_set_rounds(rala_b200_multi* m, uint32_t rounds, uint32_t final_rounds);
 /* one process per GPU: 64-byte CUDA IPC handle of local rank k's arena / the handles of all `world` ranks in rank order */
 int rala_b200_multi_export_handle(rala_b200_multi* m, int k, void* handle64);
@@ -344,6 +344,9 @@ uint64_t rala_b200_multi_launch_count(const rala_b200_multi* m);
 /* Diagnostics: device timestamps (ns) of the last barriers of local rank k, oldest first, as pairs (barrier kernel started,
  * every peer had arrived); out holds 2 x 128 values, *n_out = number of valid pairs.  Synchronises. */
 int rala_b200_multi_barrier_log(rala_b200_multi* m, int k, uint64_t* out, uint32_t* n_out);
+/* Diagnostics: the sweeps of the last containment resolution (pass 0 first, 1 final) of local rank k as pairs (victims still
+ * open when the sweep started, ns since the kernel started when it ended); out holds 2 x 48 values. Synchronises. */
+int rala_b200_multi_sweep_log(rala_b200_multi* m, int k, int pass, uint64_t* out, uint32_t* n_out);
 /* device time of the stages of the last EAGER step of local rank k (as rala_b200_graph_stage_ms) */
 int rala_b200_multi_stage_ms(rala_b200_multi* m, int k, float* ms_out /* RALA_B200_N_STAGES */);
 

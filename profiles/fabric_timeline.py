@@ -40,11 +40,10 @@ for _ in range(args.steps):
 fg.M.event_record(1)
 ms = fg.M.event_elapsed_ms() / args.steps
 log = fg.M.barrier_log(0).astype(np.int64)
-B = fg.M.barriers_per_step()
-r0, r1 = int(fg.M.caps[3]), int(fg.M.caps[4])
-names = (["events routed", "states prepared + slice pushed"] + [f"round {i}" for i in range(r0)] + ["survivors pass", "final events routed",
-         "final states prepared"] + [f"final round {i}" for i in range(r1)] + ["edges emitted + routed", "rows built + slice pushed",
-         "transitive pass + marks routed"])
+B = fg.M.BARRIERS_PER_STEP
+names = ["first pass over the records + events routed", "containment resolved (one persistent kernel) + survivors pass",
+         "final pass classified + events routed", "final containment resolved + edges emitted + routed",
+         "rows built + slice pushed", "transitive pass + marks routed"]
 last = log[-B:]
 prev_exit = log[-B - 1, 1]
 rows, compute_us, wait_us = [], 0.0, 0.0
@@ -55,7 +54,9 @@ for i in range(B):
     wait_us += wait
     prev_exit = last[i, 1]
 print(json.dumps({"rank": rank, "world": world, "ms_per_step": ms, "barriers_per_step": B, "compute_us": round(float(compute_us), 1),
-                  "wait_us": round(float(wait_us), 1), "phases [name, compute us before the barrier, wait us in it]": rows}), flush=True)
+                  "wait_us": round(float(wait_us), 1),
+                  "resolution sweeps [open victims at start, us since kernel start at end]": [[int(a), round(float(b) / 1e3, 1)] for a, b in fg.M.sweep_log(0, 0)],
+                  "phases [name, compute us before the barrier, wait us in it]": rows}), flush=True)
 dist.barrier()
 fg.close()
 dist.destroy_process_group()

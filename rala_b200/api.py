@@ -69,7 +69,7 @@ EXPORTS = [
     "rala_b200_multi_counts", "rala_b200_multi_edge_range", "rala_b200_multi_get_edges", "rala_b200_multi_get_marked",
     "rala_b200_multi_get_seq_to_node", "rala_b200_multi_get_piles", "rala_b200_multi_event_record",
     "rala_b200_multi_event_elapsed_ms", "rala_b200_multi_launch_count", "rala_b200_multi_stage_ms",
-    "rala_b200_multi_set_outputs", "rala_b200_multi_set_barrier_timeout_ms", "rala_b200_multi_set_rounds", "rala_b200_multi_barrier_log",
+    "rala_b200_multi_set_outputs", "rala_b200_multi_set_barrier_timeout_ms", "rala_b200_multi_set_rounds", "rala_b200_multi_barrier_log", "rala_b200_multi_sweep_log",
 ]
 
 _LIB = None
@@ -415,7 +415,7 @@ class Graph:
 
 
 N_CAPS = 6
-CAP_NAMES = ("events_per_pair", "edges_per_pair", "slice_edges", "rounds", "final_rounds", "local_edges")
+CAP_NAMES = ("events_per_pair", "edges_per_pair", "slice_edges", "max_sweeps", "max_final_sweeps", "local_edges")
 
 
 class MultiCounts(C.Structure):
@@ -636,8 +636,14 @@ class Multi:
         self._call("rala_b200_multi_barrier_log", C.c_int(k), _ptr(out), C.byref(n))
         return out[:int(n.value)]
 
-    def barriers_per_step(self) -> int:
-        return 8 + int(self.caps[3]) + int(self.caps[4])
+    def sweep_log(self, k: int = 0, which_pass: int = 0):
+        """(n, 2): per sweep of the last containment resolution, open victims at its start and ns since the kernel started."""
+        out = np.zeros((48, 2), dtype=np.uint64)
+        n = C.c_uint32(0)
+        self._call("rala_b200_multi_sweep_log", C.c_int(k), C.c_int(which_pass), _ptr(out), C.byref(n))
+        return out[:int(n.value)]
+
+    BARRIERS_PER_STEP = 6   # events routed, list counts, final events routed, edges routed, slices pushed, marks routed
 
     def stage_ms(self, k: int = 0) -> dict:
         ms = (C.c_float * N_STAGES)()

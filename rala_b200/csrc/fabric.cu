@@ -281,26 +281,38 @@ void launch_push_slice(Launch& L, Peers P, ArenaLayout A) {
     L.count++;
 }
 
-// raise the state of an OWNED pile; a change is pushed to every replica
-__device__ __forceinline__ void raise_state(const Peers& P, const ArenaLayout& A, uint32_t* S, uint32_t x, uint32_t val) {
-    const uint32_t old = atomicMax(&S[x], val);
-    if (old < val)
+// raise the state of an OWNED pile (known to be at `seen` or above); a change is pushed to every replica.  No value is
+// read back (a returning atomic would add a round trip to every step of a chase): when another thread raised the state
+// in between, the push is repeated, which is harmless (max-reductions).
+__device__ __forceinline__ void raise_state(const Peers& P, const ArenaLayout& A, uint32_t* S, uint32_t x, uint32_t val, uint32_t seen,
+                                            bool& pushed) {
+    if (val <= seen) return;
+    atomicMax(&S[x], val);
+    if (P.world > 1) {
+        pushed = true;
         for (int q = 0; q < P.world; ++q)
             if (q != P.rank) red_max_sys(section<uint32_t>(P, q, A.S) + x, val);
+    }
 }
 
+constexpr uint32_t kNoWait = 0xFFFFFFFFu;
+
 // Settle victim v0 (owned).  Returns false when it has to wait: for a foreign container whose fate is open, or
-// because the chase budget ran out.
+// because the chase budget ran out.  In the first case every pile on the chase stack is frozen until that foreign
+// pile's state moves past the time in question; (pile, time) is noted for each of them (wait_pile / wait_time), so
+// the next sweeps test one state word instead of walking the whole chain again only to stop at the same place.
 __device__ __forceinline__ bool resolve_owned(const Peers& P, const ArenaLayout& A, uint32_t v0,
                                               const uint32_t* __restrict__ vstart, const uint32_t* __restrict__ seg_c,
-                                              uint32_t* __restrict__ seg_t, uint32_t* __restrict__ S) {
+                                              uint32_t* __restrict__ seg_t, uint32_t* __restrict__ S, uint32_t* __restrict__ wait_pile,
+                                              uint32_t* __restrict__ wait_time, bool& pushed) {
     uint32_t stack_v[kChaseDepth], stack_need[kChaseDepth];
     int sp = 0, budget = kChaseBudget;
     stack_v[0] = v0;
     stack_need[0] = kNever;
     while (sp >= 0) {
         const uint32_t v = stack_v[sp];
-        if (ld_relaxed_sys(&S[v]) & kSettled) { --sp; continue; }
+        const uint32_t cur = ld_relaxed_sys(&S[v]);
+        if (cur & kSettled) { --sp; continue; }
         const uint32_t s0 = vstart[v], s1 = vstart[v + 1];
         uint32_t best_t = kDeadEvent, best_p = 0;
         for (uint32_t p = s0; p < s1; ++p) {
@@ -308,17 +320,17 @@ __device__ __forceinline__ bool resolve_owned(const Peers& P, const ArenaLayout&
             if (t < best_t) { best_t = t; best_p = p; }
         }
         if (best_t == kDeadEvent) {               // every event found its container dead: v is never killed
-            raise_state(P, A, S, v, kSettled | kNever);
+            raise_state(P, A, S, v, kSettled | kNever, cur, pushed);
             --sp;
             continue;
         }
-        raise_state(P, A, S, v, best_t);          // v cannot die before its earliest open event
+        raise_state(P, A, S, v, best_t, cur, pushed);   // v cannot die before its earliest open event
         if (best_t > stack_need[sp]) { --sp; continue; }
         const uint32_t c = seg_c[best_p];
         const uint32_t q = c == v ? kSettled | kNever : ld_relaxed_sys(&S[c]);   // a == b record: the pile is its own (alive) container
         if (q & kSettled) {
             if ((q & kNever) > best_t) {          // container alive at best_t: the event fires
-                raise_state(P, A, S, v, kSettled | best_t);
+                raise_state(P, A, S, v, kSettled | best_t, cur, pushed);
                 --sp;
             } else {
                 seg_t[best_p] = kDeadEvent;       // container died first: the event never fires; look again
@@ -326,11 +338,17 @@ __device__ __forceinline__ bool resolve_owned(const Peers& P, const ArenaLayout&
             continue;
         }
         if (q > best_t) {                         // open, but certainly alive at best_t
-            raise_state(P, A, S, v, kSettled | best_t);
+            raise_state(P, A, S, v, kSettled | best_t, cur, pushed);
             --sp;
             continue;
         }
-        if (pile_owner(c, (uint32_t) P.world) != (uint32_t) P.rank) return false;   // foreign and open: its owner will tell
+        if (pile_owner(c, (uint32_t) P.world) != (uint32_t) P.rank) {   // foreign and open: its owner will tell
+            for (int i = 0; i <= sp; ++i) {
+                wait_pile[stack_v[i]] = c;
+                wait_time[stack_v[i]] = best_t;
+            }
+            return false;
+        }
         if (sp + 1 >= kChaseDepth || --budget <= 0) return false;
         ++sp;
         stack_v[sp] = c;
@@ -339,26 +357,73 @@ __device__ __forceinline__ bool resolve_owned(const Peers& P, const ArenaLayout&
     return true;
 }
 
-// one round over the worklist of open owned victims: in = work[round & 1], out = the other one; three rotating counters
-__global__ void __launch_bounds__(256) k_fabric_round(Peers P, ArenaLayout A, const uint32_t* __restrict__ vstart,
-                                                     const uint32_t* __restrict__ seg_c, uint32_t* __restrict__ seg_t,
-                                                     uint32_t* __restrict__ work0, uint32_t* __restrict__ work1,
-                                                     uint32_t* __restrict__ n_work, uint32_t round) {
-    if (hdr_of(P, P.rank)->skip_pass) return;
-    uint32_t* S = section<uint32_t>(P, P.rank, A.S);
-    const uint32_t n = n_work[round % 3u];
-    const uint32_t* in = (round & 1u) ? work1 : work0;
-    uint32_t* out = (round & 1u) ? work0 : work1;
-    uint32_t* n_out = &n_work[(round + 1u) % 3u];
-    if (blockIdx.x == 0 && threadIdx.x == 0) n_work[(round + 2u) % 3u] = 0u;   // read last in round - 1, written next in round + 1
+// ---------------------------------------------------------------------------------------------
+// The resolution itself: ONE persistent kernel per rank and pass, no barrier with the peers inside.  The grid sweeps
+// the worklist of open owned victims again and again; every state change is pushed to the replicas as it happens, so
+// news from the peers arrives while a sweep runs, and a rank never waits for a slower peer to finish its own sweep.
+// After every sweep block 0 tells the peers how many victims are still open here (tagged with the barrier epoch of the
+// pass, so a value of the previous pass is never mistaken for a current one); the pass ends on a rank when every
+// rank has reported zero.  Ordering: each thread fences (system scope) after its pushes and before the grid barrier,
+// so a peer that reads "0 open" from this rank already holds every state this rank owns.
+// The grid is sized to be co-resident (launch_fabric_resolve), which the software grid barrier needs.
+// ---------------------------------------------------------------------------------------------
+struct ResolveCtl {
+    uint32_t arrived;   // grid barrier: blocks that have arrived, counts up for ever
+    uint32_t released;  // grid barrier: phases released so far
+    uint32_t go;        // decision of block 0 after a sweep: 1 = sweep again, 0 = the pass is over
+    uint32_t sweeps;
+    uint32_t resume, pad[3];   // sweep index the whole grid continues with
+    unsigned long long log[kSweepLog][2];   // diagnostics: (open victims at the start of the sweep, ns since the kernel started) per sweep
+};
+static_assert(sizeof(ResolveCtl) == kResolveCtlBytes, "fabric.cuh sizes the control block");
+
+__device__ __forceinline__ void grid_barrier(ResolveCtl* ctl, uint32_t& phase) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        phase += 1u;
+        __threadfence();
+        if (atomicAdd(&ctl->arrived, 1u) + 1u == phase * gridDim.x) {
+            asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(&ctl->released), "r"(phase) : "memory");
+        } else {
+            uint32_t seen;
+            do {
+                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(&ctl->released) : "memory");
+            } while ((int32_t) (seen - phase) < 0);
+        }
+    }
+    __syncthreads();
+}
+
+__device__ __forceinline__ void st_release_sys64(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// one sweep over work list `in` (n entries) by the threads first, first + stride, ...: victims that stay open go to `out`
+__device__ __forceinline__ void sweep_worklist(const Peers& P, const ArenaLayout& A, const uint32_t* __restrict__ vstart,
+                                               const uint32_t* __restrict__ seg_c, uint32_t* __restrict__ seg_t, uint32_t* __restrict__ S,
+                                               uint32_t* __restrict__ wait_pile, uint32_t* __restrict__ wait_time,
+                                               const uint32_t* __restrict__ in, uint32_t n, uint32_t* __restrict__ out,
+                                               uint32_t* __restrict__ n_out, uint32_t first_block, uint32_t n_blocks) {
     const uint32_t lane = lane_id();
-    for (uint32_t base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
+    bool pushed = false;
+    for (uint32_t base = first_block * blockDim.x; base < n; base += n_blocks * blockDim.x) {
         const uint32_t i = base + threadIdx.x;
         uint32_t v = 0;
         bool keep = false;
         if (i < n) {
             v = in[i];
-            keep = !resolve_owned(P, A, v, vstart, seg_c, seg_t, S);
+            const uint32_t f = wait_pile[v];
+            bool frozen = false;
+            if (f != kNoWait) {   // still waiting for foreign pile f to move past wait_time[v]?
+                const uint32_t q = ld_relaxed_sys(&S[f]);
+                frozen = !(q & kSettled) && q <= wait_time[v];
+            }
+            keep = frozen || !resolve_owned(P, A, v, vstart, seg_c, seg_t, S, wait_pile, wait_time, pushed);
         }
         const uint32_t m = __ballot_sync(0xFFFFFFFFu, keep);
         if (m) {
@@ -368,11 +433,131 @@ __global__ void __launch_bounds__(256) k_fabric_round(Peers P, ArenaLayout A, co
             if (keep) out[gb + __popc(m & ((1u << lane) - 1u))] = v;
         }
     }
+    // this thread's pushes have reached the replicas before anybody hears that the sweep is over (a system-scope fence is
+    // expensive: only threads that pushed something pay for it)
+    if (pushed) __threadfence_system();
 }
 
-void launch_fabric_round(Launch& L, Peers P, ArenaLayout A, ResolveBufs rb, uint32_t round) {
-    k_fabric_round<<<grid_for(A.ppr, 256, kNumSMs * 8), 256, 0, L.stream>>>(P, A, rb.vstart, rb.seg_c, rb.seg_t, rb.work0, rb.work1,
-                                                                          rb.n_work, round);
+constexpr uint32_t kTailVictims = 1024;   // at most this many open victims: block 0 finishes the pass alone (no grid barriers)
+
+__global__ void __launch_bounds__(256) k_fabric_resolve(Peers P, ArenaLayout A, const uint32_t* __restrict__ vstart,
+                                                       const uint32_t* __restrict__ seg_c, uint32_t* __restrict__ seg_t,
+                                                       uint32_t* __restrict__ work0, uint32_t* __restrict__ work1,
+                                                       uint32_t* __restrict__ n_work, uint32_t* __restrict__ wait_pile,
+                                                       uint32_t* __restrict__ wait_time, ResolveCtl* __restrict__ ctl, int pass,
+                                                       uint32_t max_sweeps, unsigned long long timeout_ns) {
+    __shared__ uint32_t s_state;   // tail loop of block 0: 0 sweep again, 1 done
+    FabricHdr* mine = hdr_of(P, P.rank);
+    if (mine->skip_pass) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) mine->rounds_needed[pass] = 1u;
+        return;
+    }
+    uint32_t* S = section<uint32_t>(P, P.rank, A.S);
+    const unsigned long long tag = (unsigned long long) mine->epoch << 32;   // no barrier runs on this rank while the kernel does
+    const uint32_t me = (uint32_t) P.rank, W = (uint32_t) P.world;
+    const unsigned long long t_start = global_timer_ns();
+    uint32_t phase = 0;
+
+    // block 0, thread 0, after a sweep: tell the peers, decide.  Returns 0 = the pass is over, 1 = sweep again.
+    auto after_sweep = [&](uint32_t sweep, uint32_t n_before) -> uint32_t {
+        const uint32_t open = n_work[(sweep + 1u) % 3u];
+        for (uint32_t q = 0; q < W; ++q) st_release_sys64(&hdr_of(P, (int) q)->progress[me], tag | open);
+        uint32_t go = 1u;
+        bool dead = ld_relaxed_sys(&mine->dead) != 0u || global_timer_ns() - t_start > timeout_ns;
+        if (open == 0u) {   // everything here is settled and pushed: wait until that is true everywhere
+            while (!dead) {
+                bool all = true;
+                for (uint32_t q = 0; q < W; ++q) all = all && ld_acquire_sys64(&mine->progress[q]) == tag;
+                if (all) break;
+                __nanosleep(100);
+                dead = ld_relaxed_sys(&mine->dead) != 0u || global_timer_ns() - t_start > timeout_ns;
+            }
+            go = 0u;
+        } else {
+            if (open == n_before) __nanosleep(200);   // nothing settled in this sweep: give the peers' news a moment to arrive
+            if (sweep + 1u >= max_sweeps) {
+                atomicOr(&mine->error, (uint32_t) FE_ROUNDS);
+                go = 0u;
+            }
+        }
+        if (dead) {
+            atomicOr(&mine->error, (uint32_t) FE_TIMEOUT);
+            if (atomicExch(&mine->dead, 1u) == 0u) {
+                mine->dead_epoch = mine->epoch;
+                mine->dead_peer = 0xFFFFu;
+            }
+            go = 0u;
+        }
+        ctl->sweeps = sweep + 1u;
+        if (sweep < (uint32_t) kSweepLog) {
+            ctl->log[sweep][0] = n_before;
+            ctl->log[sweep][1] = global_timer_ns() - t_start;
+        }
+        if (!go) mine->rounds_needed[pass] = (open == 0u && !dead) ? sweep + 1u : 0u;
+        return go;
+    };
+
+    for (uint32_t sweep = 0;; ++sweep) {
+        const uint32_t n = n_work[sweep % 3u];
+        if (blockIdx.x == 0 && threadIdx.x == 0) n_work[(sweep + 2u) % 3u] = 0u;   // read last in sweep - 1, written next in sweep + 1
+        sweep_worklist(P, A, vstart, seg_c, seg_t, S, wait_pile, wait_time, (sweep & 1u) ? work1 : work0, n, (sweep & 1u) ? work0 : work1,
+                       &n_work[(sweep + 1u) % 3u], blockIdx.x, gridDim.x);
+        grid_barrier(ctl, phase);
+        if (blockIdx.x == 0) {
+            uint32_t go = 0;
+            if (threadIdx.x == 0) {
+                go = after_sweep(sweep, n);
+                s_state = go;
+            }
+            __syncthreads();
+            go = s_state;
+            // few victims left: this block finishes alone, sweep after sweep, while the others wait at the barrier below
+            // (a sweep of the whole grid costs two grid barriers and ~15 us whatever its size; profiles/r02k)
+            uint32_t ts = sweep + 1u;
+            while (go && n_work[ts % 3u] <= kTailVictims) {
+                __syncthreads();
+                const uint32_t tn = n_work[ts % 3u];
+                if (threadIdx.x == 0) n_work[(ts + 2u) % 3u] = 0u;
+                sweep_worklist(P, A, vstart, seg_c, seg_t, S, wait_pile, wait_time, (ts & 1u) ? work1 : work0, tn, (ts & 1u) ? work0 : work1,
+                               &n_work[(ts + 1u) % 3u], 0u, 1u);
+                __syncthreads();
+                if (threadIdx.x == 0) s_state = after_sweep(ts, tn);
+                __syncthreads();
+                go = s_state;
+                ++ts;
+            }
+            if (threadIdx.x == 0) {
+                ctl->go = go;
+                ctl->resume = ts;   // the sweep the whole grid continues with (only when go == 1: the list grew back over the tail size — it cannot)
+                __threadfence();
+            }
+        }
+        grid_barrier(ctl, phase);
+        uint32_t go;
+        asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(go) : "l"(&ctl->go) : "memory");
+        if (!go) break;
+        uint32_t resume;
+        asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(resume) : "l"(&ctl->resume) : "memory");
+        sweep = resume - 1u;
+    }
+}
+
+int fabric_resolve_max_blocks() {
+    int per_sm = 0, dev = 0, sms = kNumSMs;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fabric_resolve, 256, 0);
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (per_sm < 1) per_sm = 1;
+    return per_sm * sms;
+}
+
+void launch_fabric_resolve(Launch& L, Peers P, ArenaLayout A, ResolveBufs rb, uint32_t* wait /* 2 x (n_piles + 64) words */, uint32_t* ctl,
+                           int pass, uint32_t max_sweeps, unsigned long long timeout_ns, int blocks) {
+    const size_t stride = (size_t) A.n_piles + 64;
+    cudaMemsetAsync(ctl, 0, sizeof(ResolveCtl), L.stream);
+    cudaMemsetAsync(wait, 0xFF, stride * 4, L.stream);   // wait_pile = kNoWait (wait_time is only read next to a valid wait_pile)
+    k_fabric_resolve<<<blocks, 256, 0, L.stream>>>(P, A, rb.vstart, rb.seg_c, rb.seg_t, rb.work0, rb.work1, rb.n_work, wait, wait + stride,
+                                                  reinterpret_cast<ResolveCtl*>(ctl), pass, max_sweeps, timeout_ns);
     L.count++;
 }
 
@@ -633,7 +818,7 @@ void preload_fabric() {
     cudaFuncGetAttributes(&a, k_gather_events);
     cudaFuncGetAttributes(&a, k_fabric_prepare);
     cudaFuncGetAttributes(&a, k_push_slice);
-    cudaFuncGetAttributes(&a, k_fabric_round);
+    cudaFuncGetAttributes(&a, k_fabric_resolve);
     cudaFuncGetAttributes(&a, k_time_bases_mail);
     cudaFuncGetAttributes(&a, k_node_bounds);
     cudaFuncGetAttributes(&a, k_clear_bytes16);

@@ -24,6 +24,8 @@ namespace rb {
 constexpr int kMaxRanks = 16;
 constexpr int kMailSlots = 8;
 constexpr int kBarrierLog = 128;
+constexpr int kSweepLog = 48;
+constexpr int kResolveCtlBytes = 32 + kSweepLog * 16;
 
 // mail slots: small scalars a rank publishes to every peer inside a barrier
 enum Mail { M_UNSETTLED = 0, M_NOVL, M_NINL, M_NEDGES, M_SENT_TO_YOU, M_EMITTED, M_SPARE1, M_SPARE2 };
@@ -47,6 +49,7 @@ struct FabricHdr {
     uint32_t pad[4];
     uint32_t mail[2][kMaxRanks][kMailSlots];        // [epoch parity][source rank][slot]
     uint32_t sent[2][kMaxRanks][kMaxRanks];         // [epoch parity][source rank][destination]: edges routed src -> dst
+    unsigned long long progress[kMaxRanks];         // progress[q]: (epoch of the pass << 32 | victims still open on rank q), written by q after every sweep
     unsigned long long tlog[kBarrierLog][2];        // ring by epoch: %globaltimer when the barrier kernel started / when every peer had arrived
 };
 
@@ -109,7 +112,11 @@ const uint32_t* skip_flag(const Peers& P);   // device address of this rank's sk
 void launch_fabric_prepare(Launch& L, Peers P, ArenaLayout A, Events ev, const uint32_t* n_events, uint32_t ev_cap, ResolveBufs rb,
                            const uint32_t* tmin);
 void launch_push_slice(Launch& L, Peers P, ArenaLayout A);
-void launch_fabric_round(Launch& L, Peers P, ArenaLayout A, ResolveBufs rb, uint32_t round);
+// ctl: kResolveCtlBytes zeroable bytes of device memory per rank and pass; blocks: co-resident grid size (fabric_resolve_max_blocks() shared
+// between the ranks that live on one device)
+void launch_fabric_resolve(Launch& L, Peers P, ArenaLayout A, ResolveBufs rb, uint32_t* wait /* 2 x (n_piles + 64) words */, uint32_t* ctl,
+                           int pass, uint32_t max_sweeps, unsigned long long timeout_ns, int blocks);
+int fabric_resolve_max_blocks();
 void launch_time_bases_mail(Launch& L, Peers P, uint32_t* bases);
 void launch_node_bounds(Launch& L, Peers P, ArenaLayout A, const uint32_t* n_nodes_ptr, BuildMeta* meta);
 void launch_clear_bytes16(Launch& L, uint8_t* p, const uint32_t* n_ptr, uint32_t cap);

@@ -28,12 +28,13 @@ struct FabricRank {
     DevBuf arena;
     Peers P{};
     ArenaLayout A{};
-    DevBuf meta, out_cnt, tmin, col_eid, T;
+    DevBuf meta, out_cnt, tmin, wait, col_eid, T;
     void* ipc_mapped[kMaxRanks]{};
     cudaGraphExec_t exec[2] = {nullptr, nullptr};   // [0] repeated run, [1] first run after set_piles (phase_events copies the table the other way)
     uint64_t graph_launches[2] = {0, 0};
     cudaEvent_t ev[2]{};
     uint64_t n_rec = 0;
+    int resolve_blocks = 1;   // co-resident grid of the resolution kernel (shared with the other ranks on the same device)
 
     BuildMeta* meta_dev() const { return meta.as<BuildMeta>(); }
     uint32_t* cnt_ev(int pass) const { return out_cnt.as<uint32_t>() + pass * kMaxRanks; }
@@ -145,6 +146,13 @@ extern "C" int rala_b200_multi_create(rala_b200_multi** out, const int* devices,
         fr.P.rank = fr.rank;
         fr.P.world = world;
     }
+    for (FabricRank& fr : m->ranks) {   // the resolution kernels of all ranks on one device must be resident together
+        int sharing = 0;
+        for (const FabricRank& other : m->ranks) sharing += other.device == fr.device ? 1 : 0;
+        cudaSetDevice(fr.device);
+        const int fit = fabric_resolve_max_blocks() / (2 * sharing);   // half of what fits: other streams keep their share
+        fr.resolve_blocks = fit < 1 ? 1 : (fit > kNumSMs * 4 ? kNumSMs * 4 : fit);
+    }
     *out = m;
     return RALA_B200_OK;
 }
@@ -164,7 +172,7 @@ extern "C" void rala_b200_multi_destroy(rala_b200_multi* m) {
         cudaSetDevice(fr.device);
         if (fr.ev[0]) cudaEventDestroy(fr.ev[0]);
         if (fr.ev[1]) cudaEventDestroy(fr.ev[1]);
-        DevBuf* bufs[] = {&fr.arena, &fr.meta, &fr.out_cnt, &fr.tmin, &fr.col_eid, &fr.T};
+        DevBuf* bufs[] = {&fr.arena, &fr.meta, &fr.out_cnt, &fr.tmin, &fr.wait, &fr.col_eid, &fr.T};
         for (DevBuf* b : bufs) b->release();
         if (fr.g) rala_b200_graph_destroy(fr.g);
         rala_b200_destroy(fr.ctx);
@@ -236,8 +244,8 @@ extern "C" int rala_b200_multi_default_caps(rala_b200_multi* m, uint64_t* caps) 
     caps[RALA_B200_CAP_EVENTS] = align_up(n_max / (W > 1 ? 4 : 1) + 4096, 256);
     caps[RALA_B200_CAP_EDGES] = align_up(n_max / (W > 1 ? 2 : 1) * (W > 1 ? 1 : 2) + 4096, 256);
     caps[RALA_B200_CAP_SLICE] = align_up(n_max + 4096, 256);
-    caps[RALA_B200_CAP_ROUNDS] = W > 1 ? 24 : 2;
-    caps[RALA_B200_CAP_FINAL_ROUNDS] = W > 1 ? 12 : 2;
+    caps[RALA_B200_CAP_ROUNDS] = 4096;         // sweeps after which the resolution gives up: it ends by itself long before
+    caps[RALA_B200_CAP_FINAL_ROUNDS] = 4096;
     caps[RALA_B200_CAP_LOCAL_EDGES] = 0;
     for (const FabricRank& fr : m->ranks)
         caps[RALA_B200_CAP_LOCAL_EDGES] = fr.g->edge_cap > caps[RALA_B200_CAP_LOCAL_EDGES] ? fr.g->edge_cap : caps[RALA_B200_CAP_LOCAL_EDGES];
@@ -293,8 +301,9 @@ extern "C" int rala_b200_multi_reserve(rala_b200_multi* m, const uint64_t* caps)
         MCU(m, fr.arena.reserve(A.total));
         MCU(m, cudaMemset(fr.arena.p, 0, align_up(sizeof(FabricHdr), 4096)));
         MCU(m, fr.meta.reserve(align_up(sizeof(BuildMeta), 256)));
-        MCU(m, fr.out_cnt.reserve(3 * kMaxRanks * 4));
+        MCU(m, fr.out_cnt.reserve(3 * kMaxRanks * 4 + 2 * kResolveCtlBytes));   // + the control block of the resolution kernel, per pass
         MCU(m, fr.tmin.reserve(((size_t) m->n_piles + 64) * 4));
+        MCU(m, fr.wait.reserve(((size_t) m->n_piles + 64) * 8));
         MCU(m, fr.col_eid.reserve(W * (size_t) A.cap_slice * 4 + 256));
         // result bytes of the transitive pass, indexed by GLOBAL edge id: an id is < world x the edges one rank can emit,
         // whatever happened to the exchange buffers (nothing clears the array: the row fill clears the bytes it needs)
@@ -422,20 +431,10 @@ static int resolve_owned_piles(rala_b200_multi* m, FabricRank& fr, int pass) {
     launch_scan_u32(L, rb.vcursor, rb.vstart, g->n_piles + 1, status, ticket, skip_flag(fr.P));
     launch_fabric_prepare(L, fr.P, fr.A, g->events_view(), g->cnt() + C_EV, g->ev_cap, rb, fr.tmin.as<uint32_t>());
     launch_push_slice(L, fr.P, fr.A);
-    Publish meet = no_mail(m);
-    meet.skippable = 1;
-    launch_fabric_barrier(L, fr.P, meet);
-    for (uint32_t r = 0; r < rounds; ++r) {
-        launch_fabric_round(L, fr.P, fr.A, rb, r);
-        Publish pub = no_mail(m);
-        pub.scalar[M_UNSETTLED] = rb.n_work + (r + 1u) % 3u;
-        pub.bookkeeping = 1;
-        pub.pass = pass;
-        pub.round = (int) r;
-        pub.last_round = (int) rounds - 1;
-        pub.skippable = 1;
-        launch_fabric_barrier(L, fr.P, pub);
-    }
+    // no barrier: a state that has not arrived yet reads as "open, cannot die before time 0", which only makes its
+    // dependants wait for the next sweep
+    launch_fabric_resolve(L, fr.P, fr.A, rb, fr.wait.as<uint32_t>(), fr.out_cnt.as<uint32_t>() + 3 * kMaxRanks + pass * (kResolveCtlBytes / 4), pass, rounds, 1000000ull * m->barrier_timeout_ms,
+                          fr.resolve_blocks);
     MCU(m, end_stage(g, ST_K1B_KERNEL));
     // every replica now holds every pile's final state: piles with a finite death time die (graph.cpp:471,477,838,842)
     // (a skipped pass killed nobody: the table and the liveness bitmap stay as they are)
@@ -744,23 +743,12 @@ extern "C" int rala_b200_multi_plan(rala_b200_multi* m) {
         int fits = 0;
         if (!rc) rc = rala_b200_multi_demand(m, need, &fits);
         if (rc) return rc;
-        const uint64_t r0 = need[RALA_B200_CAP_ROUNDS] + 2, r1 = need[RALA_B200_CAP_FINAL_ROUNDS] + 2;
-        if (fits) {
-            // keep the buffers, trim the rounds to what the data needs (+ 2: pushes of the same round may or may not be
-            // seen by a peer, so the count can vary by one between runs): every spare round costs two launches
-            if (r0 < caps[RALA_B200_CAP_ROUNDS] || r1 < caps[RALA_B200_CAP_FINAL_ROUNDS]) {
-                caps[RALA_B200_CAP_ROUNDS] = r0 < caps[RALA_B200_CAP_ROUNDS] ? r0 : caps[RALA_B200_CAP_ROUNDS];
-                caps[RALA_B200_CAP_FINAL_ROUNDS] = r1 < caps[RALA_B200_CAP_FINAL_ROUNDS] ? r1 : caps[RALA_B200_CAP_FINAL_ROUNDS];
-                rc = rala_b200_multi_set_rounds(m, (uint32_t) caps[RALA_B200_CAP_ROUNDS], (uint32_t) caps[RALA_B200_CAP_FINAL_ROUNDS]);
-                if (rc) return rc;
-            }
-            return RALA_B200_OK;
-        }
+        if (fits) return RALA_B200_OK;
         for (int i = 0; i < 3; ++i)
             if (need[i] > caps[i]) caps[i] = align_up(need[i] + need[i] / 4 + 1024, 256);
         if (need[RALA_B200_CAP_LOCAL_EDGES] > caps[RALA_B200_CAP_LOCAL_EDGES]) caps[RALA_B200_CAP_LOCAL_EDGES] = need[RALA_B200_CAP_LOCAL_EDGES];
-        if (r0 > caps[RALA_B200_CAP_ROUNDS]) caps[RALA_B200_CAP_ROUNDS] = r0;
-        if (r1 > caps[RALA_B200_CAP_FINAL_ROUNDS]) caps[RALA_B200_CAP_FINAL_ROUNDS] = r1;
+        if (need[RALA_B200_CAP_ROUNDS] > caps[RALA_B200_CAP_ROUNDS]) caps[RALA_B200_CAP_ROUNDS] = need[RALA_B200_CAP_ROUNDS];
+        if (need[RALA_B200_CAP_FINAL_ROUNDS] > caps[RALA_B200_CAP_FINAL_ROUNDS]) caps[RALA_B200_CAP_FINAL_ROUNDS] = need[RALA_B200_CAP_FINAL_ROUNDS];
     }
     return mfail(m, RALA_B200_ERR_LIMIT, "plan: the exchange buffers still did not fit after 6 attempts");
 }
@@ -862,6 +850,21 @@ extern "C" int rala_b200_multi_barrier_log(rala_b200_multi* m, int k, uint64_t* 
         out[2 * i] = h->tlog[e % kBarrierLog][0];
         out[2 * i + 1] = h->tlog[e % kBarrierLog][1];
     }
+    *n_out = n;
+    return RALA_B200_OK;
+}
+
+// diagnostics: per sweep of the last resolution of `pass` on local rank k: (open victims at its start, ns since the kernel started)
+extern "C" int rala_b200_multi_sweep_log(rala_b200_multi* m, int k, int pass, uint64_t* out /* 2 x 48 */, uint32_t* n_out) {
+    if (!m || k < 0 || k >= m->n_local || pass < 0 || pass > 1 || !out || !n_out) return RALA_B200_ERR_ARG;
+    if (!m->reserved) return mfail(m, RALA_B200_ERR_STATE, "sweep_log: nothing has run");
+    FabricRank& fr = m->ranks[k];
+    MCU(m, cudaSetDevice(fr.device));
+    MCU(m, cudaStreamSynchronize(fr.ctx->L.stream));
+    std::vector<uint32_t> raw(kResolveCtlBytes / 4);
+    MCU(m, cudaMemcpy(raw.data(), fr.out_cnt.as<uint32_t>() + 3 * kMaxRanks + pass * (kResolveCtlBytes / 4), kResolveCtlBytes, cudaMemcpyDeviceToHost));
+    const uint32_t n = raw[3] < (uint32_t) kSweepLog ? raw[3] : (uint32_t) kSweepLog;
+    memcpy(out, raw.data() + 8, (size_t) n * 16);
     *n_out = n;
     return RALA_B200_OK;
 }

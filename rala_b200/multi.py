@@ -385,7 +385,7 @@ class FabricGraph:
 
     def plan(self, max_attempts: int = 6):
         """Size the exchange buffers from real steps: run, read what the step needed, grow what did not fit (all ranks
-        together), until a step fits; then trim the resolution rounds to what the data needs (+ 2)."""
+        together), until a step fits."""
         if self.caps is None:
             self.connect()
         for _ in range(max_attempts):
@@ -394,18 +394,14 @@ class FabricGraph:
             need, fits = self.M.demand()
             agreed = self._max_over_ranks(list(need) + [0 if fits else 1])
             need, misfit = np.array(agreed[:-1], dtype=np.uint64), agreed[-1]
-            r0, r1 = int(need[3]) + 2, int(need[4]) + 2
             if not misfit:
-                if r0 < self.caps[3] or r1 < self.caps[4]:
-                    self.caps[3], self.caps[4] = min(r0, int(self.caps[3])), min(r1, int(self.caps[4]))
-                    self.M.set_rounds(int(self.caps[3]), int(self.caps[4]))
                 self.M.use_cuda_graph(True)
                 return self
             caps = self.caps.copy()
             for i in range(3):
                 if need[i] > caps[i]:
                     caps[i] = (int(need[i]) * 5 // 4 + 1024 + 255) // 256 * 256
-            caps[3], caps[4], caps[5] = max(int(caps[3]), r0), max(int(caps[4]), r1), max(int(caps[5]), int(need[5]))
+            caps[3], caps[4], caps[5] = max(int(caps[3]), int(need[3])), max(int(caps[4]), int(need[4])), max(int(caps[5]), int(need[5]))
             self.connect(caps)
         raise api.RalaB200Error("plan: the exchange buffers still did not fit")
 
@@ -542,7 +538,15 @@ def _share_through_files(rank, world, arrays: dict):
     """Single node: every rank leaves its arrays in a directory rank 0 names; rank 0 reads them all back."""
     import shutil
     import tempfile
-    box = [tempfile.mkdtemp(prefix="rala_b200_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None) if rank == 0 else None]
+    need = torch.tensor([sum(int(v.nbytes) for v in arrays.values())], dtype=torch.int64, device=torch.device("cuda", torch.cuda.current_device()))
+    dist.all_reduce(need)
+    where = None
+    if rank == 0:   # the RAM disk when it has room for everything (it is often only 64 MB inside a container), else the default temp dir
+        for cand in ("/dev/shm", tempfile.gettempdir()):
+            if os.path.isdir(cand) and shutil.disk_usage(cand).free > 1.2 * int(need.item()) + (64 << 20):
+                where = cand
+                break
+    box = [tempfile.mkdtemp(prefix="rala_b200_", dir=where) if rank == 0 else None]
     dist.broadcast_object_list(box, src=0)
     for k, v in arrays.items():
         np.save(os.path.join(box[0], f"{k}_{rank}.npy"), v)
