@@ -117,41 +117,87 @@ void launch_fabric_barrier(Launch& L, Peers P, Publish pub) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// Containment events -> the rank that owns the victim pile (fused all-to-all: every event is stored straight
-// into the owner's inbox, block = this rank).  Slots come from a local counter per destination, one atomic per
-// destination and warp.  The counter keeps counting beyond the capacity, so it is also the observed demand.
+// Routing: items (containment events, edges) -> the arena of the rank that owns them, a fused all-to-all.  A block
+// takes 1024 items, sorts them by destination in shared memory (counting sort over <= 16 bins), reserves one run of
+// slots per destination with ONE global atomic each, and writes every run with consecutive threads on consecutive
+// addresses: 512 contiguous bytes per column and destination on average at world = 8.  (Letting each warp store its own
+// items wrote 16-byte pieces at world = 8, one NVLink write each: profiles/r02n, 60 - 90 us slower per routing.)
+// The per-destination counters keep counting beyond the capacity, so they are also the observed demand.
 // ---------------------------------------------------------------------------------------------
+constexpr int kRouteTile = 1024;
+
+template <int COLS>
+struct RouteSmem {
+    uint32_t cnt[kMaxRanks], base[kMaxRanks], off[kMaxRanks + 1];
+    uint32_t buf[COLS][kRouteTile];
+    uint8_t dst[kRouteTile];
+};
+
+// dest[r] / val[r][c]: this thread's items r = 0..3 of the tile (dest = 0xFF: no item).  block_cols: start of this rank's
+// block in the destination's inbox, as a word offset from the destination's arena section; cap = capacity of a column.
+template <int COLS>
+__device__ __forceinline__ void route_tile(RouteSmem<COLS>& sh, const Peers& P, size_t section_off, size_t block_words, uint32_t cap,
+                                           const uint32_t (&dest)[4], const uint32_t (&val)[4][COLS], uint32_t* __restrict__ out_cnt) {
+    const uint32_t tid = threadIdx.x, W = (uint32_t) P.world;
+    if (tid < (uint32_t) kMaxRanks) sh.cnt[tid] = 0u;
+    __syncthreads();
+    uint32_t rank[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) rank[r] = dest[r] != 0xFFu ? atomicAdd(&sh.cnt[dest[r]], 1u) : 0u;
+    __syncthreads();
+    if (tid < W) sh.base[tid] = sh.cnt[tid] ? atomicAdd(&out_cnt[tid], sh.cnt[tid]) : 0u;
+    if (tid == 0) {
+        uint32_t run = 0;
+        for (uint32_t q = 0; q < W; ++q) {
+            sh.off[q] = run;
+            run += sh.cnt[q];
+        }
+        sh.off[W] = run;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        if (dest[r] == 0xFFu) continue;
+        const uint32_t pos = sh.off[dest[r]] + rank[r];
+#pragma unroll
+        for (int c = 0; c < COLS; ++c) sh.buf[c][pos] = val[r][c];
+        sh.dst[pos] = (uint8_t) dest[r];
+    }
+    __syncthreads();
+    const uint32_t total = sh.off[W];
+    for (uint32_t pos = tid; pos < total; pos += blockDim.x) {
+        const uint32_t q = sh.dst[pos], slot = sh.base[q] + (pos - sh.off[q]);
+        if (slot < cap) {
+            uint32_t* blk = reinterpret_cast<uint32_t*>(P.base[q] + section_off) + block_words;
+#pragma unroll
+            for (int c = 0; c < COLS; ++c) blk[(size_t) c * cap + slot] = sh.buf[c][pos];
+        }
+    }
+    __syncthreads();
+}
+
+// containment events -> the rank that owns the victim pile (inbox block = this rank)
 __global__ void __launch_bounds__(256) k_route_events(Peers P, ArenaLayout A, Events ev, const uint32_t* __restrict__ n_events,
                                                      uint32_t ev_cap, uint32_t* __restrict__ out_cnt) {
-    const uint32_t n = min(*n_events, ev_cap), lane = lane_id();
-    const uint32_t me = (uint32_t) P.rank;
-    for (uint32_t base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {   // block-uniform bound: full warps vote
-        const uint32_t i = base + threadIdx.x;
-        const bool ok = i < n;
-        uint32_t v = 0, c = 0, t = 0, q = 0;
-        if (ok) {
-            v = ev.v[i]; c = ev.c[i]; t = ev.t[i];
-            q = pile_owner(v, (uint32_t) P.world);
-        }
-        const uint32_t active = __ballot_sync(0xFFFFFFFFu, ok);
-        if (ok) {
-            const uint32_t peers = __match_any_sync(active, q);
-            const uint32_t leader = __ffs(peers) - 1u, rank = __popc(peers & ((1u << lane) - 1u));
-            uint32_t slot = 0;
-            if (lane == leader) slot = atomicAdd(&out_cnt[q], (uint32_t) __popc(peers));
-            slot = __shfl_sync(peers, slot, leader) + rank;
-            if (slot < A.cap_ev) {
-                uint32_t* blk = section<uint32_t>(P, (int) q, A.ev_inbox) + (size_t) me * 3u * A.cap_ev;
-                blk[slot] = v;
-                blk[(size_t) A.cap_ev + slot] = c;
-                blk[2 * (size_t) A.cap_ev + slot] = t;
+    __shared__ RouteSmem<3> sh;
+    const uint32_t n = min(*n_events, ev_cap);
+    for (uint32_t base = blockIdx.x * kRouteTile; base < n; base += gridDim.x * kRouteTile) {
+        uint32_t dest[4], val[4][3];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const uint32_t i = base + r * 256u + threadIdx.x;
+            dest[r] = 0xFFu;
+            if (i < n) {
+                val[r][0] = ev.v[i]; val[r][1] = ev.c[i]; val[r][2] = ev.t[i];
+                dest[r] = pile_owner(val[r][0], (uint32_t) P.world);
             }
         }
+        route_tile<3>(sh, P, A.ev_inbox, (size_t) P.rank * 3u * A.cap_ev, A.cap_ev, dest, val, out_cnt);
     }
 }
 
 void launch_route_events(Launch& L, Peers P, ArenaLayout A, Events ev, const uint32_t* n_events, uint32_t ev_cap, uint32_t* out_cnt) {
-    k_route_events<<<grid_for(ev_cap, 256, kNumSMs * 4), 256, 0, L.stream>>>(P, A, ev, n_events, ev_cap, out_cnt);
+    k_route_events<<<grid_for(ev_cap, kRouteTile, kNumSMs * 4), 256, 0, L.stream>>>(P, A, ev, n_events, ev_cap, out_cnt);
     L.count++;
 }
 
@@ -262,6 +308,33 @@ void launch_fabric_prepare(Launch& L, Peers P, ArenaLayout A, Events ev, const u
     L.count++;
 }
 
+// everything a containment pass starts from, in one launch (six memset nodes otherwise): pile states of the replica and
+// the per-victim histogram to 0, earliest-event times and the "waiting for" notes to ~0, worklist counters and the control
+// block of the resolution kernel to 0.  The arrays are padded to a multiple of 64 words.
+__global__ void __launch_bounds__(256) k_pass_reset(uint4* __restrict__ S, uint4* __restrict__ hist, uint4* __restrict__ tmin,
+                                                   uint4* __restrict__ wait_pile, uint32_t n4, uint32_t* __restrict__ n_work,
+                                                   uint32_t* __restrict__ ctl, uint32_t ctl_words) {
+    const uint4 zero = make_uint4(0u, 0u, 0u, 0u), ones = make_uint4(~0u, ~0u, ~0u, ~0u);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += gridDim.x * blockDim.x) {
+        S[i] = zero;
+        hist[i] = zero;
+        tmin[i] = ones;
+        wait_pile[i] = ones;
+    }
+    if (blockIdx.x == 0) {
+        if (threadIdx.x < 4) n_work[threadIdx.x] = 0u;
+        for (uint32_t i = threadIdx.x; i < ctl_words; i += blockDim.x) ctl[i] = 0u;
+    }
+}
+
+void launch_pass_reset(Launch& L, Peers P, ArenaLayout A, ResolveBufs rb, uint32_t* tmin, uint32_t* wait, uint32_t* ctl) {
+    const uint32_t n4 = (A.n_piles + 64u) / 4u;   // every array holds n_piles + 64 words
+    k_pass_reset<<<grid_for(n4, 256, kNumSMs * 4), 256, 0, L.stream>>>(
+        reinterpret_cast<uint4*>(P.base[P.rank] + A.S), reinterpret_cast<uint4*>(rb.vcursor), reinterpret_cast<uint4*>(tmin),
+        reinterpret_cast<uint4*>(wait), n4, rb.n_work, ctl, (uint32_t) (kResolveCtlBytes / 4));
+    L.count++;
+}
+
 // the initial states of the owned piles -> every replica: one warp per owned block of 32 piles (128 contiguous bytes)
 __global__ void __launch_bounds__(256) k_push_slice(Peers P, ArenaLayout A) {
     if (hdr_of(P, P.rank)->skip_pass) return;
@@ -281,18 +354,12 @@ void launch_push_slice(Launch& L, Peers P, ArenaLayout A) {
     L.count++;
 }
 
-// raise the state of an OWNED pile (known to be at `seen` or above); a change is pushed to every replica.  No value is
-// read back (a returning atomic would add a round trip to every step of a chase): when another thread raised the state
-// in between, the push is repeated, which is harmless (max-reductions).
-__device__ __forceinline__ void raise_state(const Peers& P, const ArenaLayout& A, uint32_t* S, uint32_t x, uint32_t val, uint32_t seen,
-                                            bool& pushed) {
-    if (val <= seen) return;
-    atomicMax(&S[x], val);
-    if (P.world > 1) {
-        pushed = true;
-        for (int q = 0; q < P.world; ++q)
-            if (q != P.rank) red_max_sys(section<uint32_t>(P, q, A.S) + x, val);
-    }
+// tell every replica the state of an OWNED pile (max-reduction: replicas only ever move forward)
+__device__ __forceinline__ void push_state(const Peers& P, const ArenaLayout& A, uint32_t x, uint32_t val, bool& pushed) {
+    if (P.world == 1) return;
+    pushed = true;
+    for (int q = 0; q < P.world; ++q)
+        if (q != P.rank) red_max_sys(section<uint32_t>(P, q, A.S) + x, val);
 }
 
 constexpr uint32_t kNoWait = 0xFFFFFFFFu;
@@ -301,14 +368,25 @@ constexpr uint32_t kNoWait = 0xFFFFFFFFu;
 // because the chase budget ran out.  In the first case every pile on the chase stack is frozen until that foreign
 // pile's state moves past the time in question; (pile, time) is noted for each of them (wait_pile / wait_time), so
 // the next sweeps test one state word instead of walking the whole chain again only to stop at the same place.
+// Replicas hear about a pile ONCE per visit: when it settles, or, if it stays open, its new lower bound when the chase
+// leaves it (a bound that is overtaken by the settled state within the same visit is never sent).
 __device__ __forceinline__ bool resolve_owned(const Peers& P, const ArenaLayout& A, uint32_t v0,
                                               const uint32_t* __restrict__ vstart, const uint32_t* __restrict__ seg_c,
                                               uint32_t* __restrict__ seg_t, uint32_t* __restrict__ S, uint32_t* __restrict__ wait_pile,
                                               uint32_t* __restrict__ wait_time, bool& pushed) {
-    uint32_t stack_v[kChaseDepth], stack_need[kChaseDepth];
+    uint32_t stack_v[kChaseDepth], stack_need[kChaseDepth], stack_bound[kChaseDepth];   // bound: raised locally, not pushed yet (0: nothing)
     int sp = 0, budget = kChaseBudget;
     stack_v[0] = v0;
     stack_need[0] = kNever;
+    stack_bound[0] = 0u;
+    auto settle = [&](uint32_t v, uint32_t val) {
+        atomicMax(&S[v], val);
+        push_state(P, A, v, val, pushed);
+    };
+    auto leave_open = [&](int from) {   // the piles stack[from .. sp] stay open: send the bounds that were raised on the way
+        for (int i = from; i <= sp; ++i)
+            if (stack_bound[i]) push_state(P, A, stack_v[i], stack_bound[i], pushed);
+    };
     while (sp >= 0) {
         const uint32_t v = stack_v[sp];
         const uint32_t cur = ld_relaxed_sys(&S[v]);
@@ -320,17 +398,24 @@ __device__ __forceinline__ bool resolve_owned(const Peers& P, const ArenaLayout&
             if (t < best_t) { best_t = t; best_p = p; }
         }
         if (best_t == kDeadEvent) {               // every event found its container dead: v is never killed
-            raise_state(P, A, S, v, kSettled | kNever, cur, pushed);
+            settle(v, kSettled | kNever);
             --sp;
             continue;
         }
-        raise_state(P, A, S, v, best_t, cur, pushed);   // v cannot die before its earliest open event
-        if (best_t > stack_need[sp]) { --sp; continue; }
+        if (best_t > cur) {                       // v cannot die before its earliest open event
+            atomicMax(&S[v], best_t);
+            stack_bound[sp] = best_t;
+        }
+        if (best_t > stack_need[sp]) {            // whoever asked only cares about earlier times: v stays open
+            leave_open(sp);
+            --sp;
+            continue;
+        }
         const uint32_t c = seg_c[best_p];
         const uint32_t q = c == v ? kSettled | kNever : ld_relaxed_sys(&S[c]);   // a == b record: the pile is its own (alive) container
         if (q & kSettled) {
             if ((q & kNever) > best_t) {          // container alive at best_t: the event fires
-                raise_state(P, A, S, v, kSettled | best_t, cur, pushed);
+                settle(v, kSettled | best_t);
                 --sp;
             } else {
                 seg_t[best_p] = kDeadEvent;       // container died first: the event never fires; look again
@@ -338,7 +423,7 @@ __device__ __forceinline__ bool resolve_owned(const Peers& P, const ArenaLayout&
             continue;
         }
         if (q > best_t) {                         // open, but certainly alive at best_t
-            raise_state(P, A, S, v, kSettled | best_t, cur, pushed);
+            settle(v, kSettled | best_t);
             --sp;
             continue;
         }
@@ -347,12 +432,17 @@ __device__ __forceinline__ bool resolve_owned(const Peers& P, const ArenaLayout&
                 wait_pile[stack_v[i]] = c;
                 wait_time[stack_v[i]] = best_t;
             }
+            leave_open(0);
             return false;
         }
-        if (sp + 1 >= kChaseDepth || --budget <= 0) return false;
+        if (sp + 1 >= kChaseDepth || --budget <= 0) {
+            leave_open(0);
+            return false;
+        }
         ++sp;
         stack_v[sp] = c;
         stack_need[sp] = best_t;
+        stack_bound[sp] = 0u;
     }
     return true;
 }
@@ -438,7 +528,7 @@ __device__ __forceinline__ void sweep_worklist(const Peers& P, const ArenaLayout
     if (pushed) __threadfence_system();
 }
 
-constexpr uint32_t kTailVictims = 1024;   // at most this many open victims: block 0 finishes the pass alone (no grid barriers)
+constexpr uint32_t kTailVictims = 256;    // at most this many open victims (one per thread): block 0 finishes the pass alone (no grid barriers)
 
 __global__ void __launch_bounds__(256) k_fabric_resolve(Peers P, ArenaLayout A, const uint32_t* __restrict__ vstart,
                                                        const uint32_t* __restrict__ seg_c, uint32_t* __restrict__ seg_t,
@@ -459,9 +549,9 @@ __global__ void __launch_bounds__(256) k_fabric_resolve(Peers P, ArenaLayout A, 
     uint32_t phase = 0;
 
     // block 0, thread 0, after a sweep: tell the peers, decide.  Returns 0 = the pass is over, 1 = sweep again.
+    // (the count was published to the peers by the lanes of warp 0, see publish_open)
     auto after_sweep = [&](uint32_t sweep, uint32_t n_before) -> uint32_t {
         const uint32_t open = n_work[(sweep + 1u) % 3u];
-        for (uint32_t q = 0; q < W; ++q) st_release_sys64(&hdr_of(P, (int) q)->progress[me], tag | open);
         uint32_t go = 1u;
         bool dead = ld_relaxed_sys(&mine->dead) != 0u || global_timer_ns() - t_start > timeout_ns;
         if (open == 0u) {   // everything here is settled and pushed: wait until that is true everywhere
@@ -497,6 +587,13 @@ __global__ void __launch_bounds__(256) k_fabric_resolve(Peers P, ArenaLayout A, 
         return go;
     };
 
+    // block 0, warp 0: lane q tells rank q how many victims are still open here.  One release store per lane, all at once:
+    // eight of them issued by one thread one after the other cost ~25 us per sweep on 8 GPUs (profiles/r02n)
+    auto publish_open = [&](uint32_t sweep) {
+        if (threadIdx.x < W) st_release_sys64(&hdr_of(P, (int) threadIdx.x)->progress[me], tag | n_work[(sweep + 1u) % 3u]);
+        __syncwarp();
+    };
+
     for (uint32_t sweep = 0;; ++sweep) {
         const uint32_t n = n_work[sweep % 3u];
         if (blockIdx.x == 0 && threadIdx.x == 0) n_work[(sweep + 2u) % 3u] = 0u;   // read last in sweep - 1, written next in sweep + 1
@@ -505,6 +602,7 @@ __global__ void __launch_bounds__(256) k_fabric_resolve(Peers P, ArenaLayout A, 
         grid_barrier(ctl, phase);
         if (blockIdx.x == 0) {
             uint32_t go = 0;
+            if (threadIdx.x < 32) publish_open(sweep);
             if (threadIdx.x == 0) {
                 go = after_sweep(sweep, n);
                 s_state = go;
@@ -521,6 +619,7 @@ __global__ void __launch_bounds__(256) k_fabric_resolve(Peers P, ArenaLayout A, 
                 sweep_worklist(P, A, vstart, seg_c, seg_t, S, wait_pile, wait_time, (ts & 1u) ? work1 : work0, tn, (ts & 1u) ? work0 : work1,
                                &n_work[(ts + 1u) % 3u], 0u, 1u);
                 __syncthreads();
+                if (threadIdx.x < 32) publish_open(ts);
                 if (threadIdx.x == 0) s_state = after_sweep(ts, tn);
                 __syncthreads();
                 go = s_state;
@@ -553,9 +652,7 @@ int fabric_resolve_max_blocks() {
 
 void launch_fabric_resolve(Launch& L, Peers P, ArenaLayout A, ResolveBufs rb, uint32_t* wait /* 2 x (n_piles + 64) words */, uint32_t* ctl,
                            int pass, uint32_t max_sweeps, unsigned long long timeout_ns, int blocks) {
-    const size_t stride = (size_t) A.n_piles + 64;
-    cudaMemsetAsync(ctl, 0, sizeof(ResolveCtl), L.stream);
-    cudaMemsetAsync(wait, 0xFF, stride * 4, L.stream);   // wait_pile = kNoWait (wait_time is only read next to a valid wait_pile)
+    const size_t stride = (size_t) A.n_piles + 64;   // wait_pile | wait_time; launch_pass_reset cleared wait_pile and the control block
     k_fabric_resolve<<<blocks, 256, 0, L.stream>>>(P, A, rb.vstart, rb.seg_c, rb.seg_t, rb.work0, rb.work1, rb.n_work, wait, wait + stride,
                                                   reinterpret_cast<ResolveCtl*>(ctl), pass, max_sweeps, timeout_ns);
     L.count++;
@@ -626,39 +723,29 @@ __device__ __forceinline__ uint32_t owner_of(const uint32_t* bounds, uint32_t wo
 __global__ void __launch_bounds__(256) k_route_edges(Peers P, ArenaLayout A, const uint32_t* __restrict__ src, const uint32_t* __restrict__ dst,
                                                     const uint32_t* __restrict__ len, const uint32_t* __restrict__ n_edges, uint32_t edge_cap,
                                                     const BuildMeta* __restrict__ meta, uint32_t* __restrict__ out_cnt) {
+    __shared__ RouteSmem<4> sh;
     __shared__ uint32_t s_bounds[kMaxRanks + 1];
     if (threadIdx.x <= (uint32_t) P.world) s_bounds[threadIdx.x] = meta->node_begin[threadIdx.x];
     __syncthreads();
-    const uint32_t n = min(*n_edges, edge_cap), lane = lane_id(), me = (uint32_t) P.rank;
-    for (uint32_t base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
-        const uint32_t e = base + threadIdx.x;
-        const bool ok = e < n;
-        uint32_t s = 0, d = 0, l = 0, q = 0;
-        if (ok) {
-            s = src[e]; d = dst[e]; l = len[e];
-            q = owner_of(s_bounds, (uint32_t) P.world, s);
-        }
-        const uint32_t active = __ballot_sync(0xFFFFFFFFu, ok);
-        if (ok) {
-            const uint32_t peers = __match_any_sync(active, q);
-            const uint32_t leader = __ffs(peers) - 1u, rank = __popc(peers & ((1u << lane) - 1u));
-            uint32_t slot = 0;
-            if (lane == leader) slot = atomicAdd(&out_cnt[q], (uint32_t) __popc(peers));
-            slot = __shfl_sync(peers, slot, leader) + rank;
-            if (slot < A.cap_edge) {
-                uint32_t* blk = section<uint32_t>(P, (int) q, A.edge_inbox) + (size_t) me * 4u * A.cap_edge;
-                blk[slot] = s;
-                blk[(size_t) A.cap_edge + slot] = d;
-                blk[2 * (size_t) A.cap_edge + slot] = l;
-                blk[3 * (size_t) A.cap_edge + slot] = e;
+    const uint32_t n = min(*n_edges, edge_cap);
+    for (uint32_t base = blockIdx.x * kRouteTile; base < n; base += gridDim.x * kRouteTile) {
+        uint32_t dest[4], val[4][4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const uint32_t e = base + r * 256u + threadIdx.x;
+            dest[r] = 0xFFu;
+            if (e < n) {
+                val[r][0] = src[e]; val[r][1] = dst[e]; val[r][2] = len[e]; val[r][3] = e;
+                dest[r] = owner_of(s_bounds, (uint32_t) P.world, val[r][0]);
             }
         }
+        route_tile<4>(sh, P, A.edge_inbox, (size_t) P.rank * 4u * A.cap_edge, A.cap_edge, dest, val, out_cnt);
     }
 }
 
 void launch_route_edges(Launch& L, Peers P, ArenaLayout A, const uint32_t* src, const uint32_t* dst, const uint32_t* len,
                         const uint32_t* n_edges, uint32_t edge_cap, const BuildMeta* meta, uint32_t* out_cnt) {
-    k_route_edges<<<grid_for(edge_cap, 256, kNumSMs * 4), 256, 0, L.stream>>>(P, A, src, dst, len, n_edges, edge_cap, meta, out_cnt);
+    k_route_edges<<<grid_for(edge_cap, kRouteTile, kNumSMs * 4), 256, 0, L.stream>>>(P, A, src, dst, len, n_edges, edge_cap, meta, out_cnt);
     L.count++;
 }
 
@@ -819,6 +906,7 @@ void preload_fabric() {
     cudaFuncGetAttributes(&a, k_fabric_prepare);
     cudaFuncGetAttributes(&a, k_push_slice);
     cudaFuncGetAttributes(&a, k_fabric_resolve);
+    cudaFuncGetAttributes(&a, k_pass_reset);
     cudaFuncGetAttributes(&a, k_time_bases_mail);
     cudaFuncGetAttributes(&a, k_node_bounds);
     cudaFuncGetAttributes(&a, k_clear_bytes16);

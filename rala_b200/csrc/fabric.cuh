@@ -112,6 +112,9 @@ const uint32_t* skip_flag(const Peers& P);   // device address of this rank's sk
 void launch_fabric_prepare(Launch& L, Peers P, ArenaLayout A, Events ev, const uint32_t* n_events, uint32_t ev_cap, ResolveBufs rb,
                            const uint32_t* tmin);
 void launch_push_slice(Launch& L, Peers P, ArenaLayout A);
+// before the events of a pass are routed: clears the replica's pile states, the victim histogram, tmin, the wait notes,
+// the worklist counters and the resolution kernel's control block (ctl: kResolveCtlBytes)
+void launch_pass_reset(Launch& L, Peers P, ArenaLayout A, ResolveBufs rb, uint32_t* tmin, uint32_t* wait, uint32_t* ctl);
 // ctl: kResolveCtlBytes zeroable bytes of device memory per rank and pass; blocks: co-resident grid size (fabric_resolve_max_blocks() shared
 // between the ranks that live on one device)
 void launch_fabric_resolve(Launch& L, Peers P, ArenaLayout A, ResolveBufs rb, uint32_t* wait /* 2 x (n_piles + 64) words */, uint32_t* ctl,

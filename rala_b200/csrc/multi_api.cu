@@ -39,6 +39,7 @@ struct FabricRank {
     BuildMeta* meta_dev() const { return meta.as<BuildMeta>(); }
     uint32_t* cnt_ev(int pass) const { return out_cnt.as<uint32_t>() + pass * kMaxRanks; }
     uint32_t* cnt_edges() const { return out_cnt.as<uint32_t>() + 2 * kMaxRanks; }
+    uint32_t* ctl(int pass) const { return out_cnt.as<uint32_t>() + 3 * kMaxRanks + pass * (kResolveCtlBytes / 4); }
     FabricHdr* hdr() const { return arena.as<FabricHdr>(); }
     template <class T> T* sec(size_t off) const { return reinterpret_cast<T*>(arena.as<uint8_t>() + off); }
 };
@@ -401,8 +402,10 @@ static Publish no_mail(const rala_b200_multi* m) {
 static int route_and_meet(rala_b200_multi* m, FabricRank& fr, int pass) {
     rala_b200_graph* g = fr.g;
     Launch& L = fr.ctx->L;
-    // states of FOREIGN piles are only ever written by their owners' pushes, which start after the barrier below
-    MCU(m, cudaMemsetAsync(fr.sec<uint8_t>(fr.A.S), 0, ((size_t) fr.A.n_piles + 64) * 4, L.stream));
+    // States of FOREIGN piles are only ever written by their owners' pushes, which start after the barrier below: the
+    // replica is cleared here, together with everything else the resolution of this pass starts from (the classify kernel
+    // before this call was the last user of the victim histogram).
+    launch_pass_reset(L, fr.P, fr.A, resolve_bufs(g), fr.tmin.as<uint32_t>(), fr.wait.as<uint32_t>(), fr.ctl(pass));
     launch_route_events(L, fr.P, fr.A, g->events_view(), g->cnt() + C_EV, g->ev_cap, fr.cnt_ev(pass));
     Publish pub = no_mail(m);
     pub.per_dst = fr.cnt_ev(pass);
@@ -421,9 +424,6 @@ static int resolve_owned_piles(rala_b200_multi* m, FabricRank& fr, int pass) {
     const ResolveBufs rb = resolve_bufs(g);
     const uint32_t rounds = (uint32_t) m->caps[pass ? RALA_B200_CAP_FINAL_ROUNDS : RALA_B200_CAP_ROUNDS];
     MCU(m, stage_event(g, g->ev_start[ST_K1B_KERNEL]));
-    MCU(m, cudaMemsetAsync(fr.tmin.p, 0xFF, ((size_t) fr.A.n_piles + 64) * 4, L.stream));
-    MCU(m, clear_victim_histogram(g));
-    MCU(m, cudaMemsetAsync(rb.n_work, 0, 16, L.stream));
     launch_gather_events(L, fr.P, fr.A, g->events_view(), g->ev_cap, g->cnt() + C_EV, rb.vcursor, fr.tmin.as<uint32_t>());
     unsigned long long* status;
     uint32_t* ticket;
@@ -433,7 +433,7 @@ static int resolve_owned_piles(rala_b200_multi* m, FabricRank& fr, int pass) {
     launch_push_slice(L, fr.P, fr.A);
     // no barrier: a state that has not arrived yet reads as "open, cannot die before time 0", which only makes its
     // dependants wait for the next sweep
-    launch_fabric_resolve(L, fr.P, fr.A, rb, fr.wait.as<uint32_t>(), fr.out_cnt.as<uint32_t>() + 3 * kMaxRanks + pass * (kResolveCtlBytes / 4), pass, rounds, 1000000ull * m->barrier_timeout_ms,
+    launch_fabric_resolve(L, fr.P, fr.A, rb, fr.wait.as<uint32_t>(), fr.ctl(pass), pass, rounds, 1000000ull * m->barrier_timeout_ms,
                           fr.resolve_blocks);
     MCU(m, end_stage(g, ST_K1B_KERNEL));
     // every replica now holds every pile's final state: piles with a finite death time die (graph.cpp:471,477,838,842)
@@ -862,7 +862,7 @@ extern "C" int rala_b200_multi_sweep_log(rala_b200_multi* m, int k, int pass, ui
     MCU(m, cudaSetDevice(fr.device));
     MCU(m, cudaStreamSynchronize(fr.ctx->L.stream));
     std::vector<uint32_t> raw(kResolveCtlBytes / 4);
-    MCU(m, cudaMemcpy(raw.data(), fr.out_cnt.as<uint32_t>() + 3 * kMaxRanks + pass * (kResolveCtlBytes / 4), kResolveCtlBytes, cudaMemcpyDeviceToHost));
+    MCU(m, cudaMemcpy(raw.data(), fr.ctl(pass), kResolveCtlBytes, cudaMemcpyDeviceToHost));
     const uint32_t n = raw[3] < (uint32_t) kSweepLog ? raw[3] : (uint32_t) kSweepLog;
     memcpy(out, raw.data() + 8, (size_t) n * 16);
     *n_out = n;
