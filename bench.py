@@ -35,6 +35,8 @@ WORKLOADS = {
     # name: (genome bp per GPU, coverage, read length, description)
     "c3": (100_000_000, 40, 10000, "configs[2]: synthetic 100 Mbp genome, 40x 10 kbp reads (~400k reads), shuffled read ids"),
     "c1": (5_000_000, 30, 10000, "configs[0]: synthetic 5 Mbp genome, 30x 10 kbp reads (~15k reads)"),
+    "c2": (5_000_000, 60, 10000, "configs[1]: synthetic 5 Mbp genome, 60x, injected repeats, chimeras, adapters, +-30 bp noise (pile trimming, promotion)"),
+    "c5": (20_000_000, 30, 10000, "configs[4]: 20 Mbp genome, 30x, segmental repeats: 8 hub reads with ~2 600 spokes each (node degrees > 2 000)"),
     "c4s": (387_500_000, 30, 10000, "configs[3] shard: 3.1 Gbp / 8 per GPU, 30x 10 kbp reads (31.4 M overlap records per GPU, pairs listed once)"),
 }
 K1_BYTES_PER_OVERLAP = 41      # 24 read + 16 trimmed coords + 1 type (+ pile table amortised)
@@ -134,6 +136,12 @@ def ncu_traffic(kernels):
 def make_dataset(workload: str, n_gpus: int, seed: int = 3):
     from rala_b200 import synth
     genome, cov, rl, _ = WORKLOADS[workload]
+    if workload == "c2":   # BASELINE.json configs[1] (tests/datasets.py CONFIGS["c2"]): only meaningful through the CLI (--cli), the
+        #                    pile table changes between the passes
+        return synth.generate(genome * n_gpus, cov, rl, len_sd=3000, seed=2, min_ovl=1000, noise=30, chimera_frac=0.03,
+                              adapter_frac=0.05, repeats=(1, 12, 4000))
+    if workload == "c5":   # BASELINE.json configs[4]: 8 hub reads with ~2 600 spokes each on the uniform background
+        return synth.generate_repeat_hubs(genome * n_gpus, cov, rl, seed=5)
     return synth.generate(genome * n_gpus, cov, rl, seed=seed)
 
 
@@ -361,9 +369,91 @@ def run_single(args):
         "gpu_launches": int(launches), "lib": os.path.relpath(api.LIB_PATH, ROOT),
         "roofline": roof, "cpu_baseline": cpu, "clocks": clocks,
     }
+    if not args.no_cpu_baseline:
+        # the honest drop-in number: whole-program wall time of both CLIs on configs[0] (configs[1] / [2]: bench.py --cli)
+        line["cli_baseline"] = cli_compare("c1")
     print(json.dumps(line))
     G.close()
     ctx.close()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# The drop-in CLI (host/_build/rala_b200: the reference's own front end and CLI with the hot path on the GPU) next to
+# the unmodified reference CLI (oracle/_ref/rala), on FASTA + PAF files of a workload.  This is the only way to time
+# the NOISY path (configs[1]): hill breaking, pit rounds and promotion need the reference's Pile code between the passes.
+# ---------------------------------------------------------------------------------------------------------------
+DROPIN = os.path.join(ROOT, "host", "_build", "rala_b200")
+REFCLI = os.path.join(ROOT, "oracle", "_ref", "rala")
+
+
+def _logger_lines(stderr: str) -> dict:
+    import re
+    out = {}
+    for line in stderr.splitlines():
+        m = re.match(r"\[(rala::[\w:]+)\] ?(.*?) (\d+\.\d+) s$", line.strip())
+        if m:
+            out[(m.group(1) + " " + m.group(2)).strip()] = float(m.group(3))
+        m = re.search(r"(number of [\w ]+) = (\d+)", line)
+        if m:
+            out[m.group(1)] = int(m.group(2))
+    return out
+
+
+def cli_compare(workload: str, devices: str | None = None, keep_dir: str | None = None) -> dict:
+    """Wall time and logger phase lines of both CLIs on the same files; the drop-in also reports its device stages."""
+    if not (os.path.exists(DROPIN) and os.path.exists(REFCLI)):
+        return {"unavailable": "host/_build/rala_b200 or oracle/_ref/rala not built (needs /root/reference at build time)"}
+    ds = make_dataset(workload, 1)
+    threads = str(os.cpu_count() or 1)
+    with tempfile.TemporaryDirectory(dir=keep_dir) as tmp:
+        fa, paf = os.path.join(tmp, "reads.fasta"), os.path.join(tmp, "overlaps.paf")
+        t0 = time.perf_counter()
+        ds.write_fasta(fa)
+        ds.write_paf(paf)
+        t_write = time.perf_counter() - t0
+        env = dict(os.environ, RALA_B200_REPORT="1")
+        if devices:
+            env["RALA_B200_DEVICES"] = devices
+        t0 = time.perf_counter()
+        got = subprocess.run([DROPIN, "-t", threads, fa, paf], capture_output=True, text=True, env=env)
+        t_dropin = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        ref = subprocess.run([REFCLI, "-t", threads, fa, paf], capture_output=True, text=True)   # CPU baseline leg
+        t_ref = time.perf_counter() - t0
+    if got.returncode != 0 or ref.returncode != 0:
+        return {"error": (got.stderr[-600:] if got.returncode else ref.stderr[-600:])}
+    reports = [json.loads(l.split("] ", 1)[1]) for l in got.stderr.splitlines() if l.startswith("[rala_b200::report]")]
+    lg, lr = _logger_lines(got.stderr), _logger_lines(ref.stderr)
+    same = all(lg.get(k) == lr.get(k) for k in ("number of nodes", "number of edges", "number of transitive edges"))
+    return {"workload": WORKLOADS[workload][3], "threads": int(threads), "reads": ds.n_reads, "overlaps": ds.n_overlaps,
+            "fasta_paf_written_s": round(t_write, 2), "dropin_wall_s": round(t_dropin, 2), "reference_wall_s": round(t_ref, 2),
+            "same_node_edge_transitive_counts": same, "dropin_devices": devices or "one",
+            "dropin_report": reports, "dropin_logger": lg, "reference_logger": lr,
+            "note": "whole-program wall times: FASTA / PAF parsing, pile analysis and sequence handling are the reference's own "
+                    "host code in both; the logger lines show where the hot path sits inside them"}
+
+
+def run_cli(args):
+    r = cli_compare(args.workload, args.devices)
+    line = {"metric": "drop-in CLI vs reference CLI", "cli_baseline": r}
+    rep = {x.get("stage"): x for x in r.get("dropin_report", [])}
+    c = rep.get("construct")
+    if c and "device_ms" in c:
+        ms = c["device_ms"]
+        t = rep.get("remove_transitive_edges", {}).get("device_ms", {}).get("transitive", 0.0)
+        total = sum(ms.values()) + t
+        peak, peak_src = measured_peaks()
+        retrim_gbs = K1_BYTES_PER_OVERLAP * c["list_entries_retrimmed"] / (ms["retrim"] * 1e-3) / 1e9 if ms["retrim"] > 0 else 0.0
+        line.update({"value": c["edges"] / (total * 1e-3) if total > 0 else None, "unit": "edges/s (device time of the hot-path stages)",
+                     "config": {"workload": WORKLOADS[args.workload][3], "retrim_passes_executed": c["retrim_passes_executed"],
+                                "pit_rounds": c["pit_rounds"], "n_overlaps": c["records"], "edges": c["edges"]},
+                     "device_ms": dict(ms, transitive=t, total=total),
+                     "roofline": {"bound": "hbm", "kernel": "k_list_pass (re-trim / promote passes)", "achieved": retrim_gbs, "peak": peak,
+                                  "unit": "GB/s", "frac": retrim_gbs / peak, "traffic": None, "peak_source": peak_src,
+                                  "algorithmic_bytes": K1_BYTES_PER_OVERLAP * c["list_entries_retrimmed"],
+                                  "note": "41 B per list entry and pass (SURVEY.md 8d); the lists hold ~10^5 entries on this workload, so the "
+                                          "passes are launch-latency bound, far from the bandwidth roofline"}})
+    print(json.dumps(line))
 
 
 def run_ab(args):
@@ -417,6 +507,8 @@ def main():
     ap.add_argument("--skip-parity", action="store_true", help="N > 1: do not verify the assembled result on rank 0")
     ap.add_argument("--parity-oracle-max", type=int, default=60_000_000,
                     help="N > 1: run the plain-C oracle on the whole batch when it has at most this many records")
+    ap.add_argument("--cli", action="store_true", help="time the drop-in CLI against the reference CLI on FASTA + PAF files of the workload")
+    ap.add_argument("--devices", default=None, help="--cli: RALA_B200_DEVICES for the drop-in (e.g. 0,1)")
     ap.add_argument("--force-multi", action="store_true", help="run the multi-GPU path even with one rank (under torchrun)")
     ap.add_argument("--ab", action="store_true", help="time the product library against the one-switch-off builds (rala_b200/variants/)")
     args = ap.parse_args()
@@ -427,6 +519,9 @@ def main():
     if args.ab:
         run_ab(args)
         return
+    if args.cli:
+        run_cli(args)
+        return
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.gpus > 1 and "WORLD_SIZE" not in os.environ:
         # started as plain `python bench.py --gpus N`: one rank per GPU needs the launcher the driver uses
@@ -434,8 +529,8 @@ def main():
                                   "--master-addr", "127.0.0.1", "--master-port", os.environ.get("MASTER_PORT", "29533"),
                                   os.path.abspath(__file__)] + sys.argv[1:])
     if args.gpus > 1 or world > 1 or args.force_multi:
-        from rala_b200 import multi
-        multi.bench_main(args)
+        import bench_multi
+        bench_multi.bench_main(args)
         return
     run_single(args)
 

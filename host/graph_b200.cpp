@@ -50,8 +50,22 @@ using rala::Pile;
 // rala::Graph has no room for a new member: sessions are keyed by the graph they belong to.
 struct Attached {
     std::unique_ptr<Session> session;
+    std::unique_ptr<MultiSession> multi;   // RALA_B200_DEVICES with >= 2 entries and a frozen pile table
     uint64_t n_nodes = 0, n_edges = 0;
 };
+
+// RALA_B200_REPORT=1: device time per stage and the counts of the hot path as one JSON line on stderr (bench.py reads
+// it to time the noisy path through the real host code: hill breaking, pit rounds, promotion)
+struct Report {
+    bool on = getenv("RALA_B200_REPORT") != nullptr;
+    double classify = 0, retrim = 0, finalize = 0, build = 0, transitive = 0;
+    uint32_t retrim_passes = 0, pit_rounds = 0;
+    uint64_t list_entries_retrimmed = 0;
+};
+Report& report() {
+    static Report r;
+    return r;
+}
 std::unordered_map<const Graph*, Attached>& attached() {
     static std::unordered_map<const Graph*, Attached> a;
     return a;
@@ -121,6 +135,10 @@ void construct(Graph& g, const std::string& sensitive_overlaps_path) {
         return;
     }
 
+    // CUDA start-up (context, module load: ~1.5 s, more than the whole reference run on configs[0]) happens on another
+    // thread while the unchanged front end parses the files and analyses the piles
+    auto early_session = std::async(std::launch::async, []() { return new Session("rala::Graph::construct"); });
+
     g.initialize();   // unchanged front end: name_to_id_, piles_, is_valid_overlap_ (graph.cpp:244-425)
 
     (*g.logger_)();
@@ -152,113 +170,184 @@ void construct(Graph& g, const std::string& sensitive_overlaps_path) {
     }
 
     auto& slot = attached()[&g];
-    slot.session.reset(new Session("rala::Graph::construct"));
-    Session& s = *slot.session;
 
-    std::vector<rala_hill_t> hills;
+    // RALA_B200_DEVICES=0,1,...: the same hot path on several GPUs (rala_b200_multi_*).  Its pile table is frozen, so it
+    // applies when no pile has a chimeric hill or pit (Pile::break_over_chimeric_hills / _pits, :704-720 / :785-797, then
+    // leave every pile as it is and no pass re-trims anything) and no -s filter sits between finalize and build.
+    const std::vector<int> devices = devices_from_env();
+    bool frozen = sensitive_overlaps_path.empty();
     for (const auto& p : g.piles_) {
-        if (p == nullptr) continue;
-        for (const auto& h : p->chimeric_hills_) hills.push_back(rala_hill_t{static_cast<uint32_t>(p->id()), h.first, h.second});
+        if (p != nullptr && p->has_chimeric_region()) { frozen = false; break; }
     }
-    upload_piles(g, s);
-    s.set_hills(hills);
-    s.set_overlaps(records);
-    records = rala_b200::OverlapColumns();
+    const bool use_multi = devices.size() >= 2 && frozen;
+    if (devices.size() >= 2 && !frozen) {
+        fprintf(stderr, "[rala::Graph::construct] warning: piles with chimeric regions (or -s) need host pile breaking between the "
+                "passes: using one device instead of %zu!\n", devices.size());
+    }
+    std::vector<uint32_t> seq_to_node;
+    std::vector<rala_edge_t> edges;
+    uint64_t device_nodes = 0;
 
-    s.classify();   // :448-517 on the device: trim, type, hill counters, ordered containment, dead-pile filter
+    if (use_multi) {
+        delete early_session.get();   // it only warmed CUDA up: the ranks have their own contexts
+        slot.multi.reset(new MultiSession("rala::Graph::construct", devices));
+        MultiSession& m = *slot.multi;
+        std::vector<rala_pile_t> table;
+        std::vector<uint8_t> flags;
+        export_piles(g, table, flags);
+        m.set_piles(table, flags);
+        const size_t n = records.a_id.size(), world = devices.size();
+        const size_t per = ((n + world - 1) / world + 3) / 4 * 4;   // contiguous file ranges of equal length
+        for (size_t k = 0; k < world; ++k) m.set_shard(static_cast<int>(k), records, std::min(n, k * per), std::min(n, (k + 1) * per));
+        m.run();   // :443-518, :831-877, :553-632 and :1281-1318 on all devices
+        records = rala_b200::OverlapColumns();
+        const auto after = m.piles();
+        for (size_t i = 0; i < g.piles_.size(); ++i) {
+            if (g.piles_[i] != nullptr && after[i].end == 0u) g.piles_[i].reset();
+        }
+        (*g.logger_)("[rala::Graph::construct] loaded overlaps");
+        (*g.logger_)();
+        (*g.logger_)("[rala::Graph::preprocess]");
+        const auto c = m.counts();
+        device_nodes = c.n_nodes;
+        seq_to_node = m.seq_to_node();
+        edges = m.edges();
+        if (report().on) {
+            fprintf(stderr, "[rala_b200::report] {\"stage\": \"construct\", \"ranks\": %d, \"records\": %llu, \"containment_events\": %llu, "
+                    "\"nodes\": %u, \"edges\": %llu, \"resolution_sweeps\": %u, \"kernel_launches\": %llu}\n", m.ranks(),
+                    (unsigned long long) c.n_records, (unsigned long long) c.n_candidates, c.n_nodes, (unsigned long long) c.n_edges,
+                    c.n_rounds, (unsigned long long) m.kernel_launches());
+        }
+    } else {
+        slot.session.reset(early_session.get());
+        Session& s = *slot.session;
 
-    {   // Pile::check_chimeric_hills (pile.cpp:457-469) ran on the device: hand the counters back
-        const auto cov = s.hill_coverage();
-        size_t k = 0;
+        std::vector<rala_hill_t> hills;
         for (const auto& p : g.piles_) {
             if (p == nullptr) continue;
-            for (size_t j = 0; j < p->chimeric_hills_.size(); ++j, ++k) p->chimeric_hill_coverage_[j] += cov[k];
+            for (const auto& h : p->chimeric_hills_) hills.push_back(rala_hill_t{static_cast<uint32_t>(p->id()), h.first, h.second});
         }
-    }
-    apply_kills(g, s);
-
-    (*g.logger_)("[rala::Graph::construct] loaded overlaps");
-
-    // ---- Graph::preprocess(overlaps, internals), graph.cpp:699-880 ----------------------------------
-    (*g.logger_)();
-    {
-        std::vector<std::future<void>> thread_futures;
-        for (const auto& it : g.piles_) {   // :704-720, host (Pile)
-            if (it == nullptr) continue;
-            thread_futures.emplace_back(g.thread_pool_->submit_task(
-                [&](uint64_t i) -> void {
-                    if (g.piles_[i]->has_chimeric_hill() && g.piles_[i]->break_over_chimeric_hills() == false) {
-                        g.piles_[i].reset();
-                    }
-                }, it->id()));
-        }
-        for (const auto& it : thread_futures) it.wait();
-        thread_futures.clear();
-
         upload_piles(g, s);
-        s.retrim();   // :722-736
+        s.set_hills(hills);
+        s.set_overlaps(records);
+        records = rala_b200::OverlapColumns();
 
-        while (true) {
-            // :740-783: connected components over `overlaps`; only the component's median matters, so any labelling does
-            const auto conn = s.connections();
-            std::vector<uint32_t> parent(g.piles_.size());
-            std::iota(parent.begin(), parent.end(), 0u);
-            auto find = [&](uint32_t x) {
-                while (parent[x] != x) {
-                    parent[x] = parent[parent[x]];
-                    x = parent[x];
-                }
-                return x;
-            };
-            std::vector<bool> touched(g.piles_.size(), false);
-            for (size_t i = 0; i + 1 < conn.size(); i += 2) {
-                uint32_t a = find(conn[i]), b = find(conn[i + 1]);
-                touched[conn[i]] = touched[conn[i + 1]] = true;
-                if (a != b) parent[std::max(a, b)] = std::min(a, b);
+        s.classify();   // :448-517 on the device: trim, type, hill counters, ordered containment, dead-pile filter
+        if (report().on) report().classify += s.stage_ms()[0];
+
+        {   // Pile::check_chimeric_hills (pile.cpp:457-469) ran on the device: hand the counters back
+            const auto cov = s.hill_coverage();
+            size_t k = 0;
+            for (const auto& p : g.piles_) {
+                if (p == nullptr) continue;
+                for (size_t j = 0; j < p->chimeric_hills_.size(); ++j, ++k) p->chimeric_hill_coverage_[j] += cov[k];
             }
-            std::unordered_map<uint32_t, std::vector<uint32_t>> components;
-            for (uint32_t i = 0; i < g.piles_.size(); ++i) {
-                if (touched[i]) components[find(i)].emplace_back(i);
+        }
+        apply_kills(g, s);
+
+        (*g.logger_)("[rala::Graph::construct] loaded overlaps");
+
+        // ---- Graph::preprocess(overlaps, internals), graph.cpp:699-880 ----------------------------------
+        (*g.logger_)();
+        {
+            std::vector<std::future<void>> thread_futures;
+            for (const auto& it : g.piles_) {   // :704-720, host (Pile)
+                if (it == nullptr) continue;
+                thread_futures.emplace_back(g.thread_pool_->submit_task(
+                    [&](uint64_t i) -> void {
+                        if (g.piles_[i]->has_chimeric_hill() && g.piles_[i]->break_over_chimeric_hills() == false) {
+                            g.piles_[i].reset();
+                        }
+                    }, it->id()));
             }
-            for (const auto& kv : components) {   // :774-797, host (Pile)
-                const auto& component = kv.second;
-                std::vector<uint16_t> medians;
-                for (const auto& it : component) medians.emplace_back(g.piles_[it]->median());
-                std::nth_element(medians.begin(), medians.begin() + medians.size() / 2, medians.end());
-                uint16_t component_median = medians[medians.size() / 2];
-                for (const auto& it : component) {
-                    thread_futures.emplace_back(g.thread_pool_->submit_task(
-                        [&](uint64_t i) -> void {
-                            if (g.piles_[i]->break_over_chimeric_pits(component_median) == false) g.piles_[i].reset();
-                        }, it));
-                }
-                for (const auto& it : thread_futures) it.wait();
-                thread_futures.clear();
-            }
+            for (const auto& it : thread_futures) it.wait();
+            thread_futures.clear();
 
             upload_piles(g, s);
-            if (!s.retrim_promote()) break;   // :799-828
+            if (report().on) {
+                const auto c = s.counts();
+                report().list_entries_retrimmed += c.n_overlaps + c.n_internals;
+            }
+            s.retrim();   // :722-736
+            if (report().on) {
+                report().retrim += s.stage_ms()[1];
+                report().retrim_passes += 1;
+            }
+
+            while (true) {
+                // :740-783: connected components over `overlaps`; only the component's median matters, so any labelling does
+                const auto conn = s.connections();
+                std::vector<uint32_t> parent(g.piles_.size());
+                std::iota(parent.begin(), parent.end(), 0u);
+                auto find = [&](uint32_t x) {
+                    while (parent[x] != x) {
+                        parent[x] = parent[parent[x]];
+                        x = parent[x];
+                    }
+                    return x;
+                };
+                std::vector<bool> touched(g.piles_.size(), false);
+                for (size_t i = 0; i + 1 < conn.size(); i += 2) {
+                    uint32_t a = find(conn[i]), b = find(conn[i + 1]);
+                    touched[conn[i]] = touched[conn[i + 1]] = true;
+                    if (a != b) parent[std::max(a, b)] = std::min(a, b);
+                }
+                std::unordered_map<uint32_t, std::vector<uint32_t>> components;
+                for (uint32_t i = 0; i < g.piles_.size(); ++i) {
+                    if (touched[i]) components[find(i)].emplace_back(i);
+                }
+                for (const auto& kv : components) {   // :774-797, host (Pile)
+                    const auto& component = kv.second;
+                    std::vector<uint16_t> medians;
+                    for (const auto& it : component) medians.emplace_back(g.piles_[it]->median());
+                    std::nth_element(medians.begin(), medians.begin() + medians.size() / 2, medians.end());
+                    uint16_t component_median = medians[medians.size() / 2];
+                    for (const auto& it : component) {
+                        thread_futures.emplace_back(g.thread_pool_->submit_task(
+                            [&](uint64_t i) -> void {
+                                if (g.piles_[i]->break_over_chimeric_pits(component_median) == false) g.piles_[i].reset();
+                            }, it));
+                    }
+                    for (const auto& it : thread_futures) it.wait();
+                    thread_futures.clear();
+                }
+
+                upload_piles(g, s);
+                if (report().on) {
+                    const auto c = s.counts();
+                    report().list_entries_retrimmed += c.n_overlaps + c.n_internals;
+                }
+                const bool changed = s.retrim_promote();   // :799-828
+                if (report().on) {
+                    report().retrim += s.stage_ms()[1];
+                    report().retrim_passes += 1;
+                    report().pit_rounds += 1;
+                }
+                if (!changed) break;
+            }
+
+            s.finalize();   // :831-877
+            if (report().on) report().finalize += s.stage_ms()[2];
+            apply_kills(g, s);
+        }
+        (*g.logger_)("[rala::Graph::preprocess]");
+
+        // ---- Graph::preprocess(overlaps, sensitive_overlaps_path), :523 / :882-1054: host, unchanged -------
+        if (!sensitive_overlaps_path.empty()) {
+            std::vector<std::unique_ptr<Overlap>> overlaps;
+            for (const auto& r : s.overlaps()) {
+                // numeric constructor (overlap.cpp:12-20): ids are 1-based there, orientation = a_rc != b_rc
+                overlaps.emplace_back(new Overlap(static_cast<uint64_t>(r.a_id) + 1, static_cast<uint64_t>(r.b_id) + 1, 0.0, 0,
+                    0, r.a_begin, r.a_end, 0, r.flags & 1u, r.b_begin, r.b_end, 0));
+                overlaps.back()->is_transmuted_ = true;
+            }
+            g.preprocess(overlaps, sensitive_overlaps_path);
+            std::vector<rala_ovl_t> kept;
+            kept.reserve(overlaps.size());
+            for (const auto& it : overlaps) kept.emplace_back(marshal(*it, true));
+            s.replace_overlaps(kept);
         }
 
-        s.finalize();   // :831-877
-        apply_kills(g, s);
-    }
-    (*g.logger_)("[rala::Graph::preprocess]");
-
-    // ---- Graph::preprocess(overlaps, sensitive_overlaps_path), :523 / :882-1054: host, unchanged -------
-    if (!sensitive_overlaps_path.empty()) {
-        std::vector<std::unique_ptr<Overlap>> overlaps;
-        for (const auto& r : s.overlaps()) {
-            // numeric constructor (overlap.cpp:12-20): ids are 1-based there, orientation = a_rc != b_rc
-            overlaps.emplace_back(new Overlap(static_cast<uint64_t>(r.a_id) + 1, static_cast<uint64_t>(r.b_id) + 1, 0.0, 0,
-                0, r.a_begin, r.a_end, 0, r.flags & 1u, r.b_begin, r.b_end, 0));
-            overlaps.back()->is_transmuted_ = true;
-        }
-        g.preprocess(overlaps, sensitive_overlaps_path);
-        std::vector<rala_ovl_t> kept;
-        kept.reserve(overlaps.size());
-        for (const auto& it : overlaps) kept.emplace_back(marshal(*it, true));
-        s.replace_overlaps(kept);
     }
 
     (*g.logger_)();
@@ -283,10 +372,26 @@ void construct(Graph& g, const std::string& sensitive_overlaps_path) {
     (*g.logger_)();
 
     // ---- assembly graph: ids, lengths and adjacency from the device (:553-632) -------------------------
-    s.build();
-    const auto counts = s.counts();
-    const auto seq_to_node = s.seq_to_node();
-    const auto edges = s.edges();
+    if (!use_multi) {
+        Session& s = *slot.session;
+        s.build();
+        if (report().on) report().build += s.stage_ms()[3];
+        const auto counts = s.counts();
+        device_nodes = counts.n_nodes;
+        seq_to_node = s.seq_to_node();
+        edges = s.edges();
+        if (report().on) {
+            fprintf(stderr, "[rala_b200::report] {\"stage\": \"construct\", \"ranks\": 1, \"records\": %llu, \"overlaps\": %llu, \"internals\": %llu, "
+                    "\"containment_events\": %llu, \"final_containment_events\": %llu, \"nodes\": %u, \"edges\": %llu, "
+                    "\"retrim_passes_executed\": %u, \"pit_rounds\": %u, \"list_entries_retrimmed\": %llu, "
+                    "\"device_ms\": {\"classify\": %.4f, \"retrim\": %.4f, \"finalize\": %.4f, \"build\": %.4f}, \"kernel_launches\": %llu}\n",
+                    (unsigned long long) counts.n_records, (unsigned long long) counts.n_overlaps, (unsigned long long) counts.n_internals,
+                    (unsigned long long) counts.n_candidates, (unsigned long long) counts.n_final_candidates, counts.n_nodes,
+                    (unsigned long long) counts.n_edges, report().retrim_passes, report().pit_rounds,
+                    (unsigned long long) report().list_entries_retrimmed, report().classify, report().retrim,
+                    report().finalize, report().build, (unsigned long long) s.kernel_launches());
+        }
+    }
 
     uint64_t node_id = 0;
     for (uint64_t i = 0; i < sequences.size(); ++i) {   // :555-574: strings stay host work
@@ -304,8 +409,8 @@ void construct(Graph& g, const std::string& sensitive_overlaps_path) {
         g.nodes_.emplace_back(std::move(node_complement));
         sequences[i].reset();
     }
-    if (g.nodes_.size() != counts.n_nodes) {
-        fprintf(stderr, "[rala::Graph::construct] error: %zu nodes on the host, %u on the device!\n", g.nodes_.size(), counts.n_nodes);
+    if (g.nodes_.size() != device_nodes) {
+        fprintf(stderr, "[rala::Graph::construct] error: %zu nodes on the host, %lu on the device!\n", g.nodes_.size(), device_nodes);
         exit(1);
     }
 
@@ -344,19 +449,34 @@ uint32_t remove_transitive_edges(Graph& g) {
 
     bool untouched = false;   // is the device-resident graph still the host's graph?
     auto it = attached().find(&g);
-    if (it != attached().end() && it->second.session != nullptr && it->second.n_edges == g.edges_.size() &&
+    if (it != attached().end() && (it->second.session != nullptr || it->second.multi != nullptr) && it->second.n_edges == g.edges_.size() &&
         it->second.n_nodes == g.nodes_.size()) {
         untouched = true;
         for (const auto& e : g.edges_) {
             if (e == nullptr || e->is_marked_) { untouched = false; break; }
         }
     }
-    if (untouched) {
+    if (untouched && it->second.multi != nullptr) {
+        MultiSession& m = *it->second.multi;   // the marks were computed with the graph, on all devices (:1283-1318)
+        m.where("rala::Graph::remove_transitive_edges");
+        marked = m.marked();
+        const auto c = m.counts();
+        n_pairs = c.n_transitive_pairs;
+        if (report().on)
+            fprintf(stderr, "[rala_b200::report] {\"stage\": \"remove_transitive_edges\", \"ranks\": %d, \"two_hop_visits\": %llu, "
+                    "\"transitive_pairs\": %llu, \"heavy_items\": %u}\n", m.ranks(), (unsigned long long) c.n_two_hop,
+                    (unsigned long long) c.n_transitive_pairs, c.n_heavy_items);
+    } else if (untouched) {
         Session& s = *it->second.session;
         s.where("rala::Graph::remove_transitive_edges");
         s.transitive();   // :1283-1318 on the CSR left by construct
         marked = s.marked();
-        n_pairs = s.counts().n_transitive_pairs;
+        const auto c = s.counts();
+        n_pairs = c.n_transitive_pairs;
+        if (report().on)
+            fprintf(stderr, "[rala_b200::report] {\"stage\": \"remove_transitive_edges\", \"two_hop_visits\": %llu, \"transitive_pairs\": %llu, "
+                    "\"heavy_items\": %u, \"device_ms\": {\"transitive\": %.4f}}\n", (unsigned long long) c.n_two_hop,
+                    (unsigned long long) c.n_transitive_pairs, c.n_heavy_items, s.stage_ms()[4]);
     } else {
         // the graph was edited since construct (or built elsewhere): marshal the live edges; pairs stay adjacent
         std::vector<rala_edge_t> live;

@@ -33,6 +33,10 @@ public:
     explicit Session(const std::string& where, int device = 0) : where_(where) {
         const char* env = getenv("RALA_B200_DEVICE");
         if (env != nullptr) device = atoi(env);
+        if (getenv("RALA_B200_DEVICES") != nullptr) {   // a multi-GPU session may follow in this process (see MultiSession)
+            setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0);
+            if (env == nullptr) device = atoi(getenv("RALA_B200_DEVICES"));   // the first device of the list
+        }
         int rc = rala_b200_create(&ctx_, device);
         if (rc != RALA_B200_OK) {
             fprintf(stderr, "[%s] error: no usable B200 (sm_100) device %d (status %d); "
@@ -139,6 +143,13 @@ public:
 
     uint64_t kernel_launches() const { return rala_b200_launch_count(ctx_); }
 
+    // device time (ms) of the last run of each stage: classify, retrim, finalize, build, transitive, then single kernels
+    std::vector<float> stage_ms() {
+        std::vector<float> ms(RALA_B200_N_STAGES, 0.f);
+        check(rala_b200_graph_stage_ms(graph_, ms.data()), "stage_ms");
+        return ms;
+    }
+
 private:
     void check(int rc, const char* what) {
         if (rc == RALA_B200_OK) return;
@@ -152,5 +163,109 @@ private:
     rala_b200_graph* graph_ = nullptr;
     uint32_t n_piles_ = 0, n_hills_ = 0;
 };
+
+// The same hot path on several GPUs (rala_b200_multi_*): one rank per entry of `devices`, records cut into contiguous
+// file ranges, the pile table frozen (clean data: no chimeric hills or pits, so no host pile breaking between the passes).
+class MultiSession {
+public:
+    MultiSession(const std::string& where, const std::vector<int>& devices) : where_(where), n_(static_cast<int>(devices.size())) {
+        // ranks that share a GPU wait for each other inside kernels: every stream needs its own hardware queue (read by
+        // the CUDA runtime when it initialises, i.e. at the first CUDA call of this process, which is the one below)
+        setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0);
+        int rc = rala_b200_multi_create(&m_, devices.data(), n_, 0, n_);
+        if (rc != RALA_B200_OK) {
+            fprintf(stderr, "[%s] error: no usable B200 (sm_100) devices for %d ranks (status %d); "
+                "the CUDA path has no CPU fallback!\n", where_.c_str(), n_, rc);
+            exit(1);
+        }
+    }
+    ~MultiSession() { if (m_ != nullptr) rala_b200_multi_destroy(m_); }
+    MultiSession(const MultiSession&) = delete;
+    MultiSession& operator=(const MultiSession&) = delete;
+
+    void where(const std::string& w) { where_ = w; }
+    int ranks() const { return n_; }
+
+    void set_piles(const std::vector<rala_pile_t>& piles, const std::vector<uint8_t>& flags) {
+        n_piles_ = static_cast<uint32_t>(piles.size());
+        check(rala_b200_multi_set_piles(m_, piles.data(), flags.empty() ? nullptr : flags.data(), n_piles_), "set_piles");
+    }
+    // records [begin, end) of the file go to rank k (contiguous ranges in rank order)
+    void set_shard(int k, const OverlapColumns& c, size_t begin, size_t end) {
+        check(rala_b200_multi_set_overlaps_columns(m_, k, c.a_id.data() + begin, c.b_id.data() + begin, c.a_begin.data() + begin,
+                                                   c.a_end.data() + begin, c.b_begin.data() + begin, c.b_end.data() + begin,
+                                                   end - begin, begin), "set_overlaps_columns");
+    }
+    // sizes the exchange buffers from a first step, then runs classify .. transitive on every rank
+    void run() {
+        check(rala_b200_multi_plan(m_), "plan");
+        check(rala_b200_multi_run(m_), "run");
+        check(rala_b200_multi_synchronize(m_), "synchronize");
+    }
+    rala_b200_multi_counts_t counts() {
+        rala_b200_multi_counts_t c;
+        check(rala_b200_multi_counts(m_, &c), "counts");
+        return c;
+    }
+    std::vector<rala_pile_t> piles() {
+        std::vector<rala_pile_t> p(n_piles_);
+        if (n_piles_) check(rala_b200_multi_get_piles(m_, p.data()), "get_piles");
+        return p;
+    }
+    std::vector<uint32_t> seq_to_node() {
+        std::vector<uint32_t> s(n_piles_);
+        if (n_piles_) check(rala_b200_multi_get_seq_to_node(m_, s.data()), "get_seq_to_node");
+        return s;
+    }
+    // the whole edge list / removed-edge set in edge-id order: every rank holds the ids it emitted
+    std::vector<rala_edge_t> edges() {
+        std::vector<rala_edge_t> e(counts().n_edges);
+        for (int k = 0; k < n_; ++k) {
+            uint64_t first = 0, n = 0;
+            check(rala_b200_multi_edge_range(m_, k, &first, &n), "edge_range");
+            if (n) check(rala_b200_multi_get_edges(m_, k, e.data() + first), "get_edges");
+        }
+        return e;
+    }
+    std::vector<uint8_t> marked() {
+        std::vector<uint8_t> mk(counts().n_edges);
+        for (int k = 0; k < n_; ++k) {
+            uint64_t first = 0, n = 0;
+            check(rala_b200_multi_edge_range(m_, k, &first, &n), "edge_range");
+            if (n) check(rala_b200_multi_get_marked(m_, k, mk.data() + first), "get_marked");
+        }
+        return mk;
+    }
+    uint64_t kernel_launches() const { return rala_b200_multi_launch_count(m_); }
+
+private:
+    void check(int rc, const char* what) {
+        if (rc == RALA_B200_OK) return;
+        fprintf(stderr, "[%s] error: rala_b200 multi %s failed (status %d): %s!\n", where_.c_str(), what, rc,
+            rala_b200_multi_last_error(m_));
+        exit(1);
+    }
+
+    std::string where_;
+    rala_b200_multi* m_ = nullptr;
+    int n_ = 0;
+    uint32_t n_piles_ = 0;
+};
+
+// RALA_B200_DEVICES=0,1,2,3: the devices of the multi-GPU session (an id may repeat: several ranks on one GPU)
+inline std::vector<int> devices_from_env() {
+    std::vector<int> d;
+    const char* env = getenv("RALA_B200_DEVICES");
+    if (env == nullptr) return d;
+    std::string s(env);
+    size_t pos = 0;
+    while (pos <= s.size()) {
+        size_t comma = s.find(',', pos);
+        if (comma == std::string::npos) comma = s.size();
+        if (comma > pos) d.push_back(atoi(s.substr(pos, comma - pos).c_str()));
+        pos = comma + 1;
+    }
+    return d;
+}
 
 }  // namespace rala_b200

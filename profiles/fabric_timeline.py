@@ -15,6 +15,7 @@ import torch  # noqa: E402
 import torch.distributed as dist  # noqa: E402
 
 import bench  # noqa: E402
+import bench_multi  # noqa: E402
 from rala_b200 import multi  # noqa: E402
 
 ap = argparse.ArgumentParser()
@@ -26,7 +27,7 @@ local_rank = int(os.environ.get("LOCAL_RANK", str(rank)))
 torch.cuda.set_device(local_rank)
 device = torch.device("cuda", local_rank)
 dist.init_process_group("nccl", device_id=device)
-records, piles, t0, n_total = multi._global_dataset(args, rank, world, device)
+records, piles, t0, n_total = bench_multi._global_dataset(args, rank, world, device)
 fg = multi.FabricGraph(local_rank, rank, world)
 fg.set_inputs(records, piles, None, t0)
 fg.plan()

@@ -321,14 +321,22 @@ extern "C" int rala_b200_graph_set_piles(rala_b200_graph* g, const rala_pile_t* 
     CU(ctx, cudaSetDevice(ctx->device));
     if (n_piles >= (1u << 31)) return fail(ctx, RALA_B200_ERR_LIMIT, "too many piles");
     // event_code (common.cuh) and the packed table (end | flags << 30) rely on the documented limit: valid regions end below 2^30
-    // (one branch-free pass, the table is re-uploaded for every batch; the offender is only looked for when there is one)
-    uint32_t bad = 0;
-    for (uint32_t i = 0; i < n_piles; ++i)
-        bad |= (piles[i].end >> 30) | (uint32_t) ((piles[i].end != 0u) & (piles[i].begin > piles[i].end));
-    if (bad) {
+    // (two branch-free passes over the table as 64-bit words, begin in the low half: it is re-uploaded for every batch; the
+    // offender is only looked for when there is one)
+    {
+        static_assert(sizeof(rala_pile_t) == 8, "a pile is one 64-bit word: begin | end << 32");
+        unsigned long long any = 0, inverted = 0;
         for (uint32_t i = 0; i < n_piles; ++i) {
-            if (piles[i].end >= (1u << 30)) return fail(ctx, RALA_B200_ERR_LIMIT, "pile %u ends at %u: read lengths must be < 2^30", i, piles[i].end);
-            if (piles[i].end && piles[i].begin > piles[i].end) return fail(ctx, RALA_B200_ERR_ARG, "pile %u: begin %u > end %u", i, piles[i].begin, piles[i].end);
+            unsigned long long w;
+            memcpy(&w, &piles[i], 8);
+            any |= w;
+            inverted += (unsigned long long) (((uint32_t) w > (uint32_t) (w >> 32)) & ((w >> 32) != 0));
+        }
+        if ((any >> 62) || inverted) {
+            for (uint32_t i = 0; i < n_piles; ++i) {
+                if (piles[i].end >= (1u << 30)) return fail(ctx, RALA_B200_ERR_LIMIT, "pile %u ends at %u: read lengths must be < 2^30", i, piles[i].end);
+                if (piles[i].end && piles[i].begin > piles[i].end) return fail(ctx, RALA_B200_ERR_ARG, "pile %u: begin %u > end %u", i, piles[i].begin, piles[i].end);
+            }
         }
     }
     CU(ctx, g->piles.reserve((size_t) n_piles * 8 + 16));

@@ -250,3 +250,66 @@ def hub_graph(n_hubs: int = 4, spokes: int = 2500, links_per_spoke: int = 6, see
                     add(s, t, max(1, int(pos[k + d] - pos[k]) + jitter), int(pos[k + d] - pos[k]) + 7)
     e = np.asarray(edges, dtype=np.uint32)
     return 2 * n_reads, e
+
+
+def generate_repeat_hubs(genome_len: int = 20_000_000, coverage: float = 30, read_len: int = 10000, n_hubs: int = 8,
+                         spokes: int = 2601, chain: int = 3, internals_per_spoke: int = 3, seed: int = 5) -> Dataset:
+    """BASELINE.json configs[4]: a genome with segmental repeats that give node degrees > 2 000 THROUGH the whole hot path
+    (classification, containment, edges, transitive reduction), not only at the graph boundary.
+
+    On top of a uniform ``generate()`` background, every hub read ends in a 3 kbp repeat unit that ``spokes`` other reads
+    (from as many other copies of the repeat) begin with.  Geometry, in read coordinates:
+      hub - spoke      hub[L - o, L) ~ spoke[0, o), 1000 <= o <= 2900: begin offsets differ by L - o >= 7100 > 5 % of L, so the
+                       type is a dovetail (overlap.cpp:236-258), never a near-containment, and the hub keeps every spoke;
+      spoke chains     the spokes of one repeat copy are `chain` reads tiled 600 - 900 bp apart (again > 5 % of L), all
+                       pairwise overlaps listed: hub -> 2nd / 3rd spoke and 1st -> 3rd spoke are transitive
+                       (graph.cpp:1301-1306), hub -> 1st is not;
+      spoke - spoke    a few overlaps per spoke between DIFFERENT copies, confined to the repeat: they diverge behind it,
+                       so they type as internal (kX, overlap.cpp:221-224), the way an overlapper reports repeats.
+    The new reads overlap nothing else, so none of them is contained: the hub's out-degree is exactly `spokes`."""
+    base = generate(genome_len, coverage, read_len, seed=seed)
+    rng = np.random.Generator(np.random.PCG64(seed + 1000))
+    L = read_len
+    n0 = base.n_reads
+    loci = (spokes + chain - 1) // chain
+    rows = []
+    next_id = n0
+    for _h in range(n_hubs):
+        hub = next_id
+        next_id += 1
+        fam = []   # (read id, repeat bases at its start)
+        for _l in range(loci):
+            o = 2900 - int(rng.integers(0, 200))
+            ids, offs = [], []
+            for k in range(chain):
+                if len(fam) + len(ids) >= spokes or o < 1000:
+                    break
+                ids.append(next_id)
+                offs.append(o)
+                next_id += 1
+                o -= int(rng.integers(600, 901))
+            # hub - spoke, listed under the lower id (the hub was created first)
+            for r, ov in zip(ids, offs):
+                rows.append((hub, r, L - ov, L, 0, ov, 0))
+            # the chain's own tiling overlaps: read j starts offs[i] - offs[j] bases after read i
+            for i in range(len(ids)):
+                for j in range(i + 1, len(ids)):
+                    d = offs[i] - offs[j]
+                    rows.append((ids[i], ids[j], d, L, 0, L - d, 0))
+            fam += list(zip(ids, offs))
+        # repeat-induced overlaps between different copies: the common part of the two repeat prefixes
+        fam_ids = np.array([f[0] for f in fam])
+        fam_o = np.array([f[1] for f in fam])
+        for k in range(len(fam)):
+            for p in rng.choice(len(fam), size=internals_per_spoke, replace=False).tolist():
+                if abs(int(fam_ids[p]) - int(fam_ids[k])) < chain:   # same copy (or itself): already listed above
+                    continue
+                a, b = (k, p) if fam_ids[k] < fam_ids[p] else (p, k)
+                m = int(min(fam_o[a], fam_o[b]))
+                rows.append((int(fam_ids[a]), int(fam_ids[b]), int(fam_o[a]) - m, int(fam_o[a]), int(fam_o[b]) - m, int(fam_o[b]), 0))
+    extra = np.unique(np.asarray(rows, dtype=np.uint32), axis=0)
+    rec = np.concatenate([base.records, extra])
+    rec = rec[np.lexsort((rec[:, 2], rec[:, 1], rec[:, 0]))]
+    read_len_out = np.concatenate([base.read_len, np.full(next_id - n0, L, dtype=np.uint32)])
+    return Dataset(read_len=read_len_out, records=np.ascontiguousarray(rec), genome_len=genome_len,
+                   meta=dict(base.meta, n_hubs=n_hubs, spokes=spokes, chain=chain, first_hub=n0))

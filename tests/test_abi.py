@@ -23,7 +23,7 @@ def test_library_exports_every_declared_symbol():
     missing = [n for n in names if not hasattr(lib, n)]
     assert not missing, missing
     assert set(api.EXPORTS) == set(names), set(api.EXPORTS) ^ set(names)
-    assert lib.rala_b200_abi_version() == 1
+    assert lib.rala_b200_abi_version() == 2
 
 
 def test_no_device_means_failure_not_fallback():

@@ -87,3 +87,36 @@ def test_dropin_matches_reference_cli(tmp_path, name):
     if ref.stdout == ref2.stdout and _counters(ref.stderr) == _counters(ref2.stderr):
         assert have == want
         assert got.stdout == ref.stdout
+
+
+@pytest.mark.gpu
+@needs_binaries
+def test_dropin_on_two_ranks_matches_reference_cli(tmp_path):
+    """RALA_B200_DEVICES=0,0: the multi-GPU session (rala_b200_multi_*) behind the same CLI, two ranks sharing device 0 here
+    (two GPUs in production).  Clean data: the pile table is frozen, which is what the multi-GPU session covers."""
+    fa, paf = _write(str(tmp_path), "g_clean", **datasets.GOLDEN["g_clean"])
+    threads = str(min(os.cpu_count() or 1, 16))
+    env = dict(os.environ, RALA_B200_DEVICES="0,0", RALA_B200_REPORT="1")
+    ref, got = _run(REFCLI, ["-p", "-t", threads, fa, paf]), _run(DROPIN, ["-p", "-t", threads, fa, paf], env=env)
+    assert ref.returncode == 0 and got.returncode == 0, got.stderr[-2000:]
+    assert '"ranks": 2' in got.stderr, "the multi-GPU session did not run"
+    assert _counters(got.stderr) == _counters(ref.stderr) and "number of edges" in _counters(got.stderr)
+    assert got.stdout == ref.stdout
+    ref, got = _run(REFCLI, ["-t", threads, fa, paf]), _run(DROPIN, ["-t", threads, fa, paf], env=env)
+    assert ref.returncode == 0 and got.returncode == 0, got.stderr[-2000:]
+    for key in ("number of nodes", "number of edges", "number of transitive edges"):
+        assert _counters(got.stderr)[key] == _counters(ref.stderr)[key], key
+
+
+@pytest.mark.gpu
+@needs_binaries
+def test_dropin_falls_back_to_one_device_when_piles_change(tmp_path):
+    """Chimeric pits / hills need the host's pile breaking between the passes: the CLI says so and uses one device."""
+    fa, paf = _write(str(tmp_path), "g_noisy", **datasets.GOLDEN["g_noisy"])
+    threads = str(min(os.cpu_count() or 1, 16))
+    env = dict(os.environ, RALA_B200_DEVICES="0,0", RALA_B200_REPORT="1")
+    ref, got = _run(REFCLI, ["-p", "-t", threads, fa, paf]), _run(DROPIN, ["-p", "-t", threads, fa, paf], env=env)
+    assert ref.returncode == 0 and got.returncode == 0, got.stderr[-2000:]
+    assert "using one device instead of 2" in got.stderr and '"ranks": 1' in got.stderr
+    assert _counters(got.stderr) == _counters(ref.stderr)
+    assert got.stdout == ref.stdout

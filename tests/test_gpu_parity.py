@@ -419,3 +419,35 @@ def test_pile_table_limits_are_enforced(ctx):
     with pytest.raises(api.RalaB200Error, match="begin"):
         G.set_piles(np.array([[15, 9985], [9000, 100]], np.uint32))
     G.close()
+
+
+def test_config5_repeat_hubs_whole_pipeline(ctx):
+    """BASELINE.json configs[4] at full size (20 Mbp background, 8 hubs with ~2 600 spokes each): node degrees > 2 000
+    through classification, containment, edge creation and the transitive pass (heavy block-per-node path), on one GPU
+    and on four ranks."""
+    ds = synth.generate_repeat_hubs()
+    piles = ds.flat_piles()
+    P = O.Pipeline(ds.records, piles).run()
+    deg = np.bincount(P.edges[:, 0], minlength=P.n_nodes)
+    assert deg.max() > 2000 and int((deg > 2000).sum()) == 8
+    G = api.Graph(ctx)
+    G.set_piles(piles).set_hills(None).set_overlaps(ds.records)
+    for _ in range(3):   # eager, captured, replayed
+        G.run()
+    c = G.counts()
+    assert c["n_heavy_items"] > 0, "degrees > 64 go to the block-per-node path"
+    assert_same(G.edges(), P.edges, "edges")
+    assert_same(G.marked(), P.marked, "marks")
+    ovl, inl = G.lists()
+    assert_same(inl, P.int, "internals")
+    assert c["n_transitive_pairs"] == P.n_pairs
+    G.close()
+    M = api.Multi([0, 0, 0, 0])
+    M.set_piles(piles).set_shards(ds.records).plan()
+    for _ in range(3):
+        M.run()
+    e, m = M.all_edges()
+    assert_same(e, P.edges, "edges (4 ranks)")
+    assert_same(m, P.marked, "marks (4 ranks)")
+    assert M.counts()["n_heavy_items"] > 0
+    M.close()

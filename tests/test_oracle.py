@@ -119,3 +119,27 @@ def test_oracle_matches_reference_hotpath_frozen_piles(tmp_path):
     assert_same(P.edges, O.load_u32(prefix + ".stage.edges.u32", 3), "edges")
     assert_same(P.marked, O.load_u32(prefix + ".stage.removed.u32").astype(np.uint8), "removed")
     assert_same(P.ovl, O.load_u32(prefix + ".stage.s4.ovl.u32", 7), "final overlaps")
+
+
+@pytest.mark.skipif(not O.have_ref(), reason="oracle/_ref not built (needs /root/reference)")
+def test_config5_repeat_hubs_reference_builds_degrees_above_2000(tmp_path):
+    """BASELINE.json configs[4]: the high-repeat dataset pushed through the REFERENCE's own hot path (trim, type, ordered
+    containment, Node / Edge creation, remove_transitive_edges) keeps node degrees > 2 000, and the oracle agrees with
+    the reference on it bit for bit."""
+    from rala_b200 import synth
+    ds = synth.generate_repeat_hubs(genome_len=3_000_000, n_hubs=3)
+    piles = ds.flat_piles()
+    prefix = str(tmp_path / "c5")
+    O.write_hotpath_inputs(prefix, ds.records, piles, None, None, ds.read_len)
+    O.ref_run(["hotpath", prefix, prefix])
+    edges = O.load_u32(prefix + ".stage.edges.u32", 3)
+    removed = O.load_u32(prefix + ".stage.removed.u32").astype(np.uint8)
+    deg = np.bincount(edges[:, 0])
+    assert deg.max() > 2000 and int((deg > 2000).sum()) == 3, f"max out-degree {deg.max()}"
+    hub = int(np.argmax(deg))
+    out = np.nonzero(edges[:, 0] == hub)[0]
+    assert 1000 < int(removed[out].sum()) < out.shape[0], "some, not all, of a hub's edges are transitive"
+    P = O.Pipeline(ds.records, piles).run()
+    assert_same(P.edges, edges, "edges")
+    assert_same(P.marked, removed, "removed")
+    assert P.int.shape[0] > 1000, "repeat-induced overlaps between different copies are internal"
