@@ -63,7 +63,7 @@ def build(verbose: bool = False, force: bool = False) -> str:
 
 # A/B libraries: the product with ONE optimisation switched off each (common.cuh RB_OPT_*), for bench.py --ab.
 VARIANTS = {"no_events": "RB_OPT_EVENTS", "no_reloc": "RB_OPT_RELOC", "no_fill": "RB_OPT_FILL",
-            "no_conc": "RB_OPT_CONC", "no_bsearch": "RB_OPT_BSEARCH", "no_fuse": "RB_OPT_FUSE"}
+            "no_conc": "RB_OPT_CONC", "no_fuse": "RB_OPT_FUSE"}
 VARIANT_DIR = os.path.join(HERE, "variants")
 
 

@@ -16,9 +16,6 @@
 #ifndef RB_OPT_FILL
 #define RB_OPT_FILL 1     // four independent atomics in flight per thread in the CSR fill
 #endif
-#ifndef RB_OPT_BSEARCH
-#define RB_OPT_BSEARCH 1  // transitive pass, low-degree nodes: branch-free binary search instead of a hash table
-#endif
 #ifndef RB_OPT_FUSE
 #define RB_OPT_FUSE 1     // small dependent-free kernels of the containment resolution share a launch
 #endif
@@ -263,36 +260,5 @@ __device__ __forceinline__ unsigned long long lookback_exclusive(unsigned long l
     if (lane == 0) st_status(status + tile, kStateInc | ((exclusive + aggregate) & kCountMask));
     return exclusive;
 }
-
-// ---------------------------------------------------------------------------------------------
-// TMA 1-D bulk copy global -> shared with mbarrier completion (cp.async.bulk; SASS: UBLKCP).
-// ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t) __cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "WAIT_%=:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra DONE_%=;\n"
-        "bra WAIT_%=;\n"
-        "DONE_%=:\n"
-        "}\n" ::"r"(smem_addr(bar)), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                     smem_addr(dst_smem)),
-                 "l"(src_gmem), "r"(bytes), "r"(smem_addr(bar))
-                 : "memory");
-}
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 }  // namespace rb

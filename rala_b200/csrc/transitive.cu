@@ -4,9 +4,10 @@
 // (SURVEY.md A.4):  cand(a,c) = highest-id edge a->c;  T(e = cand(a,c)) = exists a->b, b->c with
 // comparable(len_ab + len_bc, len_e, 0.12);  marked(e) = T(e) | T(e^1);  return = #{j : marked(2j)}.
 //
-// Per node a the neighbour set N+(a) is staged in shared memory as an open-addressing hash table
-// keyed by destination (value = edge id << 32 | length, merged with max => "highest id wins" for
-// parallel edges, graph.cpp:1291-1293).  The two-hop stream  { (b, j) : b in N+(a), j < deg(b) }  is
+// Per node a the neighbour set N+(a) is staged in shared memory: rank-sorted by (destination, edge id) and searched with
+// a branch-free binary search on the group path (the last key <= x is the highest edge id: "highest id wins" for
+// parallel edges, graph.cpp:1291-1293), an open-addressing hash table keyed by destination (value = edge id << 32 |
+// length, merged with max) on the light and heavy paths.  The two-hop stream  { (b, j) : b in N+(a), j < deg(b) }  is
 // FLATTENED: lanes take consecutive flat indices, so several short rows N+(b) are in flight per
 // iteration and every load is an 8-byte (dst, len) element of a contiguous CSR row.
 //   group path : 8 lanes per node, 4 nodes per warp   (2 <= deg <= 16 and <= 4096 two-hop visits: almost every
@@ -26,8 +27,6 @@ constexpr uint32_t kEmpty = 0xFFFFFFFFu;
 constexpr int kGroupLanes = 8;
 constexpr int kGroupsPerWarp = 32 / kGroupLanes;
 constexpr int kGroupMaxDeg = 16;
-constexpr int kGroupLog2Cap = 5;                    // 32 slots per group: load factor <= 0.5
-constexpr int kGroupCap = 1 << kGroupLog2Cap;
 constexpr uint32_t kGroupMaxVisits = 4096;
 constexpr int kLightMaxDeg = 64;
 constexpr int kLightCap = 128;
@@ -105,7 +104,6 @@ __device__ __forceinline__ uint32_t group_inclusive_scan(uint32_t v, uint32_t gl
     return v;
 }
 
-#if RB_OPT_BSEARCH
 // Membership of a two-hop destination in N+(a) is a BRANCH-FREE binary search over the (at most 16) neighbours,
 // sorted by (destination, edge id) with a rank sort during set-up: four dependent shared-memory loads, the same
 // for every lane.  The open-addressing table this replaces cost 48 % of the kernel's instructions at 7 of 32
@@ -286,164 +284,6 @@ __global__ void __launch_bounds__(kLightWarps * 32, 6) k_transitive_group(
     visits = warp_sum64(visits);
     if (lane == 0 && visits) atomicAdd(reinterpret_cast<unsigned long long*>(counters + C_HOP_LO), visits);
 }
-#else
-struct GroupSmem {
-    uint32_t keys[kGroupCap];
-    uint32_t eid[kGroupCap];    // highest edge id a->key (graph.cpp:1291-1293)
-    uint32_t lo[kGroupCap];     // comparable(sum, len of that edge)  <=>  sum - lo <= rng
-    uint32_t rng[kGroupCap];
-    uint32_t nrow[kGroupMaxDeg];
-    uint32_t nlen[kGroupMaxDeg];
-    uint32_t noff[kGroupMaxDeg + 1];
-    uint32_t hit;               // bit s: the candidate in slot s passed the test
-};
-
-__global__ void __launch_bounds__(kLightWarps * 32, 6) k_transitive_group(
-    const uint32_t* __restrict__ row_ptr, const uint2* __restrict__ col, const uint32_t* __restrict__ col_eid,
-    uint8_t* __restrict__ T, uint32_t node_begin, uint32_t node_end, const uint32_t* __restrict__ node_range,
-    const uint32_t* __restrict__ n_nodes_ptr, uint32_t* __restrict__ work_counter, HeavyItems heavy,
-    uint32_t* __restrict__ counters) {
-    __shared__ GroupSmem smem[kLightWarps][kGroupsPerWarp];
-    const uint32_t lane = lane_id(), gl = lane & (kGroupLanes - 1), grp = lane / kGroupLanes;
-    GroupSmem& S = smem[warp_id()][grp];
-    if (node_range) {
-        node_begin = node_range[0];
-        node_end = node_range[1];
-    }
-    const uint32_t n_end = min(node_end, *n_nodes_ptr);
-    unsigned long long visits = 0;
-
-    while (true) {
-        uint32_t base = 0;
-        if (lane == 0) base = atomicAdd(work_counter, 32u);
-        base = node_begin + __shfl_sync(0xFFFFFFFFu, base, 0);
-        if (base >= n_end) break;
-        uint32_t r0 = 0, deg = 0;
-        if (base + lane < n_end) {
-            r0 = row_ptr[base + lane];
-            deg = row_ptr[base + lane + 1] - r0;
-        }
-#pragma unroll 1
-        for (uint32_t round = 0; round < 32 / kGroupsPerWarp; ++round) {
-            const uint32_t from = round * kGroupsPerWarp + grp;
-            const uint32_t a = base + from;
-            const uint32_t ra0 = __shfl_sync(0xFFFFFFFFu, r0, from);
-            const uint32_t d = __shfl_sync(0xFFFFFFFFu, deg, from);
-            bool act = d >= 2u && d <= (uint32_t) kGroupMaxDeg;   // < 2 neighbours: no two-hop witness can exist
-            if (!__any_sync(0xFFFFFFFFu, act)) continue;
-            if (act) {
-#pragma unroll
-                for (uint32_t s = gl; s < (uint32_t) kGroupCap; s += kGroupLanes) {
-                    S.keys[s] = kEmpty;
-                    S.eid[s] = 0u;
-                }
-                if (gl == 0) S.hit = 0u;
-            }
-            __syncwarp();
-            uint32_t dg[2] = {0u, 0u}, my_slot[2] = {kEmpty, kEmpty}, my_eid[2] = {0u, 0u}, my_len[2] = {0u, 0u};
-            if (act) {
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const uint32_t i = gl + h * kGroupLanes;
-                    if (i < d) {
-                        const uint2 e = col[ra0 + i];
-                        my_eid[h] = col_eid[ra0 + i];
-                        my_len[h] = e.y;
-                        uint32_t sl = hash_slot(e.x, kGroupLog2Cap);
-                        while (true) {
-                            const uint32_t prev = atomicCAS(&S.keys[sl], kEmpty, e.x);
-                            if (prev == kEmpty || prev == e.x) break;
-                            sl = (sl + 1u) & (kGroupCap - 1);
-                        }
-                        atomicMax(&S.eid[sl], my_eid[h]);
-                        my_slot[h] = sl;
-                        const uint32_t rs = row_ptr[e.x];
-                        dg[h] = row_ptr[e.x + 1] - rs;
-                        S.nrow[i] = rs;
-                        S.nlen[i] = e.y;
-                    }
-                }
-            }
-            const uint32_t inc0 = group_inclusive_scan(dg[0], gl), inc1 = group_inclusive_scan(dg[1], gl);
-            const uint32_t tot0 = __shfl_sync(0xFFFFFFFFu, inc0, kGroupLanes - 1, kGroupLanes);
-            const uint32_t W = tot0 + __shfl_sync(0xFFFFFFFFu, inc1, kGroupLanes - 1, kGroupLanes);
-            if (act) {
-                if (gl < d) S.noff[gl] = inc0 - dg[0];
-                if (gl + kGroupLanes < d) S.noff[gl + kGroupLanes] = tot0 + inc1 - dg[1];
-                if (gl == 0) S.noff[d] = W;
-            }
-            __syncwarp();
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {   // the winner of each slot publishes its acceptance interval
-                if (my_slot[h] != kEmpty && S.eid[my_slot[h]] == my_eid[h]) {
-                    const uint2 iv = comparable_interval(my_len[h]);
-                    S.lo[my_slot[h]] = iv.x;
-                    S.rng[my_slot[h]] = iv.y;
-                }
-            }
-            __syncwarp();
-            if (act && W > kGroupMaxVisits) {   // short row, very long rows behind it: give the node to a block
-                if (gl == 0) {
-                    const uint32_t hb = atomicAdd(&counters[C_HEAVY], 1u);
-                    if (hb < heavy.cap) {
-                        heavy.node[hb] = a;
-                        heavy.hash_chunk[hb] = 0;
-                        heavy.nbr_chunk[hb] = 0;
-                    } else {
-                        counters[C_OVERFLOW] = 1u;
-                    }
-                }
-                act = false;
-            }
-            if (act) {
-                if (gl == 0) visits += W;
-                uint32_t i = 0;
-                for (uint32_t f0 = 0; f0 < W; f0 += 4 * kGroupLanes) {
-                    uint2 e[4];
-                    uint32_t lab[4];
-                    bool ok[4];
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        const uint32_t f = f0 + u * kGroupLanes + gl;
-                        ok[u] = f < W;
-                        if (ok[u]) {
-                            while (f >= S.noff[i + 1]) ++i;
-                            e[u] = col[S.nrow[i] + (f - S.noff[i])];
-                            lab[u] = S.nlen[i];
-                        }
-                    }
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        if (ok[u]) {
-                            uint32_t s = hash_slot(e[u].x, kGroupLog2Cap);
-                            while (true) {
-                                const uint32_t k = S.keys[s];
-                                if (k == e[u].x) {
-                                    if (!((S.hit >> s) & 1u) && lab[u] + e[u].y - S.lo[s] <= S.rng[s]) atomicOr(&S.hit, 1u << s);   // graph.cpp:1301-1306
-                                    break;
-                                }
-                                if (k == kEmpty) break;
-                                s = (s + 1u) & (kGroupCap - 1);
-                            }
-                        }
-                    }
-                }
-            }
-            __syncwarp();
-            if (act) {
-                const uint32_t h = S.hit;
-#pragma unroll
-                for (uint32_t s = gl; s < (uint32_t) kGroupCap; s += kGroupLanes) {
-                    if ((h >> s) & 1u) T[S.eid[s]] = 1;
-                }
-            }
-            __syncwarp();
-        }
-    }
-    visits = warp_sum64(visits);
-    if (lane == 0 && visits) atomicAdd(reinterpret_cast<unsigned long long*>(counters + C_HOP_LO), visits);
-}
-#endif   // RB_OPT_BSEARCH
 
 struct LightSmem {
     unsigned long long vals[kLightCap];
