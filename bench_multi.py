@@ -234,6 +234,10 @@ def bench_main(args):
 
     # ---- end to end: pinned host shard -> device, one step, the edges this rank emitted + their marks back ---------
     cols_pin = torch.from_numpy(api.records_to_columns(records)).pin_memory()   # 24 B / record, the device layout
+    packed = api.records_to_packed(records) if kind == "fabric" else None       # 12 B / record when coordinates fit 16 bits
+    ok = torch.tensor([0 if packed is None else 1], dtype=torch.int32, device=device)
+    dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+    packed_pin = packed.pin() if int(ok.item()) else None
     piles_pin = torch.from_numpy(piles).pin_memory()
     e2e_steps = max(3, min(steps, 10))
     n_out = max(int(e_mine.shape[0]), 1) if kind == "fabric" else max(E, 1)
@@ -244,7 +248,10 @@ def bench_main(args):
 
         def e2e_step():
             dg.M.set_piles(piles_pin)
-            dg.M.set_overlaps_columns(0, cols_pin, t0)
+            if packed_pin is not None:
+                dg.M.set_overlaps_packed(0, packed_pin, t0)
+            else:
+                dg.M.set_overlaps_columns(0, cols_pin, t0)
             dg.M.run()
             dg.M.synchronize()           # edges_pin / marked_pin are complete
     else:
@@ -299,9 +306,9 @@ def bench_main(args):
                        "exchange_capacities": dict(zip(api.CAP_NAMES, [int(x) for x in dg.caps])) if kind == "fabric" else dg.caps},
             "parity": parity,
             "wall_ms_per_step": float(t[1].item()) / steps,
-            "e2e": {"value": E / e2e_s, "unit": "edges/s", "h2d_bytes_per_step": int((cols_pin.numel() * 4 + piles.nbytes) * world),
+            "e2e": {"value": E / e2e_s, "unit": "edges/s", "h2d_bytes_per_step": int(((packed_pin.nbytes if packed_pin is not None else cols_pin.numel() * 4) + piles.nbytes) * world),
                     "d2h_bytes_per_step": int(13 * E) if kind == "fabric" else int(13 * E), "ms_per_step": 1e3 * e2e_s,
-                    "path": "per rank: set_piles + set_overlaps_columns (pinned) + run + the rows / marks of the edges the rank emitted "
+                    "path": "per rank: set_piles + " + ("set_overlaps_packed (pinned, 12 B/record)" if packed_pin is not None else "set_overlaps_columns (pinned, 24 B/record)") + " + run + the rows / marks of the edges the rank emitted "
                             "written to pinned host memory by the GPU + synchronize"},
             "gpu_launches": int(launches) * (world if kind == "fabric" else 1),
             "roofline": {"bound": "hbm", "kernel": "k_classify_first", "achieved": k1_gbs, "peak": peak, "unit": "GB/s",

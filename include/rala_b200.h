@@ -143,6 +143,17 @@ int rala_b200_graph_set_overlaps(rala_b200_graph* g, const rala_ovl_t* ovl, uint
 int rala_b200_graph_set_overlaps_columns(rala_b200_graph* g, const uint32_t* a_id, const uint32_t* b_id,
                                          const uint32_t* a_begin, const uint32_t* a_end, const uint32_t* b_begin,
                                          const uint32_t* b_end, uint64_t n);
+/* The same records in a COMPACT host form for the PCIe link: 12 bytes per record instead of 24 (the upload is 85 % of an
+ * end-to-end step).  It relies on two properties of the data the reference consumes: a PAF / MHAP lists the overlaps
+ * of one query together (graph.cpp:343-350 assumes the same grouping), and read coordinates of today's long reads fit
+ * 16 bits (the caller checks: every coordinate < 65 536, otherwise it uses the column form).
+ *   group k = records [group_end[k-1], group_end[k]) (group_end[-1] = 0), all with a_id = query_id[k] (< 2^31)
+ *   b_id[i]   as in the column form (bit 31 = orientation)
+ *   a_span[i] = a_begin | a_end << 16,   b_span[i] = b_begin | b_end << 16
+ * An INVALID record (RALA_OVL_INVALID) is passed with both spans 0: Overlap::trim rejects it in every pass
+ * (overlap.cpp:139-142), which is all "invalid" means on this path.  Expanded on the device into the column layout. */
+int rala_b200_graph_set_overlaps_packed(rala_b200_graph* g, const uint32_t* query_id, const uint32_t* group_end, uint32_t n_groups,
+                                        const uint32_t* b_id, const uint32_t* a_span, const uint32_t* b_span, uint64_t n);
 int rala_b200_graph_set_piles(rala_b200_graph* g, const rala_pile_t* piles, const uint8_t* flags /* nullable */,
                               uint32_t n_piles);
 /* Optional: have build / transitive / run write their results STRAIGHT into caller memory the GPU can address
@@ -306,6 +317,8 @@ int rala_b200_multi_set_piles(rala_b200_multi* m, const rala_pile_t* piles, cons
 int rala_b200_multi_set_overlaps(rala_b200_multi* m, int k, const rala_ovl_t* ovl, uint64_t n, uint64_t t0);
 int rala_b200_multi_set_overlaps_columns(rala_b200_multi* m, int k, const uint32_t* a_id, const uint32_t* b_id, const uint32_t* a_begin,
                                          const uint32_t* a_end, const uint32_t* b_begin, const uint32_t* b_end, uint64_t n, uint64_t t0);
+int rala_b200_multi_set_overlaps_packed(rala_b200_multi* m, int k, const uint32_t* query_id, const uint32_t* group_end, uint32_t n_groups,
+                                        const uint32_t* b_id, const uint32_t* a_span, const uint32_t* b_span, uint64_t n, uint64_t t0);
 /* as rala_b200_graph_set_outputs, for the edges local rank k emits (edge ids rala_b200_multi_edge_range) and their marks */
 int rala_b200_multi_set_outputs(rala_b200_multi* m, int k, rala_edge_t* edges_out, uint64_t edges_cap, uint8_t* marked_out,
                                 uint64_t marked_cap);

@@ -52,6 +52,7 @@ EXPORTS = [
     "rala_b200_graph_get_lists", "rala_b200_graph_get_seq_to_node", "rala_b200_graph_get_edges",
     "rala_b200_graph_get_marked", "rala_b200_graph_stage_ms", "rala_b200_graph_set_kept_overlaps",
     "rala_b200_graph_use_cuda_graph", "rala_b200_graph_set_overlaps_columns", "rala_b200_graph_set_outputs",
+    "rala_b200_graph_set_overlaps_packed", "rala_b200_multi_set_overlaps_packed",
     # multi-GPU phases
     "rala_b200_create_on_stream", "rala_b200_graph_set_shard", "rala_b200_graph_phase_events",
     "rala_b200_graph_events_count", "rala_b200_graph_export_events", "rala_b200_graph_import_events",
@@ -130,6 +131,53 @@ def records_to_columns(records) -> np.ndarray:
     cols[1] = (r[:, 1] & ~top) | ((r[:, 6] & 1) << 31)
     cols[2:6] = r[:, 2:6].T
     return cols
+
+
+class PackedRecords:
+    """Host form of rala_b200_graph_set_overlaps_packed: 12 bytes per record (+ 8 per query group) instead of 24."""
+
+    def __init__(self, query_id, group_end, b_id, a_span, b_span):
+        self.query_id, self.group_end, self.b_id, self.a_span, self.b_span = query_id, group_end, b_id, a_span, b_span
+
+    @property
+    def n(self) -> int:
+        return int(self.b_id.shape[0])
+
+    @property
+    def nbytes(self) -> int:
+        return sum(int(x.numel() * x.element_size()) if hasattr(x, "numel") else int(x.nbytes)
+                   for x in (self.query_id, self.group_end, self.b_id, self.a_span, self.b_span))
+
+    def pin(self):
+        """The same arrays in pinned host memory (torch), for asynchronous uploads."""
+        import torch
+        return PackedRecords(*[torch.from_numpy(np.ascontiguousarray(x)).pin_memory() for x in
+                               (self.query_id, self.group_end, self.b_id, self.a_span, self.b_span)])
+
+
+def records_to_packed(records):
+    """rala_ovl_t rows (n, 7), grouped by query as a PAF lists them -> PackedRecords, or None when a coordinate does not fit
+    16 bits or an id needs bit 31 (use records_to_columns then).  Invalid records travel with both spans 0."""
+    r = np.ascontiguousarray(records, dtype=np.uint32).reshape(-1, 7)
+    n = r.shape[0]
+    if n == 0:
+        return None
+    bad = ((r[:, 6] & 2) != 0) | (r[:, 0] >= 0x80000000) | (r[:, 1] >= 0x80000000)
+    if (r[~bad, 2:6] >= 65536).any():
+        return None
+    a = np.where(bad, np.uint32(0), r[:, 0])          # an invalid record joins whatever group it sits in: id 0 is as good as any
+    a = a.copy()
+    # keep the grouping tight: an invalid record takes the id of its predecessor (it is rejected whatever its ids are)
+    if bad.any():
+        idx = np.where(~bad, np.arange(n), 0)
+        np.maximum.accumulate(idx, out=idx)
+        a = r[idx, 0] * (~bad[idx]).astype(np.uint32)
+    change = np.nonzero(a[1:] != a[:-1])[0] + 1
+    group_end = np.concatenate([change, [n]]).astype(np.uint32)
+    query_id = a[np.concatenate([[0], change])].astype(np.uint32)
+    span = lambda lo, hi: np.where(bad, np.uint32(0), lo | (hi << 16)).astype(np.uint32)   # noqa: E731
+    b_id = np.where(bad, np.uint32(0), r[:, 1] | ((r[:, 6] & 1) << 31)).astype(np.uint32)
+    return PackedRecords(query_id, group_end, b_id, span(r[:, 2], r[:, 3]), span(r[:, 4], r[:, 5]))
 
 
 class Context:
@@ -254,6 +302,13 @@ class Graph:
             raise RalaB200Error("set_overlaps_columns needs six columns of equal length")
         self._keep = list(cols)
         self._call("rala_b200_graph_set_overlaps_columns", *[_ptr(c) for c in cols], C.c_uint64(n))
+        return self
+
+    def set_overlaps_packed(self, p: PackedRecords):
+        """The compact upload (records_to_packed): 12 B per record cross PCIe, expanded on the device."""
+        self._keep = [p]
+        self._call("rala_b200_graph_set_overlaps_packed", _ptr(p.query_id), _ptr(p.group_end), C.c_uint32(int(p.query_id.shape[0])),
+                   _ptr(p.b_id), _ptr(p.a_span), _ptr(p.b_span), C.c_uint64(p.n))
         return self
 
     def set_outputs(self, edges_out=None, marked_out=None):
@@ -496,6 +551,12 @@ class Multi:
             raise RalaB200Error("set_overlaps_columns needs six columns of equal length")
         self._keep[("rec", k)] = cols
         self._call("rala_b200_multi_set_overlaps_columns", C.c_int(k), *[_ptr(c) for c in cols], C.c_uint64(n), C.c_uint64(t0))
+        return self
+
+    def set_overlaps_packed(self, k: int, p: PackedRecords, t0: int):
+        self._keep[("rec", k)] = p
+        self._call("rala_b200_multi_set_overlaps_packed", C.c_int(k), _ptr(p.query_id), _ptr(p.group_end),
+                   C.c_uint32(int(p.query_id.shape[0])), _ptr(p.b_id), _ptr(p.a_span), _ptr(p.b_span), C.c_uint64(p.n), C.c_uint64(t0))
         return self
 
     def set_outputs(self, k: int, edges_out=None, marked_out=None):

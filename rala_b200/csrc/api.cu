@@ -287,6 +287,31 @@ extern "C" int rala_b200_graph_set_overlaps_columns(rala_b200_graph* g, const ui
     return RALA_B200_OK;
 }
 
+// Compact upload (12 B / record): b_id lands in place, the two span columns and the group table go through the staging
+// buffer and are expanded by one kernel.
+extern "C" int rala_b200_graph_set_overlaps_packed(rala_b200_graph* g, const uint32_t* query_id, const uint32_t* group_end, uint32_t n_groups,
+                                                   const uint32_t* b_id, const uint32_t* a_span, const uint32_t* b_span, uint64_t n) {
+    if (!g || (n && (!query_id || !group_end || !b_id || !a_span || !b_span || !n_groups))) return RALA_B200_ERR_ARG;
+    rala_b200_ctx* ctx = g->ctx;
+    if (n >= (1ull << 31)) return fail(ctx, RALA_B200_ERR_LIMIT, "too many overlap records (%llu >= 2^31)", (unsigned long long) n);
+    CU(ctx, cudaSetDevice(ctx->device));
+    int rc = reserve_for_records(g, n);
+    if (rc) return rc;
+    if (!n) return RALA_B200_OK;
+    const size_t col = align_up(((size_t) n + 4) * 4, 256), grp = align_up((size_t) n_groups * 4, 256);
+    CU(ctx, g->rec.reserve(2 * col + 2 * grp));
+    char* st = g->rec.as<char>();
+    uint32_t *d_a = (uint32_t*) st, *d_b = (uint32_t*) (st + col), *d_q = (uint32_t*) (st + 2 * col), *d_e = (uint32_t*) (st + 2 * col + grp);
+    CU(ctx, cudaMemcpyAsync(g->recs.view.b, b_id, (size_t) n * 4, cudaMemcpyHostToDevice, ctx->L.stream));
+    CU(ctx, cudaMemcpyAsync(d_a, a_span, (size_t) n * 4, cudaMemcpyHostToDevice, ctx->L.stream));
+    CU(ctx, cudaMemcpyAsync(d_b, b_span, (size_t) n * 4, cudaMemcpyHostToDevice, ctx->L.stream));
+    CU(ctx, cudaMemcpyAsync(d_q, query_id, (size_t) n_groups * 4, cudaMemcpyHostToDevice, ctx->L.stream));
+    CU(ctx, cudaMemcpyAsync(d_e, group_end, (size_t) n_groups * 4, cudaMemcpyHostToDevice, ctx->L.stream));
+    launch_unpack_records(ctx->L, d_q, d_e, n_groups, d_a, d_b, (uint32_t) n, g->recs.view);
+    CU(ctx, cudaGetLastError());
+    return RALA_B200_OK;
+}
+
 // Results straight into the caller's memory (pinned host memory or device memory the GPU can address).
 extern "C" int rala_b200_graph_set_outputs(rala_b200_graph* g, rala_edge_t* edges_out, uint64_t edges_cap, uint8_t* marked_out,
                                            uint64_t marked_cap) {
@@ -404,13 +429,13 @@ cudaError_t clear_victim_histogram(rala_b200_graph* g) {
     return cudaMemsetAsync(resolve_bufs(g).vcursor, 0, ((size_t) g->n_piles + 64) * 4, g->ctx->L.stream);
 }
 
-static int resolve_containment(rala_b200_graph* g, bool decode) {
+static int resolve_containment(rala_b200_graph* g, bool decode, bool skip_if_empty) {
     rala_b200_ctx* ctx = g->ctx;
     unsigned long long* status;
     uint32_t* ticket;
     scan_state(g, (uint64_t) g->n_piles + 1, &status, &ticket);
     launch_resolve(ctx->L, g->events_view(), g->cnt() + C_EV, g->ev_cap, resolve_bufs(g), g->n_piles, g->cnt(), status, ticket,
-                   ctx->coop_blocks, decode);
+                   ctx->coop_blocks, decode, skip_if_empty);
     CU(ctx, cudaGetLastError());
     return RALA_B200_OK;
 }
@@ -445,7 +470,11 @@ static int phase_resolve(rala_b200_graph* g, bool first_pass) {
     // sits between the resolution and k_apply_deaths, which then decodes the states itself
     const bool fused_decode = RB_OPT_FUSE && !(first_pass && g->n_hills);
     CU(ctx, stage_event(g, g->ev_start[ST_K1B_KERNEL]));
-    int rc = resolve_containment(g, !fused_decode);
+    // The final pass (graph.cpp:831-866) has no events at all on clean data: scan, scatter, resolution and the sweep over the
+    // pile table then return at once (nobody dies; the death times of the first pass, all "never" for the piles still
+    // in the lists, stay in place).  The first pass always runs: it also builds the liveness bitmap.
+    const bool skip_if_empty = RB_OPT_FUSE && !first_pass && fused_decode;
+    int rc = resolve_containment(g, !fused_decode, skip_if_empty);
     if (rc) return rc;
     CU(ctx, end_stage(g, ST_K1B_KERNEL));
     if (first_pass && g->n_hills) {
@@ -454,7 +483,8 @@ static int phase_resolve(rala_b200_graph* g, bool first_pass) {
                              h + g->n_hills, h + 2 * (size_t) g->n_hills, g->n_hills,
                              g->hills.as<uint32_t>() + 3 * (size_t) g->n_hills, g->dbuf.as<uint32_t>(), g->n_piles, g->cnt());
     }
-    launch_apply_deaths(ctx->L, g->piles.as<uint2>(), g->dbuf.as<uint32_t>(), g->n_piles, g->cnt(), g->alive_bits.as<uint32_t>(), fused_decode);
+    launch_apply_deaths(ctx->L, g->piles.as<uint2>(), g->dbuf.as<uint32_t>(), g->n_piles, g->cnt(), g->alive_bits.as<uint32_t>(), fused_decode,
+                        nullptr, skip_if_empty ? g->cnt() + C_EV : nullptr);
     CU(ctx, cudaGetLastError());
     return RALA_B200_OK;
 }

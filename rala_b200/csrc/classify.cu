@@ -52,6 +52,42 @@ __global__ void k_records_to_soa(const uint32_t* __restrict__ aos, uint32_t n, L
     }
 }
 
+// compact upload -> columns (rala_b200_graph_set_overlaps_packed): four records per thread; the query id comes from the
+// group table (one binary search per thread, then a short walk), the coordinates from two 16 + 16 bit words
+__global__ void __launch_bounds__(256) k_unpack_records(const uint32_t* __restrict__ query_id, const uint32_t* __restrict__ group_end,
+                                                       uint32_t n_groups, const uint32_t* __restrict__ a_span,
+                                                       const uint32_t* __restrict__ b_span, uint32_t n, List recs) {
+    const uint32_t n4 = (n + 3u) / 4u;
+    for (uint32_t q = blockIdx.x * blockDim.x + threadIdx.x; q < n4; q += gridDim.x * blockDim.x) {
+        const uint32_t i0 = 4u * q;
+        uint32_t lo = 0, hi = n_groups;   // first group whose end lies behind record i0
+        while (lo < hi) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (__ldg(group_end + mid) <= i0) lo = mid + 1; else hi = mid;
+        }
+        uint32_t k = lo, end = k < n_groups ? __ldg(group_end + k) : 0xFFFFFFFFu;
+        const uint4 sa = reinterpret_cast<const uint4*>(a_span)[q], sb = reinterpret_cast<const uint4*>(b_span)[q];
+        const uint32_t wa[4] = {sa.x, sa.y, sa.z, sa.w}, wb[4] = {sb.x, sb.y, sb.z, sb.w};
+        uint32_t a[4], ab[4], ae[4], bb[4], be[4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            while (i0 + r >= end && k + 1 < n_groups) {
+                ++k;
+                end = __ldg(group_end + k);
+            }
+            const bool have = i0 + r < n && k < n_groups && i0 + r < end;
+            a[r] = have ? (__ldg(query_id + k) & ~kInvalidBit) : kInvalidBit;   // records behind the last group do not exist
+            ab[r] = wa[r] & 0xFFFFu; ae[r] = wa[r] >> 16;
+            bb[r] = wb[r] & 0xFFFFu; be[r] = wb[r] >> 16;
+        }
+        reinterpret_cast<uint4*>(recs.a)[q] = make_uint4(a[0], a[1], a[2], a[3]);
+        reinterpret_cast<uint4*>(recs.ab)[q] = make_uint4(ab[0], ab[1], ab[2], ab[3]);
+        reinterpret_cast<uint4*>(recs.ae)[q] = make_uint4(ae[0], ae[1], ae[2], ae[3]);
+        reinterpret_cast<uint4*>(recs.bb)[q] = make_uint4(bb[0], bb[1], bb[2], bb[3]);
+        reinterpret_cast<uint4*>(recs.be)[q] = make_uint4(be[0], be[1], be[2], be[3]);
+    }
+}
+
 __device__ __forceinline__ void unpack4(const uint4 v, uint32_t (&out)[4]) {
     out[0] = v.x; out[1] = v.y; out[2] = v.z; out[3] = v.w;
 }
@@ -434,8 +470,9 @@ __global__ void k_hill_coverage(List recs, uint32_t t0, const uint2* __restrict_
 // they are turned into death times (kInf = never) on the way, which saves the separate k_decode_state launch.
 template <bool DECODE>
 __global__ void k_apply_deaths(uint2* __restrict__ piles, uint32_t* __restrict__ dbuf, uint32_t n_piles,
-                               const uint32_t* __restrict__ counters, uint32_t* __restrict__ alive_bits, const uint32_t* __restrict__ skip) {
-    if (skip && *skip) return;
+                               const uint32_t* __restrict__ counters, uint32_t* __restrict__ alive_bits, const uint32_t* __restrict__ skip,
+                               const uint32_t* __restrict__ run_if) {
+    if ((skip && *skip) || (run_if && *run_if == 0u)) return;
     uint32_t* D = dbuf + (size_t) counters[C_DSEL] * n_piles;
     for (uint32_t base = blockIdx.x * blockDim.x; base < n_piles; base += gridDim.x * blockDim.x) {
         const uint32_t i = base + threadIdx.x;
@@ -659,6 +696,13 @@ void launch_records_to_soa(Launch& L, const uint32_t* aos, uint32_t n, List recs
     L.count++;
 }
 
+void launch_unpack_records(Launch& L, const uint32_t* query_id, const uint32_t* group_end, uint32_t n_groups, const uint32_t* a_span,
+                           const uint32_t* b_span, uint32_t n, List recs) {
+    if (n == 0) return;
+    k_unpack_records<<<grid_for((n + 3) / 4, 256, kNumSMs * 8), 256, 0, L.stream>>>(query_id, group_end, n_groups, a_span, b_span, n, recs);
+    L.count++;
+}
+
 void launch_classify_events(Launch& L, List recs, uint32_t n, uint32_t t0, const uint2* piles, uint32_t n_piles,
                             Events ev, uint32_t ev_cap, uint32_t* vcount, uint32_t* hill_rec, uint32_t hill_cap, uint32_t* counters) {
     if (n == 0) return;
@@ -702,10 +746,10 @@ void launch_hill_coverage(Launch& L, List recs, uint32_t t0, const uint2* piles,
 }
 
 void launch_apply_deaths(Launch& L, uint2* piles, uint32_t* dbuf, uint32_t n_piles, const uint32_t* counters,
-                         uint32_t* alive_bits, bool decode, const uint32_t* skip) {
+                         uint32_t* alive_bits, bool decode, const uint32_t* skip, const uint32_t* run_if) {
     if (n_piles == 0) return;
-    if (decode) k_apply_deaths<true><<<grid_for(n_piles, 256, kNumSMs * 8), 256, 0, L.stream>>>(piles, dbuf, n_piles, counters, alive_bits, skip);
-    else k_apply_deaths<false><<<grid_for(n_piles, 256, kNumSMs * 8), 256, 0, L.stream>>>(piles, dbuf, n_piles, counters, alive_bits, skip);
+    if (decode) k_apply_deaths<true><<<grid_for(n_piles, 256, kNumSMs * 8), 256, 0, L.stream>>>(piles, dbuf, n_piles, counters, alive_bits, skip, run_if);
+    else k_apply_deaths<false><<<grid_for(n_piles, 256, kNumSMs * 8), 256, 0, L.stream>>>(piles, dbuf, n_piles, counters, alive_bits, skip, run_if);
     L.count++;
 }
 
@@ -781,6 +825,7 @@ void launch_list_connections(Launch& L, List l, const uint32_t* n_ptr, uint32_t 
 void preload_classify() {
     cudaFuncAttributes a;
     cudaFuncGetAttributes(&a, k_records_to_soa);
+    cudaFuncGetAttributes(&a, k_unpack_records);
     cudaFuncGetAttributes(&a, k_classify_events<3>);
     cudaFuncGetAttributes(&a, k_classify_survivors);
     cudaFuncGetAttributes(&a, k_scan_runs);

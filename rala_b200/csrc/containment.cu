@@ -100,7 +100,8 @@ __global__ void __launch_bounds__(256) k_resolve_prepare(Events ev, const uint32
                                                         uint32_t* __restrict__ vcursor, uint32_t* __restrict__ seg_c,
                                                         uint32_t* __restrict__ seg_t, const uint32_t* __restrict__ vstart,
                                                         uint32_t n_piles, uint32_t* __restrict__ S, uint32_t* __restrict__ work,
-                                                        uint32_t* __restrict__ n_work, uint32_t fill_blocks) {
+                                                        uint32_t* __restrict__ n_work, uint32_t fill_blocks, int skip_if_empty) {
+    if (skip_if_empty && *n_events == 0u) return;
     if (blockIdx.x < fill_blocks) {
         const uint32_t n = min(*n_events, ev_cap);
         const uint32_t stride = fill_blocks * blockDim.x;   // four independent load -> atomic -> store chains per thread
@@ -204,7 +205,14 @@ __global__ void __launch_bounds__(256) k_resolve(const uint32_t* __restrict__ vs
                                                 uint32_t* __restrict__ seg_t, uint32_t* __restrict__ S,
                                                 uint32_t* __restrict__ work0, uint32_t* __restrict__ work1,
                                                 uint32_t* __restrict__ n_work /* 3 rotating counters */,
-                                                uint32_t* __restrict__ counters) {
+                                                uint32_t* __restrict__ counters, const uint32_t* __restrict__ n_events, int skip_if_empty) {
+    if (skip_if_empty && *n_events == 0u) {   // every block takes this branch: no grid barrier is left waiting
+        if (blockIdx.x == 0 && threadIdx.x == 0) {
+            counters[C_ROUNDS] = 0u;
+            counters[C_DSEL] = 0u;
+        }
+        return;
+    }
     cg::grid_group grid = cg::this_grid();
     const uint32_t stride = gridDim.x * blockDim.x, gtid = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t lane = lane_id();
@@ -298,14 +306,15 @@ int resolve_max_blocks() {
 
 // vcursor holds the per-victim event histogram on entry (filled by the classify kernels)
 void launch_resolve(Launch& L, Events ev, const uint32_t* n_events, uint32_t ev_cap, ResolveBufs rb, uint32_t n_piles,
-                    uint32_t* counters, unsigned long long* status, uint32_t* ticket, int coop_blocks, bool decode) {
-    launch_scan_u32(L, rb.vcursor, rb.vstart, n_piles + 1, status, ticket);
+                    uint32_t* counters, unsigned long long* status, uint32_t* ticket, int coop_blocks, bool decode, bool skip_if_empty) {
+    int skip = skip_if_empty ? 1 : 0;
+    launch_scan_u32(L, rb.vcursor, rb.vstart, n_piles + 1, status, ticket, nullptr, skip_if_empty ? n_events : nullptr);
     cudaMemsetAsync(rb.n_work, 0, 16, L.stream);
 #if RB_OPT_FUSE
     {
         const int fill_blocks = grid_for(ev_cap, 1024, kNumSMs * 4), init_blocks = grid_for(n_piles, 256, kNumSMs * 4);
         k_resolve_prepare<<<fill_blocks + init_blocks, 256, 0, L.stream>>>(ev, n_events, ev_cap, rb.vcursor, rb.seg_c, rb.seg_t, rb.vstart,
-                                                                         n_piles, rb.S, rb.work0, rb.n_work, (uint32_t) fill_blocks);
+                                                                         n_piles, rb.S, rb.work0, rb.n_work, (uint32_t) fill_blocks, skip);
         L.count++;
     }
 #else
@@ -314,7 +323,7 @@ void launch_resolve(Launch& L, Events ev, const uint32_t* n_events, uint32_t ev_
     k_resolve_init<<<grid_for(n_piles, 256, kNumSMs * 8), 256, 0, L.stream>>>(rb.vstart, n_piles, rb.S, rb.work0, rb.n_work);
     L.count++;
 #endif
-    void* args[] = {&rb.vstart, &rb.seg_c, &rb.seg_t, &rb.S, &rb.work0, &rb.work1, &rb.n_work, &counters};
+    void* args[] = {&rb.vstart, &rb.seg_c, &rb.seg_t, &rb.S, &rb.work0, &rb.work1, &rb.n_work, &counters, &n_events, &skip};
     cudaLaunchCooperativeKernel((void*) k_resolve, dim3(coop_blocks), dim3(256), args, 0, L.stream);
     L.count++;
     if (decode) {   // otherwise k_apply_deaths decodes while it applies (no consumer in between)

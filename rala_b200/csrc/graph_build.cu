@@ -129,8 +129,9 @@ __global__ void k_degree_hist(const uint32_t* __restrict__ src, const uint32_t* 
 // Each thread owns 4 consecutive values (one 16-byte load).
 __global__ void __launch_bounds__(kTileThreads) k_scan_degrees(uint32_t* __restrict__ cursor, uint32_t* __restrict__ row_ptr,
                                                               uint32_t n, unsigned long long* __restrict__ status,
-                                                              uint32_t* __restrict__ ticket, const uint32_t* __restrict__ skip) {
-    if (skip && *skip) return;
+                                                              uint32_t* __restrict__ ticket, const uint32_t* __restrict__ skip,
+                                                              const uint32_t* __restrict__ run_if) {
+    if ((skip && *skip) || (run_if && *run_if == 0u)) return;
     __shared__ uint32_t s_warp[kTileWarps];
     __shared__ uint32_t s_tile;
     __shared__ unsigned long long s_base;
@@ -358,8 +359,8 @@ void launch_time_bases(Launch& L, const uint32_t* counts, uint32_t rank, uint32_
 
 // exclusive scan of n values: exclusive_out[i] and values_inout[i] both receive the prefix
 void launch_scan_u32(Launch& L, uint32_t* values_inout, uint32_t* exclusive_out, uint32_t n, unsigned long long* status,
-                     uint32_t* ticket, const uint32_t* skip) {
-    k_scan_degrees<<<grid_for(n, kTile, kNumSMs * 8), kTileThreads, 0, L.stream>>>(values_inout, exclusive_out, n, status, ticket, skip);
+                     uint32_t* ticket, const uint32_t* skip, const uint32_t* run_if) {
+    k_scan_degrees<<<grid_for(n, kTile, kNumSMs * 8), kTileThreads, 0, L.stream>>>(values_inout, exclusive_out, n, status, ticket, skip, run_if);
     L.count++;
 }
 
@@ -367,7 +368,7 @@ void launch_build_csr(Launch& L, GraphArrays g, uint32_t n_nodes_max, uint32_t e
                       unsigned long long* status, uint32_t* ticket) {
     // row_ptr has n_nodes_max + 1 entries; degrees beyond the live node count are zero
     k_scan_degrees<<<grid_for(n_nodes_max + 1, kTile, kNumSMs * 8), kTileThreads, 0, L.stream>>>(
-        g.cursor, g.row_ptr, n_nodes_max + 1, status, ticket, nullptr);
+        g.cursor, g.row_ptr, n_nodes_max + 1, status, ticket, nullptr, nullptr);
     L.count++;
     k_fill_csr<<<grid_for(edge_cap, 256, kNumSMs * 8), 256, 0, L.stream>>>(g.src, g.dst, g.len, counters + C_EDGES,
                                                                             edge_cap, g.cursor, g.col, g.col_eid, g.T);

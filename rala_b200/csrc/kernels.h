@@ -54,6 +54,8 @@ inline void join_side(Launch& L, int k) {
 
 // classify.cu
 void launch_records_to_soa(Launch& L, const uint32_t* aos, uint32_t n, List recs);
+void launch_unpack_records(Launch& L, const uint32_t* query_id, const uint32_t* group_end, uint32_t n_groups, const uint32_t* a_span,
+                           const uint32_t* b_span, uint32_t n, List recs);
 void launch_classify_events(Launch& L, List recs, uint32_t n, uint32_t t0, const uint2* piles, uint32_t n_piles,
                             Events ev, uint32_t ev_cap, uint32_t* vcount, uint32_t* hill_rec, uint32_t hill_cap, uint32_t* counters);
 // runs of the survivors pass (128 records each): packed counts (overlaps | internals << 16) and the scanned offsets
@@ -68,9 +70,10 @@ void launch_hill_coverage(Launch& L, List recs, uint32_t t0, const uint2* piles,
                           uint32_t hill_cap, const uint32_t* hill_pile, const uint32_t* hill_begin,
                           const uint32_t* hill_end, uint32_t n_hills, uint32_t* hill_cov, const uint32_t* dbuf,
                           uint32_t n_piles, const uint32_t* counters);
-// skip: optional device flag; non-zero = do nothing (multi-GPU: a containment pass without events)
+// skip: optional device flag, non-zero = do nothing (multi-GPU: a containment pass without events); run_if: optional device
+// count, zero = do nothing (single GPU: the final containment pass when it has no events)
 void launch_apply_deaths(Launch& L, uint2* piles, uint32_t* dbuf, uint32_t n_piles, const uint32_t* counters,
-                         uint32_t* alive_bits, bool decode, const uint32_t* skip = nullptr);
+                         uint32_t* alive_bits, bool decode, const uint32_t* skip = nullptr, const uint32_t* run_if = nullptr);
 void launch_list_pass(Launch& L, int mode, List in, const uint32_t* n_in, uint32_t in_cap, const uint2* piles, List out_a,
                       uint32_t* n_out_a, List out_b, uint32_t* n_out_b, const uint32_t* b_base, uint32_t cap,
                       const uint32_t* dbuf, uint32_t n_piles, const uint32_t* time_base, const uint32_t* counters,
@@ -100,12 +103,14 @@ int resolve_max_blocks();
 void launch_events_hist(Launch& L, Events ev, const uint32_t* n_events, uint32_t ev_cap, uint32_t* vcount);
 // decode = false leaves the resolution's state encoding in rb.S: the following launch_apply_deaths(decode = true) turns
 // it into death times while it applies them (one launch less when nothing reads the death times in between)
+// skip_if_empty: with no events at all every kernel returns at once (nobody dies; rb.S is left as it is)
 void launch_resolve(Launch& L, Events ev, const uint32_t* n_events, uint32_t ev_cap, ResolveBufs rb, uint32_t n_piles,
-                    uint32_t* counters, unsigned long long* status, uint32_t* ticket, int coop_blocks, bool decode);
+                    uint32_t* counters, unsigned long long* status, uint32_t* ticket, int coop_blocks, bool decode,
+                    bool skip_if_empty = false);
 
 // graph_build.cu
 void launch_scan_u32(Launch& L, uint32_t* values_inout, uint32_t* exclusive_out, uint32_t n, unsigned long long* status,
-                     uint32_t* ticket, const uint32_t* skip = nullptr);
+                     uint32_t* ticket, const uint32_t* skip = nullptr, const uint32_t* run_if = nullptr);
 struct GraphArrays {
     uint32_t* seq_to_node;   // n_piles
     uint32_t *src, *dst, *len;   // edge id order

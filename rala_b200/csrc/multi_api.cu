@@ -226,6 +226,23 @@ extern "C" int rala_b200_multi_set_overlaps_columns(rala_b200_multi* m, int k, c
     return RALA_B200_OK;
 }
 
+extern "C" int rala_b200_multi_set_overlaps_packed(rala_b200_multi* m, int k, const uint32_t* query_id, const uint32_t* group_end,
+                                                   uint32_t n_groups, const uint32_t* b_id, const uint32_t* a_span, const uint32_t* b_span,
+                                                   uint64_t n, uint64_t t0) {
+    if (!m || k < 0 || k >= m->n_local) return RALA_B200_ERR_ARG;
+    FabricRank& fr = m->ranks[k];
+    if (t0 + n >= (1ull << 31)) return mfail(m, RALA_B200_ERR_LIMIT, "file positions must stay below 2^31");
+    const bool same_shape = n == fr.n_rec && m->reserved;
+    MRC(m, fr, rala_b200_graph_set_overlaps_packed(fr.g, query_id, group_end, n_groups, b_id, a_span, b_span, n));
+    MRC(m, fr, rala_b200_graph_set_shard(fr.g, (uint32_t) t0, fr.rank, m->world));
+    if (!same_shape) {
+        m->reserved = false;
+        drop_graphs(m);
+    }
+    fr.n_rec = n;
+    return RALA_B200_OK;
+}
+
 extern "C" int rala_b200_multi_set_outputs(rala_b200_multi* m, int k, rala_edge_t* edges_out, uint64_t edges_cap, uint8_t* marked_out,
                                            uint64_t marked_cap) {
     if (!m || k < 0 || k >= m->n_local) return RALA_B200_ERR_ARG;

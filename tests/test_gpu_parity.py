@@ -451,3 +451,37 @@ def test_config5_repeat_hubs_whole_pipeline(ctx):
     assert_same(m, P.marked, "marks (4 ranks)")
     assert M.counts()["n_heavy_items"] > 0
     M.close()
+
+
+def test_packed_upload_matches_the_row_form(ctx):
+    """rala_b200_graph_set_overlaps_packed (12 B / record: query groups + b_id + two 16|16-bit spans) leaves exactly the
+    records set_overlaps leaves: same lists after classify, same edges and marks; invalid records, a record count that is
+    not a multiple of 4, single-record groups and one huge group included."""
+    ds = synth.generate(1_000_000, 40, 8000, len_sd=2500, seed=42, noise=80, dual=True)
+    rec = ds.records[:-3].copy()                 # n % 4 != 0
+    rec[7, 6] |= 2                               # invalid records: alone, at a group start, a run of them
+    first_of_group = np.nonzero(rec[1:, 0] != rec[:-1, 0])[0] + 1
+    rec[first_of_group[5], 6] |= 2
+    rec[1000:1010, 6] |= 2
+    piles = ds.flat_piles()
+    p = api.records_to_packed(rec)
+    assert p is not None and p.nbytes < 13 * rec.shape[0]
+    G = api.Graph(ctx)
+    G.set_piles(piles).set_hills(None).set_overlaps(rec)
+    G.run()
+    want = (G.lists(), G.edges(), G.marked(), G.piles())
+    G.set_piles(piles).set_overlaps_packed(p)
+    G.run()
+    got = (G.lists(), G.edges(), G.marked(), G.piles())
+    assert_same(got[0][0], want[0][0], "overlaps")
+    assert_same(got[0][1], want[0][1], "internals")
+    assert_same(got[1], want[1], "edges")
+    assert_same(got[2], want[2], "marks")
+    assert_same(got[3], want[3], "piles")
+    P = O.Pipeline(rec, piles).run()
+    assert_same(got[1], P.edges, "edges vs oracle")
+    # coordinates beyond 16 bits: the packer declines, the caller uses the column form
+    big = rec.copy()
+    big[3, 3] = 70000
+    assert api.records_to_packed(big) is None
+    G.close()
