@@ -462,7 +462,7 @@ struct ResolveCtl {
     uint32_t released;  // grid barrier: phases released so far
     uint32_t go;        // decision of block 0 after a sweep: 1 = sweep again, 0 = the pass is over
     uint32_t sweeps;
-    uint32_t resume, pad[3];   // sweep index the whole grid continues with
+    uint32_t settled, pad[3];  // poll phase: victims that have been settled by the thread that watches them
     unsigned long long log[kSweepLog][2];   // diagnostics: (open victims at the start of the sweep, ns since the kernel started) per sweep
 };
 static_assert(sizeof(ResolveCtl) == kResolveCtlBytes, "fabric.cuh sizes the control block");
@@ -528,8 +528,6 @@ __device__ __forceinline__ void sweep_worklist(const Peers& P, const ArenaLayout
     if (pushed) __threadfence_system();
 }
 
-constexpr uint32_t kTailVictims = 256;    // at most this many open victims (one per thread): block 0 finishes the pass alone (no grid barriers)
-
 __global__ void __launch_bounds__(256) k_fabric_resolve(Peers P, ArenaLayout A, const uint32_t* __restrict__ vstart,
                                                        const uint32_t* __restrict__ seg_c, uint32_t* __restrict__ seg_t,
                                                        uint32_t* __restrict__ work0, uint32_t* __restrict__ work1,
@@ -548,10 +546,9 @@ __global__ void __launch_bounds__(256) k_fabric_resolve(Peers P, ArenaLayout A, 
     const unsigned long long t_start = global_timer_ns();
     uint32_t phase = 0;
 
-    // block 0, thread 0, after a sweep: tell the peers, decide.  Returns 0 = the pass is over, 1 = sweep again.
-    // (the count was published to the peers by the lanes of warp 0, see publish_open)
-    auto after_sweep = [&](uint32_t sweep, uint32_t n_before) -> uint32_t {
-        const uint32_t open = n_work[(sweep + 1u) % 3u];
+    // block 0, thread 0, after a sweep that left `open` victims: decide.  Returns 0 = the pass is over, 1 = sweep again.
+    // (`open` was published to the peers by the lanes of warp 0, see publish_open)
+    auto after_sweep = [&](uint32_t sweep, uint32_t n_before, uint32_t open) -> uint32_t {
         uint32_t go = 1u;
         bool dead = ld_relaxed_sys(&mine->dead) != 0u || global_timer_ns() - t_start > timeout_ns;
         if (open == 0u) {   // everything here is settled and pushed: wait until that is true everywhere
@@ -563,12 +560,9 @@ __global__ void __launch_bounds__(256) k_fabric_resolve(Peers P, ArenaLayout A, 
                 dead = ld_relaxed_sys(&mine->dead) != 0u || global_timer_ns() - t_start > timeout_ns;
             }
             go = 0u;
-        } else {
-            if (open == n_before) __nanosleep(200);   // nothing settled in this sweep: give the peers' news a moment to arrive
-            if (sweep + 1u >= max_sweeps) {
-                atomicOr(&mine->error, (uint32_t) FE_ROUNDS);
-                go = 0u;
-            }
+        } else if (sweep + 1u >= max_sweeps) {
+            atomicOr(&mine->error, (uint32_t) FE_ROUNDS);
+            go = 0u;
         }
         if (dead) {
             atomicOr(&mine->error, (uint32_t) FE_TIMEOUT);
@@ -589,45 +583,67 @@ __global__ void __launch_bounds__(256) k_fabric_resolve(Peers P, ArenaLayout A, 
 
     // block 0, warp 0: lane q tells rank q how many victims are still open here.  One release store per lane, all at once:
     // eight of them issued by one thread one after the other cost ~25 us per sweep on 8 GPUs (profiles/r02n)
-    auto publish_open = [&](uint32_t sweep) {
-        if (threadIdx.x < W) st_release_sys64(&hdr_of(P, (int) threadIdx.x)->progress[me], tag | n_work[(sweep + 1u) % 3u]);
+    auto publish_open = [&](uint32_t open) {
+        if (threadIdx.x < W) st_release_sys64(&hdr_of(P, (int) threadIdx.x)->progress[me], tag | open);
         __syncwarp();
     };
 
+    const uint32_t n_threads = gridDim.x * blockDim.x, gtid = blockIdx.x * blockDim.x + threadIdx.x;
     for (uint32_t sweep = 0;; ++sweep) {
         const uint32_t n = n_work[sweep % 3u];
         if (blockIdx.x == 0 && threadIdx.x == 0) n_work[(sweep + 2u) % 3u] = 0u;   // read last in sweep - 1, written next in sweep + 1
+        const uint32_t* out = (sweep & 1u) ? work0 : work1;
         sweep_worklist(P, A, vstart, seg_c, seg_t, S, wait_pile, wait_time, (sweep & 1u) ? work1 : work0, n, (sweep & 1u) ? work0 : work1,
                        &n_work[(sweep + 1u) % 3u], blockIdx.x, gridDim.x);
         grid_barrier(ctl, phase);
+        uint32_t open;
+        asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(open) : "l"(&n_work[(sweep + 1u) % 3u]) : "memory");
+        const bool poll = open != 0u && open <= n_threads;
+
+        if (poll) {
+            // Every open victim gets a thread of its own, which watches the one foreign state its chain is frozen on and
+            // goes on the moment it moves: the rest of the pass costs the longest cross-rank dependency chain (a push over
+            // NVLink + a few local hops per link) instead of one whole-grid sweep, two grid barriers and the longest local
+            // chase of the sweep per link (8 - 12 sweeps of 30 - 80 us on 8 GPUs, profiles/r02n).
+            bool gave_up = false;
+            if (gtid < open) {
+                const uint32_t v = out[gtid];
+                for (uint32_t it = 1;; ++it) {
+                    if ((it & 255u) == 0u && (ld_relaxed_sys(&mine->dead) != 0u || global_timer_ns() - t_start > timeout_ns)) {
+                        gave_up = true;
+                        break;
+                    }
+                    const uint32_t f = wait_pile[v];
+                    if (f != kNoWait) {
+                        const uint32_t q = ld_relaxed_sys(&S[f]);
+                        if (!(q & kSettled) && q <= wait_time[v]) {
+                            __nanosleep(64);
+                            continue;
+                        }
+                    }
+                    bool pushed = false;
+                    const bool done = resolve_owned(P, A, v, vstart, seg_c, seg_t, S, wait_pile, wait_time, pushed);
+                    if (pushed) __threadfence_system();   // before this victim counts as settled
+                    if (done) break;
+                }
+                if (gave_up) atomicExch(&mine->dead, 1u);
+                atomicAdd(&ctl->settled, 1u);
+            }
+        }
         if (blockIdx.x == 0) {
-            uint32_t go = 0;
-            if (threadIdx.x < 32) publish_open(sweep);
-            if (threadIdx.x == 0) {
-                go = after_sweep(sweep, n);
-                s_state = go;
+            if (poll && threadIdx.x == 0) {   // all victims of this rank settled (or somebody gave up)?
+                uint32_t got;
+                do {
+                    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(got) : "l"(&ctl->settled) : "memory");
+                    if (got < open) __nanosleep(100);
+                } while (got < open);
+                s_state = 0u;
             }
             __syncthreads();
-            go = s_state;
-            // few victims left: this block finishes alone, sweep after sweep, while the others wait at the barrier below
-            // (a sweep of the whole grid costs two grid barriers and ~15 us whatever its size; profiles/r02k)
-            uint32_t ts = sweep + 1u;
-            while (go && n_work[ts % 3u] <= kTailVictims) {
-                __syncthreads();
-                const uint32_t tn = n_work[ts % 3u];
-                if (threadIdx.x == 0) n_work[(ts + 2u) % 3u] = 0u;
-                sweep_worklist(P, A, vstart, seg_c, seg_t, S, wait_pile, wait_time, (ts & 1u) ? work1 : work0, tn, (ts & 1u) ? work0 : work1,
-                               &n_work[(ts + 1u) % 3u], 0u, 1u);
-                __syncthreads();
-                if (threadIdx.x < 32) publish_open(ts);
-                if (threadIdx.x == 0) s_state = after_sweep(ts, tn);
-                __syncthreads();
-                go = s_state;
-                ++ts;
-            }
+            const uint32_t left = poll ? 0u : open;
+            if (threadIdx.x < 32) publish_open(left);
             if (threadIdx.x == 0) {
-                ctl->go = go;
-                ctl->resume = ts;   // the sweep the whole grid continues with (only when go == 1: the list grew back over the tail size — it cannot)
+                ctl->go = after_sweep(poll ? sweep + 1u : sweep, poll ? open : n, left);
                 __threadfence();
             }
         }
@@ -635,9 +651,6 @@ __global__ void __launch_bounds__(256) k_fabric_resolve(Peers P, ArenaLayout A, 
         uint32_t go;
         asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(go) : "l"(&ctl->go) : "memory");
         if (!go) break;
-        uint32_t resume;
-        asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(resume) : "l"(&ctl->resume) : "memory");
-        sweep = resume - 1u;
     }
 }
 
