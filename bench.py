@@ -43,6 +43,16 @@ K1_BYTES_PER_OVERLAP = 41      # 24 read + 16 trimmed coords + 1
 K3_BYTES_PER_VISIT = 8         # each two-hop visit streams one (dst, len)
 
 
+def workload_config(workload: str, n_gpus: int) -> dict:
+    """The `config` object of a bench line: what the workload IS (identical in this arm and in --impl reference, for any N);
+    what a run counted on it goes into `counts`."""
+    genome, cov, rl, desc = WORKLOADS[workload]
+    return {"workload": desc if n_gpus == 1 else f"{n_gpus} x ({desc}), read ids shuffled globally",
+            "genome_bp": genome * n_gpus, "coverage": cov, "read_len": rl, "n_gpus": n_gpus,
+            "l2": "inputs larger than L2: every GPU streams its whole record shard (hundreds of MB) in every step",
+            "scaling": "weak: the genome grows with the number of GPUs"}
+
+
 def measured_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -184,6 +194,7 @@ def run_reference_arm(args):
         return
     from rala_b200 import synth
     genome, cov, rl, desc = WORKLOADS[args.workload]
+    genome *= max(args.gpus, 1)            # weak scaling: the workload of the N-GPU arm is N x the genome
     passes = max(args.steps + args.warmup, 1)
     with tempfile.TemporaryDirectory() as tmp:
         probe_g = min(genome, 5_000_000)
@@ -210,7 +221,9 @@ def run_reference_arm(args):
         "impl": "reference", "metric": "graph_edges_per_sec", "value": value, "unit": "edges/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u32+f64", "data": "synthetic",
-        "config": {"workload": desc, "n_overlaps": ds.n_overlaps, "n_reads": ds.n_reads, "edges": edges},
+        "config": workload_config(args.workload, max(args.gpus, 1)),
+        "counts": {"n_overlaps": ds.n_overlaps, "n_reads": ds.n_reads, "edges": edges,
+                   "note": "counts of the bounded sample one step runs on (cpu_baseline.sample)"},
         "cpu_baseline": {"value": value, "unit": "edges/s", "cores": 1, "kind": kind, "sample": sample,
                          "host_cores_available": os.cpu_count(),
                          "note": "the reference runs this path single-threaded regardless of -t (graph.cpp:443-518, 576-632, 1281-1335)"},
@@ -372,12 +385,12 @@ def run_single(args):
         "metric": "graph_edges_per_sec", "value": value, "unit": "edges/s", "n_gpus": 1, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u32", "data": "synthetic",
-        "config": {"workload": WORKLOADS[args.workload][3], "n_overlaps": n_ovl, "n_reads": n_reads, "edges": E,
+        "config": workload_config(args.workload, 1),
+        "counts": {"n_overlaps": n_ovl, "n_reads": n_reads, "edges": E,
                    "nodes": counts["n_nodes"], "two_hop_visits": counts["n_two_hop"], "transitive_pairs": counts["n_transitive_pairs"],
                    "containment_events": counts["n_candidates"], "fixpoint_rounds": counts["n_rounds"],
                    "heavy_items": counts["n_heavy_items"], "retrim_passes_executed": 0,
-                   "l2": f"inputs larger than L2 ({ds.records.nbytes / 1e6:.0f} MB of records streamed per step)",
-                   "parallelism": "1 GPU"},
+                   "record_bytes_streamed_per_step": int(ds.records.nbytes * 6 // 7), "parallelism": "1 GPU"},
         "wall_ms_per_step": wall_ms / args.steps,
         "e2e": e2e,
         "gpu_launches": int(launches), "lib": os.path.relpath(api.LIB_PATH, ROOT),

@@ -295,12 +295,12 @@ def bench_main(args):
             "metric": "graph_edges_per_sec", "value": E / (ms_per_step * 1e-3), "unit": "edges/s", "n_gpus": world,
             "steps": steps, "warmup": warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
-            "config": {"workload": f"{world} x ({bench.WORKLOADS[args.workload][3]}), read ids shuffled globally",
-                       "n_overlaps": n_total_records, "n_overlaps_per_gpu": int(records.shape[0]), "n_reads": int(piles.shape[0]),
+            "config": bench.workload_config(args.workload, world),
+            "counts": {"n_overlaps": n_total_records, "n_overlaps_per_gpu": int(records.shape[0]), "n_reads": int(piles.shape[0]),
                        "edges": E, "nodes": n_nodes, "two_hop_visits": n_two_hop, "transitive_pairs": n_pairs,
                        "containment_events": n_events, "final_containment_events": n_final_events, "resolution_rounds": rounds,
                        "parallelism": parallelism, "transport": kind,
-                       "l2": f"inputs larger than L2 (each rank streams its {records.nbytes * 6 // 7 / 1e6:.0f} MB record shard per step)",
+                       "record_bytes_streamed_per_rank_per_step": int(records.nbytes * 6 // 7),
                        "step_graph": "one CUDA graph per rank and step (kernels only: the exchanges are kernels)" if kind == "fabric"
                                      else "eager (NCCL collectives between the phases)",
                        "exchange_capacities": dict(zip(api.CAP_NAMES, [int(x) for x in dg.caps])) if kind == "fabric" else dg.caps},
