@@ -7,7 +7,7 @@ ROOT=$(cd "$(dirname "$0")/.." && pwd)
 TMP=$(mktemp -d)
 git -C "$ROOT" worktree add -f "$TMP/src" "$COMMIT" > /dev/null
 mkdir -p "$TMP/obj" "$ROOT/rala_b200/variants"
-for f in classify containment graph_build transitive api; do
+for f in $(cd "$TMP/src/rala_b200/csrc" && ls *.cu | sed 's/\.cu$//'); do
     nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC --expt-relaxed-constexpr \
          -c "$TMP/src/rala_b200/csrc/$f.cu" -o "$TMP/obj/$f.o" &
 done

@@ -66,28 +66,46 @@ __global__ void __launch_bounds__(kTileThreads) k_emit_edges(List ovl, const uin
         if (tile >= num_tiles) break;
         int dest[kTileItems];
         uint32_t e_src[kTileItems], e_dst[kTileItems], e_len[kTileItems], c_len[kTileItems];
+        // all gathers of the thread's four entries are issued before the first one is used: the entry (7 columns), then
+        // both piles and both node ids (they only depend on the ids), 16 independent gathers in flight per thread
+        // (issuing them entry by entry, behind the liveness test of the entry before, left the kernel at 15 % issue activity)
+        Entry e[kTileItems];
+        bool have[kTileItems];
 #pragma unroll
         for (int r = 0; r < kTileItems; ++r) {
             const uint32_t idx = tile * kTile + r * kTileThreads + tid;
+            have[r] = idx < n;
+            e[r] = load_entry(ovl, have[r] ? idx : 0u);
+        }
+        uint2 pa[kTileItems], pb[kTileItems];
+        uint32_t na[kTileItems], nb[kTileItems];
+#pragma unroll
+        for (int r = 0; r < kTileItems; ++r) {
+            pa[r] = __ldg(piles + e[r].a);
+            pb[r] = __ldg(piles + e[r].b);
+            na[r] = __ldg(seq_to_node + e[r].a);
+            nb[r] = __ldg(seq_to_node + e[r].b);
+        }
+#pragma unroll
+        for (int r = 0; r < kTileItems; ++r) {
             dest[r] = 0;
-            if (idx < n) {
-                Entry e = load_entry(ovl, idx);
-                const Pile pa = load_pile(piles, e.a), pb = load_pile(piles, e.b);
-                if (pa.alive() && pb.alive()) {
-                    const Rel q = relative(e.c, e.ori, pa, pb);
-                    const uint8_t t = classify(e.c, q);                      // it->type(piles_) at :594 / :612
-                    const uint32_t na = seq_to_node[e.a], nb = seq_to_node[e.b] + e.ori;   // :578-580
-                    if (t == kAB) {                                          // :594-610
-                        dest[r] = 1;
-                        e_src[r] = na; e_dst[r] = nb;
-                        e_len[r] = q.a0 - q.b0;
-                        c_len[r] = (q.bl - q.b1) - (q.al - q.a1);
-                    } else if (t == kBA) {                                   // :612-629
-                        dest[r] = 1;
-                        e_src[r] = nb; e_dst[r] = na;
-                        e_len[r] = q.b0 - q.a0;
-                        c_len[r] = (q.al - q.a1) - (q.bl - q.b1);
-                    }
+            Pile A, B;
+            A.begin = pa[r].x; A.end = pa[r].y & kEndMask; A.flags = pa[r].y >> 30;
+            B.begin = pb[r].x; B.end = pb[r].y & kEndMask; B.flags = pb[r].y >> 30;
+            if (have[r] && A.alive() && B.alive()) {
+                const Rel q = relative(e[r].c, e[r].ori, A, B);
+                const uint8_t t = classify(e[r].c, q);                       // it->type(piles_) at :594 / :612
+                const uint32_t node_a = na[r], node_b = nb[r] + e[r].ori;    // :578-580
+                if (t == kAB) {                                              // :594-610
+                    dest[r] = 1;
+                    e_src[r] = node_a; e_dst[r] = node_b;
+                    e_len[r] = q.a0 - q.b0;
+                    c_len[r] = (q.bl - q.b1) - (q.al - q.a1);
+                } else if (t == kBA) {                                       // :612-629
+                    dest[r] = 1;
+                    e_src[r] = node_b; e_dst[r] = node_a;
+                    e_len[r] = q.b0 - q.a0;
+                    c_len[r] = (q.al - q.a1) - (q.bl - q.b1);
                 }
             }
         }
@@ -130,8 +148,9 @@ __global__ void k_degree_hist(const uint32_t* __restrict__ src, const uint32_t* 
 __global__ void __launch_bounds__(kTileThreads) k_scan_degrees(uint32_t* __restrict__ cursor, uint32_t* __restrict__ row_ptr,
                                                               uint32_t n, unsigned long long* __restrict__ status,
                                                               uint32_t* __restrict__ ticket, const uint32_t* __restrict__ skip,
-                                                              const uint32_t* __restrict__ run_if) {
+                                                              const uint32_t* __restrict__ run_if, const uint32_t* __restrict__ live) {
     if ((skip && *skip) || (run_if && *run_if == 0u)) return;
+    if (live) n = min(n, *live + 1u);   // values behind the live count are zero and nobody reads their prefix
     __shared__ uint32_t s_warp[kTileWarps];
     __shared__ uint32_t s_tile;
     __shared__ unsigned long long s_base;
@@ -360,7 +379,7 @@ void launch_time_bases(Launch& L, const uint32_t* counts, uint32_t rank, uint32_
 // exclusive scan of n values: exclusive_out[i] and values_inout[i] both receive the prefix
 void launch_scan_u32(Launch& L, uint32_t* values_inout, uint32_t* exclusive_out, uint32_t n, unsigned long long* status,
                      uint32_t* ticket, const uint32_t* skip, const uint32_t* run_if) {
-    k_scan_degrees<<<grid_for(n, kTile, kNumSMs * 8), kTileThreads, 0, L.stream>>>(values_inout, exclusive_out, n, status, ticket, skip, run_if);
+    k_scan_degrees<<<grid_for(n, kTile, kNumSMs * 8), kTileThreads, 0, L.stream>>>(values_inout, exclusive_out, n, status, ticket, skip, run_if, nullptr);
     L.count++;
 }
 
@@ -368,7 +387,7 @@ void launch_build_csr(Launch& L, GraphArrays g, uint32_t n_nodes_max, uint32_t e
                       unsigned long long* status, uint32_t* ticket) {
     // row_ptr has n_nodes_max + 1 entries; degrees beyond the live node count are zero
     k_scan_degrees<<<grid_for(n_nodes_max + 1, kTile, kNumSMs * 8), kTileThreads, 0, L.stream>>>(
-        g.cursor, g.row_ptr, n_nodes_max + 1, status, ticket, nullptr, nullptr);
+        g.cursor, g.row_ptr, n_nodes_max + 1, status, ticket, nullptr, nullptr, counters + C_NODES);
     L.count++;
     k_fill_csr<<<grid_for(edge_cap, 256, kNumSMs * 8), 256, 0, L.stream>>>(g.src, g.dst, g.len, counters + C_EDGES,
                                                                             edge_cap, g.cursor, g.col, g.col_eid, g.T);
