@@ -226,7 +226,9 @@ def run_reference_arm(args):
                    "note": "counts of the bounded sample one step runs on (cpu_baseline.sample)"},
         "cpu_baseline": {"value": value, "unit": "edges/s", "cores": 1, "kind": kind, "sample": sample,
                          "host_cores_available": os.cpu_count(),
-                         "note": "the reference runs this path single-threaded regardless of -t (graph.cpp:443-518, 576-632, 1281-1335)"},
+                         "note": "the reference runs this path single-threaded regardless of -t (graph.cpp:443-518, 576-632, 1281-1335); "
+                                 "its time includes Node / Edge allocation, the transitive_edges_ sort and remove_marked_objects, which "
+                                 "the GPU arm's e2e (flat edge rows + marks in host memory) does not"},
         "e2e": {"value": value, "unit": "edges/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
@@ -378,7 +380,10 @@ def run_single(args):
         r = cpu_reference_run(ds, piles)
         cpu = {"value": r["edges"] / r["seconds"], "unit": "edges/s", "cores": r["cores"], "kind": r["kind"],
                "sample": f"full batch ({n_ovl} overlap records, {r['edges']} edges) in {r['seconds']:.2f} s",
-               "host_cores_available": os.cpu_count(), "phases_s": {k: v for k, v in r["phases"].items() if k.startswith("t_")}}
+               "host_cores_available": os.cpu_count(), "phases_s": {k: v for k, v in r["phases"].items() if k.startswith("t_")},
+               "scope_note": "the CPU arm's time includes Node / Edge object allocation, the sort of transitive_edges_ and "
+                             "remove_marked_objects (oracle/ref_harness.cpp); the GPU arm's e2e ends with flat edge rows and marks "
+                             "in pinned host memory: not like for like at the object level (whole programs: cli_baseline)"}
         assert r["edges"] == E, f"CPU baseline built {r['edges']} edges, GPU {E}"
 
     line = {

@@ -11,7 +11,7 @@ run 420 29517 bench.py --gpus 8 --steps 100 --warmup 3 > $OUT/bench_${TAG}_n8.js
 tail -2 $OUT/bench_${TAG}_n8.err | cut -c1-300; cut -c1-1500 $OUT/bench_${TAG}_n8.json
 run 600 29518 bench.py --gpus 8 --steps 50 --warmup 3 --workload c4s > $OUT/bench_${TAG}_c4s_n8.json 2> $OUT/bench_${TAG}_c4s_n8.err; echo "bench c4s n8 rc=$?"
 tail -2 $OUT/bench_${TAG}_c4s_n8.err | cut -c1-300; cut -c1-1500 $OUT/bench_${TAG}_c4s_n8.json
-timeout 400 python -m pytest tests/test_multi_gpu.py -m gpu -x -q -k "one_process_per_gpu" > $OUT/pytest_multi_${TAG}.log 2>&1; echo "pytest rc=$?" | tee -a $OUT/pytest_multi_${TAG}.log
+timeout 400 python -m pytest tests/test_multi_gpu.py -m gpu -x -q -k "one_process_per_gpu and (8 or 4)" > $OUT/pytest_multi_${TAG}.log 2>&1; echo "pytest rc=$?" | tee -a $OUT/pytest_multi_${TAG}.log
 tail -3 $OUT/pytest_multi_${TAG}.log | cut -c1-300
 run 300 29519 profiles/fabric_timeline.py > $OUT/timeline_${TAG}_n8.json 2> $OUT/timeline_${TAG}_n8.err; echo "timeline rc=$?"
 head -c 1800 $OUT/timeline_${TAG}_n8.json
