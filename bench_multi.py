@@ -107,7 +107,8 @@ def _share_through_files(rank, world, arrays: dict):
     """Single node: every rank leaves its arrays in a directory rank 0 names; rank 0 reads them all back."""
     import shutil
     import tempfile
-    need = torch.tensor([sum(int(v.nbytes) for v in arrays.values())], dtype=torch.int64, device=torch.device("cuda", torch.cuda.current_device()))
+    plumbing = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
+    need = torch.tensor([sum(int(v.nbytes) for v in arrays.values())], dtype=torch.int64, device=plumbing)
     dist.all_reduce(need)
     where = None
     if rank == 0:   # the RAM disk when it has room for everything (it is often only 64 MB inside a container), else the default temp dir

@@ -352,10 +352,11 @@ def shard_bounds(n_records: int, world: int):
 class FabricGraph:
     """One rank of rala_b200_multi.  Collective calls (every rank must make them): connect(), plan()."""
 
-    def __init__(self, local_rank: int, rank: int, world: int, group=None):
+    def __init__(self, local_rank: int, rank: int, world: int, group=None, session=None):
         self.rank, self.world, self.group = rank, world, group
-        self.device = torch.device("cuda", local_rank)
-        self.M = api.Multi([local_rank], first_rank=rank, world=world)
+        self.device = torch.device("cuda", local_rank) if session is None else torch.device("cpu")
+        # session: anything with the interface of api.Multi (tests/test_multi_gloo.py drives the set-up logic on CPU with a stand-in)
+        self.M = api.Multi([local_rank], first_rank=rank, world=world) if session is None else session
         self.caps = None
 
     # ---- inputs (local) ---------------------------------------------------------------------------------------

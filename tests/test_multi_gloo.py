@@ -271,3 +271,117 @@ def test_shard_bounds():
         assert b[0][0] == 0 and b[-1][1] == n
         assert all(b[i][1] == b[i + 1][0] for i in range(w - 1))
         assert all(lo % 4 == 0 for lo, hi in b if lo < n)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# The product path's host side (multi.FabricGraph): capacity agreement, handle exchange in rank order, the
+# grow-until-it-fits loop.  The session is a stand-in with the interface of api.Multi; the kernels behind the real one
+# are covered on the GPU (tests/test_multi_fabric.py, tests/test_multi_gpu.py).
+# ---------------------------------------------------------------------------------------------------------------
+class StubMulti:
+    """Needs `need` per capacity (different on every rank); a step fits when every capacity is at least the GLOBAL need."""
+
+    def __init__(self, rank, world, need, default):
+        self.rank, self.world, self.need, self.default = rank, world, np.array(need, np.uint64), np.array(default, np.uint64)
+        self.caps = None
+        self.handles = None
+        self.log = []
+
+    def default_caps(self):
+        return self.default.copy()
+
+    def reserve(self, caps):
+        self.caps = np.array(caps, np.uint64)
+        self.handles = None
+        self.log.append(("reserve", self.caps.tolist()))
+        return self
+
+    def export_handle(self, k):
+        assert self.caps is not None
+        return bytes([self.rank]) * 32 + int(self.caps[0]).to_bytes(32, "little")
+
+    def import_handles(self, blob):
+        assert len(blob) == 64 * self.world
+        self.handles = [blob[64 * q:64 * q + 64] for q in range(self.world)]
+        return self
+
+    def use_cuda_graph(self, on):
+        self.log.append(("graph", bool(on)))
+        return self
+
+    def run(self):
+        assert self.handles is not None, "a step before the arenas were connected"
+        self.log.append(("run",))
+        return self
+
+    def synchronize(self):
+        return self
+
+    def demand(self):
+        fits = bool((self.need[:3] <= self.caps[:3]).all())
+        return self.need.copy(), fits
+
+
+def _fabric_worker(rank, world, port, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        # rank r needs more events the higher r is; rank 0 alone needs a large slice; defaults differ per rank
+        need = [1000 * (rank + 1), 500, 9000 if rank == 0 else 100, 3 + rank, 1, 4000 + rank]
+        default = [1500, 600 + rank, 800, 4096, 4096, 4000 + rank]
+        stub = StubMulti(rank, world, need, default)
+        fg = multi.FabricGraph(0, rank, world, session=stub)
+        fg.plan()
+        np.savez(os.path.join(out_dir, f"f{rank}.npz"), caps=fg.caps, handles=np.frombuffer(b"".join(stub.handles), np.uint8),
+                 reserves=np.array([e[1] for e in stub.log if e[0] == "reserve"], np.uint64),
+                 runs=sum(1 for e in stub.log if e[0] == "run"), graph=[e[1] for e in stub.log if e[0] == "graph"][-1])
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_fabric_graph_agrees_on_capacities_and_regrows(world, tmp_path):
+    mp.spawn(_fabric_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    got = [np.load(tmp_path / f"f{r}.npz") for r in range(world)]
+    for r, z in enumerate(got):
+        # every rank ends with the SAME capacities, large enough for the neediest rank
+        assert np.array_equal(z["caps"], got[0]["caps"])
+        assert z["caps"][0] >= 1000 * world and z["caps"][2] >= 9000 and z["caps"][1] >= 600 + world - 1
+        # first reservation = element-wise maximum of the ranks' defaults; then it grew (events at world 3, the slice always)
+        assert z["reserves"][0].tolist() == [1500, 600 + world - 1, 800, 4096, 4096, 4000 + world - 1]
+        assert len(z["reserves"]) == 2 and int(z["runs"]) == 2 and bool(z["graph"]) is True
+        # handles arrive in rank order and were exchanged AFTER the last reservation (they carry the capacity)
+        h = z["handles"].reshape(world, 64)
+        assert [int(h[q, 0]) for q in range(world)] == list(range(world))
+        assert all(int.from_bytes(bytes(h[q, 32:64]), "little") == int(z["caps"][0]) for q in range(world))
+
+
+def _share_worker(rank, world, port, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import bench_multi
+        got = bench_multi._share_through_files(rank, world, {"edges": np.full((rank + 1, 3), rank, np.uint32),
+                                                             "first": np.array([10 * rank], np.int64)})
+        if rank == 0:
+            assert [g.shape[0] for g in got["edges"]] == list(range(1, world + 1))
+            assert all(int(got["edges"][r][0, 0]) == r and int(got["first"][r][0]) == 10 * r for r in range(world))
+            open(os.path.join(out_dir, "ok"), "w").write("1")
+        else:
+            assert got is None
+    finally:
+        dist.destroy_process_group()
+
+
+def test_bench_parity_gate_collects_every_ranks_arrays_in_rank_order(tmp_path):
+    """bench_multi._share_through_files: how rank 0 gets the other ranks' edge rows and marks for the parity gate."""
+    mp.spawn(_share_worker, args=(3, _free_port(), str(tmp_path)), nprocs=3, join=True)
+    assert (tmp_path / "ok").exists()
+
+
+def test_shard_bounds_are_contiguous_aligned_and_cover_everything():
+    for n in (0, 1, 5, 1023, 1024, 100_003):
+        for world in (1, 2, 3, 8):
+            b = multi.shard_bounds(n, world)
+            assert len(b) == world and b[0][0] == 0 and b[-1][1] == n
+            assert all(lo <= hi and (lo % 4 == 0 or lo == hi) for lo, hi in b) and all(b[i][1] == b[i + 1][0] for i in range(world - 1))
