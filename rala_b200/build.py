@@ -72,7 +72,7 @@ def variant_path(name: str) -> str:
 
 
 # other settings of a tunable, same product otherwise
-TUNINGS = {"reloc8": ["-DRB_RELOC_LANES=8"], "no_packrow": ["-DRB_GROUP_PACKROW=0"]}
+TUNINGS = {"no_packrow": ["-DRB_GROUP_PACKROW=0"]}
 
 
 def build_variants(verbose: bool = False):

@@ -391,41 +391,54 @@ __global__ void k_relocate(List tmp, List out, uint32_t cap, const uint32_t* __r
     }
 }
 
-// The same move with one WARP (or a smaller lane group, RB_RELOC_LANES) per run, both lists in one launch: the run's survivors (~7 % of 512 records) are
-// contiguous in the scratch list and in the final list, so every column is read and written in coalesced pieces and
-// nobody searches for its run (k_relocate: a binary search per warp and a walk per lane, 28 + 3 us in profiles/r01h).
-#ifndef RB_RELOC_LANES
-#define RB_RELOC_LANES 32   // lanes per run; 8 (four runs in flight per warp, a run holds ~36 survivors) is built as a tuning variant
-#endif
-constexpr uint32_t kRelocLanes = RB_RELOC_LANES;
+// The same move, one BLOCK per 32 consecutive runs.  The survivors of 32 runs are one contiguous piece of the final list
+// (~1 150 entries on clean data), so the threads take consecutive OUTPUT positions: every column is written fully
+// coalesced, and read in contiguous pieces of a run.  Each warp holds the 32 runs' offsets in its lanes and finds the
+// run of a position with a 5-step binary search over them (shuffles).  (One warp per run, ~36 entries each, was 28 000
+// short dependent chains: count / offset loads, then one and a bit half-empty iterations: 34 us, profiles/r02a.)
+constexpr uint32_t kRelocRuns = 32;
+
+__device__ __forceinline__ void relocate_piece(const List& tmp, const List& out, uint32_t cap, uint32_t run0, uint32_t my_off,
+                                               uint32_t first, uint32_t total) {
+    const uint32_t lane = lane_id(), warp = warp_id();
+    for (uint32_t k = warp * 32u; k < total; k += kTileThreads) {   // block-uniform trip count per warp: all lanes shuffle
+        const uint32_t d = first + k + lane;
+        uint32_t l = 0;   // the largest run l of the 32 whose first output position is <= d
+#pragma unroll
+        for (uint32_t step = 16; step > 0; step >>= 1) {
+            const uint32_t v = __shfl_sync(0xFFFFFFFFu, my_off, (l + step) & 31u);
+            if (l + step < kRelocRuns && v <= d) l += step;
+        }
+        const uint32_t off = __shfl_sync(0xFFFFFFFFu, my_off, l);
+        if (k + lane < total) {
+            const uint32_t s = (run0 + l) * kRunRecords + (d - off);
+            if (s < cap && d < cap) {
+                out.a[d] = tmp.a[s]; out.b[d] = tmp.b[s];
+                out.ab[d] = tmp.ab[s]; out.ae[d] = tmp.ae[s];
+                out.bb[d] = tmp.bb[s]; out.be[d] = tmp.be[s];
+                out.tag[d] = tmp.tag[s];
+            }
+        }
+    }
+}
 
 __global__ void __launch_bounds__(kTileThreads) k_relocate_runs(List tmp_a, List out_a, List tmp_b, List out_b, uint32_t cap,
                                                                const uint32_t* __restrict__ run_cnt, const uint32_t* __restrict__ off_a,
                                                                const uint32_t* __restrict__ off_b, uint32_t num_runs) {
-    const uint32_t gl = threadIdx.x & (kRelocLanes - 1);
-    const uint32_t groups = gridDim.x * (kTileThreads / kRelocLanes);
-    for (uint32_t run = blockIdx.x * (kTileThreads / kRelocLanes) + threadIdx.x / kRelocLanes; run < num_runs; run += groups) {
-        const uint32_t c = __ldg(run_cnt + run), base = run * kRunRecords;
-        const uint32_t na = c & 0xFFFFu, nb = c >> 16;
-        const uint32_t oa = __ldg(off_a + run), ob = __ldg(off_b + run);
-        for (uint32_t j = gl; j < na; j += kRelocLanes) {
-            const uint32_t s = base + j, d = oa + j;
-            if (s < cap && d < cap) {
-                out_a.a[d] = tmp_a.a[s]; out_a.b[d] = tmp_a.b[s];
-                out_a.ab[d] = tmp_a.ab[s]; out_a.ae[d] = tmp_a.ae[s];
-                out_a.bb[d] = tmp_a.bb[s]; out_a.be[d] = tmp_a.be[s];
-                out_a.tag[d] = tmp_a.tag[s];
-            }
-        }
-        for (uint32_t j = gl; j < nb; j += kRelocLanes) {
-            const uint32_t s = base + j, d = ob + j;
-            if (s < cap && d < cap) {
-                out_b.a[d] = tmp_b.a[s]; out_b.b[d] = tmp_b.b[s];
-                out_b.ab[d] = tmp_b.ab[s]; out_b.ae[d] = tmp_b.ae[s];
-                out_b.bb[d] = tmp_b.bb[s]; out_b.be[d] = tmp_b.be[s];
-                out_b.tag[d] = tmp_b.tag[s];
-            }
-        }
+    const uint32_t lane = lane_id();
+    const uint32_t supers = (num_runs + kRelocRuns - 1) / kRelocRuns;
+    for (uint32_t sr = blockIdx.x; sr < supers; sr += gridDim.x) {
+        const uint32_t run0 = sr * kRelocRuns, run = run0 + lane;
+        // lanes behind the last run repeat its end, so the search never lands on them
+        const uint32_t last = num_runs - 1u, r = min(run, last);
+        const uint32_t c = __ldg(run_cnt + r);
+        uint32_t oa = __ldg(off_a + r), ob = __ldg(off_b + r);
+        if (run > last) { oa += c & 0xFFFFu; ob += c >> 16; }
+        const uint32_t na = run <= last ? (c & 0xFFFFu) : 0u, nb = run <= last ? (c >> 16) : 0u;
+        const uint32_t first_a = __shfl_sync(0xFFFFFFFFu, oa, 0), first_b = __shfl_sync(0xFFFFFFFFu, ob, 0);
+        const uint32_t total_a = __shfl_sync(0xFFFFFFFFu, oa + na, 31) - first_a, total_b = __shfl_sync(0xFFFFFFFFu, ob + nb, 31) - first_b;
+        relocate_piece(tmp_a, out_a, cap, run0, oa, first_a, total_a);
+        relocate_piece(tmp_b, out_b, cap, run0, ob, first_b, total_b);
     }
 }
 
@@ -724,7 +737,7 @@ void launch_classify_survivors(Launch& L, List recs, uint32_t n, const uint2* pi
                                                                                        n_inl, status, ticket);
     L.count++;
 #if RB_OPT_RELOC
-    k_relocate_runs<<<grid_for(num_runs, kTileThreads / RB_RELOC_LANES, kNumSMs * 8), kTileThreads, 0, L.stream>>>(tmp_ovl, ovl, tmp_inl, inl, cap, runs.cnt,
+    k_relocate_runs<<<grid_for(num_runs, kRelocRuns, kNumSMs * 8), kTileThreads, 0, L.stream>>>(tmp_ovl, ovl, tmp_inl, inl, cap, runs.cnt,
                                                                                                runs.off_a, runs.off_b, num_runs);
     L.count++;
 #else
