@@ -302,7 +302,11 @@ def run_single(args):
                               else ["k_transitive_group", "k_transitive_light", "k_transitive_heavy"],
             "whole_step": {"algorithmic_bytes": int(step_bytes), "gbs": step_bytes / (ms_per_step * 1e-3) / 1e9,
                            "frac": step_bytes / (ms_per_step * 1e-3) / 1e9 / peak},
-            "kernels": {"k_classify_first": {"ms": k1_ms, "algorithmic_bytes": k1_bytes, "gbs": k1_gbs, "frac": k1_gbs / peak},
+            "kernels": {"k_classify_first": {"ms": k1_ms, "algorithmic_bytes": k1_bytes, "gbs": k1_gbs, "frac": k1_gbs / peak,
+                                             "note": "41 B / record is SURVEY.md 8(d)'s model (24 read + 16 trimmed coordinates + 1 type written); "
+                                                     "this design writes coordinates only for the ~7 % survivors and reads the two id columns twice: "
+                                                     "its own minimum is ~32 B / record, i.e. the same time is " +
+                                                     f"{32 * n_ovl / (k1_ms * 1e-3) / 1e9 / peak:.3f} of the peak on that count"},
                         "k_transitive": {"ms": k3_ms, "algorithmic_bytes": k3_bytes, "gbs": k3_gbs, "frac": k3_gbs / peak}},
             # the per-stage rates reported next to the metric (eager-chain stage timers)
             "rates": {"k1_overlaps_per_s": n_ovl / (k1_ms * 1e-3) if k1_ms > 0 else None,

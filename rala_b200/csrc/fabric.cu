@@ -44,6 +44,12 @@ static inline int grid_for(uint64_t n, int per_block, int max_blocks) {
     if (b < 1) b = 1;
     return (int) (b < (uint64_t) max_blocks ? b : (uint64_t) max_blocks);
 }
+// x-dimension of a grid whose y-dimension is the source rank: about 8 blocks per SM over the whole grid, at least one per SM
+// (with kNumSMs blocks per source the inbox kernels ran on 148 blocks at world = 1 and took 2 - 3 x their time, profiles/r02v)
+static inline int blocks_per_source(int world) {
+    const int b = kNumSMs * 8 / (world < 1 ? 1 : world);
+    return b < kNumSMs ? kNumSMs : b;
+}
 
 // ---------------------------------------------------------------------------------------------
 // Barrier.  Lane q publishes this rank's mail to peer q, makes everything this rank pushed before visible
@@ -234,7 +240,7 @@ __global__ void __launch_bounds__(256) k_gather_events(Peers P, ArenaLayout A, E
 
 void launch_gather_events(Launch& L, Peers P, ArenaLayout A, Events ev, uint32_t ev_cap, uint32_t* n_events_out, uint32_t* vcount,
                           uint32_t* tmin) {
-    dim3 grid(grid_for(A.cap_ev, 256, kNumSMs), P.world);
+    dim3 grid(grid_for(A.cap_ev, 256, blocks_per_source(P.world)), P.world);
     k_gather_events<<<grid, 256, 0, L.stream>>>(P, A, ev, ev_cap, n_events_out, vcount, tmin);
     L.count++;
 }
@@ -467,7 +473,9 @@ struct ResolveCtl {
 };
 static_assert(sizeof(ResolveCtl) == kResolveCtlBytes, "fabric.cuh sizes the control block");
 
-__device__ __forceinline__ void grid_barrier(ResolveCtl* ctl, uint32_t& phase) {
+// `deadline` (ns, %globaltimer): a grid that is not resident as a whole, or a peer that never answers block 0, must not hang
+// the GPU: after the deadline the waiting blocks mark the fabric dead and go on (the step's results are void then)
+__device__ __forceinline__ void grid_barrier(ResolveCtl* ctl, uint32_t& phase, uint32_t* dead, unsigned long long deadline) {
     __syncthreads();
     if (threadIdx.x == 0) {
         phase += 1u;
@@ -475,9 +483,13 @@ __device__ __forceinline__ void grid_barrier(ResolveCtl* ctl, uint32_t& phase) {
         if (atomicAdd(&ctl->arrived, 1u) + 1u == phase * gridDim.x) {
             asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(&ctl->released), "r"(phase) : "memory");
         } else {
-            uint32_t seen;
+            uint32_t seen, spins = 0;
             do {
                 asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(&ctl->released) : "memory");
+                if ((++spins & 4095u) == 0u && global_timer_ns() > deadline) {
+                    atomicExch(dead, 1u);
+                    break;
+                }
             } while ((int32_t) (seen - phase) < 0);
         }
     }
@@ -595,7 +607,7 @@ __global__ void __launch_bounds__(256) k_fabric_resolve(Peers P, ArenaLayout A, 
         const uint32_t* out = (sweep & 1u) ? work0 : work1;
         sweep_worklist(P, A, vstart, seg_c, seg_t, S, wait_pile, wait_time, (sweep & 1u) ? work1 : work0, n, (sweep & 1u) ? work0 : work1,
                        &n_work[(sweep + 1u) % 3u], blockIdx.x, gridDim.x);
-        grid_barrier(ctl, phase);
+        grid_barrier(ctl, phase, &mine->dead, t_start + 2ull * timeout_ns);
         uint32_t open;
         asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(open) : "l"(&n_work[(sweep + 1u) % 3u]) : "memory");
         const bool poll = open != 0u && open <= n_threads;
@@ -647,7 +659,7 @@ __global__ void __launch_bounds__(256) k_fabric_resolve(Peers P, ArenaLayout A, 
                 __threadfence();
             }
         }
-        grid_barrier(ctl, phase);
+        grid_barrier(ctl, phase, &mine->dead, t_start + 2ull * timeout_ns);
         uint32_t go;
         asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(go) : "l"(&ctl->go) : "memory");
         if (!go) break;
@@ -811,7 +823,7 @@ __global__ void __launch_bounds__(256) k_inbox_degree(Peers P, ArenaLayout A, co
 }
 
 void launch_inbox_degree(Launch& L, Peers P, ArenaLayout A, const BuildMeta* meta, uint32_t* degree) {
-    dim3 grid(grid_for(A.cap_edge, 256, kNumSMs), P.world);
+    dim3 grid(grid_for(A.cap_edge, 256, blocks_per_source(P.world)), P.world);
     k_inbox_degree<<<grid, 256, 0, L.stream>>>(P, A, meta, degree);
     L.count++;
 }
@@ -841,7 +853,7 @@ __global__ void __launch_bounds__(256) k_inbox_fill(Peers P, ArenaLayout A, cons
 }
 
 void launch_inbox_fill(Launch& L, Peers P, ArenaLayout A, const BuildMeta* meta, uint32_t* cursor, uint32_t* col_eid, uint8_t* T) {
-    dim3 grid(grid_for(A.cap_edge, 256, kNumSMs), P.world);
+    dim3 grid(grid_for(A.cap_edge, 256, blocks_per_source(P.world)), P.world);
     k_inbox_fill<<<grid, 256, 0, L.stream>>>(P, A, meta, cursor, col_eid, T);
     L.count++;
 }
@@ -862,7 +874,7 @@ __global__ void __launch_bounds__(256) k_push_csr(Peers P, ArenaLayout A, const 
 }
 
 void launch_push_csr(Launch& L, Peers P, ArenaLayout A, const BuildMeta* meta, const uint32_t* row_ptr_local) {
-    dim3 grid(grid_for(A.cap_slice, 1024, kNumSMs), P.world);
+    dim3 grid(grid_for(A.cap_slice, 1024, blocks_per_source(P.world)), P.world);
     k_push_csr<<<grid, 256, 0, L.stream>>>(P, A, meta, row_ptr_local);
     L.count++;
 }

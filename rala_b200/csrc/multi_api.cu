@@ -12,7 +12,6 @@
 //   graph.cpp:1281-1318 transitive marks        owner of the source node, on the replicated CSR; results go back to
 //                                               the rank that emitted the edge, which forms marked(e) = T(e) | T(e^1)
 #include <cstddef>
-#include <ctime>
 
 #include "fabric.cuh"
 #include "session.h"
@@ -151,8 +150,11 @@ extern "C" int rala_b200_multi_create(rala_b200_multi** out, const int* devices,
         int sharing = 0;
         for (const FabricRank& other : m->ranks) sharing += other.device == fr.device ? 1 : 0;
         cudaSetDevice(fr.device);
-        const int fit = fabric_resolve_max_blocks() / (2 * sharing);   // half of what fits: other streams keep their share
-        fr.resolve_blocks = fit < 1 ? 1 : (fit > kNumSMs * 4 ? kNumSMs * 4 : fit);
+        // A rank that has its GPU to itself takes what fits minus one block per SM (nothing else of this rank runs beside
+        // the resolution); ranks that share a GPU take half of their share, so that everybody's grid is resident at once.
+        const int all = fabric_resolve_max_blocks();
+        const int fit = sharing == 1 ? all - kNumSMs : all / (2 * sharing);
+        fr.resolve_blocks = fit < 1 ? 1 : fit;
     }
     *out = m;
     return RALA_B200_OK;
@@ -609,22 +611,11 @@ static const PhaseFn kPhases[] = {phase_a_events, phase_b_resolve,  phase_c_surv
 // Phases outermost, ranks innermost: with several ranks in one process no rank's stream ever holds more than one
 // phase that its peers have not been given yet (a barrier kernel waits on the GPU for the peers' kernels).
 static int enqueue_step(rala_b200_multi* m) {
-    static const bool trace = getenv("RALA_B200_FABRIC_TRACE") != nullptr;   // diagnostics only: host time spent enqueueing each phase
-    int idx = 0;
-    for (PhaseFn phase : kPhases) {
+    for (PhaseFn phase : kPhases)
         for (FabricRank& fr : m->ranks) {
-            timespec t0, t1;
-            if (trace) clock_gettime(CLOCK_MONOTONIC, &t0);
             int rc = phase(m, fr);
-            if (trace) {
-                clock_gettime(CLOCK_MONOTONIC, &t1);
-                fprintf(stderr, "[fabric] phase %d rank %d enqueued in %.3f ms\n", idx, fr.rank,
-                        1e3 * (t1.tv_sec - t0.tv_sec) + 1e-6 * (t1.tv_nsec - t0.tv_nsec));
-            }
             if (rc) return rc;
         }
-        ++idx;
-    }
     return RALA_B200_OK;
 }
 
