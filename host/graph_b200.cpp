@@ -446,6 +446,8 @@ void construct(Graph& g, const std::string& sensitive_overlaps_path) {
 uint32_t remove_transitive_edges(Graph& g) {
     std::vector<uint8_t> marked;
     uint64_t n_pairs = 0;
+    std::vector<uint32_t> suffix_off, suffix_ids, prefix_off, prefix_ids;   // adjacency after the removal, from the device
+    bool have_adjacency = false;
 
     bool untouched = false;   // is the device-resident graph still the host's graph?
     auto it = attached().find(&g);
@@ -477,6 +479,10 @@ uint32_t remove_transitive_edges(Graph& g) {
             fprintf(stderr, "[rala_b200::report] {\"stage\": \"remove_transitive_edges\", \"two_hop_visits\": %llu, \"transitive_pairs\": %llu, "
                     "\"heavy_items\": %u, \"device_ms\": {\"transitive\": %.4f}}\n", (unsigned long long) c.n_two_hop,
                     (unsigned long long) c.n_transitive_pairs, c.n_heavy_items, s.stage_ms()[4]);
+        // what remove_marked_objects would leave in every suffix_edges_ / prefix_edges_ (ascending edge id, marked ones gone)
+        s.adjacency(0, true, suffix_off, suffix_ids);
+        s.adjacency(1, true, prefix_off, prefix_ids);
+        have_adjacency = true;
     } else {
         // the graph was edited since construct (or built elsewhere): marshal the live edges; pairs stay adjacent
         std::vector<rala_edge_t> live;
@@ -510,7 +516,22 @@ uint32_t remove_transitive_edges(Graph& g) {
     }
     std::sort(g.transitive_edges_.begin(), g.transitive_edges_.end());
 
-    g.remove_marked_objects();   // :1332, host, unchanged (stable adjacency compaction)
+    if (have_adjacency) {
+        // :1332 remove_marked_objects (:2118-2151): the same end state, written from the device's adjacency view instead of
+        // one erase + compaction per marked edge: the surviving edges of every node in their (ascending) order, the marked
+        // Edge objects released, marked_edges_ empty.  (No node is marked on this path.)
+        for (uint64_t v = 0; v < g.nodes_.size(); ++v) {
+            auto& node = g.nodes_[v];
+            node->suffix_edges_.clear();
+            for (uint32_t p = suffix_off[v]; p < suffix_off[v + 1]; ++p) node->suffix_edges_.emplace_back(g.edges_[suffix_ids[p]].get());
+            node->prefix_edges_.clear();
+            for (uint32_t p = prefix_off[v]; p < prefix_off[v + 1]; ++p) node->prefix_edges_.emplace_back(g.edges_[prefix_ids[p]].get());
+        }
+        for (const auto& id : g.marked_edges_) g.edges_[id].reset();
+        g.marked_edges_.clear();
+    } else {
+        g.remove_marked_objects();   // :1332, host, unchanged (stable adjacency compaction)
+    }
 
     return static_cast<uint32_t>(n_pairs);
 }

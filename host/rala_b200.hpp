@@ -133,6 +133,16 @@ public:
         return m;
     }
 
+    // per node the ids of its out- (which = 0) or in-edges (which = 1), ascending, without the removed edges when skip_marked
+    void adjacency(int which, bool skip_marked, std::vector<uint32_t>& off, std::vector<uint32_t>& ids) {
+        const auto c = counts();
+        off.assign(static_cast<size_t>(c.n_nodes) + 1, 0u);
+        ids.assign(static_cast<size_t>(c.n_edges) + 1, 0u);
+        uint64_t n = 0;
+        check(rala_b200_graph_get_adjacency(graph_, which, skip_marked ? 1 : 0, off.data(), ids.data(), &n), "get_adjacency");
+        ids.resize(n);
+    }
+
     // Graph::remove_transitive_edges on an edge list that is no longer the device-resident one
     uint64_t transitive_reduce(uint32_t n_nodes, const std::vector<rala_edge_t>& edges, std::vector<uint8_t>& marked_out) {
         uint64_t n_pairs = 0;

@@ -196,6 +196,11 @@ int rala_b200_graph_set_kept_overlaps(rala_b200_graph* g, const rala_ovl_t* kept
 int rala_b200_graph_get_seq_to_node(rala_b200_graph* g, uint32_t* out /* n_piles; 0xFFFFFFFF = dead */);
 int rala_b200_graph_get_edges(rala_b200_graph* g, rala_edge_t* out /* n_edges */);
 int rala_b200_graph_get_marked(rala_b200_graph* g, uint8_t* out /* n_edges */);
+/* Adjacency VIEW, built on the device: off_out[v] .. off_out[v + 1] delimit, in ids_out, the ids of node v's out-edges (which = 0:
+ * suffix_edges_, graph.cpp:603 / 625) or in-edges (which = 1: prefix_edges_, :605-606 / 622-624) in ascending edge id, as the
+ * reference keeps them; with skip_marked != 0 (after transitive) without the removed edges: the adjacency
+ * Graph::remove_marked_objects leaves (graph.cpp:2118-2151).  off_out: n_nodes + 1 words, ids_out: n_edges words. */
+int rala_b200_graph_get_adjacency(rala_b200_graph* g, int which, int skip_marked, uint32_t* off_out, uint32_t* ids_out, uint64_t* n_ids_out);
 
 /* Device time of the last run of each stage, CUDA events on the context's stream (ms).
  * Order: classify, retrim, finalize, build, transitive (whole stages), then single kernels:

@@ -52,7 +52,7 @@ EXPORTS = [
     "rala_b200_graph_get_lists", "rala_b200_graph_get_seq_to_node", "rala_b200_graph_get_edges",
     "rala_b200_graph_get_marked", "rala_b200_graph_stage_ms", "rala_b200_graph_set_kept_overlaps",
     "rala_b200_graph_use_cuda_graph", "rala_b200_graph_set_overlaps_columns", "rala_b200_graph_set_outputs",
-    "rala_b200_graph_set_overlaps_packed", "rala_b200_multi_set_overlaps_packed",
+    "rala_b200_graph_set_overlaps_packed", "rala_b200_multi_set_overlaps_packed", "rala_b200_graph_get_adjacency",
     # multi-GPU phases
     "rala_b200_create_on_stream", "rala_b200_graph_set_shard", "rala_b200_graph_phase_events",
     "rala_b200_graph_events_count", "rala_b200_graph_export_events", "rala_b200_graph_import_events",
@@ -422,6 +422,16 @@ class Graph:
             out = np.zeros(n, dtype=np.uint8)
         self._call("rala_b200_graph_get_marked", _ptr(out))
         return out
+
+    def adjacency(self, which: int = 0, skip_marked: bool = False):
+        """(off, ids): per node the ids of its out- (which = 0) or in-edges (which = 1) in ascending edge id, built on the
+        device; skip_marked: without the removed edges (what Graph::remove_marked_objects leaves, graph.cpp:2118-2151)."""
+        c = self.counts()
+        off = np.zeros(c["n_nodes"] + 1, dtype=np.uint32)
+        ids = np.zeros(max(c["n_edges"], 1), dtype=np.uint32)
+        n = C.c_uint64(0)
+        self._call("rala_b200_graph_get_adjacency", C.c_int(which), C.c_int(1 if skip_marked else 0), _ptr(off), _ptr(ids), C.byref(n))
+        return off, ids[:int(n.value)]
 
     def stage_ms(self) -> dict:
         ms = (C.c_float * N_STAGES)()

@@ -1030,6 +1030,44 @@ extern "C" int rala_b200_graph_get_marked(rala_b200_graph* g, uint8_t* out) {
     return RALA_B200_OK;
 }
 
+// suffix_edges_ / prefix_edges_ of every node as the reference keeps them (ascending edge id), optionally after the removal of
+// the marked edges: graph.cpp:603-606 / 622-625 and 2118-2151
+extern "C" int rala_b200_graph_get_adjacency(rala_b200_graph* g, int which, int skip_marked, uint32_t* off_out, uint32_t* ids_out,
+                                             uint64_t* n_ids_out) {
+    if (!g || !off_out || !ids_out || !n_ids_out || which < 0 || which > 1) return RALA_B200_ERR_ARG;
+    rala_b200_ctx* ctx = g->ctx;
+    if (g->state < 4) return fail(ctx, RALA_B200_ERR_STATE, "get_adjacency: build first");
+    if (skip_marked && g->state < 5) return fail(ctx, RALA_B200_ERR_STATE, "get_adjacency: transitive first (or pass skip_marked = 0)");
+    uint32_t h[C_COUNT];
+    int rc = read_counters(g, h);
+    if (rc) return rc;
+    const uint32_t n_nodes = h[C_NODES], n_edges = h[C_EDGES];
+    *n_ids_out = 0;
+    CU(ctx, cudaSetDevice(ctx->device));
+    DevBuf deg, rp, tmp, sorted;
+    CU(ctx, deg.reserve(((size_t) n_nodes + 8) * 4));
+    CU(ctx, rp.reserve(((size_t) n_nodes + 8) * 4));
+    CU(ctx, tmp.reserve(((size_t) n_edges + 8) * 4));
+    CU(ctx, sorted.reserve(((size_t) n_edges + 8) * 4));
+    GraphArrays ga = g->graph_view();
+    g->scan_used = 0;
+    CU(ctx, cudaMemsetAsync(g->scan_pool.p, 0, g->scan_pool_words * 8, ctx->L.stream));
+    unsigned long long* status;
+    uint32_t* ticket;
+    scan_state(g, (uint64_t) n_nodes + 1, &status, &ticket);
+    launch_adjacency_view(ctx->L, which ? ga.dst : ga.src, skip_marked ? ga.marked : nullptr, g->cnt() + C_EDGES, g->edge_cap, n_nodes,
+                          deg.as<uint32_t>(), rp.as<uint32_t>(), tmp.as<uint32_t>(), sorted.as<uint32_t>(), status, ticket);
+    CU(ctx, cudaGetLastError());
+    CU(ctx, cudaMemcpyAsync(off_out, rp.p, ((size_t) n_nodes + 1) * 4, cudaMemcpyDeviceToHost, ctx->L.stream));
+    CU(ctx, cudaStreamSynchronize(ctx->L.stream));
+    const uint32_t total = off_out[n_nodes];
+    if (total) CU(ctx, cudaMemcpyAsync(ids_out, sorted.p, (size_t) total * 4, cudaMemcpyDeviceToHost, ctx->L.stream));
+    CU(ctx, cudaStreamSynchronize(ctx->L.stream));
+    *n_ids_out = total;
+    deg.release(); rp.release(); tmp.release(); sorted.release();
+    return RALA_B200_OK;
+}
+
 extern "C" int rala_b200_graph_stage_ms(rala_b200_graph* g, float* ms_out) {
     if (!g || !ms_out) return RALA_B200_ERR_ARG;
     rala_b200_ctx* ctx = g->ctx;

@@ -242,6 +242,41 @@ __global__ void k_fill_csr(const uint32_t* __restrict__ src, const uint32_t* __r
 #endif
 }
 
+// ---------------------------------------------------------------------------------------------
+// Adjacency VIEW for the host (rala_b200_graph_get_adjacency): per node the ids of its out- (key = src) or in-edges
+// (key = dst) in ASCENDING EDGE ID, marked edges left out on request: what suffix_edges_ / prefix_edges_ hold after
+// Graph::remove_marked_objects (graph.cpp:2118-2151, shrinkToFit :31-54).  Off the hot step (a download path): counting
+// sort by node with atomic slots, then every row is ordered by a rank sort (edge ids are distinct).
+// ---------------------------------------------------------------------------------------------
+__global__ void k_adj_hist(const uint32_t* __restrict__ key, const uint8_t* __restrict__ marked, const uint32_t* __restrict__ n_edges_ptr,
+                           uint32_t edge_cap, uint32_t n_nodes, uint32_t* __restrict__ degree) {
+    const uint32_t n = min(*n_edges_ptr, edge_cap);
+    for (uint32_t e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x)
+        if (!(marked && marked[e]) && key[e] < n_nodes) atomicAdd(&degree[key[e]], 1u);
+}
+
+__global__ void k_adj_fill(const uint32_t* __restrict__ key, const uint8_t* __restrict__ marked, const uint32_t* __restrict__ n_edges_ptr,
+                           uint32_t edge_cap, uint32_t n_nodes, uint32_t* __restrict__ cursor, uint32_t* __restrict__ ids) {
+    const uint32_t n = min(*n_edges_ptr, edge_cap);
+    for (uint32_t e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x)
+        if (!(marked && marked[e]) && key[e] < n_nodes) ids[atomicAdd(&cursor[key[e]], 1u)] = e;
+}
+
+// one warp per row: out[row start + #(ids of the row below mine)] = mine
+__global__ void __launch_bounds__(256) k_adj_sort_rows(const uint32_t* __restrict__ row_ptr, uint32_t n_nodes, const uint32_t* __restrict__ ids,
+                                                      uint32_t* __restrict__ sorted) {
+    const uint32_t lane = lane_id(), warps = gridDim.x * (blockDim.x / 32);
+    for (uint32_t row = blockIdx.x * (blockDim.x / 32) + warp_id(); row < n_nodes; row += warps) {
+        const uint32_t r0 = row_ptr[row], d = row_ptr[row + 1] - r0;
+        for (uint32_t i = lane; i < d; i += 32) {
+            const uint32_t mine = ids[r0 + i];
+            uint32_t rank = 0;
+            for (uint32_t j = 0; j < d; ++j) rank += ids[r0 + j] < mine ? 1u : 0u;
+            sorted[r0 + rank] = mine;
+        }
+    }
+}
+
 // edge columns -> rala_edge_t rows (download path).  Rows are staged in shared memory and leave as 16-byte stores
 // of consecutive threads: `out` may be pinned HOST memory the GPU writes over PCIe (rala_b200_graph_set_outputs),
 // where three strided 4-byte stores per row would triple the number of write transactions.
@@ -332,6 +367,21 @@ static inline int grid_for(uint64_t n, int per_block, int max_blocks) {
     return (int) (b < (uint64_t) max_blocks ? b : (uint64_t) max_blocks);
 }
 
+void launch_adjacency_view(Launch& L, const uint32_t* key, const uint8_t* marked, const uint32_t* n_edges_ptr, uint32_t edge_cap,
+                           uint32_t n_nodes, uint32_t* degree_cursor, uint32_t* row_ptr, uint32_t* ids_tmp, uint32_t* ids_sorted,
+                           unsigned long long* status, uint32_t* ticket) {
+    cudaMemsetAsync(degree_cursor, 0, ((size_t) n_nodes + 8) * 4, L.stream);
+    k_adj_hist<<<grid_for(edge_cap, 256, kNumSMs * 8), 256, 0, L.stream>>>(key, marked, n_edges_ptr, edge_cap, n_nodes, degree_cursor);
+    L.count++;
+    k_scan_degrees<<<grid_for(n_nodes + 1, kTile, kNumSMs * 8), kTileThreads, 0, L.stream>>>(degree_cursor, row_ptr, n_nodes + 1, status, ticket,
+                                                                                          nullptr, nullptr, nullptr);
+    L.count++;
+    k_adj_fill<<<grid_for(edge_cap, 256, kNumSMs * 8), 256, 0, L.stream>>>(key, marked, n_edges_ptr, edge_cap, n_nodes, degree_cursor, ids_tmp);
+    L.count++;
+    k_adj_sort_rows<<<grid_for(n_nodes, 8, kNumSMs * 8), 256, 0, L.stream>>>(row_ptr, n_nodes, ids_tmp, ids_sorted);
+    L.count++;
+}
+
 void launch_node_ids(Launch& L, const uint2* piles, uint32_t n_piles, uint32_t* seq_to_node, uint32_t* counters,
                      unsigned long long* status, uint32_t* ticket) {
     if (n_piles == 0) return;
@@ -400,6 +450,9 @@ void launch_build_csr(Launch& L, GraphArrays g, uint32_t n_nodes_max, uint32_t e
 void preload_graph_build() {
     cudaFuncAttributes a;
     cudaFuncGetAttributes(&a, k_node_ids);
+    cudaFuncGetAttributes(&a, k_adj_hist);
+    cudaFuncGetAttributes(&a, k_adj_fill);
+    cudaFuncGetAttributes(&a, k_adj_sort_rows);
     cudaFuncGetAttributes(&a, k_emit_edges);
     cudaFuncGetAttributes(&a, k_degree_hist);
     cudaFuncGetAttributes(&a, k_scan_degrees);

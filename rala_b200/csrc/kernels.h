@@ -133,6 +133,10 @@ void launch_export_padded(Launch& L, const uint32_t* c0, const uint32_t* c1, con
 void launch_import_gathered(Launch& L, const uint32_t* gathered, uint32_t cap, uint32_t world, uint32_t* d0, uint32_t* d1,
                             uint32_t* d2, uint32_t dst_cap, uint32_t* n_out, uint32_t* overflow);
 void launch_time_bases(Launch& L, const uint32_t* counts, uint32_t rank, uint32_t world, uint32_t* bases);
+// host-facing adjacency view: ids of the (unmarked) edges per node, ascending edge id; key = src (suffix) or dst (prefix) column
+void launch_adjacency_view(Launch& L, const uint32_t* key, const uint8_t* marked, const uint32_t* n_edges_ptr, uint32_t edge_cap,
+                           uint32_t n_nodes, uint32_t* degree_cursor, uint32_t* row_ptr, uint32_t* ids_tmp, uint32_t* ids_sorted,
+                           unsigned long long* status, uint32_t* ticket);
 void launch_build_csr(Launch& L, GraphArrays g, uint32_t n_nodes_max, uint32_t edge_cap, uint32_t* counters,
                       unsigned long long* status, uint32_t* ticket);
 

@@ -485,3 +485,23 @@ def test_packed_upload_matches_the_row_form(ctx):
     big[3, 3] = 70000
     assert api.records_to_packed(big) is None
     G.close()
+
+
+@pytest.mark.parametrize("kind", ["noisy_dual", "hubs"])
+def test_adjacency_view_matches_the_reference_adjacency(ctx, kind):
+    """rala_b200_graph_get_adjacency: suffix_edges_ / prefix_edges_ in ascending edge id, before and after the removal of the
+    transitive edges (graph.cpp:603-625, 2118-2151), against the oracle's adjacency (pinned to the reference's dumps)."""
+    ds = (synth.generate(1_000_000, 40, 8000, len_sd=2500, seed=42, noise=80, dual=True) if kind == "noisy_dual"
+          else synth.generate_repeat_hubs(genome_len=2_000_000, n_hubs=2))
+    piles = ds.flat_piles()
+    P = O.Pipeline(ds.records, piles).run()
+    G = api.Graph(ctx)
+    G.set_piles(piles).set_hills(None).set_overlaps(ds.records)
+    G.run()
+    for which in (0, 1):
+        for skip in (False, True):
+            off, ids = G.adjacency(which, skip)
+            want_off, want_ids = O.adjacency(P.n_nodes, P.edges, P.marked if skip else None, which)
+            assert_same(off, want_off, f"offsets which={which} skip={skip}")
+            assert_same(ids, want_ids, f"ids which={which} skip={skip}")
+    G.close()
