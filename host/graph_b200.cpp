@@ -102,6 +102,35 @@ void apply_kills(Graph& g, Session& s) {
     }
 }
 
+// Overlap::transmute (overlap.cpp:36-82) with the query's name -> id lookup remembered from the record before: a PAF lists
+// a query's overlaps together, so 97 % of the a-side hash lookups repeat the previous one.  The reference's own loop gets a
+// similar saving for free (its transmute returns after the a-side once pile a has been killed, overlap.cpp:51); here the
+// piles only die on the device afterwards, so without this the drop-in did 2 lookups (~105 ns each) for every record and
+// this pass was 2.4 s slower than the reference's on configs[2] (profiles/r02z_cli_c3.json).  Same results, same errors.
+struct QueryMemo {
+    std::string name;
+    uint64_t id = 0;
+    bool found = false, valid = false;
+};
+
+bool transmute_memo(Overlap& o, const std::vector<std::unique_ptr<Pile>>& piles,
+                    const std::unordered_map<std::string, uint64_t>& name_to_id, QueryMemo& memo) {
+    if (o.is_transmuted_) return true;
+    if (!o.a_name_.empty()) {
+        if (!memo.valid || memo.name != o.a_name_) {
+            auto it = name_to_id.find(o.a_name_);
+            memo.name = o.a_name_;
+            memo.found = it != name_to_id.end();
+            memo.id = memo.found ? it->second : 0;
+            memo.valid = true;
+        }
+        if (!memo.found) return false;
+        o.a_id_ = memo.id;
+        std::string().swap(o.a_name_);
+    }
+    return o.transmute(piles, name_to_id);   // a-side done (its name is empty now): length checks, the b-side, is_transmuted_
+}
+
 rala_ovl_t marshal(const Overlap& o, bool valid) {
     rala_ovl_t r;
     r.a_id = valid ? static_cast<uint32_t>(o.a_id_) : 0u;
@@ -154,13 +183,14 @@ void construct(Graph& g, const std::string& sensitive_overlaps_path) {
     {
         std::vector<std::unique_ptr<Overlap>> chunk;
         uint64_t num_overlaps = 0;
+        QueryMemo memo;
         g.oparser_->reset();
         while (true) {
             auto status = g.oparser_->parse_objects(chunk, rala::kChunkSize);
             for (uint64_t i = 0; i < chunk.size(); ++i) {
                 // :450-451; transmute() sees the piles as initialize() left them: its "pile is already dead" gate for
                 // piles killed LATER in the loop is what the device resolves
-                bool valid = g.is_valid_overlap_[num_overlaps + i] && chunk[i]->transmute(g.piles_, g.name_to_id_);
+                bool valid = g.is_valid_overlap_[num_overlaps + i] && transmute_memo(*chunk[i], g.piles_, g.name_to_id_, memo);
                 marshal(*chunk[i], valid, records);
             }
             num_overlaps += chunk.size();
