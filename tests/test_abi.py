@@ -72,3 +72,33 @@ def test_records_to_columns_layout():
     assert [int(x) & 0x7FFFFFFF for x in c[1]] == [9, 7, 3, 4, 4, 2]
     assert np.array_equal(c[2:6].T, rec[:, 2:6])
     assert api.records_to_columns(np.zeros((0, 7), np.uint32)).shape == (6, 0)
+
+
+def test_records_to_packed_round_trips_through_the_column_layout():
+    """api.records_to_packed: host side of rala_b200_graph_set_overlaps_packed (12 B per record).  Expanding it on the host
+    the way k_unpack_records does must give the column layout of records_to_columns for every valid record, and both spans
+    0 (which Overlap::trim rejects) for every invalid one."""
+    import numpy as np
+    from rala_b200 import api, synth
+    ds = synth.generate(400_000, 30, 9000, len_sd=2500, seed=21, noise=60, dual=True)
+    rec = ds.records.copy()
+    rec[0, 6] |= 2                      # invalid first record
+    rec[50:53, 6] |= 2                  # a run of invalid records inside a group
+    starts = np.nonzero(rec[1:, 0] != rec[:-1, 0])[0] + 1
+    rec[starts[3], 6] |= 2              # invalid first record of a group
+    p = api.records_to_packed(rec)
+    assert p is not None and p.n == rec.shape[0] and p.nbytes < 12.5 * rec.shape[0]
+    assert np.all(np.diff(p.group_end.astype(np.int64)) > 0) and int(p.group_end[-1]) == rec.shape[0]
+    a = np.repeat(p.query_id, np.diff(np.concatenate([[0], p.group_end]).astype(np.int64)))
+    cols = api.records_to_columns(rec)
+    bad = (cols[0] >> 31) == 1
+    assert bad.sum() == 5
+    assert np.array_equal(a[~bad], cols[0][~bad]) and np.array_equal(p.b_id[~bad], cols[1][~bad])
+    assert np.array_equal((p.a_span & 0xFFFF)[~bad], cols[2][~bad]) and np.array_equal((p.a_span >> 16)[~bad], cols[3][~bad])
+    assert np.array_equal((p.b_span & 0xFFFF)[~bad], cols[4][~bad]) and np.array_equal((p.b_span >> 16)[~bad], cols[5][~bad])
+    assert not p.a_span[bad].any() and not p.b_span[bad].any() and (a[bad] < ds.n_reads).all()
+    # coordinates that need more than 16 bits, or ids that need bit 31: the packer declines
+    big = rec.copy()
+    big[10, 5] = 65536
+    assert api.records_to_packed(big) is None
+    assert api.records_to_packed(np.zeros((0, 7), np.uint32)) is None
