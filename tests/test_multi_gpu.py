@@ -41,7 +41,7 @@ def _flags(ds):
 
 def _worker(rank, world, port, out_dir, transport, same_device):
     import signal
-    signal.alarm(300)    # a rank stuck waiting for a peer must not hold the GPU suite (and the box) for its whole time limit
+    signal.alarm(420)    # a rank stuck waiting for a peer must not hold the GPU suite (and the box) for its whole time limit
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dev = 0 if same_device else rank
     torch.cuda.set_device(dev)
@@ -56,7 +56,7 @@ def _worker(rank, world, port, out_dir, transport, same_device):
         shard = np.ascontiguousarray(ds.records[lo:hi])
         if transport == "fabric":
             fg = multi.FabricGraph(dev, rank, world)
-            fg.M.set_barrier_timeout_ms(20000 if same_device else 5000)
+            fg.M.set_barrier_timeout_ms(60000 if same_device else 10000)
             fg.set_inputs(shard, piles, flags, lo)
             fg.plan()
             for _ in range(2 if same_device else 4):     # eager, captured, replayed
