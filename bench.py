@@ -520,8 +520,16 @@ def run_ab(args):
             c = G.counts()
             import zlib
             crc = zlib.crc32(G.marked().tobytes(), zlib.crc32(G.edges().tobytes()))   # an experiment must not change a single bit
-            out.setdefault(name, {"ms_per_step": [], "edges": c["n_edges"], "pairs": c["n_transitive_pairs"],
-                                  "edges_marks_crc32": crc})["ms_per_step"].append(ms)
+            rec = out.setdefault(name, {"ms_per_step": [], "edges": c["n_edges"], "pairs": c["n_transitive_pairs"],
+                                        "edges_marks_crc32": crc})
+            rec["ms_per_step"].append(ms)
+            G.use_cuda_graph(False)   # stage timers exist in the eager chain only: which stage an experiment moved
+            acc = {}
+            for _ in range(5):
+                G.run()
+                for k, v in G.stage_ms().items():
+                    acc.setdefault(k, []).append(v)
+            rec["stage_us_eager"] = {k: round(1e3 * float(np.median(v)), 1) for k, v in acc.items()}
             G.close()
             ctx.close()
     base = min(out["product"]["ms_per_step"])

@@ -72,7 +72,10 @@ def variant_path(name: str) -> str:
 
 
 # other settings of a tunable, same product otherwise
-TUNINGS = {"no_packrow": ["-DRB_GROUP_PACKROW=0"]}
+TUNINGS = {"no_packrow": ["-DRB_GROUP_PACKROW=0"], "aos": ["-DRB_OPT_AOS=1"], "aos_u1": ["-DRB_OPT_AOS=1", "-DRB_RELOC_UNROLL=1"],
+           "aos_u3": ["-DRB_OPT_AOS=1", "-DRB_RELOC_UNROLL=3"], "emit2": ["-DRB_EMIT_ITEMS=2"], "emit1": ["-DRB_EMIT_ITEMS=1"],
+           "ev2_4": ["-DRB_EVENTS_ITEMS=2", "-DRB_EVENTS_MINB=4"], "ev2_5": ["-DRB_EVENTS_ITEMS=2", "-DRB_EVENTS_MINB=5"],
+           "ev2_6": ["-DRB_EVENTS_ITEMS=2", "-DRB_EVENTS_MINB=6"]}
 
 
 def build_variants(verbose: bool = False):

@@ -687,7 +687,7 @@ extern "C" int rala_b200_graph_build(rala_b200_graph* g) {
     uint32_t* ticket;
     scan_state(g, g->n_piles, &status, &ticket);
     launch_node_ids(ctx->L, g->piles.as<uint2>(), g->n_piles, g->seq_to_node.as<uint32_t>(), g->cnt(), status, ticket);
-    scan_state(g, g->cap, &status, &ticket);
+    scan_state(g, emit_scan_span(g->cap), &status, &ticket);
     launch_emit_edges(ctx->L, g->ovl[g->ovl_cur].view, g->cnt() + g->slot_ovl, g->cap, g->piles.as<uint2>(), g->graph_view(),
                       g->edge_cap, g->cnt(), status, ticket);
     // the edge list is final: rows into the caller's buffer on a forked stream, beside the CSR build and (inside a
@@ -1296,7 +1296,7 @@ extern "C" int rala_b200_graph_phase_emit_edges(rala_b200_graph* g, uint32_t* n_
     uint32_t* ticket;
     scan_state(g, g->n_piles, &status, &ticket);
     launch_node_ids(ctx->L, g->piles.as<uint2>(), g->n_piles, g->seq_to_node.as<uint32_t>(), g->cnt(), status, ticket);
-    scan_state(g, g->cap, &status, &ticket);
+    scan_state(g, emit_scan_span(g->cap), &status, &ticket);
     launch_emit_edges(ctx->L, g->ovl[g->ovl_cur].view, g->cnt() + g->slot_ovl, g->cap, g->piles.as<uint2>(), g->graph_view(),
                       g->edge_cap, g->cnt(), status, ticket);
     CU(ctx, cudaGetLastError());

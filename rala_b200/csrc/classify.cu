@@ -31,6 +31,12 @@ namespace rb {
 // barriers in the first pass.  The second pass reads only the two id columns (8 B / record) plus one
 // bit per pile of an L1-resident liveness bitmap, and gathers the coordinates of the few survivors.
 // =============================================================================================
+#ifndef RB_EVENTS_ITEMS
+#define RB_EVENTS_ITEMS 4   // consecutive records per thread in k_classify_events (one 16-byte load per column)
+#endif
+#ifndef RB_EVENTS_MINB
+#define RB_EVENTS_MINB 3    // its resident blocks per SM
+#endif
 constexpr int kRecItems = 4;                              // consecutive records per thread (one uint4 per column)
 constexpr int kRecTile = kTileThreads * kRecItems;        // records per block iteration
 constexpr uint32_t kInvalidBit = 0x80000000u;             // in column a
@@ -92,16 +98,25 @@ __device__ __forceinline__ void unpack4(const uint4 v, uint32_t (&out)[4]) {
     out[0] = v.x; out[1] = v.y; out[2] = v.z; out[3] = v.w;
 }
 
+// R consecutive values of a column, one 16- or 8-byte load (q counts groups of R values)
+__device__ __forceinline__ void load_group(const uint32_t* __restrict__ col, uint32_t q, uint32_t (&out)[4]) {
+    unpack4(reinterpret_cast<const uint4*>(col)[q], out);
+}
+__device__ __forceinline__ void load_group(const uint32_t* __restrict__ col, uint32_t q, uint32_t (&out)[2]) {
+    const uint2 v = reinterpret_cast<const uint2*>(col)[q];
+    out[0] = v.x; out[1] = v.y;
+}
+
 constexpr int kEvStage = 96;   // per-warp staging of events before one aggregated global append
 
-template <int MINB>
+template <int MINB, int R>
 __global__ void __launch_bounds__(kTileThreads, MINB) k_classify_events(
     List recs, uint32_t n, uint32_t t0, const uint2* __restrict__ piles, uint32_t n_piles,
     Events ev, uint32_t ev_cap, uint32_t* __restrict__ vcount, uint32_t* __restrict__ hill_rec, uint32_t hill_cap,
     uint32_t* __restrict__ counters) {
     __shared__ uint32_t s_ev[kTileWarps][3][kEvStage];
     const uint32_t lane = lane_id(), warp = warp_id();
-    const uint32_t n4 = (n + 3u) / 4u;
+    const uint32_t n4 = (n + R - 1u) / R;   // groups of R records
     uint32_t staged = 0;   // warp-uniform
 
     auto flush = [&]() {
@@ -121,22 +136,22 @@ __global__ void __launch_bounds__(kTileThreads, MINB) k_classify_events(
 
     for (uint32_t qbase = blockIdx.x * kTileThreads; qbase < n4; qbase += gridDim.x * kTileThreads) {
         const uint32_t q = qbase + threadIdx.x;
-        uint32_t a[4], b[4], ab[4], ae[4], bb[4], be[4];
-        uint2 pa[4], pb[4];
-        bool live[4];
+        uint32_t a[R], b[R], ab[R], ae[R], bb[R], be[R];
+        uint2 pa[R], pb[R];
+        bool live[R];
         if (q < n4) {
-            unpack4(reinterpret_cast<const uint4*>(recs.a)[q], a);
-            unpack4(reinterpret_cast<const uint4*>(recs.b)[q], b);
-            unpack4(reinterpret_cast<const uint4*>(recs.ab)[q], ab);
-            unpack4(reinterpret_cast<const uint4*>(recs.ae)[q], ae);
-            unpack4(reinterpret_cast<const uint4*>(recs.bb)[q], bb);
-            unpack4(reinterpret_cast<const uint4*>(recs.be)[q], be);
+            load_group(recs.a, q, a);
+            load_group(recs.b, q, b);
+            load_group(recs.ab, q, ab);
+            load_group(recs.ae, q, ae);
+            load_group(recs.bb, q, bb);
+            load_group(recs.be, q, be);
         }
         // all eight pile gathers of the thread's records are in flight before the first one is used
 #pragma unroll
-        for (int r = 0; r < kRecItems; ++r) {
+        for (int r = 0; r < R; ++r) {
             const uint32_t idb = b[r] & 0x7FFFFFFFu;
-            live[r] = q < n4 && 4u * q + r < n && !(a[r] & kInvalidBit) && a[r] < n_piles && idb < n_piles;   // graph.cpp:450-451
+            live[r] = q < n4 && (uint32_t) R * q + r < n && !(a[r] & kInvalidBit) && a[r] < n_piles && idb < n_piles;   // graph.cpp:450-451
             pa[r] = pb[r] = make_uint2(0u, 0u);   // a dead pile: rejects itself
             if (live[r]) {
                 pa[r] = __ldg(piles + a[r]);
@@ -144,7 +159,7 @@ __global__ void __launch_bounds__(kTileThreads, MINB) k_classify_events(
             }
         }
 #pragma unroll
-        for (int r = 0; r < kRecItems; ++r) {
+        for (int r = 0; r < R; ++r) {
             bool is_ev = false;
             uint32_t evv = 0, evc = 0;
 #if RB_OPT_EVENTS
@@ -156,7 +171,7 @@ __global__ void __launch_bounds__(kTileThreads, MINB) k_classify_events(
                 const uint32_t fa = pa[r].y >> 30, fb = pb[r].y >> 30;
                 if ((code & 1u) && ((fa | fb) & 1u)) {                                                      // :457-462, resolved by k_hill_coverage
                     uint32_t slot = atomicAdd(&counters[C_HILL], 1u);
-                    if (slot < hill_cap) hill_rec[slot] = 4u * q + r;
+                    if (slot < hill_cap) hill_rec[slot] = (uint32_t) R * q + r;
                 }
                 const bool ev_b = (code & 2u) && !(fb & 2u);                                                // :469-474
                 const bool ev_a = (code & 4u) && !(fa & 2u);                                                // :475-480
@@ -174,7 +189,7 @@ __global__ void __launch_bounds__(kTileThreads, MINB) k_classify_events(
                 if (A.alive() && B.alive() && trim(c, ori, A, B)) {                          // :451-452
                     if ((A.flags | B.flags) & 1u) {                                          // :457-462, resolved by k_hill_coverage
                         uint32_t slot = atomicAdd(&counters[C_HILL], 1u);
-                        if (slot < hill_cap) hill_rec[slot] = 4u * q + r;
+                        if (slot < hill_cap) hill_rec[slot] = (uint32_t) R * q + r;
                     }
                     const uint8_t t = classify(c, relative(c, ori, A, B));
                     if (t == kB && !(B.flags & 2u)) {                                        // :469-474
@@ -192,7 +207,7 @@ __global__ void __launch_bounds__(kTileThreads, MINB) k_classify_events(
                     const uint32_t p = staged + __popc(m & ((1u << lane) - 1u));
                     s_ev[warp][0][p] = evv;
                     s_ev[warp][1][p] = evc;
-                    s_ev[warp][2][p] = t0 + 4u * q + r;
+                    s_ev[warp][2][p] = t0 + (uint32_t) R * q + r;
                 }
                 staged += __popc(m);
                 __syncwarp();
@@ -202,6 +217,13 @@ __global__ void __launch_bounds__(kTileThreads, MINB) k_classify_events(
     }
     if (staged) flush();
 }
+
+#if RB_OPT_AOS
+// Scratch of the survivors pass: one 32-byte entry per slot, kept as two 16-byte halves in the two spare list buffers
+// (a list buffer holds 25 B per entry of capacity, a half needs 16): {a, b | ori << 31, ab, ae} and {bb, be, tag, -}.
+__device__ __forceinline__ uint4* scratch_lo(const List& spare_ovl) { return reinterpret_cast<uint4*>(spare_ovl.a); }
+__device__ __forceinline__ uint4* scratch_hi(const List& spare_inl) { return reinterpret_cast<uint4*>(spare_inl.a); }
+#endif
 
 // Survivors pass.  Every warp owns RUNS of 512 consecutive records (4 x 4 per lane): it writes the survivors of a
 // run, in record order, to the run's own slot range of the scratch lists (slot = record index of the run's
@@ -265,6 +287,7 @@ __global__ void __launch_bounds__(kTileThreads) k_classify_survivors(
         total = group_base;
         __syncwarp();
         uint32_t n_a = 0, n_b = 0;   // warp-uniform: survivors of the run so far (`overlaps`, `internals`)
+        const uint32_t run_len = min((uint32_t) kRunRecords, n - run * kRunRecords);
         for (uint32_t k0 = 0; k0 < total; k0 += 32) {
             const uint32_t k = k0 + lane;
             int dest = 0;
@@ -285,6 +308,16 @@ __global__ void __launch_bounds__(kTileThreads) k_classify_survivors(
             }
             const uint32_t ma = __ballot_sync(0xFFFFFFFFu, dest == 1), mb = __ballot_sync(0xFFFFFFFFu, dest == 2);
             const uint32_t below = (1u << lane) - 1u;
+#if RB_OPT_AOS
+            if (dest) {   // one 32-byte scratch entry, two 16-byte stores: `overlaps` fill the run's slots from the front, `internals` from the back
+                const uint32_t p = dest == 1 ? run * kRunRecords + n_a + __popc(ma & below)
+                                             : run * kRunRecords + run_len - 1u - (n_b + __popc(mb & below));
+                if (p < cap) {
+                    scratch_lo(tmp_ovl)[p] = make_uint4(e.a, e.b | (e.ori << 31), e.c.ab, e.c.ae);
+                    scratch_hi(tmp_inl)[p] = make_uint4(e.c.bb, e.c.be, tag, 0u);
+                }
+            }
+#else
             if (dest == 1) {
                 const uint32_t p = run * kRunRecords + n_a + __popc(ma & below);
                 if (p < cap) store_entry(tmp_ovl, p, e, tag);
@@ -292,6 +325,7 @@ __global__ void __launch_bounds__(kTileThreads) k_classify_survivors(
                 const uint32_t p = run * kRunRecords + n_b + __popc(mb & below);
                 if (p < cap) store_entry(tmp_inl, p, e, tag);
             }
+#endif
             n_a += __popc(ma);
             n_b += __popc(mb);
         }
@@ -422,9 +456,56 @@ __device__ __forceinline__ void relocate_piece(const List& tmp, const List& out,
     }
 }
 
+#if RB_OPT_AOS
+#ifndef RB_RELOC_UNROLL
+#define RB_RELOC_UNROLL 2
+#endif
+// The move out of the 32-byte scratch entries: two 16-byte loads per entry (consecutive output positions read consecutive
+// slots of a run), seven coalesced column stores.  U positions per thread and trip: the loads of all of them are issued
+// before the first store, the trips of a block are a chain of dependent memory latencies otherwise.
+template <bool BACK, int U>
+__device__ __forceinline__ void relocate_scratch_piece(const uint4* __restrict__ lo, const uint4* __restrict__ hi, const List& out,
+                                                       uint32_t cap, uint32_t n, uint32_t run0, uint32_t my_off, uint32_t first,
+                                                       uint32_t total) {
+    const uint32_t lane = lane_id(), warp = warp_id();
+    for (uint32_t k = warp * 32u; k < total; k += kTileThreads * U) {   // block-uniform trip count per warp: all lanes shuffle
+        uint4 vlo[U], vhi[U];
+        uint32_t d[U];
+        bool ok[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const uint32_t kk = k + u * kTileThreads + lane;
+            d[u] = first + kk;
+            uint32_t l = 0;   // the largest run l of the 32 whose first output position is <= d
+#pragma unroll
+            for (uint32_t step = 16; step > 0; step >>= 1) {
+                const uint32_t v = __shfl_sync(0xFFFFFFFFu, my_off, (l + step) & 31u);
+                if (l + step < kRelocRuns && v <= d[u]) l += step;
+            }
+            const uint32_t j = d[u] - __shfl_sync(0xFFFFFFFFu, my_off, l), base = (run0 + l) * kRunRecords;
+            const uint32_t s = BACK ? base + min((uint32_t) kRunRecords, n - base) - 1u - j : base + j;   // internals sit at the back of the run's slots
+            ok[u] = kk < total && s < cap && d[u] < cap;
+            if (ok[u]) {
+                vlo[u] = __ldg(lo + s);
+                vhi[u] = __ldg(hi + s);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (ok[u]) {
+                out.a[d[u]] = vlo[u].x; out.b[d[u]] = vlo[u].y;
+                out.ab[d[u]] = vlo[u].z; out.ae[d[u]] = vlo[u].w;
+                out.bb[d[u]] = vhi[u].x; out.be[d[u]] = vhi[u].y;
+                out.tag[d[u]] = (uint8_t) vhi[u].z;
+            }
+        }
+    }
+}
+#endif
+
 __global__ void __launch_bounds__(kTileThreads) k_relocate_runs(List tmp_a, List out_a, List tmp_b, List out_b, uint32_t cap,
                                                                const uint32_t* __restrict__ run_cnt, const uint32_t* __restrict__ off_a,
-                                                               const uint32_t* __restrict__ off_b, uint32_t num_runs) {
+                                                               const uint32_t* __restrict__ off_b, uint32_t num_runs, uint32_t n) {
     const uint32_t lane = lane_id();
     const uint32_t supers = (num_runs + kRelocRuns - 1) / kRelocRuns;
     for (uint32_t sr = blockIdx.x; sr < supers; sr += gridDim.x) {
@@ -437,8 +518,13 @@ __global__ void __launch_bounds__(kTileThreads) k_relocate_runs(List tmp_a, List
         const uint32_t na = run <= last ? (c & 0xFFFFu) : 0u, nb = run <= last ? (c >> 16) : 0u;
         const uint32_t first_a = __shfl_sync(0xFFFFFFFFu, oa, 0), first_b = __shfl_sync(0xFFFFFFFFu, ob, 0);
         const uint32_t total_a = __shfl_sync(0xFFFFFFFFu, oa + na, 31) - first_a, total_b = __shfl_sync(0xFFFFFFFFu, ob + nb, 31) - first_b;
+#if RB_OPT_AOS
+        relocate_scratch_piece<false, RB_RELOC_UNROLL>(scratch_lo(tmp_a), scratch_hi(tmp_b), out_a, cap, n, run0, oa, first_a, total_a);
+        relocate_scratch_piece<true, 1>(scratch_lo(tmp_a), scratch_hi(tmp_b), out_b, cap, n, run0, ob, first_b, total_b);
+#else
         relocate_piece(tmp_a, out_a, cap, run0, oa, first_a, total_a);
         relocate_piece(tmp_b, out_b, cap, run0, ob, first_b, total_b);
+#endif
     }
 }
 
@@ -720,7 +806,7 @@ void launch_classify_events(Launch& L, List recs, uint32_t n, uint32_t t0, const
                             Events ev, uint32_t ev_cap, uint32_t* vcount, uint32_t* hill_rec, uint32_t hill_cap, uint32_t* counters) {
     if (n == 0) return;
     // 3 blocks / SM at 80 registers: 4 and 5 blocks (64 / 48 registers) lost 15 and 25 us per step (profiles/r02a_ab.json)
-    k_classify_events<3><<<grid_for(n, kRecTile, kNumSMs * 3), kTileThreads, 0, L.stream>>>(recs, n, t0, piles, n_piles, ev, ev_cap, vcount,
+    k_classify_events<RB_EVENTS_MINB, RB_EVENTS_ITEMS><<<grid_for(n, kTileThreads * RB_EVENTS_ITEMS, kNumSMs * RB_EVENTS_MINB), kTileThreads, 0, L.stream>>>(recs, n, t0, piles, n_piles, ev, ev_cap, vcount,
                                                                                           hill_rec, hill_cap, counters);
     L.count++;
 }
@@ -738,7 +824,7 @@ void launch_classify_survivors(Launch& L, List recs, uint32_t n, const uint2* pi
     L.count++;
 #if RB_OPT_RELOC
     k_relocate_runs<<<grid_for(num_runs, kRelocRuns, kNumSMs * 8), kTileThreads, 0, L.stream>>>(tmp_ovl, ovl, tmp_inl, inl, cap, runs.cnt,
-                                                                                               runs.off_a, runs.off_b, num_runs);
+                                                                                               runs.off_a, runs.off_b, num_runs, n);
     L.count++;
 #else
     k_relocate<<<grid_for(cap, 256, kNumSMs * 8), 256, 0, L.stream>>>(tmp_ovl, ovl, cap, runs.off_a, n_ovl, num_runs);
@@ -839,7 +925,7 @@ void preload_classify() {
     cudaFuncAttributes a;
     cudaFuncGetAttributes(&a, k_records_to_soa);
     cudaFuncGetAttributes(&a, k_unpack_records);
-    cudaFuncGetAttributes(&a, k_classify_events<3>);
+    cudaFuncGetAttributes(&a, k_classify_events<RB_EVENTS_MINB, RB_EVENTS_ITEMS>);
     cudaFuncGetAttributes(&a, k_classify_survivors);
     cudaFuncGetAttributes(&a, k_scan_runs);
     cudaFuncGetAttributes(&a, k_relocate_runs);

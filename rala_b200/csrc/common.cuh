@@ -13,6 +13,13 @@
 #ifndef RB_OPT_RELOC
 #define RB_OPT_RELOC 1    // warp-per-run relocation of the survivors
 #endif
+#ifndef RB_OPT_AOS
+#define RB_OPT_AOS 1      // scratch of the survivors pass as 32-byte entries (two 16-byte halves) instead of seven columns
+#endif
+#if !RB_OPT_RELOC
+#undef RB_OPT_AOS
+#define RB_OPT_AOS 0
+#endif
 #ifndef RB_OPT_FILL
 #define RB_OPT_FILL 1     // four independent atomics in flight per thread in the CSR fill
 #endif

@@ -47,7 +47,11 @@ __global__ void __launch_bounds__(kTileThreads) k_node_ids(const uint2* __restri
 
 // Two edges per dovetail overlap, ids 2j / 2j+1 in list order (graph.cpp:576-632), plus the
 // out-degree histogram the CSR build needs.
-__global__ void __launch_bounds__(kTileThreads) k_emit_edges(List ovl, const uint32_t* __restrict__ n_ptr, uint32_t cap,
+#ifndef RB_EMIT_MINB
+#define RB_EMIT_MINB 1
+#endif
+constexpr int kEmitTile = kTileThreads * kEmitItems;
+__global__ void __launch_bounds__(kTileThreads, RB_EMIT_MINB) k_emit_edges(List ovl, const uint32_t* __restrict__ n_ptr, uint32_t cap,
                                                             const uint2* __restrict__ piles,
                                                             const uint32_t* __restrict__ seq_to_node,
                                                             uint32_t* __restrict__ src, uint32_t* __restrict__ dst,
@@ -58,36 +62,36 @@ __global__ void __launch_bounds__(kTileThreads) k_emit_edges(List ovl, const uin
     __shared__ TileShared sh;
     const uint32_t tid = threadIdx.x;
     const uint32_t n = min(*n_ptr, cap);
-    const uint32_t num_tiles = (n + kTile - 1) / kTile;
+    const uint32_t num_tiles = (n + kEmitTile - 1) / kEmitTile;
     while (true) {
         if (tid == 0) sh.tile = atomicAdd(ticket, 1u);
         __syncthreads();
         const uint32_t tile = sh.tile;
         if (tile >= num_tiles) break;
-        int dest[kTileItems];
-        uint32_t e_src[kTileItems], e_dst[kTileItems], e_len[kTileItems], c_len[kTileItems];
+        int dest[kEmitItems];
+        uint32_t e_src[kEmitItems], e_dst[kEmitItems], e_len[kEmitItems], c_len[kEmitItems];
         // all gathers of the thread's four entries are issued before the first one is used: the entry (7 columns), then
         // both piles and both node ids (they only depend on the ids), 16 independent gathers in flight per thread
         // (issuing them entry by entry, behind the liveness test of the entry before, left the kernel at 15 % issue activity)
-        Entry e[kTileItems];
-        bool have[kTileItems];
+        Entry e[kEmitItems];
+        bool have[kEmitItems];
 #pragma unroll
-        for (int r = 0; r < kTileItems; ++r) {
-            const uint32_t idx = tile * kTile + r * kTileThreads + tid;
+        for (int r = 0; r < kEmitItems; ++r) {
+            const uint32_t idx = tile * kEmitTile + r * kTileThreads + tid;
             have[r] = idx < n;
             e[r] = load_entry(ovl, have[r] ? idx : 0u);
         }
-        uint2 pa[kTileItems], pb[kTileItems];
-        uint32_t na[kTileItems], nb[kTileItems];
+        uint2 pa[kEmitItems], pb[kEmitItems];
+        uint32_t na[kEmitItems], nb[kEmitItems];
 #pragma unroll
-        for (int r = 0; r < kTileItems; ++r) {
+        for (int r = 0; r < kEmitItems; ++r) {
             pa[r] = __ldg(piles + e[r].a);
             pb[r] = __ldg(piles + e[r].b);
             na[r] = __ldg(seq_to_node + e[r].a);
             nb[r] = __ldg(seq_to_node + e[r].b);
         }
 #pragma unroll
-        for (int r = 0; r < kTileItems; ++r) {
+        for (int r = 0; r < kEmitItems; ++r) {
             dest[r] = 0;
             Pile A, B;
             A.begin = pa[r].x; A.end = pa[r].y & kEndMask; A.flags = pa[r].y >> 30;
@@ -109,16 +113,16 @@ __global__ void __launch_bounds__(kTileThreads) k_emit_edges(List ovl, const uin
                 }
             }
         }
-        uint32_t pos[kTileItems];
+        uint32_t pos[kEmitItems];
         unsigned long long inclusive = 0;
-        tile_rank<kTileItems>(sh, status, tile, dest, pos, &inclusive);
+        tile_rank<kEmitItems>(sh, status, tile, dest, pos, &inclusive);
         if (tid == 0 && tile == num_tiles - 1) {
             counters[C_DOVETAILS] = count_a(inclusive);
             counters[C_EDGES] = 2u * count_a(inclusive);
             if (2ull * count_a(inclusive) > edge_cap) counters[C_OVERFLOW] = 1u;
         }
 #pragma unroll
-        for (int r = 0; r < kTileItems; ++r) {
+        for (int r = 0; r < kEmitItems; ++r) {
             if (dest[r] && 2ull * pos[r] + 1 < edge_cap) {
                 const uint32_t j = pos[r];
                 // edge 2j = (from -> to), edge 2j+1 = (to^1 -> from^1): one 8-byte store per column
@@ -392,7 +396,7 @@ void launch_node_ids(Launch& L, const uint2* piles, uint32_t n_piles, uint32_t* 
 
 void launch_emit_edges(Launch& L, List ovl, const uint32_t* n_ptr, uint32_t cap, const uint2* piles, GraphArrays g,
                        uint32_t edge_cap, uint32_t* counters, unsigned long long* status, uint32_t* ticket) {
-    k_emit_edges<<<grid_for(cap, kTile, kNumSMs * 8), kTileThreads, 0, L.stream>>>(
+    k_emit_edges<<<grid_for(cap, kEmitTile, kNumSMs * 8), kTileThreads, 0, L.stream>>>(
         ovl, n_ptr, cap, piles, g.seq_to_node, g.src, g.dst, g.len, edge_cap, g.cursor, counters, status, ticket);
     L.count++;
 }

@@ -123,6 +123,12 @@ struct GraphArrays {
 };
 void launch_node_ids(Launch& L, const uint2* piles, uint32_t n_piles, uint32_t* seq_to_node, uint32_t* counters,
                      unsigned long long* status, uint32_t* ticket);
+// entries per thread of k_emit_edges (its tiles are 256 x this); its look-back scan needs one status word per tile
+#ifndef RB_EMIT_ITEMS
+#define RB_EMIT_ITEMS 4
+#endif
+constexpr int kEmitItems = RB_EMIT_ITEMS;
+inline uint64_t emit_scan_span(uint64_t cap) { return cap * (4 / kEmitItems); }   // in units of the common 1024-entry tile
 void launch_emit_edges(Launch& L, List ovl, const uint32_t* n_ptr, uint32_t cap, const uint2* piles, GraphArrays g,
                        uint32_t edge_cap, uint32_t* counters, unsigned long long* status, uint32_t* ticket);
 void launch_pack_edges(Launch& L, cudaStream_t stream, GraphArrays g, uint32_t edge_cap, const uint32_t* n_edges_ptr, uint32_t* out);

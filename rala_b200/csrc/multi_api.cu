@@ -520,7 +520,7 @@ static int phase_f_edges(rala_b200_multi* m, FabricRank& fr) {
     scan_state(g, g->n_piles, &status, &ticket);
     launch_node_ids(L, g->piles.as<uint2>(), g->n_piles, g->seq_to_node.as<uint32_t>(), g->cnt(), status, ticket);
     launch_node_bounds(L, fr.P, fr.A, g->cnt() + C_NODES, fr.meta_dev());
-    scan_state(g, g->cap, &status, &ticket);
+    scan_state(g, emit_scan_span(g->cap), &status, &ticket);
     GraphArrays ga = g->graph_view();
     ga.cursor = nullptr;   // no local degree histogram: the owners count what they receive
     launch_emit_edges(L, g->ovl[g->ovl_cur].view, g->cnt() + g->slot_ovl, g->cap, g->piles.as<uint2>(), ga, g->edge_cap, g->cnt(), status, ticket);
