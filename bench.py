@@ -500,6 +500,9 @@ def run_ab(args):
     piles = ds.flat_piles()
     libs = [("product", api.LIB_PATH, None)] + [(k, B.variant_path(k), None) for k in list(B.VARIANTS) + list(B.TUNINGS)
                                                 if os.path.exists(B.variant_path(k))]
+    if args.variants:
+        keep = set(args.variants.split(","))
+        libs = [l for l in libs if l[0] == "product" or l[0] in keep]
     prev = B.variant_path("prev")   # the previous commit's library, when profiles/capture_ab.sh built it
     if os.path.exists(prev):
         libs.append(("prev", prev, None))
@@ -554,6 +557,7 @@ def main():
     ap.add_argument("--cli", action="store_true", help="time the drop-in CLI against the reference CLI on FASTA + PAF files of the workload")
     ap.add_argument("--devices", default=None, help="--cli: RALA_B200_DEVICES for the drop-in (e.g. 0,1)")
     ap.add_argument("--force-multi", action="store_true", help="run the multi-GPU path even with one rank (under torchrun)")
+    ap.add_argument("--variants", default="", help="with --ab: only these variants (comma separated)")
     ap.add_argument("--ab", action="store_true", help="time the product library against the one-switch-off builds (rala_b200/variants/)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup

@@ -62,8 +62,8 @@ def build(verbose: bool = False, force: bool = False) -> str:
 
 
 # A/B libraries: the product with ONE optimisation switched off each (common.cuh RB_OPT_*), for bench.py --ab.
-VARIANTS = {"no_events": "RB_OPT_EVENTS", "no_reloc": "RB_OPT_RELOC", "no_fill": "RB_OPT_FILL",
-            "no_conc": "RB_OPT_CONC", "no_fuse": "RB_OPT_FUSE"}
+VARIANTS = {"no_events": "RB_OPT_EVENTS", "no_reloc": "RB_OPT_RELOC", "no_aos": "RB_OPT_AOS", "no_fill": "RB_OPT_FILL",
+            "no_rank": "RB_OPT_RANK", "no_conc": "RB_OPT_CONC", "no_fuse": "RB_OPT_FUSE"}
 VARIANT_DIR = os.path.join(HERE, "variants")
 
 
@@ -72,10 +72,7 @@ def variant_path(name: str) -> str:
 
 
 # other settings of a tunable, same product otherwise
-TUNINGS = {"no_packrow": ["-DRB_GROUP_PACKROW=0"], "aos": ["-DRB_OPT_AOS=1"], "aos_u1": ["-DRB_OPT_AOS=1", "-DRB_RELOC_UNROLL=1"],
-           "aos_u3": ["-DRB_OPT_AOS=1", "-DRB_RELOC_UNROLL=3"], "emit2": ["-DRB_EMIT_ITEMS=2"], "emit1": ["-DRB_EMIT_ITEMS=1"],
-           "ev2_4": ["-DRB_EVENTS_ITEMS=2", "-DRB_EVENTS_MINB=4"], "ev2_5": ["-DRB_EVENTS_ITEMS=2", "-DRB_EVENTS_MINB=5"],
-           "ev2_6": ["-DRB_EVENTS_ITEMS=2", "-DRB_EVENTS_MINB=6"]}
+TUNINGS = {"no_packrow": ["-DRB_GROUP_PACKROW=0"]}
 
 
 def build_variants(verbose: bool = False):

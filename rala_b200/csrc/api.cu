@@ -206,6 +206,9 @@ int reserve_edges(rala_b200_graph* g, uint32_t edge_cap) {
     CU(ctx, g->edges.reserve(align_up((size_t) edge_cap * 4, 256) * 3));
     CU(ctx, g->col.reserve((size_t) edge_cap * 8));
     CU(ctx, g->col_eid.reserve((size_t) edge_cap * 4));
+#if RB_OPT_RANK
+    CU(ctx, g->edge_rank.reserve((size_t) edge_cap * 4));
+#endif
     CU(ctx, g->T.reserve(align_up(edge_cap, 256)));
     CU(ctx, g->marked.reserve(align_up(edge_cap, 256)));
     g->heavy_cap = edge_cap / 16 + 4096;
@@ -698,7 +701,7 @@ extern "C" int rala_b200_graph_build(rala_b200_graph* g) {
         g->download_pending = true;
     }
     scan_state(g, (uint64_t) g->n_nodes_max + 1, &status, &ticket);
-    launch_build_csr(ctx->L, g->graph_view(), g->n_nodes_max, g->edge_cap, g->cnt(), status, ticket);
+    launch_build_csr(ctx->L, g->graph_view(), g->n_nodes_max, g->edge_cap, g->cnt(), status, ticket, RB_OPT_RANK != 0);
     if (g->download_pending && !g->in_run) {
         join_side(ctx->L, 0);
         g->download_pending = false;

@@ -109,6 +109,11 @@ __device__ __forceinline__ void load_group(const uint32_t* __restrict__ col, uin
 
 constexpr int kEvStage = 96;   // per-warp staging of events before one aggregated global append
 
+// Tried and measured (profiles/r02ac_ab.json): staging the record tiles in shared memory with bulk copies (cp.async.bulk +
+// mbarrier, 2 .. 4 tiles deep) made this kernel SLOWER, 126 .. 172 us against 109 us: it is bound by the integer ALU pipe
+// (65 % of its peak at 57 % issue activity, profiles/r02v), not by load latency, and the block-wide hand-over of a stage
+// keeps the eight warps of a block in step.  A software prefetch of the next trip's lines into L2 changed nothing; two
+// records per thread at 4 .. 6 blocks per SM lost 6 .. 15 us (profiles/r02aa_ab.json).
 template <int MINB, int R>
 __global__ void __launch_bounds__(kTileThreads, MINB) k_classify_events(
     List recs, uint32_t n, uint32_t t0, const uint2* __restrict__ piles, uint32_t n_piles,
@@ -237,7 +242,16 @@ __device__ __forceinline__ uint4* scratch_hi(const List& spare_inl) { return rei
 //      warp scan ranks all four 128-record groups at once: one byte per group, each <= 128);
 //   2. trim + type run over the queue with (almost) every lane busy, instead of sixteen times over mostly idle
 //      warps (the first version of this kernel executed 12 of 32 lanes per instruction, profiles/r01f).
-__global__ void __launch_bounds__(kTileThreads) k_classify_survivors(
+// 5 resident blocks per SM (48 registers, 28 bytes of spill) and a grid of two waves: survivors stage 83 us against 91 us at
+// 4 resident blocks (64 registers); one persistent wave loses 15 us, 6 resident blocks spill 104 bytes and win nothing
+// (profiles/r02ae_ab.json, r02af_ab.json)
+#ifndef RB_SURV_MINB
+#define RB_SURV_MINB 5
+#endif
+#ifndef RB_SURV_BLOCKS
+#define RB_SURV_BLOCKS 10   // grid = this many blocks per SM at most
+#endif
+__global__ void __launch_bounds__(kTileThreads, RB_SURV_MINB) k_classify_survivors(
     List recs, uint32_t n, const uint2* __restrict__ piles, const uint32_t* __restrict__ alive_bits, uint32_t n_piles,
     List tmp_ovl, List tmp_inl, uint32_t cap, uint32_t* __restrict__ run_cnt) {
     __shared__ uint16_t s_queue[kTileWarps][kRunRecords];
@@ -816,7 +830,7 @@ void launch_classify_survivors(Launch& L, List recs, uint32_t n, const uint2* pi
                                RunBufs runs, unsigned long long* status, uint32_t* ticket) {
     if (n == 0) return;   // n_ovl / n_inl were zeroed by the caller
     const uint32_t num_runs = (n + kRunRecords - 1) / kRunRecords;
-    k_classify_survivors<<<grid_for(num_runs, kTileWarps, kNumSMs * 8), kTileThreads, 0, L.stream>>>(
+    k_classify_survivors<<<grid_for(num_runs, kTileWarps, kNumSMs * RB_SURV_BLOCKS), kTileThreads, 0, L.stream>>>(
         recs, n, piles, alive_bits, n_piles, tmp_ovl, tmp_inl, cap, runs.cnt);
     L.count++;
     k_scan_runs<<<grid_for(num_runs, kTile, kNumSMs * 4), kTileThreads, 0, L.stream>>>(runs.cnt, num_runs, runs.off_a, runs.off_b, n_ovl,

@@ -20,6 +20,9 @@
 #undef RB_OPT_AOS
 #define RB_OPT_AOS 0
 #endif
+#ifndef RB_OPT_RANK
+#define RB_OPT_RANK 1     // the degree count in k_emit_edges hands every edge its row slot: no atomics left in the CSR fill
+#endif
 #ifndef RB_OPT_FILL
 #define RB_OPT_FILL 1     // four independent atomics in flight per thread in the CSR fill
 #endif

@@ -47,16 +47,14 @@ __global__ void __launch_bounds__(kTileThreads) k_node_ids(const uint2* __restri
 
 // Two edges per dovetail overlap, ids 2j / 2j+1 in list order (graph.cpp:576-632), plus the
 // out-degree histogram the CSR build needs.
-#ifndef RB_EMIT_MINB
-#define RB_EMIT_MINB 1
-#endif
 constexpr int kEmitTile = kTileThreads * kEmitItems;
-__global__ void __launch_bounds__(kTileThreads, RB_EMIT_MINB) k_emit_edges(List ovl, const uint32_t* __restrict__ n_ptr, uint32_t cap,
+__global__ void __launch_bounds__(kTileThreads) k_emit_edges(List ovl, const uint32_t* __restrict__ n_ptr, uint32_t cap,
                                                             const uint2* __restrict__ piles,
                                                             const uint32_t* __restrict__ seq_to_node,
                                                             uint32_t* __restrict__ src, uint32_t* __restrict__ dst,
                                                             uint32_t* __restrict__ len, uint32_t edge_cap,
-                                                            uint32_t* __restrict__ degree, uint32_t* __restrict__ counters,
+                                                            uint32_t* __restrict__ degree, uint32_t* __restrict__ rank,
+                                                            uint32_t* __restrict__ counters,
                                                             unsigned long long* __restrict__ status,
                                                             uint32_t* __restrict__ ticket) {
     __shared__ TileShared sh;
@@ -130,8 +128,10 @@ __global__ void __launch_bounds__(kTileThreads, RB_EMIT_MINB) k_emit_edges(List 
                 reinterpret_cast<uint2*>(dst)[j] = make_uint2(e_dst[r], e_src[r] ^ 1u);
                 reinterpret_cast<uint2*>(len)[j] = make_uint2(e_len[r], c_len[r]);
                 if (degree) {   // nullptr: the edges are routed to the owners of their source nodes, who count them
-                    atomicAdd(&degree[e_src[r]], 1u);
-                    atomicAdd(&degree[e_dst[r] ^ 1u], 1u);
+                    const uint32_t r0 = atomicAdd(&degree[e_src[r]], 1u);
+                    const uint32_t r1 = atomicAdd(&degree[e_dst[r] ^ 1u], 1u);
+                    // the count an edge found is its slot inside its row (any order of a row is as good as another)
+                    if (rank) reinterpret_cast<uint2*>(rank)[j] = make_uint2(r0, r1);
                 }
             }
         }
@@ -205,10 +205,17 @@ __global__ void __launch_bounds__(kTileThreads) k_scan_degrees(uint32_t* __restr
 // Also clears the per-edge "transitive test passed" bytes T[0 .. n rounded up to 16) for the pass that follows
 // (k_finalize_marks reads whole 16-byte groups): a memset of the buffer's CAPACITY (2 x the record count) would
 // write ~15 x more bytes than there are edges.
+// eight edges in flight per thread, or twice the blocks, changed nothing (profiles/r02ab_ab.json)
+#ifndef RB_FILL_INFLIGHT
+#define RB_FILL_INFLIGHT 4
+#endif
+#ifndef RB_FILL_BLOCKS
+#define RB_FILL_BLOCKS 8   // per SM
+#endif
 __global__ void k_fill_csr(const uint32_t* __restrict__ src, const uint32_t* __restrict__ dst,
                            const uint32_t* __restrict__ len, const uint32_t* __restrict__ n_edges_ptr, uint32_t edge_cap,
                            uint32_t* __restrict__ cursor, uint2* __restrict__ col, uint32_t* __restrict__ col_eid,
-                           uint8_t* __restrict__ T) {
+                           uint8_t* __restrict__ T, const uint32_t* __restrict__ rank, const uint32_t* __restrict__ row_ptr) {
     const uint32_t n = min(*n_edges_ptr, edge_cap);
     {
         const uint32_t n16 = (n + 15u) / 16u;   // T is padded to a multiple of 256 bytes
@@ -218,18 +225,28 @@ __global__ void k_fill_csr(const uint32_t* __restrict__ src, const uint32_t* __r
 #if RB_OPT_FILL
     // load -> returning atomic -> store is a chain of three dependent round trips: keep four edges of it in flight
     const uint32_t stride = gridDim.x * blockDim.x;
-    for (uint32_t e0 = blockIdx.x * blockDim.x + threadIdx.x; e0 < n; e0 += 4u * stride) {
-        uint32_t s[4], d[4], l[4], p[4];
+    constexpr int F = RB_FILL_INFLIGHT;
+    for (uint32_t e0 = blockIdx.x * blockDim.x + threadIdx.x; e0 < n; e0 += F * stride) {
+        uint32_t s[F], d[F], l[F], p[F];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
+        for (int k = 0; k < F; ++k) {
             const uint32_t e = e0 + k * stride;
             if (e < n) { s[k] = src[e]; d[k] = dst[e]; l[k] = len[e]; }
         }
+        if (rank) {   // slots were handed out while the degrees were counted: a gather instead of a returning atomic
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-            if (e0 + k * stride < n) p[k] = atomicAdd(&cursor[s[k]], 1u);
+            for (int k = 0; k < F; ++k)
+                if (e0 + k * stride < n) p[k] = rank[e0 + k * stride];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
+            for (int k = 0; k < F; ++k)
+                if (e0 + k * stride < n) p[k] += row_ptr[s[k]];
+        } else {
+#pragma unroll
+            for (int k = 0; k < F; ++k)
+                if (e0 + k * stride < n) p[k] = atomicAdd(&cursor[s[k]], 1u);
+        }
+#pragma unroll
+        for (int k = 0; k < F; ++k) {
             const uint32_t e = e0 + k * stride;
             if (e < n) {
                 col[p[k]] = make_uint2(d[k], l[k]);
@@ -397,7 +414,7 @@ void launch_node_ids(Launch& L, const uint2* piles, uint32_t n_piles, uint32_t* 
 void launch_emit_edges(Launch& L, List ovl, const uint32_t* n_ptr, uint32_t cap, const uint2* piles, GraphArrays g,
                        uint32_t edge_cap, uint32_t* counters, unsigned long long* status, uint32_t* ticket) {
     k_emit_edges<<<grid_for(cap, kEmitTile, kNumSMs * 8), kTileThreads, 0, L.stream>>>(
-        ovl, n_ptr, cap, piles, g.seq_to_node, g.src, g.dst, g.len, edge_cap, g.cursor, counters, status, ticket);
+        ovl, n_ptr, cap, piles, g.seq_to_node, g.src, g.dst, g.len, edge_cap, g.cursor, RB_OPT_RANK ? g.rank : nullptr, counters, status, ticket);
     L.count++;
 }
 
@@ -438,13 +455,14 @@ void launch_scan_u32(Launch& L, uint32_t* values_inout, uint32_t* exclusive_out,
 }
 
 void launch_build_csr(Launch& L, GraphArrays g, uint32_t n_nodes_max, uint32_t edge_cap, uint32_t* counters,
-                      unsigned long long* status, uint32_t* ticket) {
+                      unsigned long long* status, uint32_t* ticket, bool ranked) {
     // row_ptr has n_nodes_max + 1 entries; degrees beyond the live node count are zero
     k_scan_degrees<<<grid_for(n_nodes_max + 1, kTile, kNumSMs * 8), kTileThreads, 0, L.stream>>>(
         g.cursor, g.row_ptr, n_nodes_max + 1, status, ticket, nullptr, nullptr, counters + C_NODES);
     L.count++;
-    k_fill_csr<<<grid_for(edge_cap, 256, kNumSMs * 8), 256, 0, L.stream>>>(g.src, g.dst, g.len, counters + C_EDGES,
-                                                                            edge_cap, g.cursor, g.col, g.col_eid, g.T);
+    k_fill_csr<<<grid_for(edge_cap, 256, kNumSMs * RB_FILL_BLOCKS), 256, 0, L.stream>>>(g.src, g.dst, g.len, counters + C_EDGES,
+                                                                            edge_cap, g.cursor, g.col, g.col_eid, g.T,
+                                                                            ranked ? g.rank : nullptr, g.row_ptr);
     L.count++;
 }
 

@@ -118,12 +118,14 @@ struct GraphArrays {
     uint32_t* cursor;        // n_nodes_max + 1 (degree histogram, then fill cursor)
     uint2* col;              // CSR (dst, len)
     uint32_t* col_eid;       // CSR edge id
+    uint32_t* rank;          // per edge: its position inside its source row, as handed out by the degree count in k_emit_edges
     uint8_t* T;              // per edge: transitive test passed
     uint8_t* marked;         // per edge: removed
 };
 void launch_node_ids(Launch& L, const uint2* piles, uint32_t n_piles, uint32_t* seq_to_node, uint32_t* counters,
                      unsigned long long* status, uint32_t* ticket);
-// entries per thread of k_emit_edges (its tiles are 256 x this); its look-back scan needs one status word per tile
+// entries per thread of k_emit_edges (its tiles are 256 x this); its look-back scan needs one status word per tile.
+// 2 and 1 (more, smaller tiles: a longer look-back chain) measured no faster than 4 (profiles/r02aa_ab.json).
 #ifndef RB_EMIT_ITEMS
 #define RB_EMIT_ITEMS 4
 #endif
@@ -144,7 +146,7 @@ void launch_adjacency_view(Launch& L, const uint32_t* key, const uint8_t* marked
                            uint32_t n_nodes, uint32_t* degree_cursor, uint32_t* row_ptr, uint32_t* ids_tmp, uint32_t* ids_sorted,
                            unsigned long long* status, uint32_t* ticket);
 void launch_build_csr(Launch& L, GraphArrays g, uint32_t n_nodes_max, uint32_t edge_cap, uint32_t* counters,
-                      unsigned long long* status, uint32_t* ticket);
+                      unsigned long long* status, uint32_t* ticket, bool ranked = false);
 
 // transitive.cu
 struct HeavyItems {

@@ -125,7 +125,12 @@ struct GroupSmem {
     uint32_t hit;                            // bit j: the edge at sorted position j passed the test
 };
 
-__global__ void __launch_bounds__(kLightWarps * 32, 6) k_transitive_group(
+// resident blocks per SM: 6 (40 registers) is a sharp optimum: 115 us, against 134 us at 4 or 5 and 148 us at 7 or 8
+// (profiles/r02ab_ab.json, r02ad_ab.json): the kernel lives on its shared-memory / L1 data path (69 % of peak)
+#ifndef RB_GROUP_MINB
+#define RB_GROUP_MINB 6
+#endif
+__global__ void __launch_bounds__(kLightWarps * 32, RB_GROUP_MINB) k_transitive_group(
     const uint32_t* __restrict__ row_ptr, const uint2* __restrict__ col, const uint32_t* __restrict__ col_eid,
     uint8_t* __restrict__ T, uint32_t node_begin, uint32_t node_end, const uint32_t* __restrict__ node_range,
     const uint32_t* __restrict__ n_nodes_ptr, uint32_t* __restrict__ work_counter, HeavyItems heavy,
