@@ -98,6 +98,16 @@ int rala_b200_trim_classify(rala_b200_ctx* ctx, rala_ovl_t* ovl, uint64_t n,
 int rala_b200_transitive_reduce(rala_b200_ctx* ctx, uint32_t n_nodes, uint64_t n_edges,
                                 const rala_edge_t* edges, uint8_t* marked_out, uint64_t* n_pairs);
 
+/* The duplicate filter of the front end: Graph::initialize's remove_duplicate_overlaps (graph.cpp:273-303) as driven by
+ * the grouping loop (:340-361), for n records in file order.  a_id[i] with bit 31 set (RALA_OVL_INVALID) = the record's
+ * names did not resolve (the reference holds nullptr: skipped wherever it stands); bit 31 of b_id[i] (orientation) is
+ * ignored; length[i] = Overlap::length() as parsed (PAF column 11, MHAP: the longer span).  valid_out[i] = what
+ * is_valid_overlap_[i] holds after the pass: 0 for unresolved records, self overlaps and every record of a query group but
+ * the last longest one per target.  device_ms (nullable) receives the kernel time.  SURVEY.md 8(f) row 1, first half; the
+ * coverage accumulation of the same pass (:305-321, pile.cpp:274-297) stays host code. */
+int rala_b200_filter_duplicates(rala_b200_ctx* ctx, const uint32_t* a_id, const uint32_t* b_id, const uint32_t* length,
+                                uint64_t n, uint8_t* valid_out, float* device_ms);
+
 /* ------------------------------------------------------------------------------------------------
  * Graph session: the drop-in for Graph::construct's hot loops and Graph::remove_transitive_edges.
  * Call order (what the patched Graph::construct does):

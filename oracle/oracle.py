@@ -200,6 +200,14 @@ def adjacency(n_nodes: int, edges, marked=None, which: int = 0):
 REF_BIN = os.path.join(_HERE, "_ref", "rala_ref")
 
 
+def filter_duplicates(a, b, length):
+    """is_valid_overlap_ after Graph::initialize's overlap pass (graph.cpp:273-303); a with bit 31 = unknown record."""
+    a, b, length = _u32(a), _u32(b), _u32(length)
+    valid = np.zeros(a.shape[0], dtype=np.uint8)
+    lib().ora_filter_duplicates(_p(a), _p(b), _p(length), C.c_uint64(a.shape[0]), _p(valid, C.c_uint8))
+    return valid
+
+
 def have_ref() -> bool:
     return os.path.exists(REF_BIN) and os.access(REF_BIN, os.X_OK)
 

@@ -325,3 +325,48 @@ void ora_adjacency(uint32_t n_nodes, uint64_t n_edges, const uint32_t* edges, co
                    uint32_t* off, uint32_t* ids) {
     build_suffix(n_nodes, n_edges, edges, which ? 1 : 0, marked, off, ids);
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * Front end, duplicate filter (first half): Graph::initialize, graph.cpp:273-303, driven by the
+ * grouping loop :340-361.  Literal restatement: the same loops, the same `break`, records that lost their validity keep
+ * acting on later ones (the reference only skips records whose transmute failed, i.e. nullptr).
+ * a[i] with bit 31 set = overlaps[i] == nullptr.  Parity pinned: tests/golden/dups.npz holds is_valid_overlap_ of the
+ * compiled reference for the same records (rala_ref dupfilter).
+ * ---------------------------------------------------------------------------------------------- */
+static void remove_duplicate_overlaps(const uint32_t* a, const uint32_t* b, const uint32_t* len, uint64_t begin, uint64_t end,
+                                      uint8_t* valid) {
+    for (uint64_t i = begin; i < end; ++i) {                                            /* :274 */
+        if (a[i] & 0x80000000u) continue;                                               /* :275 nullptr */
+        if (a[i] == (b[i] & 0x7FFFFFFFu)) {                                             /* :278 self overlap */
+            valid[i] = 0;                                                               /* :286 */
+            continue;
+        }
+        for (uint64_t j = i + 1; j < end; ++j) {                                        /* :290 */
+            if (a[j] & 0x80000000u) continue;
+            if ((b[i] & 0x7FFFFFFFu) != (b[j] & 0x7FFFFFFFu)) continue;                 /* :294 */
+            if (len[i] > len[j]) {                                                      /* :299 */
+                valid[j] = 0;
+            } else {
+                valid[i] = 0;
+                break;
+            }
+        }
+    }
+}
+
+void ora_filter_duplicates(const uint32_t* a, const uint32_t* b, const uint32_t* len, uint64_t n, uint8_t* valid) {
+    uint64_t c = 0;
+    for (uint64_t i = 0; i < n; ++i) valid[i] = 1;                                      /* :335 resize(..., true) */
+    for (uint64_t i = 0; i < n; ++i) {
+        if (a[i] & 0x80000000u) {                                                       /* :339-343 transmute failed */
+            valid[i] = 0;
+            continue;
+        }
+        while (a[c] & 0x80000000u) ++c;                                                 /* :345-347 */
+        if (a[c] != a[i]) {                                                             /* :348 */
+            remove_duplicate_overlaps(a, b, len, c, i, valid);
+            c = i;
+        }
+    }
+    remove_duplicate_overlaps(a, b, len, c, n, valid);                                  /* :354-356 */
+}

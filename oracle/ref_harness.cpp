@@ -662,11 +662,46 @@ int mode_transitive(int argc, char** argv) {
     return 0;
 }
 
+// The duplicate filter of the reference's front end (Graph::initialize, graph.cpp:273-303, run by :328-371): run the
+// reference's own initialize() on <reads> + <ovl>, then write one row per overlap record of the file, in file order:
+//   a_id b_id length known valid      (u32 each; ids 0xFFFFFFFF and known = 0 when a name is not in <reads>)
+// `length` is Overlap::length() as parsed (PAF column 11 / MHAP max span), `valid` is is_valid_overlap_[i].
+int mode_dupfilter(int argc, char** argv) {
+    if (argc < 5) { fprintf(stderr, "usage: rala_ref dupfilter <reads> <ovl> <out.u32> [threads]\n"); return 2; }
+    std::string reads = argv[2], ovl = argv[3], out = argv[4];
+    uint32_t threads = argc > 5 ? atoi(argv[5]) : 1;
+    auto gi = make_graph(reads, ovl, threads);
+    auto t0 = Clock::now();
+    gi->initialize();
+    double t_init = seconds_since(t0);
+    OvlVec all;
+    gi->oparser_->reset();
+    gi->oparser_->parse_objects(all, -1);
+    std::vector<uint32_t> rows;
+    rows.reserve(all.size() * 5);
+    uint64_t n_valid = 0;
+    for (uint64_t i = 0; i < all.size(); ++i) {
+        auto& o = *all[i];
+        bool known = true;
+        uint32_t a = 0xFFFFFFFFu, b = 0xFFFFFFFFu;
+        auto fa = gi->name_to_id_.find(o.a_name_);
+        auto fb = gi->name_to_id_.find(o.b_name_);
+        if (fa == gi->name_to_id_.end() || fb == gi->name_to_id_.end()) known = false;
+        if (known) { a = static_cast<uint32_t>(fa->second); b = static_cast<uint32_t>(fb->second); }
+        const bool valid = gi->is_valid_overlap_[i];
+        n_valid += valid;
+        rows.push_back(a); rows.push_back(b); rows.push_back(o.length()); rows.push_back(known ? 1u : 0u); rows.push_back(valid ? 1u : 0u);
+    }
+    write_u32(out, rows);
+    printf("{\"mode\": \"dupfilter\", \"records\": %lu, \"valid\": %lu, \"t_initialize\": %.6f}\n", all.size(), n_valid, t_init);
+    return 0;
+}
+
 }  // namespace
 
 int main(int argc, char** argv) {
     if (argc < 2) {
-        fprintf(stderr, "usage: rala_ref dump|hotpath|transitive|trimtype|comparable ...\n");
+        fprintf(stderr, "usage: rala_ref dump|hotpath|transitive|trimtype|comparable|dupfilter ...\n");
         return 2;
     }
     std::string mode = argv[1];
@@ -675,6 +710,7 @@ int main(int argc, char** argv) {
     if (mode == "transitive") return mode_transitive(argc, argv);
     if (mode == "trimtype") return mode_trimtype();
     if (mode == "comparable") return mode_comparable();
+    if (mode == "dupfilter") return mode_dupfilter(argc, argv);
     fprintf(stderr, "[rala_ref] unknown mode %s\n", mode.c_str());
     return 2;
 }

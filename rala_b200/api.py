@@ -43,7 +43,7 @@ class Counts(C.Structure):
 EXPORTS = [
     "rala_b200_abi_version", "rala_b200_create", "rala_b200_destroy", "rala_b200_last_error",
     "rala_b200_launch_count", "rala_b200_event_record", "rala_b200_event_elapsed_ms", "rala_b200_synchronize",
-    "rala_b200_trim_classify", "rala_b200_transitive_reduce",
+    "rala_b200_trim_classify", "rala_b200_transitive_reduce", "rala_b200_filter_duplicates",
     "rala_b200_graph_create", "rala_b200_graph_destroy", "rala_b200_graph_set_overlaps",
     "rala_b200_graph_set_piles", "rala_b200_graph_set_hills", "rala_b200_graph_classify",
     "rala_b200_graph_retrim", "rala_b200_graph_retrim_promote", "rala_b200_graph_finalize",
@@ -247,6 +247,18 @@ class Context:
         self.check(self.lib.rala_b200_transitive_reduce(self.handle, C.c_uint32(n_nodes), C.c_uint64(edges.shape[0]),
                                                         _ptr(edges), _ptr(marked), C.byref(n_pairs)), "transitive_reduce")
         return marked, int(n_pairs.value)
+
+    def filter_duplicates(self, a_id, b_id, length, with_time: bool = False):
+        """Graph::initialize's duplicate filter (graph.cpp:273-303, grouping :340-361) -> is_valid_overlap_ as bytes.
+        a_id with bit 31 set = unresolved record; length = Overlap::length() as parsed."""
+        a, b, ln = _np(a_id, np.uint32), _np(b_id, np.uint32), _np(length, np.uint32)
+        if not (a.shape == b.shape == ln.shape):
+            raise ValueError("filter_duplicates: the three columns must have one length")
+        valid = np.zeros(a.shape[0], dtype=np.uint8)
+        ms = C.c_float(0.0)
+        self.check(self.lib.rala_b200_filter_duplicates(self.handle, _ptr(a), _ptr(b), _ptr(ln), C.c_uint64(a.shape[0]),
+                                                        _ptr(valid), C.byref(ms)), "filter_duplicates")
+        return (valid, float(ms.value)) if with_time else valid
 
 
 class Graph:

@@ -14,7 +14,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "librala_b200.so")
-SOURCES = ["classify.cu", "containment.cu", "graph_build.cu", "transitive.cu", "api.cu", "fabric.cu", "multi_api.cu"]
+SOURCES = ["classify.cu", "containment.cu", "graph_build.cu", "transitive.cu", "api.cu", "fabric.cu", "multi_api.cu", "frontend.cu"]
 HEADERS = ["common.cuh", "lists.cuh", "kernels.h", "session.h", "fabric.cuh", os.path.join("..", "..", "include", "rala_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]

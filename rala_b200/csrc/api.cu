@@ -36,6 +36,7 @@ extern "C" int rala_b200_create(rala_b200_ctx** out, int device) {
     preload_graph_build();
     preload_transitive();
     preload_fabric();
+    preload_frontend();
     cudaGetLastError();
     cudaEventCreate(&ctx->ev[0]);
     cudaEventCreate(&ctx->ev[1]);

@@ -39,7 +39,6 @@ namespace rb {
 #endif
 constexpr int kRecItems = 4;                              // consecutive records per thread (one uint4 per column)
 constexpr int kRecTile = kTileThreads * kRecItems;        // records per block iteration
-constexpr uint32_t kInvalidBit = 0x80000000u;             // in column a
 constexpr uint32_t kRunRecords = 512;                     // survivors pass: records per warp iteration = one run
 constexpr int kRunGroups = kRunRecords / 128;             // 128-record groups per run (one 16-byte load per column, lane and group)
 

@@ -40,6 +40,7 @@ namespace rb {
 
 constexpr uint32_t kInf = 0xFFFFFFFFu;         // "never dies" death time
 constexpr uint32_t kEndMask = 0x3FFFFFFFu;     // pile.y = end | flags << 30
+constexpr uint32_t kInvalidBit = 0x80000000u;  // in the a_id column of the device records: is_valid_overlap_ false / transmute failed
 constexpr int kNumSMs = 148;
 
 enum : uint8_t { kX = 0, kA = 1, kB = 2, kAB = 3, kBA = 4, kRejected = 255 };
@@ -193,6 +194,40 @@ __host__ __device__ __forceinline__ uint2 comparable_interval(uint32_t b) {
     unsigned long long hi = (unsigned long long) b * 25ull / 22ull;
     if (hi > 0xFFFFFFFFull) hi = 0xFFFFFFFFull;
     return make_uint2((uint32_t) lo, (uint32_t) (hi - lo));   // lo <= b <= hi always
+}
+
+// ---------------------------------------------------------------------------------------------
+// Front end: the duplicate filter of Graph::initialize (graph.cpp:273-303, grouping loop :340-361).
+// A query group = a maximal run of records with the same a_id among the records whose names resolved (bit 31 of a[i]
+// set = the reference holds nullptr there: such records are skipped wherever they stand, also inside a group).  The
+// reference's nested loop (every record of a group, valid or not, knocks out the later records with the same b_id that
+// are shorter, and stops - knocked out itself - at the first one that is not) leaves exactly ONE record per (group,
+// b_id): the LAST one of maximal length().  Hence record k survives iff no later record of its group with the same b_id
+// is at least as long and no earlier one is longer.  (Why the earlier clause needs no "reaches k" condition: take the last
+// earlier record that is longer than k; everything between it and k is no longer than k, so nothing stopped it.)
+// Self overlaps (a_id == b_id) are dropped and knock out nobody (:278-288).  tests/host_dupfilter.cu checks this function
+// against the oracle's literal restatement of the loops on the CPU; tests/golden/dups.npz pins both to the reference.
+// ---------------------------------------------------------------------------------------------
+__host__ __device__ __forceinline__ bool duplicate_filter_keeps(const uint32_t* __restrict__ a, const uint32_t* __restrict__ b,
+                                                                const uint32_t* __restrict__ len, uint64_t n, uint64_t k) {
+    const uint32_t ak = a[k];
+    if (ak & kInvalidBit) return false;
+    const uint32_t bk = b[k] & 0x7FFFFFFFu;
+    if (ak == bk) return false;
+    const uint32_t lk = len[k];
+    for (uint64_t j = k + 1; j < n; ++j) {
+        const uint32_t aj = a[j];
+        if (aj & kInvalidBit) continue;
+        if (aj != ak) break;
+        if ((b[j] & 0x7FFFFFFFu) == bk && len[j] >= lk) return false;
+    }
+    for (uint64_t j = k; j-- > 0;) {
+        const uint32_t aj = a[j];
+        if (aj & kInvalidBit) continue;
+        if (aj != ak) break;
+        if ((b[j] & 0x7FFFFFFFu) == bk && len[j] > lk) return false;
+    }
+    return true;
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -167,5 +167,9 @@ void preload_containment();
 void preload_graph_build();
 void preload_transitive();
 void preload_fabric();
+void preload_frontend();
+
+// frontend.cu
+void launch_filter_duplicates(Launch& L, const uint32_t* a, const uint32_t* b, const uint32_t* len, uint32_t n, uint8_t* valid);
 
 }  // namespace rb

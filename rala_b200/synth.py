@@ -313,3 +313,76 @@ def generate_repeat_hubs(genome_len: int = 20_000_000, coverage: float = 30, rea
     read_len_out = np.concatenate([base.read_len, np.full(next_id - n0, L, dtype=np.uint32)])
     return Dataset(read_len=read_len_out, records=np.ascontiguousarray(rec), genome_len=genome_len,
                    meta=dict(base.meta, n_hubs=n_hubs, spokes=spokes, chain=chain, first_hub=n0))
+
+
+# ---------------------------------------------------------------------------------------------
+# Input of the front end's duplicate filter (Graph::initialize, graph.cpp:273-303): query groups in which the same
+# target shows up several times (repeats), with ties in the alignment length, self overlaps, records whose names are
+# not in the read set (they are skipped INSIDE a group) and queries that come back in a later group.
+# ---------------------------------------------------------------------------------------------
+@dataclass
+class DuplicateGroups:
+    read_len: np.ndarray      # (n_reads,) uint32
+    a: np.ndarray             # (n,) int64, -1 = name not in the read set
+    b: np.ndarray             # (n,) int64, -1 likewise
+    coords: np.ndarray        # (n, 4) uint32: a_begin a_end b_begin b_end
+    ori: np.ndarray           # (n,) uint8
+    length: np.ndarray        # (n,) uint32: PAF column 11, what Overlap::length() returns before any trimming
+
+    @property
+    def n(self) -> int:
+        return int(self.a.shape[0])
+
+    def columns(self):
+        """(a_id with RALA_INVALID_BIT for unknown records, b_id, length) as the device filter takes them."""
+        known = (self.a >= 0) & (self.b >= 0)
+        a = np.where(known, self.a, 0x80000000).astype(np.uint32)
+        b = np.where(known, self.b, 0).astype(np.uint32)
+        return a, b, self.length.astype(np.uint32)
+
+    def write_fasta(self, path: str, seed: int = 7) -> None:
+        Dataset(self.read_len, np.zeros((0, 7), np.uint32), 0).write_fasta(path, seed)
+
+    def write_paf(self, path: str) -> None:
+        ln = self.read_len
+        with open(path, "w") as f:
+            for i in range(self.n):
+                a, b = int(self.a[i]), int(self.b[i])
+                an, la = ("r%d" % a, int(ln[a])) if a >= 0 else ("ghost%d" % i, 9000)
+                bn, lb = ("r%d" % b, int(ln[b])) if b >= 0 else ("ghost%d" % i, 9000)
+                c = self.coords[i]
+                f.write("%s\t%d\t%d\t%d\t%s\t%s\t%d\t%d\t%d\t%d\t%d\t255\n" % (
+                    an, la, c[0], c[1], "-" if self.ori[i] else "+", bn, lb, c[2], c[3], int(self.length[i]) // 2, int(self.length[i])))
+
+
+def generate_duplicate_groups(n_reads: int = 300, n_groups: int = 500, max_group: int = 40, pool: int = 6, big_groups: int = 0,
+                              big_size: int = 3000, ghost_frac: float = 0.03, self_frac: float = 0.03, seed: int = 11) -> DuplicateGroups:
+    rng = np.random.Generator(np.random.PCG64(seed))
+    read_len = rng.integers(4000, 12000, n_reads).astype(np.uint32)
+    A, B, C, O, L = [], [], [], [], []
+    sizes = rng.integers(1, max_group + 1, n_groups).tolist()
+    for k in rng.choice(n_groups, size=min(big_groups, n_groups), replace=False).tolist():
+        sizes[k] = big_size
+    prev_a = -1
+    for g in sizes:
+        a = int(rng.integers(0, n_reads))
+        while a == prev_a:           # two groups in a row with the same query would be ONE group for the reference
+            a = int(rng.integers(0, n_reads))
+        prev_a = a
+        targets = rng.choice(n_reads, size=min(pool, n_reads), replace=False)
+        base = int(rng.integers(300, 3000))
+        for _ in range(g):
+            b = int(targets[rng.integers(0, len(targets))])
+            if rng.random() < self_frac:
+                b = a
+            ghost = rng.random() < ghost_frac
+            la, lb = int(read_len[a]), int(read_len[b])
+            span = int(rng.integers(200, min(la, lb) - 100))
+            ab = int(rng.integers(0, la - span)); bb = int(rng.integers(0, lb - span))
+            A.append(-1 if ghost and rng.random() < 0.5 else a)
+            B.append(-1 if ghost and A[-1] >= 0 else b)
+            C.append((ab, ab + span, bb, bb + span))
+            O.append(int(rng.integers(0, 2)))
+            L.append(base + int(rng.integers(0, 4)))   # few distinct lengths: ties are common
+    return DuplicateGroups(read_len, np.asarray(A, np.int64), np.asarray(B, np.int64), np.asarray(C, np.uint32),
+                           np.asarray(O, np.uint8), np.asarray(L, np.uint32))

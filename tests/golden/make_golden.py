@@ -132,9 +132,31 @@ def injected_graphs(tmp: str) -> dict:
     return out
 
 
+def duplicate_filter_vectors(tmp: str) -> dict:
+    """is_valid_overlap_ of the reference's own Graph::initialize (graph.cpp:273-303, :340-361) on query groups full of
+    repeated targets, length ties, self overlaps, unresolved names and one 1 500-record group (rala_ref dupfilter)."""
+    d = synth.generate_duplicate_groups(big_groups=1, big_size=1500)
+    d.write_fasta(os.path.join(tmp, "dups.fasta"))
+    d.write_paf(os.path.join(tmp, "dups.paf"))
+    out = os.path.join(tmp, "dups.u32")
+    summ = json.loads(O.ref_run(["dupfilter", os.path.join(tmp, "dups.fasta"), os.path.join(tmp, "dups.paf"), out, 4]).strip().splitlines()[-1])
+    rows = np.fromfile(out, dtype=np.uint32).reshape(-1, 5)
+    assert rows.shape[0] == d.n == summ["records"]
+    a, b, ln = d.columns()
+    known = rows[:, 3] == 1
+    assert np.array_equal(known, (a & 0x80000000) == 0) and np.array_equal(rows[known, 0], a[known])
+    assert np.array_equal(rows[known, 1], b[known]) and np.array_equal(rows[:, 2], ln)
+    return {"a": a, "b": b, "length": ln, "valid": rows[:, 4].astype(np.uint8)}
+
+
 def main():
     assert O.have_ref(), "build oracle/_ref first: make -C oracle"
     with tempfile.TemporaryDirectory() as tmp:
+        if "--dups-only" in sys.argv:
+            np.savez_compressed(os.path.join(datasets.GOLDEN_DIR, "dups.npz"), **duplicate_filter_vectors(tmp))
+            print("dups", "%.2f MB" % (os.path.getsize(os.path.join(datasets.GOLDEN_DIR, "dups.npz")) / 1e6))
+            return
+        np.savez_compressed(os.path.join(datasets.GOLDEN_DIR, "dups.npz"), **duplicate_filter_vectors(tmp))
         for name in datasets.GOLDEN:
             d = datasets.run_reference(name, tmp)
             summ = d.pop("summary")
